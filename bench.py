@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the force-and-drift hot path (BASELINE.json metric).
+
+  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA through the C ABI)
+  python bench.py --impl reference --steps K --warmup W    reference arm: the CPU path on the host cores
+  torchrun ... bench.py --gpus N ...                        N>1: one rank per GPU, i-sliced pl-pl + NCCL allgather
+
+Metric: FP64 pair-interactions/s of the SyMBA planetesimal disk, npl = 1e5 fully interacting massive bodies
+(BASELINE.json configs[3]; fits one GPU).  One STEP = one pass of the hot path over the resident system:
+   ah = 0 ; pl%accel_int (pl-pl gravity, radius-checked, all N(N-1)/2 pairs) ; vb += ah*dt ; pl%drift (Kepler drift)
+   ; [N>1: allgather of the drifted slices] .
+`value` = N(N-1)/2 pairs per step / step time with everything resident in HBM (strong scaling: the system is fixed,
+rows are sliced over the ranks).  `e2e` = the same step with that step's positions and velocities copied from pinned
+host memory and the accelerations/positions/velocities read back, every step.
+The sort-and-sweep encounter check and the WHM test-particle configuration (8 planets + 1e6 tp: pl->tp gravity and tp
+drift) are HBM-bound side legs of the same path; they are timed outside the K steps and reported under "extra" with
+their own roofline figures.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_PAIR_RAD = 28.0   # algorithmic flop per unordered pair with the radius check
+FLOP_PER_TPEVAL = 17.0
+DRIFT_BYTES_PER_BODY = 112.0
+SWEEP_BYTES = dict(body=56.0, sort=2 * 24.0 * 2, gather=2 * 56.0, cand=56.0, out=9.0)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--npl", type=int, default=100000)
+    ap.add_argument("--ntp", type=int, default=1000000)
+    ap.add_argument("--variant", default="auto", choices=["auto", "tri", "flat"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the sweep / tp side legs and the CPU baseline")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
+    ap.add_argument("--conservation", type=int, default=0, help="run an n-step energy/L tracking run (extra)")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([q.strip() for q in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# =====================================================================================================================
+# reference arm / CPU baseline: the oracle's reference-shaped OpenMP loops on the host cores
+# =====================================================================================================================
+def cpu_kick_sample(o, d, rows, reps=1):
+    """Time `rows` rows of the full-row pl-pl loop (swiftest_kick.f90:219-240 shape, schedule(static), all threads).
+    Returns seconds per call."""
+    n = d["n"]
+    acc = np.zeros((n, 3))
+    best = 1e300
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        o.omp_kick_tri_rad_pl_rows(d["rh"], d["Gmass"], d["radius"], acc, n, 0, rows)
+        best = min(best, time.perf_counter() - t0)
+    return best
+
+
+def cpu_baseline(d, seconds):
+    from oracle import load
+    o = load(native=True)
+    n = d["n"]
+    threads = o.omp_threads()
+    probe_rows = min(n, 8 * threads)
+    t = cpu_kick_sample(o, d, probe_rows)
+    rows = int(min(n, max(probe_rows, probe_rows * seconds / max(t, 1e-6))))
+    rows = max(threads, rows - rows % threads)
+    t = cpu_kick_sample(o, d, rows)
+    t_full = t * n / rows
+    pairs = n * (n - 1) / 2.0
+    return {"value": pairs / t_full, "unit": "pair-interactions/s", "cores": threads, "kind": "port",
+            "sample": f"{rows} of {n} rows of the full-row pl-pl loop (kick.f90:219-240 shape, OpenMP schedule(static), "
+                      f"{threads} threads, gcc -O3 -march=x86-64-v3 strict IEEE), {t:.2f} s measured, scaled to all rows",
+            "seconds_full_evaluation_est": t_full}
+
+
+def run_reference(args):
+    """--impl reference: the CPU path (oracle port; the Fortran reference cannot be built in this image) on the host
+    cores.  A step = a bounded row sample of the pl-pl kick scaled to the whole system + the full serial drift."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import load
+    from swiftest_b200 import workloads as W
+    o = load(native=True)
+    d = W.disk(args.npl, seed=3031179)
+    n = d["n"]
+    threads = o.omp_threads()
+    rows = min(n, 8 * threads)
+    t = cpu_kick_sample(o, d, rows)
+    rows = int(min(n, max(rows, rows * 2.0 / max(t, 1e-6))))  # ~2 s of CPU work per step
+    rows = max(threads, rows - rows % threads)
+    pairs = n * (n - 1) / 2.0
+    times = []
+    for it in range(args.warmup + args.steps):
+        tk = cpu_kick_sample(o, d, rows)
+        t0 = time.perf_counter()
+        x, v, fl = o.drift_all(d["mu"], d["rh"], d["vh"], d["dt"])  # serial, as in the reference (drift.f90:99-103)
+        td = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(tk * n / rows + td)
+    step = float(np.mean(times))
+    val = pairs / step
+    sample = (f"per step: {rows} of {n} rows of the full-row pl-pl loop on {threads} OpenMP threads scaled to all rows "
+              f"+ serial Kepler drift of all {n} bodies")
+    print(json.dumps({
+        "impl": "reference", "metric": "FP64 pair-interactions/s (pl-pl N=1e5)", "value": val,
+        "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n,
+                                        "loop": "triangular full-row, radius-checked", "host": "cpu"},
+        "cpu_baseline": {"value": val, "unit": "pair-interactions/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+# =====================================================================================================================
+# our arm
+# =====================================================================================================================
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    from swiftest_b200 import Context, PL, TP, LOOP_FLAT, LOOP_TRIANGULAR, shard, workloads as W
+    from swiftest_b200.context import FAM_PLPL, FAM_PLTP, FAM_DRIFT, FAM_SWEEP, FAM_ALLGATHER
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ctx = Context(local)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if not dist:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    if world > 1:
+        ident = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            ident = torch.frombuffer(bytearray(ctx.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(ident, 0)
+        ctx.comm_init(world, rank, bytes(ident.cpu().numpy().tobytes()))
+
+    # ---------------- workload: SyMBA disk, npl fully interacting bodies ----------------
+    d = W.disk(args.npl, seed=3031179)
+    n, dt = d["n"], d["dt"]
+    pairs = n * (n - 1) / 2.0
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                  mu=d["mu"], generation=1)
+    i0, i1 = shard.partition(n, world, rank)
+    ctx.pl_set_slice(i0, i1)
+    variant = {"auto": LOOP_TRIANGULAR, "tri": LOOP_TRIANGULAR, "flat": LOOP_FLAT}[args.variant]
+
+    def step():
+        ctx.flush_l2()
+        ctx.body_zero_accel(PL)
+        ctx.pl_accel_int(variant, True)
+        ctx.body_kick_velocity(PL, dt)
+        ctx.body_drift(PL, dt, want_nfail=False)
+        if world > 1:
+            ctx.pl_allgather(with_v=True)
+
+    def reset_state():
+        ctx.body_put(PL, r=d["rh"], v=d["vh"])
+
+    # ---------------- device-resident timing ----------------
+    ctx.enable_kernel_timing(True)
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    kick_ms = []
+    barrier()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+        kick_ms.append(ctx.last_kernel_ms(FAM_PLPL))
+    ms_total = ctx.timer_stop()
+    barrier()
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = max_over_ranks(ms_total / args.steps)
+    value = pairs / (ms_step * 1e-3)
+    kick_ms_avg = max_over_ranks(float(np.mean(kick_ms)))
+    fp64_peak = ctx.probe_fp64_peak()
+
+    # ---------------- end-to-end: host buffers in, results out, every step ----------------
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    h_r, h_v = pin(d["rh"]), pin(d["vh"])
+    out = {"r": pin(np.zeros((n, 3))), "v": pin(np.zeros((n, 3))), "a": pin(np.zeros((n, 3)))}
+
+    def step_e2e():
+        ctx.body_put(PL, r=h_r, v=h_v)
+        step()
+        ctx.body_get(PL, out=out)
+
+    ctx.enable_kernel_timing(False)
+    for _ in range(max(1, args.warmup)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    e2e = {"value": pairs / e2e_s, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(2 * 3 * n * 8 * world),
+           "d2h_bytes_per_step": int(3 * 3 * n * 8 * world), "ms_per_step": e2e_s * 1e3,
+           "path": "swcu_body_put(r,v) -> zero/accel_int/kick/drift[/allgather] -> swcu_body_get(r,v,a), pinned host arrays"}
+
+    hbm_peak, peak_src = peaks()
+    rows_local = i1 - i0
+    flops_kernel = FLOP_PER_PAIR_RAD * (rows_local * (n - 1) / 2.0)  # algorithmic flop of this rank's launch
+    achieved = flops_kernel / (kick_ms_avg * 1e-3) / 1e12
+    roofline = {"bound": "fp64", "kernel": "kick_rows_kernel (pl-pl gravity)", "achieved": achieved, "peak": fp64_peak,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                "peak_source": "DFMA microbenchmark run in this process (swcu_probe_fp64_peak); MEASURED_PEAKS.json holds "
+                               "no FP64 figure",
+                "algorithmic_flop_per_pair": FLOP_PER_PAIR_RAD, "kernel_ms": kick_ms_avg,
+                "executed_flop_per_pair_full_row": 40.0}
+
+    extra = {}
+    if not args.no_extra and rank == 0 and world == 1:
+        extra = side_legs(ctx, args, d, hbm_peak, peak_src)
+    cpu = None
+    if not args.no_extra and rank == 0 and world == 1:
+        try:
+            cpu = cpu_baseline(d, args.cpu_seconds)
+        except Exception as e:  # the CPU baseline is a reported figure, never a dependency of the GPU number
+            cpu = {"value": None, "unit": "pair-interactions/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+    if args.conservation and rank == 0 and world == 1:
+        extra["conservation"] = conservation_run(ctx, args.conservation)
+
+    if rank == 0:
+        line = {
+            "metric": "FP64 pair-interactions/s (pl-pl N=1e5)", "value": value, "unit": "pair-interactions/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n, "nplm": n,
+                       "loop": "triangular full-row" if variant == LOOP_TRIANGULAR else "flat third-law",
+                       "lclose": True, "step": "zero_accel+accel_int+kick_velocity+drift" + ("+allgather(r,v)" if world > 1 else ""),
+                       "sharding": f"i-slices over {world} rank(s)", "l2": "flushed between steps (256 MiB write inside the timed region)",
+                       "seed": 3031179},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "peaks": {"fp64_tflops_measured": fp64_peak, "hbm_gbs": hbm_peak, "hbm_source": peak_src},
+            "extra": extra}
+        print(json.dumps(line))
+    if dist:
+        dist.barrier()
+        ctx.comm_finalize()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def side_legs(ctx, args, d, hbm_peak, peak_src):
+    """Sweep on the same disk and the WHM tp configuration; timed outside the K headline steps."""
+    from swiftest_b200 import PL, TP, workloads as W
+    from swiftest_b200.context import FAM_PLTP, FAM_DRIFT, FAM_SWEEP
+    ex = {}
+    n = d["n"]
+    ctx.enable_kernel_timing(True)
+    ctx.body_put(PL, r=d["rh"], v=d["vh"])
+    ctx.pl_set_renc(0)
+    ms = []
+    for it in range(6):
+        ctx.flush_l2()
+        nenc = ctx.pl_encounter_check(d["dt"], fetch=False)
+        if it >= 2:
+            ms.append(ctx.last_kernel_ms(FAM_SWEEP))
+    st = ctx.encounter_stats()
+    b = SWEEP_BYTES
+    bytes_alg = n * b["body"] + 2 * n * b["sort"] / 2 + 2 * n * 56.0 + st["nbox_total"] * b["cand"] + nenc * b["out"]
+    t = float(np.mean(ms)) * 1e-3
+    ex["sweep_plpl"] = {"npl": n, "nenc": int(nenc), "nbox_total": int(st["nbox_total"]), "ms": t * 1e3,
+                        "algorithmic_bytes": bytes_alg, "roofline": {"bound": "hbm", "achieved": bytes_alg / t / 1e9,
+                                                                     "peak": hbm_peak, "unit": "GB/s",
+                                                                     "frac": bytes_alg / t / 1e9 / hbm_peak,
+                                                                     "peak_source": peak_src}}
+    # WHM: Sun + 8 planets + ntp test particles (BASELINE.json configs[1])
+    p = W.planets8_year_units()
+    ntp = args.ntp
+    tp = W.tp_cloud(ntp, seed=123)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=p["cb_Gmass"] + p["Gmass"], generation=2)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, p["cb_Gmass"]), generation=3)
+    kms, dms = [], []
+    for it in range(8):
+        ctx.flush_l2()
+        ctx.body_zero_accel(TP)
+        ctx.tp_accel_int()
+        ctx.body_kick_velocity(TP, 0.01)
+        ctx.body_drift(TP, 0.01, want_nfail=False)
+        if it >= 3:
+            kms.append(ctx.last_kernel_ms(FAM_PLTP))
+            dms.append(ctx.last_kernel_ms(FAM_DRIFT))
+    tk, td = float(np.mean(kms)) * 1e-3, float(np.mean(dms)) * 1e-3
+    kick_bytes = ntp * 76.0 + 8 * 32.0
+    ex["whm_tp"] = {"npl": 8, "ntp": ntp,
+                    "pltp_kick": {"ms": tk * 1e3, "evals_per_s": 8.0 * ntp / tk, "gflops_algorithmic": FLOP_PER_TPEVAL * 8 * ntp / tk / 1e9,
+                                  "roofline": {"bound": "hbm", "achieved": kick_bytes / tk / 1e9, "peak": hbm_peak,
+                                               "unit": "GB/s", "frac": kick_bytes / tk / 1e9 / hbm_peak}},
+                    "drift": {"ms": td * 1e3, "bodies_per_s": ntp / td,
+                              "roofline": {"bound": "hbm", "achieved": DRIFT_BYTES_PER_BODY * ntp / td / 1e9,
+                                           "peak": hbm_peak, "unit": "GB/s",
+                                           "frac": DRIFT_BYTES_PER_BODY * ntp / td / 1e9 / hbm_peak}}}
+    ms = []
+    ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
+    ctx.pl_set_renc(0)
+    for it in range(5):
+        ctx.flush_l2()
+        nenc = ctx.tp_encounter_check(0.01, fetch=False)
+        if it >= 2:
+            ms.append(ctx.last_kernel_ms(FAM_SWEEP))
+    st = ctx.encounter_stats()
+    ex["sweep_pltp"] = {"npl": 8, "ntp": ntp, "nenc": int(nenc), "nbox_total": int(st["nbox_total"]),
+                        "ms": float(np.mean(ms))}
+    ctx.enable_kernel_timing(False)
+    return ex
+
+
+def conservation_run(ctx, nsteps):
+    """Energy / angular momentum of Sun + 8 planets over nsteps helio steps: GPU path vs CPU oracle (north star)."""
+    from oracle import load
+    from swiftest_b200 import workloads as W
+    from tests.helio import GpuBackend, HelioSystem, OracleBackend
+    p = W.planets8_year_units()
+    a = HelioSystem(p["cb_Gmass"], p["Gmass"], p["rh"], p["vh"], p["radius"], OracleBackend(load()))
+    b = HelioSystem(p["cb_Gmass"], p["Gmass"], p["rh"], p["vh"], p["radius"], GpuBackend(ctx))
+    E0, L0 = a.energy_and_momentum()
+    for _ in range(nsteps):
+        a.step(0.01)
+        b.step(0.01)
+    Ea, La = a.energy_and_momentum()
+    Eb, Lb = b.energy_and_momentum()
+    return {"steps": nsteps, "dt": 0.01, "dE_cpu": (Ea - E0) / abs(E0), "dE_gpu": (Eb - E0) / abs(E0),
+            "dL_cpu": float(np.linalg.norm(La - L0) / np.linalg.norm(L0)),
+            "dL_gpu": float(np.linalg.norm(Lb - L0) / np.linalg.norm(L0)),
+            "max_position_difference": float(np.max(np.abs(a.rh - b.rh)))}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,195 @@
+/*
+ * swiftest_cuda.h -- C ABI of libswiftest_cuda.so, the B200 (sm_100a) implementation of Swiftest's
+ * force-and-drift hot path.  This is the drop-in boundary: the Fortran submodule bodies that today hold the
+ * OpenMP loops call these entry points through an iso_c_binding interface module (fortran/swiftest_cuda.f90,
+ * INTEGRATION.md).  The reference has no FFI for this path; each entry point cites the Fortran interface it
+ * replaces ("file:line" relative to /root/reference/src).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all functions return an int status (SWCU_OK == 0); on failure
+ *     swcu_last_error(ctx) holds a message and the Fortran wrapper calls base_util_exit(FAILURE).
+ *   - array layout is the Fortran one: real(DP) r(NDIM,n) column-major == double[3*n] {x1,y1,z1,x2,...};
+ *     Gmass(n), radius(n), renc(n), mu(n) contiguous doubles; logical masks are passed as int32 (0/1),
+ *     converted by the wrapper with merge(1_c_int,0_c_int,lmask) (gfortran/Intel differ in the bit pattern
+ *     of .true.); body indices crossing the interface are 1-based, nplpl/nenc are 64-bit (integer(I8B)).
+ *   - host pointers are only read/written during the call; the library owns all device memory.
+ *   - one context per process/GPU; calls are serialised by the caller (every reference call site is in
+ *     serial host code; the OpenMP regions live inside the loops this library replaces).
+ *   - there is NO CPU fallback: every compute entry point runs CUDA kernels or fails.
+ */
+#ifndef SWIFTEST_CUDA_H
+#define SWIFTEST_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct swcu_context swcu_context;
+
+enum swcu_status {
+    SWCU_OK = 0,
+    SWCU_ERR_CUDA = 1,  /* a CUDA runtime call or kernel failed */
+    SWCU_ERR_ARG = 2,   /* invalid argument */
+    SWCU_ERR_STATE = 3, /* call sequence error (e.g. fetch before check, arrays not resident) */
+    SWCU_ERR_NCCL = 4,  /* NCCL could not be loaded or a collective failed */
+    SWCU_ERR_NOGPU = 5  /* no usable sm_100 device: the product path refuses to run */
+};
+
+/* pl-pl loop shapes (param%lflatten_interactions, swiftest_io.f90:2707-2718) */
+enum swcu_loop_variant {
+    SWCU_LOOP_TRIANGULAR = 0, /* full-row kernel, ascending-j sum per row (kick.f90:219-265) */
+    SWCU_LOOP_FLAT = 1,       /* Newton's-third-law pair kernel (kick.f90:95-112), tile-generated (i,j) */
+    SWCU_LOOP_AUTO = 2        /* whichever measured faster for this (npl, nplm) on this device */
+};
+
+/* ------------------------------------------------------------------------------------------------------
+ * Context (created once per run from swiftest_util_setup_initialize_system, swiftest_util.f90:2415)
+ * ---------------------------------------------------------------------------------------------------- */
+int swcu_create(int device, swcu_context **ctx);
+int swcu_destroy(swcu_context *ctx);
+const char *swcu_last_error(const swcu_context *ctx);
+int swcu_version(void);
+/* Run all work on a caller-provided cudaStream_t (NULL restores the library's own stream). */
+int swcu_set_stream(swcu_context *ctx, void *cuda_stream);
+int swcu_synchronize(swcu_context *ctx);
+/* device properties as seen by the library: sm count, compute capability major*10+minor, bytes of HBM */
+int swcu_device_info(swcu_context *ctx, int32_t *sm_count, int32_t *cc, int64_t *mem_bytes);
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+int64_t swcu_launch_count(const swcu_context *ctx);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tier 1: array-level entry points with HOST pointers.  One call == upload, kernels, download.
+ * They mirror the specifics of the generic swiftest_kick_getacch_int_all (swiftest_module.f90:940-991),
+ * swiftest_drift_all (:513-522) and the encounter_check_all_* family (encounter_module.f90:110-161).
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* swiftest_kick_getacch_int_all_flat_rad_pl / _flat_norad_pl (kick.f90:69-115, 118-162).
+ * k_plpl == NULL: the pairs are the first nplpl entries of the canonical flattened upper triangle built by
+ *   swiftest_util_flatten_eucl_plpl (swiftest_util.f90:1090-1130); nplpl must equal
+ *   nplm*npl - nplm*(nplm+1)/2 for some 0 <= nplm <= npl (symba_util.f90:202), which is how every
+ *   reference caller uses it.  The 8-byte-per-pair table (40 GB at npl=1e5) is never materialised.
+ * k_plpl != NULL: explicit int32 pairs k_plpl(2,nplpl), 1-based (the SyMBA encounter-list call,
+ *   symba_kick.f90:61-68).
+ * radius == NULL selects the norad variant.  acc(3,npl) is updated in place (acc += ...). */
+int swcu_kick_getacch_int_all_flat_pl(swcu_context *ctx, int32_t npl, int64_t nplpl, const int32_t *k_plpl,
+                                      const double *r, const double *Gmass, const double *radius, double *acc);
+
+/* swiftest_kick_getacch_int_all_tri_rad_pl / _tri_norad_pl (kick.f90:165-271, 274-371).
+ * Rows i<=nplm interact with every j != i; rows i>nplm with j<=nplm.  radius == NULL: norad variant. */
+int swcu_kick_getacch_int_all_tri_pl(swcu_context *ctx, int32_t npl, int32_t nplm, const double *r,
+                                     const double *Gmass, const double *radius, double *acc);
+
+/* swiftest_kick_getacch_int_all_tp (kick.f90:374-415): acc(:,i) -= GMpl(j)*(rtp_i - rpl_j)/|.|^3 for lmask(i) */
+int swcu_kick_getacch_int_all_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double *rtp, const double *rpl,
+                                 const double *GMpl, const int32_t *lmask, double *acc);
+
+/* symba_kick_getacch_pl, the encounter-pair removal (symba_kick.f90:59-70): the pairs of the encounter list
+ * are evaluated again with the flat_rad kernel into a zeroed ah_enc and subtracted, ah -= ah_enc. */
+int swcu_symba_kick_subtract_encounters(swcu_context *ctx, int32_t npl, int64_t nenc, const int32_t *index1,
+                                        const int32_t *index2, const double *rh, const double *Gmass,
+                                        const double *radius, double *ah);
+
+/* swiftest_drift_all (drift.f90:60-108).  mu(n), x(3,n), v(3,n) inout; lgr/inv_c2 are param%lgr/param%inv_c2;
+ * iflag(i) is written for lmask(i) true only (0 = OK, nonzero = no convergence, drift.f90:123). */
+int swcu_drift_all(swcu_context *ctx, int32_t n, const double *mu, double *x, double *v, double dt, int32_t lgr,
+                   double inv_c2, const int32_t *lmask, int32_t *iflag);
+
+/* encounter_check_all_sort_and_sweep_plpl / _pltp / _plplm (encounter_check.f90:143-326) and the merging
+ * caller encounter_check_all_plplm (:42-109).  Two-phase because the Fortran caller allocates the
+ * intent(out) arrays after learning nenc: the check returns nenc, swcu_encounter_fetch copies the pairs.
+ * Pairs are 1-based, in canonical lexicographic (index1,index2) order; lvdotr is all .true.. */
+int swcu_encounter_check_all_sort_and_sweep_plpl(swcu_context *ctx, int32_t npl, const double *r, const double *v,
+                                                 const double *renc, double dt, int64_t *nenc);
+int swcu_encounter_check_all_sort_and_sweep_pltp(swcu_context *ctx, int32_t npl, int32_t ntp, const double *rpl,
+                                                 const double *vpl, const double *rtp, const double *vtp,
+                                                 const double *rencpl, double dt, int64_t *nenc);
+int swcu_encounter_check_all_sort_and_sweep_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt, const double *rplm,
+                                                  const double *vplm, const double *rplt, const double *vplt,
+                                                  const double *rencm, const double *renct, double dt,
+                                                  int64_t *nenc);
+int swcu_encounter_check_all_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt, const double *rplm,
+                                   const double *vplm, const double *rplt, const double *vplt, const double *rencm,
+                                   const double *renct, double dt, int64_t *nenc);
+int swcu_encounter_fetch(swcu_context *ctx, int64_t nenc, int32_t *index1, int32_t *index2, int32_t *lvdotr);
+/* statistics of the last sort-and-sweep: broad-phase candidates sum_i nbox_i, and bytes the sweep kernel read */
+int swcu_encounter_stats(swcu_context *ctx, int64_t *nbox_total, int64_t *ncandidates_emitted);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Tier 2: device-resident bodies (what the type-bound procedures pl%accel_int, tp%accel_int, body%drift,
+ * pl%/tp%encounter_check use: swiftest_module.f90:164,265,307; symba_module.f90:37-40,59-60).
+ * Arrays are uploaded only when `generation` changes -- the Fortran side bumps it in rearray_pl
+ * (swiftest_util.f90:1638), tp%spill (swiftest_discard.f90:108-111), Fraggle's pl%flatten and restart
+ * read-in, the only places the body count or ordering changes.
+ * ---------------------------------------------------------------------------------------------------- */
+enum swcu_body_kind { SWCU_PL = 0, SWCU_TP = 1 };
+
+/* Full (re)upload of one body population.  Any pointer may be NULL (that array is then zero-filled, except
+ * lmask which defaults to all-true).  r,v are (3,n); for pl `v` is whichever velocity the integrator drifts
+ * (vb for HELIO/SyMBA, helio_drift.f90:38-40).  Returns immediately if generation is unchanged and n matches. */
+int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_t nplm, const double *r, const double *v,
+                   const double *Gmass, const double *radius, const double *rhill, const double *mu,
+                   const int32_t *lmask, uint64_t generation);
+/* refresh / read back individual resident arrays (NULL pointers are skipped) */
+int swcu_body_put(swcu_context *ctx, int32_t kind, const double *r, const double *v, const double *a,
+                  const int32_t *lmask);
+int swcu_body_get(swcu_context *ctx, int32_t kind, double *r, double *v, double *a, int32_t *iflag);
+int swcu_body_count(swcu_context *ctx, int32_t kind, int32_t *n, int32_t *nplm, uint64_t *generation);
+
+/* ah = 0 (helio_kick_vb_pl zeroes ah before accel, helio_kick.f90:113) */
+int swcu_body_zero_accel(swcu_context *ctx, int32_t kind);
+/* pl%accel_int: resident rh -> resident ah +=.  lclose selects the radius-checked variants (kick.f90:29,35). */
+int swcu_pl_accel_int(swcu_context *ctx, int32_t loop_variant, int32_t lclose);
+/* tp%accel_int(param, GMpl, rhp, npl): planets come from the resident pl population (its r and Gmass). */
+int swcu_tp_accel_int(swcu_context *ctx);
+/* symba_pl%set_renc(irec) (symba_util.f90:245-267): renc = rhill * RHSCALE * RSHELL**irec */
+int swcu_pl_set_renc(swcu_context *ctx, int32_t irec);
+/* body%drift on the resident r,v with resident mu and lmask; iflag stays resident (swcu_body_get) and the
+ * number of bodies with iflag != 0 is returned in nfail */
+int swcu_body_drift(swcu_context *ctx, int32_t kind, double dt, int32_t lgr, double inv_c2, int32_t *nfail);
+/* v += a*dt for masked bodies (helio_kick_vb_pl/tp, helio_kick.f90:113-128,157-165) -- O(N) glue kept on the
+ * device so a kick-drift sequence needs no host round trip */
+int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt);
+/* pl%encounter_check / tp%encounter_check on resident r,v,renc (symba_encounter_check.f90:14-87,238-296);
+ * nplm<npl uses the plplm path.  Results via swcu_encounter_fetch. */
+int swcu_pl_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);
+int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Multi-GPU: one process (context) per GPU.  pl-pl gravity is split by contiguous i-slices with an NCCL
+ * allgather of the drifted positions (and velocities) each step; test particles are block-partitioned like
+ * swiftest_coarray_distribute_system (swiftest_coarray.f90:705-711) with the pl population replicated.
+ * ---------------------------------------------------------------------------------------------------- */
+#define SWCU_NCCL_ID_BYTES 128
+int swcu_comm_unique_id(swcu_context *ctx, void *id128);             /* rank 0: create the id, then broadcast it */
+int swcu_comm_init(swcu_context *ctx, int32_t nranks, int32_t rank, const void *id128);
+int swcu_comm_finalize(swcu_context *ctx);
+/* rows [i0,i1) (0-based, half-open) of the resident pl population that this rank kicks and drifts */
+int swcu_pl_set_slice(swcu_context *ctx, int32_t i0, int32_t i1);
+/* allgather the slices of r (and v when with_v != 0) so every rank holds the full updated population.
+ * Slices must be the balanced partition produced by swcu_partition. */
+int swcu_pl_allgather(swcu_context *ctx, int32_t with_v);
+/* balanced contiguous partition of n units over nranks: counts differ by at most one, big ranks first */
+int swcu_partition(int32_t n, int32_t nranks, int32_t rank, int32_t *i0, int32_t *i1);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Measurement helpers (CUDA events on the library's stream; probes for the roofline denominators)
+ * ---------------------------------------------------------------------------------------------------- */
+int swcu_timer_start(swcu_context *ctx);
+int swcu_timer_stop(swcu_context *ctx, double *elapsed_ms); /* synchronises on the stop event */
+/* register-resident DFMA loop: achieved FP64 TFLOP/s (2 flop per DFMA) on this device at current clocks */
+int swcu_probe_fp64_peak(swcu_context *ctx, double *tflops);
+/* device-to-device copy of `bytes`: achieved read+write GB/s */
+int swcu_probe_hbm_copy(swcu_context *ctx, int64_t bytes, double *gbs);
+/* write a buffer larger than L2 (flush between timed iterations) */
+int swcu_flush_l2(swcu_context *ctx);
+/* duration in ms of the most recent launch group of a kernel family, measured with CUDA events inside the
+ * library: 0 = pl-pl gravity, 1 = pl-tp gravity, 2 = drift, 3 = sweep (sort..compaction), 4 = allgather */
+int swcu_last_kernel_ms(swcu_context *ctx, int32_t family, double *ms);
+int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWIFTEST_CUDA_H */

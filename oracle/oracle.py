@@ -1,0 +1,215 @@
+"""ctypes binding of oracle/libswiftest_oracle.so (the CPU restatement of the reference loops).
+
+TEST INFRASTRUCTURE ONLY.  PARITY: kick / sweep unpinned, drift pinned to the reference's Python two-body
+propagation (see swiftest_oracle.h).  Arrays follow the Fortran layout r(3,n) == numpy shape (n,3) C-order.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_f64 = np.float64
+_i32 = np.int32
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _c(a, dt=_f64):
+    return np.ascontiguousarray(a, dtype=dt)
+
+
+def build(native=True):
+    subprocess.check_call(["make", "-s", "-C", _HERE, "all" if native else "libswiftest_oracle.so"])
+
+
+class Oracle:
+    def __init__(self, native=False):
+        name = "libswiftest_oracle_native.so" if native else "libswiftest_oracle.so"
+        path = os.path.join(_HERE, name)
+        if not os.path.exists(path):
+            build()
+        self.lib = L = C.CDLL(path)
+        d, i32, i64, p = C.c_double, C.c_int32, C.c_int64, C.c_void_p
+        L.swo_nplplm.restype = i64
+        L.swo_nplplm.argtypes = [i64, i64]
+        for n in ("swo_encounter_sas_plpl", "swo_encounter_tri_plpl"):
+            getattr(L, n).restype = i64
+            getattr(L, n).argtypes = [i32, p, p, p, d]
+        for n in ("swo_encounter_sas_pltp", "swo_encounter_tri_pltp"):
+            getattr(L, n).restype = i64
+            getattr(L, n).argtypes = [i32, i32, p, p, p, p, p, d]
+        for n in ("swo_encounter_sas_plplm", "swo_encounter_all_plplm"):
+            getattr(L, n).restype = i64
+            getattr(L, n).argtypes = [i32, i32, p, p, p, p, p, p, d]
+        L.swo_encounter_last_nbox_total.restype = i64
+        L.swo_encounter_fetch.argtypes = [p, p, p]
+        L.swo_kick_flat_rad_pl.argtypes = [i32, i64, p, p, p, p, p]
+        L.swo_kick_flat_norad_pl.argtypes = [i32, i64, p, p, p, p]
+        L.swo_kick_tri_rad_pl.argtypes = [i32, i32, p, p, p, p]
+        L.swo_kick_tri_norad_pl.argtypes = [i32, i32, p, p, p]
+        L.swo_kick_tri_abs_scale.argtypes = [i32, i32, p, p, p, C.c_int, p]
+        L.swo_kick_all_tp.argtypes = [i32, i32, p, p, p, p, p]
+        L.swo_symba_kick_subtract_enc.argtypes = [i32, i64, p, p, p, p, p, p]
+        L.swo_omp_kick_flat_rad_pl.argtypes = [i32, i32, p, p, p, p]
+        L.swo_omp_kick_tri_rad_pl.argtypes = [i32, i32, p, p, p, p]
+        L.swo_omp_kick_tri_rad_pl_rows.argtypes = [i32, i32, i32, i32, p, p, p, p]
+        L.swo_omp_kick_all_tp.argtypes = [i32, i32, p, p, p, p, p]
+        L.swo_drift_all.argtypes = [p, p, p, i32, C.c_int, d, d, p, p]
+        L.swo_omp_drift_all.argtypes = [p, p, p, i32, C.c_int, d, d, p, p]
+        L.swo_drift_branch.restype = i32
+        L.swo_drift_branch.argtypes = [d] * 8
+        L.swo_symba_set_renc.argtypes = [i32, p, i32, p]
+        L.swo_encounter_check_one.argtypes = [d] * 8 + [p, p]
+        L.swo_flatten_k_to_ij.argtypes = [i32, i64, p, p]
+        L.swo_flatten_ij_to_k.argtypes = [i32, i32, i32, p]
+        L.swo_omp_max_threads.restype = C.c_int
+
+    # ---------------- gravity ----------------
+    def nplplm(self, npl, nplm):
+        return int(self.lib.swo_nplplm(npl, nplm))
+
+    def kick_flat_pl(self, r, Gmass, radius, acc, nplpl=None, k_plpl=None):
+        """swiftest_kick_getacch_int_all_flat_{rad,norad}_pl; radius=None selects norad. Returns new acc."""
+        r, Gmass, acc = _c(r), _c(Gmass), _c(acc).copy()
+        npl = len(Gmass)
+        kp = None
+        if k_plpl is not None:
+            k_plpl = _c(k_plpl, _i32)
+            nplpl = k_plpl.shape[0]
+            kp = k_plpl.ctypes.data
+        elif nplpl is None:
+            nplpl = npl * (npl - 1) // 2
+        if radius is None:
+            self.lib.swo_kick_flat_norad_pl(npl, nplpl, kp, r.ctypes.data, Gmass.ctypes.data, acc.ctypes.data)
+        else:
+            radius = _c(radius)
+            self.lib.swo_kick_flat_rad_pl(npl, nplpl, kp, r.ctypes.data, Gmass.ctypes.data, radius.ctypes.data,
+                                          acc.ctypes.data)
+        return acc
+
+    def kick_tri_pl(self, r, Gmass, radius, acc, nplm=None):
+        r, Gmass, acc = _c(r), _c(Gmass), _c(acc).copy()
+        npl = len(Gmass)
+        nplm = npl if nplm is None else nplm
+        if radius is None:
+            self.lib.swo_kick_tri_norad_pl(npl, nplm, r.ctypes.data, Gmass.ctypes.data, acc.ctypes.data)
+        else:
+            radius = _c(radius)
+            self.lib.swo_kick_tri_rad_pl(npl, nplm, r.ctypes.data, Gmass.ctypes.data, radius.ctypes.data,
+                                         acc.ctypes.data)
+        return acc
+
+    def kick_tri_abs_scale(self, r, Gmass, radius, nplm=None):
+        r, Gmass = _c(r), _c(Gmass)
+        npl = len(Gmass)
+        nplm = npl if nplm is None else nplm
+        scale = np.zeros((npl, 3))
+        rad = _c(radius) if radius is not None else np.zeros(npl)
+        self.lib.swo_kick_tri_abs_scale(npl, nplm, r.ctypes.data, Gmass.ctypes.data, rad.ctypes.data,
+                                        int(radius is not None), scale.ctypes.data)
+        return scale
+
+    def kick_all_tp(self, rtp, rpl, GMpl, lmask, acc):
+        rtp, rpl, GMpl, acc = _c(rtp), _c(rpl), _c(GMpl), _c(acc).copy()
+        lmask = _c(lmask, _i32)
+        self.lib.swo_kick_all_tp(len(rtp), len(GMpl), rtp.ctypes.data, rpl.ctypes.data, GMpl.ctypes.data,
+                                 lmask.ctypes.data, acc.ctypes.data)
+        return acc
+
+    def symba_kick_subtract_enc(self, index1, index2, rh, Gmass, radius, ah):
+        rh, Gmass, radius, ah = _c(rh), _c(Gmass), _c(radius), _c(ah).copy()
+        i1, i2 = _c(index1, _i32), _c(index2, _i32)
+        self.lib.swo_symba_kick_subtract_enc(len(Gmass), len(i1), i1.ctypes.data, i2.ctypes.data, rh.ctypes.data,
+                                             Gmass.ctypes.data, radius.ctypes.data, ah.ctypes.data)
+        return ah
+
+    def omp_kick_tri_rad_pl_rows(self, r, Gmass, radius, acc, nplm, i0, i1):
+        self.lib.swo_omp_kick_tri_rad_pl_rows(len(Gmass), nplm, i0, i1, r.ctypes.data, Gmass.ctypes.data,
+                                              radius.ctypes.data, acc.ctypes.data)
+
+    def omp_kick_flat_rad_pl(self, r, Gmass, radius, acc, nplm):
+        self.lib.swo_omp_kick_flat_rad_pl(len(Gmass), nplm, r.ctypes.data, Gmass.ctypes.data, radius.ctypes.data,
+                                          acc.ctypes.data)
+
+    def omp_kick_all_tp(self, rtp, rpl, GMpl, lmask, acc):
+        self.lib.swo_omp_kick_all_tp(len(rtp), len(GMpl), rtp.ctypes.data, rpl.ctypes.data, GMpl.ctypes.data,
+                                     lmask.ctypes.data, acc.ctypes.data)
+
+    def omp_threads(self):
+        return int(self.lib.swo_omp_max_threads())
+
+    # ---------------- drift ----------------
+    def drift_all(self, mu, x, v, dt, lmask=None, lgr=False, inv_c2=0.0, omp=False):
+        """swiftest_drift_all. Returns (x, v, iflag) new arrays."""
+        x, v = _c(x).copy(), _c(v).copy()
+        n = len(x)
+        mu = np.full(n, mu, dtype=_f64) if np.isscalar(mu) else _c(mu)
+        lmask = np.ones(n, _i32) if lmask is None else _c(lmask, _i32)
+        iflag = np.zeros(n, _i32)
+        fn = self.lib.swo_omp_drift_all if omp else self.lib.swo_drift_all
+        fn(mu.ctypes.data, x.ctypes.data, v.ctypes.data, n, int(lgr), float(inv_c2), float(dt), lmask.ctypes.data,
+           iflag.ctypes.data)
+        return x, v, iflag
+
+    def drift_branch(self, mu, x, v, dt):
+        x, v = _c(x), _c(v)
+        mu = np.full(len(x), mu) if np.isscalar(mu) else mu
+        return np.array([self.lib.swo_drift_branch(float(mu[i]), *map(float, x[i]), *map(float, v[i]), float(dt))
+                         for i in range(len(x))], dtype=_i32)
+
+    # ---------------- encounters ----------------
+    def set_renc(self, rhill, irec):
+        rhill = _c(rhill)
+        renc = np.empty_like(rhill)
+        self.lib.swo_symba_set_renc(len(rhill), rhill.ctypes.data, irec, renc.ctypes.data)
+        return renc
+
+    def _fetch(self, nenc):
+        i1, i2, lv = np.empty(nenc, _i32), np.empty(nenc, _i32), np.empty(nenc, _i32)
+        if nenc:
+            self.lib.swo_encounter_fetch(i1.ctypes.data, i2.ctypes.data, lv.ctypes.data)
+        return i1, i2, lv
+
+    def encounter_plpl(self, r, v, renc, dt, triangular=False):
+        r, v, renc = _c(r), _c(v), _c(renc)
+        fn = self.lib.swo_encounter_tri_plpl if triangular else self.lib.swo_encounter_sas_plpl
+        nenc = fn(len(renc), r.ctypes.data, v.ctypes.data, renc.ctypes.data, float(dt))
+        return self._fetch(nenc)
+
+    def encounter_pltp(self, rpl, vpl, rtp, vtp, renc, dt, triangular=False):
+        rpl, vpl, rtp, vtp, renc = _c(rpl), _c(vpl), _c(rtp), _c(vtp), _c(renc)
+        fn = self.lib.swo_encounter_tri_pltp if triangular else self.lib.swo_encounter_sas_pltp
+        nenc = fn(len(renc), len(rtp), rpl.ctypes.data, vpl.ctypes.data, rtp.ctypes.data, vtp.ctypes.data,
+                  renc.ctypes.data, float(dt))
+        return self._fetch(nenc)
+
+    def encounter_plplm(self, rplm, vplm, rplt, vplt, rencm, renct, dt, merged=False):
+        a = [_c(q) for q in (rplm, vplm, rplt, vplt, rencm, renct)]
+        fn = self.lib.swo_encounter_all_plplm if merged else self.lib.swo_encounter_sas_plplm
+        nenc = fn(len(a[4]), len(a[5]), *[q.ctypes.data for q in a], float(dt))
+        return self._fetch(nenc)
+
+    def nbox_total(self):
+        return int(self.lib.swo_encounter_last_nbox_total())
+
+    def encounter_check_one(self, xr, yr, zr, vxr, vyr, vzr, renc, dt):
+        a, b = C.c_int32(0), C.c_int32(0)
+        self.lib.swo_encounter_check_one(xr, yr, zr, vxr, vyr, vzr, renc, dt, C.byref(a), C.byref(b))
+        return bool(a.value), bool(b.value)
+
+
+_cache = {}
+
+
+def load(native=False):
+    if native not in _cache:
+        _cache[native] = Oracle(native)
+    return _cache[native]

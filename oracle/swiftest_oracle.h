@@ -1,0 +1,108 @@
+/*
+ * swiftest_oracle.h -- CPU restatement of Swiftest's force-and-drift hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product: only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it,
+ * and there only as the checker / reported CPU baseline.  The CUDA product path never calls it.
+ *
+ * PARITY STATUS: the reference (Swiftest 2023.10.2, Modern Fortran) holds no function-level
+ * golden vectors or known-answer tests for kick / sweep / drift, and no
+ * Fortran compiler exists in the build container, so the reference cannot be run here.
+ *   - kick and sort-and-sweep: PARITY UNPINNED (line-by-line restatement, self-consistency checks only).
+ *   - drift: pinned to the reference's own Python two-body propagation (swiftest/tool.py
+ *     xv2el_one/el2xv_one, imported from /root/reference by tests/golden/gen_golden.py) at 1e-11.
+ *
+ * Every function cites the reference file:line it follows (paths relative to /root/reference/src).
+ * Arrays use the Fortran memory layout: r(3,n) column-major == C r[3*i + {0,1,2}].
+ * Indices crossing this interface are 1-based exactly as in the reference.
+ * Compile with -ffp-contract=off: one IEEE-754 double operation per Fortran operation, left to right.
+ */
+#ifndef SWIFTEST_ORACLE_H
+#define SWIFTEST_ORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- gravity: swiftest/swiftest_kick.f90 ---- */
+void swo_kick_one_pl(double rji2, double xr, double yr, double zr, double Gmi, double Gmj,
+                     double *axi, double *ayi, double *azi, double *axj, double *ayj, double *azj);
+void swo_kick_one_tp(double rji2, double xr, double yr, double zr, double GMpl, double *ax, double *ay, double *az);
+/* k_plpl == NULL means the canonical flattened upper-triangular order of swiftest_util_flatten_eucl_plpl */
+void swo_kick_flat_rad_pl(int32_t npl, int64_t nplpl, const int32_t *k_plpl, const double *r, const double *Gmass,
+                          const double *radius, double *acc);
+void swo_kick_flat_norad_pl(int32_t npl, int64_t nplpl, const int32_t *k_plpl, const double *r, const double *Gmass,
+                            double *acc);
+void swo_kick_tri_rad_pl(int32_t npl, int32_t nplm, const double *r, const double *Gmass, const double *radius,
+                         double *acc);
+void swo_kick_tri_norad_pl(int32_t npl, int32_t nplm, const double *r, const double *Gmass, double *acc);
+void swo_kick_all_tp(int32_t ntp, int32_t npl, const double *rtp, const double *rpl, const double *GMpl,
+                     const int32_t *lmask, double *acc);
+/* symba/symba_kick.f90:59-70 : ah -= flat_rad(encounter list) */
+void swo_symba_kick_subtract_enc(int32_t npl, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                                 const double *rh, const double *Gmass, const double *radius, double *ah);
+int64_t swo_nplplm(int64_t npl, int64_t nplm);
+void swo_flatten_k_to_ij(int32_t n, int64_t k, int32_t *i, int32_t *j);
+void swo_flatten_ij_to_k(int32_t n, int32_t i, int32_t j, int64_t *k);
+/* per-component sum of |term| over the interactions the tri kernels evaluate: the scale of the 1e-12 tolerance */
+void swo_kick_tri_abs_scale(int32_t npl, int32_t nplm, const double *r, const double *Gmass, const double *radius,
+                            int lrad, double *scale);
+
+/* reference-shaped OpenMP loops, used ONLY as the timed CPU baseline (bench.py) */
+void swo_omp_kick_flat_rad_pl(int32_t npl, int32_t nplm, const double *r, const double *Gmass, const double *radius,
+                              double *acc);
+void swo_omp_kick_tri_rad_pl(int32_t npl, int32_t nplm, const double *r, const double *Gmass, const double *radius,
+                             double *acc);
+/* row-sampled variant: only rows [i0,i1) of the full-row branch (bounded CPU sample of a big system) */
+void swo_omp_kick_tri_rad_pl_rows(int32_t npl, int32_t nplm, int32_t i0, int32_t i1, const double *r,
+                                  const double *Gmass, const double *radius, double *acc);
+void swo_omp_kick_all_tp(int32_t ntp, int32_t npl, const double *rtp, const double *rpl, const double *GMpl,
+                         const int32_t *lmask, double *acc);
+void swo_omp_drift_all(const double *mu, double *x, double *v, int32_t n, int lgr, double inv_c2, double dt,
+                       const int32_t *lmask, int32_t *iflag);
+int swo_omp_max_threads(void);
+
+/* ---- drift: swiftest/swiftest_drift.f90, swiftest/swiftest_orbel.f90:147-172 ---- */
+void swo_drift_all(const double *mu, double *x, double *v, int32_t n, int lgr, double inv_c2, double dt,
+                   const int32_t *lmask, int32_t *iflag);
+void swo_drift_one(double mu, double *rx, double *ry, double *rz, double *vx, double *vy, double *vz, double dt,
+                   int32_t *iflag);
+void swo_drift_dan(double mu, double *rx0, double *ry0, double *rz0, double *vx0, double *vy0, double *vz0,
+                   double dt0, int32_t *iflag);
+void swo_drift_kepmd(double dm, double es, double ec, double *x, double *s, double *c);
+void swo_drift_kepu(double dt, double r0, double mu, double alpha, double u, double *fp, double *c1, double *c2,
+                    double *c3, int32_t *iflag);
+void swo_drift_kepu_stumpff(double *x, double *c0, double *c1, double *c2, double *c3);
+void swo_orbel_scget(double angle, double *sx, double *cx);
+/* which branch drift_dan takes for a body: 0 kepmd fast path, 1 kepu elliptic small-dt guess,
+ * 2 kepu elliptic Danby guess (uses sin), 3 kepu hyperbolic (uses x**(1/3)) */
+int32_t swo_drift_branch(double mu, double rx, double ry, double rz, double vx, double vy, double vz, double dt);
+
+/* ---- encounters: encounter/encounter_check.f90 ---- */
+void swo_encounter_check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr, double renc,
+                             double dt, int32_t *lencounter, int32_t *lvdotr);
+void swo_symba_set_renc(int32_t npl, const double *rhill, int32_t irec, double *renc);
+/* Results are returned in library-owned buffers, canonical (index1,index2) lexicographic order, 1-based.
+ * Call swo_encounter_fetch afterwards to copy them out (mirrors the Fortran allocatable intent(out)). */
+int64_t swo_encounter_sas_plpl(int32_t npl, const double *r, const double *v, const double *renc, double dt);
+int64_t swo_encounter_sas_pltp(int32_t npl, int32_t ntp, const double *rpl, const double *vpl, const double *rtp,
+                               const double *vtp, const double *rencpl, double dt);
+int64_t swo_encounter_sas_plplm(int32_t nplm, int32_t nplt, const double *rplm, const double *vplm,
+                                const double *rplt, const double *vplt, const double *rencm, const double *renct,
+                                double dt);
+/* encounter_check_all_plplm :42-109 with sort-and-sweep: plpl on the plm block + plm x plt, index2 shifted by nplm */
+int64_t swo_encounter_all_plplm(int32_t nplm, int32_t nplt, const double *rplm, const double *vplm,
+                                const double *rplt, const double *vplt, const double *rencm, const double *renct,
+                                double dt);
+/* triangular (all-pairs) variants :436-570 -- also the brute-force superset checker for the sweep */
+int64_t swo_encounter_tri_plpl(int32_t npl, const double *r, const double *v, const double *renc, double dt);
+int64_t swo_encounter_tri_pltp(int32_t npl, int32_t ntp, const double *rpl, const double *vpl, const double *rtp,
+                               const double *vtp, const double *rencpl, double dt);
+void swo_encounter_fetch(int32_t *index1, int32_t *index2, int32_t *lvdotr);
+/* statistics of the last sort-and-sweep call: sum_i nbox_i over loverlap bodies (broad-phase candidates) */
+int64_t swo_encounter_last_nbox_total(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

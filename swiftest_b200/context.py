@@ -1,0 +1,309 @@
+"""`Context`: numpy-facing mirror of the reference's array-level interfaces over the C ABI.
+
+Method names follow the reference procedures they stand for (swiftest/swiftest_kick.f90,
+swiftest/swiftest_drift.f90, encounter/encounter_check.f90, symba/symba_kick.f90); argument meaning and the
+early-return / error behaviour are the reference's.  Every method runs CUDA kernels through
+libswiftest_cuda.so -- there is no CPU path here.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import SwcuError, load
+
+PL, TP = 0, 1
+LOOP_TRIANGULAR, LOOP_FLAT, LOOP_AUTO = 0, 1, 2
+FAM_PLPL, FAM_PLTP, FAM_DRIFT, FAM_SWEEP, FAM_ALLGATHER = range(5)
+
+_f64, _i32 = np.float64, np.int32
+
+
+def _vec3(a, n=None, name="array"):
+    a = np.ascontiguousarray(a, dtype=_f64)
+    if a.ndim != 2 or a.shape[1] != 3:
+        raise ValueError(f"{name} must have shape (n,3) (Fortran r(3,n))")
+    if n is not None and a.shape[0] != n:
+        raise ValueError(f"{name} has {a.shape[0]} bodies, expected {n}")
+    return a
+
+
+def _vec(a, n=None, dt=_f64, name="array"):
+    a = np.ascontiguousarray(a, dtype=dt)
+    if a.ndim != 1 or (n is not None and a.shape[0] != n):
+        raise ValueError(f"{name} must be a vector of length {n}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One GPU context (swcu_create).  Use as a context manager or call close()."""
+
+    def __init__(self, device=0):
+        self._L = load()
+        h = C.c_void_p()
+        rc = self._L.swcu_create(int(device), C.byref(h))
+        if rc != 0:
+            raise SwcuError({5: "no sm_100 (B200) GPU visible: swiftest_b200 has no CPU fallback",
+                             2: f"bad device index {device}"}.get(rc, f"swcu_create failed with status {rc}"))
+        self._h = h
+        self.device = device
+
+    # ---- plumbing ----
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._L.swcu_last_error(self._h)
+            raise SwcuError(f"status {rc}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.swcu_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream):
+        self._ck(self._L.swcu_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        self._ck(self._L.swcu_synchronize(self._h))
+
+    def device_info(self):
+        sm, cc, mem = C.c_int32(), C.c_int32(), C.c_int64()
+        self._ck(self._L.swcu_device_info(self._h, C.byref(sm), C.byref(cc), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": cc.value, "mem_bytes": mem.value}
+
+    def launch_count(self):
+        return int(self._L.swcu_launch_count(self._h))
+
+    # ---- tier 1: array-level, host arrays (numpy) ----
+    def kick_getacch_int_all_tri_pl(self, npl, nplm, r, Gmass, radius, acc):
+        """swiftest_kick_getacch_int_all_tri_{rad,norad}_pl (kick.f90:165-371); radius=None -> norad.
+        acc (npl,3) float64 C-contiguous is updated in place."""
+        r, Gmass = _vec3(r, npl, "r"), _vec(Gmass, npl, name="Gmass")
+        radius = None if radius is None else _vec(radius, npl, name="radius")
+        self._inplace3(acc, npl)
+        self._ck(self._L.swcu_kick_getacch_int_all_tri_pl(self._h, npl, nplm, _ptr(r), _ptr(Gmass), _ptr(radius),
+                                                          _ptr(acc)))
+        return acc
+
+    def kick_getacch_int_all_flat_pl(self, npl, nplpl, k_plpl, r, Gmass, radius, acc):
+        """swiftest_kick_getacch_int_all_flat_{rad,norad}_pl (kick.f90:69-162).  k_plpl=None: canonical flattened
+        pairs 1..nplpl; else an (nplpl,2) int32 array of 1-based pairs (Fortran k_plpl(2,nplpl))."""
+        r, Gmass = _vec3(r, npl, "r"), _vec(Gmass, npl, name="Gmass")
+        radius = None if radius is None else _vec(radius, npl, name="radius")
+        if k_plpl is not None:
+            k_plpl = np.ascontiguousarray(k_plpl, dtype=_i32)
+            if k_plpl.ndim != 2 or k_plpl.shape != (nplpl, 2):
+                raise ValueError("k_plpl must have shape (nplpl,2)")
+        self._inplace3(acc, npl)
+        self._ck(self._L.swcu_kick_getacch_int_all_flat_pl(self._h, npl, int(nplpl), _ptr(k_plpl), _ptr(r), _ptr(Gmass),
+                                                           _ptr(radius), _ptr(acc)))
+        return acc
+
+    def kick_getacch_int_all_tp(self, ntp, npl, rtp, rpl, GMpl, lmask, acc):
+        """swiftest_kick_getacch_int_all_tp (kick.f90:374-415)."""
+        rtp, rpl, GMpl = _vec3(rtp, ntp, "rtp"), _vec3(rpl, npl, "rpl"), _vec(GMpl, npl, name="GMpl")
+        lmask = _vec(lmask, ntp, _i32, "lmask")
+        self._inplace3(acc, ntp)
+        self._ck(self._L.swcu_kick_getacch_int_all_tp(self._h, ntp, npl, _ptr(rtp), _ptr(rpl), _ptr(GMpl), _ptr(lmask),
+                                                      _ptr(acc)))
+        return acc
+
+    def symba_kick_subtract_encounters(self, npl, index1, index2, rh, Gmass, radius, ah):
+        """The encounter-pair removal of symba_kick_getacch_pl (symba_kick.f90:59-70): ah -= flat_rad(list)."""
+        i1, i2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        rh, Gmass, radius = _vec3(rh, npl), _vec(Gmass, npl), _vec(radius, npl)
+        self._inplace3(ah, npl)
+        self._ck(self._L.swcu_symba_kick_subtract_encounters(self._h, npl, len(i1), _ptr(i1), _ptr(i2), _ptr(rh),
+                                                             _ptr(Gmass), _ptr(radius), _ptr(ah)))
+        return ah
+
+    def drift_all(self, mu, x, v, n, dt, lmask, iflag, lgr=False, inv_c2=0.0):
+        """swiftest_drift_all (drift.f90:60-108): x, v (n,3) and iflag (n,) int32 are updated in place."""
+        mu = _vec(mu, n, name="mu")
+        lmask = _vec(lmask, n, _i32, "lmask")
+        self._inplace3(x, n)
+        self._inplace3(v, n)
+        if not (isinstance(iflag, np.ndarray) and iflag.dtype == _i32 and iflag.flags.c_contiguous and iflag.shape == (n,)):
+            raise ValueError("iflag must be a C-contiguous int32 vector of length n")
+        self._ck(self._L.swcu_drift_all(self._h, n, _ptr(mu), _ptr(x), _ptr(v), float(dt), int(bool(lgr)), float(inv_c2),
+                                        _ptr(lmask), _ptr(iflag)))
+        return x, v, iflag
+
+    def _fetch(self, nenc):
+        i1, i2, lv = np.empty(nenc, _i32), np.empty(nenc, _i32), np.empty(nenc, _i32)
+        self._ck(self._L.swcu_encounter_fetch(self._h, nenc, _ptr(i1), _ptr(i2), _ptr(lv)))
+        return nenc, i1, i2, lv.astype(bool)
+
+    def encounter_check_all_sort_and_sweep_plpl(self, npl, r, v, renc, dt):
+        """encounter_check.f90:143-192 -> (nenc, index1, index2, lvdotr), 1-based, lexicographic order."""
+        r, v, renc = _vec3(r, npl), _vec3(v, npl), _vec(renc, npl)
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_sort_and_sweep_plpl(self._h, npl, _ptr(r), _ptr(v), _ptr(renc),
+                                                                      float(dt), C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_check_all_sort_and_sweep_pltp(self, npl, ntp, rpl, vpl, rtp, vtp, rencpl, dt):
+        """encounter_check.f90:261-326."""
+        rpl, vpl, rtp, vtp = _vec3(rpl, npl), _vec3(vpl, npl), _vec3(rtp, ntp), _vec3(vtp, ntp)
+        rencpl = _vec(rencpl, npl)
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_sort_and_sweep_pltp(self._h, npl, ntp, _ptr(rpl), _ptr(vpl), _ptr(rtp),
+                                                                      _ptr(vtp), _ptr(rencpl), float(dt), C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_check_all_sort_and_sweep_plplm(self, nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt):
+        """encounter_check.f90:195-258 (index2 counts within the plt block)."""
+        a = [_vec3(rplm, nplm), _vec3(vplm, nplm), _vec3(rplt, nplt), _vec3(vplt, nplt), _vec(rencm, nplm),
+             _vec(renct, nplt)]
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_sort_and_sweep_plplm(self._h, nplm, nplt, *[_ptr(q) for q in a],
+                                                                       float(dt), C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_check_all_plplm(self, nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt):
+        """encounter_check.f90:42-109 with SORTSWEEP: merged plpl + plm-plt list, index2 shifted by nplm."""
+        a = [_vec3(rplm, nplm), _vec3(vplm, nplm), _vec3(rplt, nplt), _vec3(vplt, nplt), _vec(rencm, nplm),
+             _vec(renct, nplt)]
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_plplm(self._h, nplm, nplt, *[_ptr(q) for q in a], float(dt),
+                                                        C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._L.swcu_encounter_stats(self._h, C.byref(a), C.byref(b)))
+        return {"nbox_total": a.value, "emitted": b.value}
+
+    # ---- tier 2: device-resident populations ----
+    def body_sync(self, kind, n, nplm=0, r=None, v=None, Gmass=None, radius=None, rhill=None, mu=None, lmask=None,
+                  generation=0):
+        r = None if r is None else _vec3(r, n)
+        v = None if v is None else _vec3(v, n)
+        arrs = [None if q is None else _vec(q, n) for q in (Gmass, radius, rhill, mu)]
+        lmask = None if lmask is None else _vec(lmask, n, _i32)
+        self._ck(self._L.swcu_body_sync(self._h, kind, n, nplm, _ptr(r), _ptr(v), *[_ptr(q) for q in arrs], _ptr(lmask),
+                                        int(generation)))
+
+    def body_put(self, kind, r=None, v=None, a=None, lmask=None):
+        r, v, a = [None if q is None else _vec3(q) for q in (r, v, a)]
+        lmask = None if lmask is None else _vec(lmask, dt=_i32)
+        self._ck(self._L.swcu_body_put(self._h, kind, _ptr(r), _ptr(v), _ptr(a), _ptr(lmask)))
+
+    def body_count(self, kind):
+        n, nplm, gen = C.c_int32(), C.c_int32(), C.c_uint64()
+        self._ck(self._L.swcu_body_count(self._h, kind, C.byref(n), C.byref(nplm), C.byref(gen)))
+        return n.value, nplm.value, gen.value
+
+    def body_get(self, kind, r=True, v=True, a=True, iflag=False, out=None):
+        """Read resident arrays back.  `out` may supply preallocated (pinned) arrays keyed 'r','v','a','iflag'."""
+        n = self.body_count(kind)[0]
+        out = dict(out or {})
+        res = {}
+        for key, want in (("r", r), ("v", v), ("a", a)):
+            if want:
+                res[key] = out.get(key) if out.get(key) is not None else np.empty((n, 3), _f64)
+        if iflag:
+            res["iflag"] = out.get("iflag") if out.get("iflag") is not None else np.empty(n, _i32)
+        self._ck(self._L.swcu_body_get(self._h, kind, _ptr(res.get("r")), _ptr(res.get("v")), _ptr(res.get("a")),
+                                       _ptr(res.get("iflag"))))
+        return res
+
+    def body_zero_accel(self, kind):
+        self._ck(self._L.swcu_body_zero_accel(self._h, kind))
+
+    def pl_accel_int(self, loop_variant=LOOP_TRIANGULAR, lclose=True):
+        self._ck(self._L.swcu_pl_accel_int(self._h, loop_variant, int(bool(lclose))))
+
+    def tp_accel_int(self):
+        self._ck(self._L.swcu_tp_accel_int(self._h))
+
+    def pl_set_renc(self, irec):
+        self._ck(self._L.swcu_pl_set_renc(self._h, irec))
+
+    def body_drift(self, kind, dt, lgr=False, inv_c2=0.0, want_nfail=True):
+        nf = C.c_int32()
+        self._ck(self._L.swcu_body_drift(self._h, kind, float(dt), int(bool(lgr)), float(inv_c2),
+                                         C.byref(nf) if want_nfail else None))
+        return nf.value
+
+    def body_kick_velocity(self, kind, dt):
+        self._ck(self._L.swcu_body_kick_velocity(self._h, kind, float(dt)))
+
+    def pl_encounter_check(self, dt, fetch=True):
+        n = C.c_int64()
+        self._ck(self._L.swcu_pl_encounter_check(self._h, float(dt), C.byref(n)))
+        return self._fetch(n.value) if fetch else n.value
+
+    def tp_encounter_check(self, dt, fetch=True):
+        n = C.c_int64()
+        self._ck(self._L.swcu_tp_encounter_check(self._h, float(dt), C.byref(n)))
+        return self._fetch(n.value) if fetch else n.value
+
+    # ---- multi-GPU ----
+    def comm_unique_id(self):
+        buf = (C.c_char * 128)()
+        self._ck(self._L.swcu_comm_unique_id(self._h, buf))
+        return bytes(buf)
+
+    def comm_init(self, nranks, rank, unique_id):
+        buf = (C.c_char * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._ck(self._L.swcu_comm_init(self._h, nranks, rank, buf))
+
+    def comm_finalize(self):
+        self._ck(self._L.swcu_comm_finalize(self._h))
+
+    def pl_set_slice(self, i0, i1):
+        self._ck(self._L.swcu_pl_set_slice(self._h, i0, i1))
+
+    def pl_allgather(self, with_v=False):
+        self._ck(self._L.swcu_pl_allgather(self._h, int(bool(with_v))))
+
+    # ---- measurement ----
+    def timer_start(self):
+        self._ck(self._L.swcu_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self._L.swcu_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def enable_kernel_timing(self, on=True):
+        self._ck(self._L.swcu_enable_kernel_timing(self._h, int(bool(on))))
+
+    def last_kernel_ms(self, family):
+        ms = C.c_double()
+        self._ck(self._L.swcu_last_kernel_ms(self._h, family, C.byref(ms)))
+        return ms.value
+
+    def probe_fp64_peak(self):
+        t = C.c_double()
+        self._ck(self._L.swcu_probe_fp64_peak(self._h, C.byref(t)))
+        return t.value
+
+    def probe_hbm_copy(self, nbytes=1 << 30):
+        g = C.c_double()
+        self._ck(self._L.swcu_probe_hbm_copy(self._h, int(nbytes), C.byref(g)))
+        return g.value
+
+    def flush_l2(self):
+        self._ck(self._L.swcu_flush_l2(self._h))
+
+    # ---- helpers ----
+    @staticmethod
+    def _inplace3(a, n):
+        if not (isinstance(a, np.ndarray) and a.dtype == _f64 and a.flags.c_contiguous and a.shape == (n, 3)):
+            raise ValueError("in/out arrays must be C-contiguous float64 of shape (n,3)")

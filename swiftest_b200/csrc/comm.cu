@@ -1,0 +1,203 @@
+// comm.cu -- multi-GPU exchange for the i-sliced pl-pl path: one process (context) per GPU, an NCCL allgather
+// of the drifted position (and velocity) slices over NVLink each step.  The reference has no counterpart
+// (its only multi-process strategy is Coarray test-particle sharding, swiftest_coarray.f90:672-733, which
+// needs no per-step traffic and maps to tp block partitioning here).
+//
+// NCCL is loaded with dlopen at swcu_comm_init so a single-GPU run has no NCCL dependency; in a torchrun
+// job the already-loaded libnccl.so.2 of PyTorch is picked up.
+#include "swcu_internal.cuh"
+
+#include <dlfcn.h>
+#include <string.h>
+
+namespace swcu {
+
+typedef struct { char internal[SWCU_NCCL_ID_BYTES]; } NcclUniqueId;
+typedef int NcclResult;
+typedef void *NcclComm;
+constexpr int NCCL_FLOAT64 = 8;  // ncclFloat64 / ncclDouble in every NCCL 2.x
+
+struct NcclApi {
+    void *handle = nullptr;
+    NcclResult (*GetUniqueId)(NcclUniqueId *) = nullptr;
+    NcclResult (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
+    NcclResult (*CommDestroy)(NcclComm) = nullptr;
+    NcclResult (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(NcclResult) = nullptr;
+};
+
+namespace {
+
+int load_nccl(swcu_context *ctx)
+{
+    if (ctx->nccl) return SWCU_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) return fail(ctx, SWCU_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+    NcclApi *api = new NcclApi;
+    api->handle = h;
+    api->GetUniqueId = (NcclResult(*)(NcclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    api->CommInitRank = (NcclResult(*)(NcclComm *, int, NcclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    api->CommDestroy = (NcclResult(*)(NcclComm))dlsym(h, "ncclCommDestroy");
+    api->AllGather =
+        (NcclResult(*)(const void *, void *, size_t, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
+    api->GetErrorString = (const char *(*)(NcclResult))dlsym(h, "ncclGetErrorString");
+    if (!api->GetUniqueId || !api->CommInitRank || !api->CommDestroy || !api->AllGather || !api->GetErrorString) {
+        delete api;
+        return fail(ctx, SWCU_ERR_NCCL, "libnccl is missing a required symbol");
+    }
+    ctx->nccl = api;
+    return SWCU_OK;
+}
+
+#define SWCU_NCCL(ctx, call)                                                                              \
+    do {                                                                                                  \
+        swcu::NcclResult r__ = (call);                                                                    \
+        if (r__ != 0)                                                                                     \
+            return swcu::fail((ctx), SWCU_ERR_NCCL, "%s failed: %s", #call, (ctx)->nccl->GetErrorString(r__)); \
+    } while (0)
+
+// pack this rank's slice of up to six SoA arrays into one contiguous send buffer [narr][maxcount]
+__global__ void pack_slice_kernel(int narr, int i0, int cnt, int maxcount, const double *a0, const double *a1,
+                                  const double *a2, const double *a3, const double *a4, const double *a5, double *send)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= maxcount) return;
+    const double *arr[6] = {a0, a1, a2, a3, a4, a5};
+    for (int c = 0; c < narr; ++c) send[(size_t)c * maxcount + t] = (t < cnt) ? arr[c][i0 + t] : 0.0;
+}
+
+// scatter the gathered [rank][narr][maxcount] buffer back into the SoA arrays (other ranks' slices only)
+__global__ void unpack_slices_kernel(int narr, int n, int nranks, int myrank, int maxcount, const double *recv, double *a0,
+                                     double *a1, double *a2, double *a3, double *a4, double *a5)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // balanced partition: the first (n % nranks) ranks own one more row
+    const int q = n / nranks, r = n % nranks;
+    int rank, off;
+    if (i < (q + 1) * r) {
+        rank = i / (q + 1);
+        off = i - rank * (q + 1);
+    } else {
+        rank = r + (i - (q + 1) * r) / (q > 0 ? q : 1);
+        off = (i - (q + 1) * r) - (rank - r) * q;
+    }
+    if (rank == myrank) return;
+    double *arr[6] = {a0, a1, a2, a3, a4, a5};
+    for (int c = 0; c < narr; ++c) arr[c][i] = recv[((size_t)rank * narr + c) * maxcount + off];
+}
+
+}  // namespace
+
+int comm_allgather_pl(swcu_context *ctx, int with_v)
+{
+    if (ctx->nranks <= 1) return SWCU_OK;
+    if (!ctx->comm) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_allgather: communicator not initialised");
+    Body &pl = ctx->pl;
+    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_allgather: pl population not resident");
+    int e0, e1;
+    swcu_partition(pl.n, ctx->nranks, ctx->rank, &e0, &e1);
+    if (e0 != pl.slice0 || e1 != pl.slice1)
+        return fail(ctx, SWCU_ERR_STATE, "swcu_pl_allgather: slice [%d,%d) is not the balanced partition [%d,%d)",
+                    pl.slice0, pl.slice1, e0, e1);
+    FamTimer ft(ctx, FAM_ALLGATHER);
+    const int narr = with_v ? 6 : 3;
+    const int maxcount = (pl.n + ctx->nranks - 1) / ctx->nranks;
+    SWCU_CUDA(ctx, ctx->sendbuf.ensure(sizeof(double) * (size_t)narr * maxcount));
+    SWCU_CUDA(ctx, ctx->recvbuf.ensure(sizeof(double) * (size_t)narr * maxcount * ctx->nranks));
+    pack_slice_kernel<<<cdiv(maxcount, 256), 256, 0, ctx->stream>>>(
+        narr, pl.slice0, pl.slice1 - pl.slice0, maxcount, pl.rx.as<double>(), pl.ry.as<double>(), pl.rz.as<double>(),
+        pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>(), ctx->sendbuf.as<double>());
+    SWCU_KERNEL_CHECK(ctx);
+    SWCU_NCCL(ctx, ctx->nccl->AllGather(ctx->sendbuf.p, ctx->recvbuf.p, (size_t)narr * maxcount, NCCL_FLOAT64,
+                                        (NcclComm)ctx->comm, ctx->stream));
+    unpack_slices_kernel<<<cdiv(pl.n, 256), 256, 0, ctx->stream>>>(
+        narr, pl.n, ctx->nranks, ctx->rank, maxcount, ctx->recvbuf.as<double>(), pl.rx.as<double>(), pl.ry.as<double>(),
+        pl.rz.as<double>(), pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>());
+    SWCU_KERNEL_CHECK(ctx);
+    return SWCU_OK;
+}
+
+void comm_release(swcu_context *ctx)
+{
+    if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy((NcclComm)ctx->comm);
+    ctx->comm = nullptr;
+    if (ctx->nccl) {
+        delete ctx->nccl;  // the library handle stays loaded for the life of the process
+        ctx->nccl = nullptr;
+    }
+    ctx->nranks = 1;
+    ctx->rank = 0;
+}
+
+}  // namespace swcu
+
+using namespace swcu;
+
+extern "C" int swcu_partition(int32_t n, int32_t nranks, int32_t rank, int32_t *i0, int32_t *i1)
+{
+    if (nranks <= 0 || rank < 0 || rank >= nranks || n < 0 || !i0 || !i1) return SWCU_ERR_ARG;
+    const int q = n / nranks, r = n % nranks;
+    *i0 = rank * q + (rank < r ? rank : r);
+    *i1 = *i0 + q + (rank < r ? 1 : 0);
+    return SWCU_OK;
+}
+
+extern "C" int swcu_comm_unique_id(swcu_context *ctx, void *id128)
+{
+    if (!ctx || !id128) return SWCU_ERR_ARG;
+    SWCU_TRY(load_nccl(ctx));
+    NcclUniqueId id;
+    SWCU_NCCL(ctx, ctx->nccl->GetUniqueId(&id));
+    memcpy(id128, &id, SWCU_NCCL_ID_BYTES);
+    return SWCU_OK;
+}
+
+extern "C" int swcu_comm_init(swcu_context *ctx, int32_t nranks, int32_t rank, const void *id128)
+{
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return SWCU_ERR_ARG;
+    if (nranks == 1) {
+        ctx->nranks = 1;
+        ctx->rank = 0;
+        return SWCU_OK;
+    }
+    if (!id128) return SWCU_ERR_ARG;
+    SWCU_TRY(load_nccl(ctx));
+    SWCU_CUDA(ctx, cudaSetDevice(ctx->device));
+    NcclUniqueId id;
+    memcpy(&id, id128, SWCU_NCCL_ID_BYTES);
+    NcclComm comm = nullptr;
+    SWCU_NCCL(ctx, ctx->nccl->CommInitRank(&comm, nranks, id, rank));
+    ctx->comm = comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_comm_finalize(swcu_context *ctx)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    comm_release(ctx);
+    return SWCU_OK;
+}
+
+extern "C" int swcu_pl_set_slice(swcu_context *ctx, int32_t i0, int32_t i1)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_set_slice: pl population not resident");
+    if (i0 < 0 || i1 < i0 || i1 > ctx->pl.n) return fail(ctx, SWCU_ERR_ARG, "swcu_pl_set_slice: bad slice [%d,%d)", i0, i1);
+    ctx->pl.slice0 = i0;
+    ctx->pl.slice1 = i1;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_pl_allgather(swcu_context *ctx, int32_t with_v)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    return comm_allgather_pl(ctx, with_v);
+}

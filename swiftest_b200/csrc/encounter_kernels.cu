@@ -1,0 +1,454 @@
+// encounter_kernels.cu -- sort-and-sweep close-encounter detection on the device.
+//
+// Replaces (reference, relative to /root/reference/src/encounter/encounter_check.f90):
+//   encounter_check_all_sort_and_sweep_plpl :143-192, _plplm :195-258, _pltp :261-326,
+//   encounter_check_sort_aabb_1D :763-792, encounter_check_sweep_aabb_single_list :905-988 and
+//   _double_list :795-902, encounter_check_all_sweep_one :329-381, encounter_check_one :573-621,
+//   encounter_check_collapse_ragged_list :624-673, encounter_check_remove_duplicates :676-760,
+//   and the merge in encounter_check_all_plplm :42-109; symba_util_set_renc (symba/symba_util.f90:245-267).
+//
+// The broad phase is ONE-dimensional on heliocentric distance |r| -/+ 1.1*renc, body i is swept
+// only when more than one foreign endpoint lies strictly inside its interval (F3), lvdotr is always true (F4).
+//
+// Pipeline (all HBM/latency bound integer + compare work, no tensor cores):
+//   K7  extents + concatenated population                     elementwise
+//   K8  device radix sort of the 2N (extent, endpoint-id) pairs (CUB DeviceRadixSort, stable => ties are
+//       ordered by position in the [rmin,rmax] array, the order the oracle fixes)
+//   K9  ibeg/iend scatter + gather of r,v,renc into sorted-endpoint order (SoA)
+//   K10 chunked sweep: every body's interval is cut into chunks of SWEEP_CHUNK endpoints, a prefix sum
+//       assigns chunks to warps (one Jupiter-sized interval over 1e6 test particles spreads over the whole
+//       GPU), lanes stream the gathered records, evaluate encounter_check_one and append hits with a
+//       warp-aggregated atomic
+//   K11 canonical order: radix sort of the 64-bit (index1<<32|index2) keys + unique
+//
+// THIS FILE IS COMPILED WITH --fmad=false so that the predicate is the same sequence of individually
+// rounded IEEE operations as the oracle: the pair list is bit-exact, not merely close.
+#include "swcu_internal.cuh"
+
+#include <cfloat>
+#include <cmath>
+#include <cub/cub.cuh>
+
+namespace swcu {
+namespace {
+
+constexpr double RSWEEP_FACTOR = 1.1;          // encounter_module.f90:21
+constexpr double RHSCALE = 6.5, RSHELL = 0.48075;  // symba_module.f90:22-23
+constexpr int SWEEP_CHUNK = 1024;
+
+struct ListDev {
+    const double *x, *y, *z, *vx, *vy, *vz, *renc;
+    int n;
+};
+
+// K7: extents (encounter_check.f90:180-185, 237-251, 305-319) and the concatenated copy of both lists
+__global__ void extent_kernel(ListDev l1, ListDev l2, int ntot, double *__restrict__ cx, double *__restrict__ cy,
+                              double *__restrict__ cz, double *__restrict__ cvx, double *__restrict__ cvy,
+                              double *__restrict__ cvz, double *__restrict__ crenc, double *__restrict__ keys,
+                              int *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    const bool in1 = i < l1.n;
+    const ListDev &l = in1 ? l1 : l2;
+    const int q = in1 ? i : i - l1.n;
+    const double x = l.x[q], y = l.y[q], z = l.z[q];
+    const double renc = l.renc ? l.renc[q] : 0.0;
+    cx[i] = x;
+    cy[i] = y;
+    cz[i] = z;
+    cvx[i] = l.vx[q];
+    cvy[i] = l.vy[q];
+    cvz[i] = l.vz[q];
+    crenc[i] = renc;
+    const double rmag = sqrt(x * x + y * y + z * z);
+    const double w = RSWEEP_FACTOR * renc;
+    keys[i] = rmag - w;         // rmin -> begin endpoint id i
+    keys[ntot + i] = rmag + w;  // rmax -> end endpoint id ntot+i
+    vals[i] = i;
+    vals[ntot + i] = ntot + i;
+}
+
+// K9: encounter_check.f90:778-789 (ibeg/iend) and :937-949 (gather into sorted order)
+__global__ void endpoint_kernel(int ntot, const int *__restrict__ sorted_id, const double *__restrict__ cx,
+                                const double *__restrict__ cy, const double *__restrict__ cz,
+                                const double *__restrict__ cvx, const double *__restrict__ cvy,
+                                const double *__restrict__ cvz, const double *__restrict__ crenc, int *__restrict__ ibeg,
+                                int *__restrict__ iend, double *__restrict__ sx, double *__restrict__ sy,
+                                double *__restrict__ sz, double *__restrict__ svx, double *__restrict__ svy,
+                                double *__restrict__ svz, double *__restrict__ srenc, int *__restrict__ sbody)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * ntot) return;
+    const int id = sorted_id[k];
+    const int body = id < ntot ? id : id - ntot;
+    if (id < ntot)
+        ibeg[body] = k;
+    else
+        iend[body] = k;
+    sx[k] = cx[body];
+    sy[k] = cy[body];
+    sz[k] = cz[body];
+    svx[k] = cvx[body];
+    svy[k] = cvy[body];
+    svz[k] = cvz[body];
+    srenc[k] = crenc[body];
+    sbody[k] = body;
+}
+
+// loverlap (:828,:951) and the number of sweep chunks of every body; nchunk has ntot+1 entries (last = 0)
+__global__ void chunk_count_kernel(int ntot, const int *__restrict__ ibeg, const int *__restrict__ iend,
+                                   int *__restrict__ nchunk, unsigned long long *__restrict__ nbox_total)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    long long nb = 0;
+    if (i < ntot) {
+        const int b = ibeg[i], e = iend[i];
+        if ((b + 1) < (e - 1)) nb = e - b - 1;  // endpoints b+1 .. e-1
+        nchunk[i] = (int)((nb + SWEEP_CHUNK - 1) / SWEEP_CHUNK);
+    } else if (i == ntot) {
+        nchunk[i] = 0;
+    }
+    for (int o = 16; o > 0; o >>= 1) nb += __shfl_down_sync(0xffffffffu, nb, o);
+    if ((threadIdx.x & 31) == 0 && nb > 0) atomicAdd(nbox_total, (unsigned long long)nb);
+}
+
+// encounter_check_one, encounter_check.f90:591-618
+__device__ __forceinline__ bool check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr,
+                                          double renc, double dt, double vsmall)
+{
+    const double r2 = xr * xr + yr * yr + zr * zr;
+    const double r2crit = renc * renc;
+    double vdotr, r2min;
+    if (r2 > r2crit) {
+        vdotr = vxr * xr + vyr * yr + vzr * zr;
+        if (vdotr > 0.0) {
+            r2min = r2;
+        } else {
+            const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
+            if (v2 <= vsmall) {
+                r2min = r2;
+            } else {
+                const double tmin = -vdotr / v2;
+                if (tmin < dt)
+                    r2min = r2 - vdotr * vdotr / v2;
+                else
+                    r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
+            }
+        }
+    } else {
+        vdotr = -1.0;
+        r2min = r2;
+    }
+    const bool lvdotr = (vdotr < 0.0);
+    return lvdotr && (r2min <= r2crit);
+}
+
+// K10: the sweep.  One warp per chunk of one body's interval.
+__global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single, const int *__restrict__ choff,
+                                                    const int *__restrict__ ibeg, const int *__restrict__ iend,
+                                                    const double *__restrict__ cx, const double *__restrict__ cy,
+                                                    const double *__restrict__ cz, const double *__restrict__ cvx,
+                                                    const double *__restrict__ cvy, const double *__restrict__ cvz,
+                                                    const double *__restrict__ crenc, const double *__restrict__ sx,
+                                                    const double *__restrict__ sy, const double *__restrict__ sz,
+                                                    const double *__restrict__ svx, const double *__restrict__ svy,
+                                                    const double *__restrict__ svz, const double *__restrict__ srenc,
+                                                    const int *__restrict__ sbody, double dt, double vsmall,
+                                                    unsigned long long *__restrict__ cand, unsigned long long cap,
+                                                    unsigned long long *__restrict__ count)
+{
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int total = choff[ntot];
+    for (int c = warp; c < total; c += nwarps) {
+        // body i with choff[i] <= c < choff[i+1]
+        int lo = 0, hi = ntot - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (choff[mid + 1] <= c)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        const int i = lo;
+        const int kb = ibeg[i] + 1 + (c - choff[i]) * SWEEP_CHUNK;
+        const int ke = min(kb + SWEEP_CHUNK, iend[i]);
+        const double xi = cx[i], yi = cy[i], zi = cz[i];
+        const double vxi = cvx[i], vyi = cvy[i], vzi = cvz[i];
+        const double renci = crenc[i];
+        const bool in1 = i < n1;
+        for (int k0 = kb; k0 < ke; k0 += 32) {
+            const int k = k0 + lane;
+            bool hit = false;
+            unsigned long long key = 0ull;
+            if (k < ke) {
+                const int j = sbody[k];
+                bool good = true;
+                if (!single) good = ((j < n1) != in1);  // only bodies of the other list (:873,:890)
+                if (good) {
+                    const double xr = sx[k] - xi, yr = sy[k] - yi, zr = sz[k] - zi;
+                    const double vxr = svx[k] - vxi, vyr = svy[k] - vyi, vzr = svz[k] - vzi;
+                    const double renc12 = renci + srenc[k];
+                    hit = check_one(xr, yr, zr, vxr, vyr, vzr, renc12, dt, vsmall);
+                    if (hit) {
+                        unsigned a, b;
+                        if (single) {  // :976-983 index1 < index2
+                            a = (unsigned)min(i, j) + 1u;
+                            b = (unsigned)max(i, j) + 1u;
+                        } else if (in1) {  // index1 = list-1 body, index2 = list-2 body
+                            a = (unsigned)i + 1u;
+                            b = (unsigned)(j - n1) + 1u;
+                        } else {
+                            a = (unsigned)j + 1u;
+                            b = (unsigned)(i - n1) + 1u;
+                        }
+                        key = ((unsigned long long)a << 32) | b;
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                unsigned long long base = 0ull;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (hit) {
+                    const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < cap) cand[pos] = key;
+                }
+            }
+        }
+    }
+}
+
+__global__ void unpack_keys_kernel(const unsigned long long *__restrict__ keys, long long n, int32_t *__restrict__ i1,
+                                   int32_t *__restrict__ i2)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    i1[k] = (int32_t)(keys[k] >> 32);
+    i2[k] = (int32_t)(keys[k] & 0xffffffffull);
+}
+
+__global__ void shift_index2_kernel(unsigned long long *keys, long long n, unsigned long long shift)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) keys[k] += shift;
+}
+
+__global__ void set_renc_kernel(int n, const double *__restrict__ rhill, double rshell_irec, double *__restrict__ renc)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) renc[i] = rhill[i] * RHSCALE * rshell_irec;
+}
+
+ListDev to_dev(const SweepList &l)
+{
+    ListDev d;
+    d.x = l.x; d.y = l.y; d.z = l.z; d.vx = l.vx; d.vy = l.vy; d.vz = l.vz; d.renc = l.renc; d.n = l.n;
+    return d;
+}
+
+}  // namespace
+
+int set_renc(swcu_context *ctx, Body &pl, int irec)
+{
+    if (pl.n <= 0) return SWCU_OK;
+    double rshell_irec = 1.0;
+    for (int i = 1; i <= irec; ++i) rshell_irec = rshell_irec * RSHELL;  // symba_util.f90:259-262
+    set_renc_kernel<<<cdiv(pl.n, 256), 256, 0, ctx->stream>>>(pl.n, pl.rhill.as<double>(), rshell_irec,
+                                                             pl.renc.as<double>());
+    SWCU_KERNEL_CHECK(ctx);
+    return SWCU_OK;
+}
+
+// Sort-and-sweep of one list (l2 == nullptr) or two lists.  Leaves the sorted unique keys in ctx->enc.uniq.
+int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out)
+{
+    auto &E = ctx->enc;
+    E.nenc = 0;
+    E.result = nullptr;
+    E.nbox_total = 0;
+    E.nemitted = 0;
+    *nenc_out = 0;
+    const int n1 = l1.n, n2 = l2 ? l2->n : 0;
+    const bool single = (l2 == nullptr);
+    if (n1 == 0 || (!single && n2 == 0)) return SWCU_OK;  // :168, :225, :291
+    const int ntot = n1 + n2;
+    const int next = 2 * ntot;
+    FamTimer ft(ctx, FAM_SWEEP);
+
+    const size_t db = sizeof(double), ib = sizeof(int);
+    DevBuf *body_arrays[] = {&E.cx, &E.cy, &E.cz, &E.cvx, &E.cvy, &E.cvz, &E.crenc};
+    for (DevBuf *d : body_arrays) SWCU_CUDA(ctx, d->ensure(db * ntot));
+    DevBuf *sorted_arrays[] = {&E.sx, &E.sy, &E.sz, &E.svx, &E.svy, &E.svz, &E.srenc};
+    for (DevBuf *d : sorted_arrays) SWCU_CUDA(ctx, d->ensure(db * next));
+    SWCU_CUDA(ctx, E.sbody.ensure(ib * next));
+    SWCU_CUDA(ctx, E.keys_in.ensure(db * next));
+    SWCU_CUDA(ctx, E.keys_out.ensure(db * next));
+    SWCU_CUDA(ctx, E.vals_in.ensure(ib * next));
+    SWCU_CUDA(ctx, E.vals_out.ensure(ib * next));
+    SWCU_CUDA(ctx, E.ibeg.ensure(ib * ntot));
+    SWCU_CUDA(ctx, E.iend.ensure(ib * ntot));
+    SWCU_CUDA(ctx, E.nchunk.ensure(ib * (ntot + 1)));
+    SWCU_CUDA(ctx, E.choff.ensure(ib * (ntot + 1)));
+    SWCU_CUDA(ctx, E.counters.ensure(64));
+    unsigned long long *d_count = E.counters.as<unsigned long long>();       // [0] candidates emitted
+    unsigned long long *d_nbox = d_count + 1;                                 // [1] sum nbox
+    int *d_nuniq = reinterpret_cast<int *>(d_count + 2);                      // [2] unique count
+    SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, 32, ctx->stream));
+
+    ListDev a = to_dev(l1), b;
+    if (l2) b = to_dev(*l2); else { b = a; b.n = 0; }
+    extent_kernel<<<cdiv(ntot, 256), 256, 0, ctx->stream>>>(a, b, ntot, E.cx.as<double>(), E.cy.as<double>(),
+                                                           E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(),
+                                                           E.cvz.as<double>(), E.crenc.as<double>(),
+                                                           E.keys_in.as<double>(), E.vals_in.as<int>());
+    SWCU_KERNEL_CHECK(ctx);
+
+    size_t tmp_sort = 0, tmp_scan = 0;
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, E.keys_in.as<double>(), E.keys_out.as<double>(),
+                                                   E.vals_in.as<int>(), E.vals_out.as<int>(), next, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, E.nchunk.as<int>(), E.choff.as<int>(), ntot + 1,
+                                                 ctx->stream));
+    SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_sort, tmp_scan)));
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortPairs(E.cub_tmp.p, tmp_sort, E.keys_in.as<double>(), E.keys_out.as<double>(),
+                                                   E.vals_in.as<int>(), E.vals_out.as<int>(), next, 0, 64, ctx->stream));
+    ctx->launches += 4;  // CUB's onesweep: histogram + 3..4 passes (counted as library launches of ours)
+
+    endpoint_kernel<<<cdiv(next, 256), 256, 0, ctx->stream>>>(
+        ntot, E.vals_out.as<int>(), E.cx.as<double>(), E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(),
+        E.cvy.as<double>(), E.cvz.as<double>(), E.crenc.as<double>(), E.ibeg.as<int>(), E.iend.as<int>(),
+        E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(), E.svy.as<double>(),
+        E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>());
+    SWCU_KERNEL_CHECK(ctx);
+
+    chunk_count_kernel<<<cdiv(ntot + 1, 256), 256, 0, ctx->stream>>>(ntot, E.ibeg.as<int>(), E.iend.as<int>(),
+                                                                    E.nchunk.as<int>(), d_nbox);
+    SWCU_KERNEL_CHECK(ctx);
+    SWCU_CUDA(ctx, cub::DeviceScan::ExclusiveSum(E.cub_tmp.p, tmp_scan, E.nchunk.as<int>(), E.choff.as<int>(), ntot + 1,
+                                                 ctx->stream));
+    ctx->launches += 1;
+
+    if (E.cand_cap < (size_t)4 * ntot + 65536) E.cand_cap = (size_t)4 * ntot + 65536;
+    const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
+    const int sweep_blocks = ctx->prop.multiProcessorCount * 8;
+    unsigned long long h_counts[2] = {0, 0};
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+        sweep_kernel<<<sweep_blocks, 128, 0, ctx->stream>>>(
+            ntot, n1, single ? 1 : 0, E.choff.as<int>(), E.ibeg.as<int>(), E.iend.as<int>(), E.cx.as<double>(),
+            E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(), E.cvz.as<double>(),
+            E.crenc.as<double>(), E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(),
+            E.svy.as<double>(), E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>(), dt, vsmall,
+            E.cand.as<unsigned long long>(), (unsigned long long)E.cand_cap, d_count);
+        SWCU_KERNEL_CHECK(ctx);
+        SWCU_CUDA(ctx, cudaMemcpyAsync(h_counts, d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_counts[0] <= E.cand_cap) break;
+        E.cand_cap = (size_t)(h_counts[0] + h_counts[0] / 4 + 1024);  // overflow: grow and sweep again
+        if (attempt == 2) return fail(ctx, SWCU_ERR_STATE, "encounter sweep: candidate buffer overflow persists");
+    }
+    E.nbox_total = (int64_t)h_counts[1];
+    E.nemitted = (int64_t)h_counts[0];
+    const long long ncand = (long long)h_counts[0];
+    if (ncand == 0) return SWCU_OK;
+
+    // K11 canonical order + duplicate removal (:976-985, :703-757)
+    SWCU_CUDA(ctx, E.cand_sorted.ensure(sizeof(unsigned long long) * ncand));
+    SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * ncand));
+    size_t tmp_k = 0, tmp_u = 0;
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_k, E.cand.as<unsigned long long>(),
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, tmp_u, E.cand_sorted.as<unsigned long long>(),
+                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
+    SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_k, tmp_u)));
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, E.cand.as<unsigned long long>(),
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(E.cub_tmp.p, tmp_u, E.cand_sorted.as<unsigned long long>(),
+                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
+    ctx->launches += 6;
+    int h_nuniq = 0;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    E.nenc = h_nuniq;
+    E.result = E.uniq.as<unsigned long long>();
+    *nenc_out = h_nuniq;
+    return SWCU_OK;
+}
+
+// encounter_check_all_plplm (:42-109): plpl on the fully interacting block, then plm x plt with index2 shifted
+// by nplm; the two lists are disjoint, the canonical order is the lexicographic sort of their union.
+int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc_out)
+{
+    auto &E = ctx->enc;
+    int64_t n_a = 0, n_b = 0;
+    SWCU_TRY(encounter_sweep(ctx, plm, nullptr, dt, &n_a));
+    const int64_t nbox_a = E.nbox_total, nem_a = E.nemitted;
+    SWCU_CUDA(ctx, E.out1.ensure(sizeof(unsigned long long) * (size_t)(n_a > 0 ? n_a : 1)));
+    if (n_a > 0)
+        SWCU_CUDA(ctx, cudaMemcpyAsync(E.out1.p, E.result, sizeof(unsigned long long) * n_a, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+    SWCU_TRY(encounter_sweep(ctx, plm, &plt, dt, &n_b));
+    E.nbox_total += nbox_a;
+    E.nemitted += nem_a;
+    const int64_t n = n_a + n_b;
+    *nenc_out = n;
+    E.nenc = n;
+    E.result = nullptr;
+    if (n == 0) return SWCU_OK;
+    SWCU_CUDA(ctx, E.merged.ensure(sizeof(unsigned long long) * 2 * (size_t)n));
+    unsigned long long *m_in = E.merged.as<unsigned long long>(), *m_out = m_in + n;
+    if (n_a > 0)
+        SWCU_CUDA(ctx, cudaMemcpyAsync(m_in, E.out1.p, sizeof(unsigned long long) * n_a, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+    if (n_b > 0) {
+        SWCU_CUDA(ctx, cudaMemcpyAsync(m_in + n_a, E.uniq.p, sizeof(unsigned long long) * n_b, cudaMemcpyDeviceToDevice,
+                                       ctx->stream));
+        shift_index2_kernel<<<cdiv(n_b, 256), 256, 0, ctx->stream>>>(m_in + n_a, n_b, (unsigned long long)plm.n);
+        SWCU_KERNEL_CHECK(ctx);
+    }
+    size_t tmp_k = 0;
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_k, m_in, m_out, n, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, E.cub_tmp.ensure(tmp_k));
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, m_in, m_out, n, 0, 64, ctx->stream));
+    ctx->launches += 4;
+    E.result = m_out;
+    return SWCU_OK;
+}
+
+}  // namespace swcu
+
+// ---- C ABI pieces that only touch encounter state ----
+extern "C" int swcu_encounter_fetch(swcu_context *ctx, int64_t nenc, int32_t *index1, int32_t *index2, int32_t *lvdotr)
+{
+    using namespace swcu;
+    if (!ctx) return SWCU_ERR_ARG;
+    auto &E = ctx->enc;
+    if (E.nenc < 0) return fail(ctx, SWCU_ERR_STATE, "swcu_encounter_fetch: no encounter check result pending");
+    if (nenc != E.nenc) return fail(ctx, SWCU_ERR_ARG, "swcu_encounter_fetch: nenc=%lld but the last check found %lld",
+                                    (long long)nenc, (long long)E.nenc);
+    if (nenc == 0) return SWCU_OK;
+    SWCU_CUDA(ctx, E.out1.ensure(sizeof(int32_t) * (size_t)nenc));
+    SWCU_CUDA(ctx, E.out2.ensure(sizeof(int32_t) * (size_t)nenc));
+    unpack_keys_kernel<<<cdiv(nenc, 256), 256, 0, ctx->stream>>>(E.result, nenc, E.out1.as<int32_t>(), E.out2.as<int32_t>());
+    SWCU_KERNEL_CHECK(ctx);
+    if (index1) SWCU_CUDA(ctx, cudaMemcpyAsync(index1, E.out1.p, sizeof(int32_t) * nenc, cudaMemcpyDeviceToHost, ctx->stream));
+    if (index2) SWCU_CUDA(ctx, cudaMemcpyAsync(index2, E.out2.p, sizeof(int32_t) * nenc, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (lvdotr)
+        for (int64_t k = 0; k < nenc; ++k) lvdotr[k] = 1;  // lencounter = lvdotr .and. ... (:617-618): always true
+    return SWCU_OK;
+}
+
+extern "C" int swcu_encounter_stats(swcu_context *ctx, int64_t *nbox_total, int64_t *ncandidates_emitted)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    if (nbox_total) *nbox_total = ctx->enc.nbox_total;
+    if (ncandidates_emitted) *ncandidates_emitted = ctx->enc.nemitted;
+    return SWCU_OK;
+}

@@ -1,0 +1,714 @@
+// swcu_api.cu -- the C ABI of libswiftest_cuda.so (include/swiftest_cuda.h): context management, the
+// host-pointer (tier 1) entry points, the device-resident (tier 2) entry points, and measurement helpers.
+#include "swcu_internal.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace swcu;
+
+#define SWCU_VERSION_NUMBER 100
+
+namespace {
+
+int env_int(const char *name, int dflt)
+{
+    const char *v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// ---------------- probes ----------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double seed)
+{
+    // 16 independent DFMA chains per thread, register resident
+    double a[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) a[k] = seed + 1e-3 * (threadIdx.x + k);
+    const double m = 1.0000000001, c = 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a[k] = fma(a[k], m, c);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += a[k];
+    if (s == 12345.6789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true; keeps the chains alive
+}
+
+__global__ void flush_kernel(double *buf, size_t n, double v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+}
+
+__global__ void mask_merge_iflag_kernel(int n, const int32_t *lmask, const int32_t *computed, int32_t *inout)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && lmask[i] != 0) inout[i] = computed[i];
+}
+
+int check_ctx(swcu_context *ctx)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return fail(ctx, SWCU_ERR_CUDA, "cudaSetDevice(%d): %s", ctx->device, cudaGetErrorString(e));
+    return SWCU_OK;
+}
+
+Body &body_of(swcu_context *ctx, int kind) { return kind == SWCU_TP ? ctx->tp : ctx->pl; }
+
+// upload a double array or fill it with a default
+int put_or_fill(swcu_context *ctx, const double *h, int n, DevBuf &d, double dflt)
+{
+    SWCU_CUDA(ctx, d.ensure(sizeof(double) * (size_t)std::max(n, 1)));
+    if (n <= 0) return SWCU_OK;
+    if (h) {
+        SWCU_CUDA(ctx, cudaMemcpyAsync(d.p, h, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        return SWCU_OK;
+    }
+    return fill_f64(ctx, d.as<double>(), dflt, n);
+}
+
+int put_or_fill_vec3(swcu_context *ctx, const double *h, int n, int slot, DevBuf &x, DevBuf &y, DevBuf &z)
+{
+    if (h) return upload_vec3(ctx, h, n, slot, x, y, z);
+    SWCU_CUDA(ctx, x.ensure(sizeof(double) * (size_t)std::max(n, 1)));
+    SWCU_CUDA(ctx, y.ensure(sizeof(double) * (size_t)std::max(n, 1)));
+    SWCU_CUDA(ctx, z.ensure(sizeof(double) * (size_t)std::max(n, 1)));
+    SWCU_TRY(fill_f64(ctx, x.as<double>(), 0.0, n));
+    SWCU_TRY(fill_f64(ctx, y.as<double>(), 0.0, n));
+    return fill_f64(ctx, z.as<double>(), 0.0, n);
+}
+
+SweepList sweep_list(const Body &b, int off, int n, bool with_renc)
+{
+    SweepList l;
+    l.x = b.rx.as<double>() + off;
+    l.y = b.ry.as<double>() + off;
+    l.z = b.rz.as<double>() + off;
+    l.vx = b.vx.as<double>() + off;
+    l.vy = b.vy.as<double>() + off;
+    l.vz = b.vz.as<double>() + off;
+    l.renc = with_renc ? b.renc.as<double>() + off : nullptr;
+    l.n = n;
+    return l;
+}
+
+// stage a tier-1 population: positions (+ velocities, renc) into a scratch Body
+int stage_population(swcu_context *ctx, Body &b, int n, const double *r, const double *v, const double *renc)
+{
+    SWCU_TRY(ensure_body(ctx, b, n));
+    b.n = n;
+    b.nplm = n;
+    SWCU_TRY(upload_vec3(ctx, r, n, 0, b.rx, b.ry, b.rz));
+    if (v) SWCU_TRY(upload_vec3(ctx, v, n, 1, b.vx, b.vy, b.vz));
+    if (renc) SWCU_TRY(put_or_fill(ctx, renc, n, b.renc, 0.0));
+    return SWCU_OK;
+}
+
+}  // namespace
+
+// ======================================================================================================
+// context
+// ======================================================================================================
+extern "C" int swcu_version(void) { return SWCU_VERSION_NUMBER; }
+
+extern "C" int swcu_create(int device, swcu_context **out)
+{
+    if (!out) return SWCU_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return SWCU_ERR_NOGPU;
+    if (device < 0 || device >= ndev) return SWCU_ERR_ARG;
+    swcu_context *ctx = new (std::nothrow) swcu_context;
+    if (!ctx) return SWCU_ERR_CUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&ctx->prop, device) != cudaSuccess) {
+        delete ctx;
+        return SWCU_ERR_CUDA;
+    }
+    if (ctx->prop.major < 10 && !getenv("SWCU_ALLOW_ANY_ARCH")) {  // the library holds sm_100a code only
+        delete ctx;
+        return SWCU_ERR_NOGPU;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return SWCU_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    for (int f = 0; f < FAM_COUNT; ++f) {
+        cudaEventCreate(&ctx->fam_ev0[f]);
+        cudaEventCreate(&ctx->fam_ev1[f]);
+    }
+    ctx->tune_ib = env_int("SWCU_KICK_IB", 0);
+    ctx->tune_nsplit = env_int("SWCU_KICK_NSPLIT", 0);
+    ctx->tune_variant = env_int("SWCU_KICK_VARIANT", -1);
+    *out = ctx;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_destroy(swcu_context *ctx)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    comm_release(ctx);
+    ctx->pl.release();
+    ctx->tp.release();
+    ctx->s_pl.release();
+    ctx->s_tp.release();
+    for (auto &b : ctx->stage) b.release();
+    for (auto &b : ctx->istage) b.release();
+    ctx->partial.release();
+    ctx->scratch64.release();
+    ctx->flush.release();
+    ctx->sendbuf.release();
+    ctx->recvbuf.release();
+    auto &E = ctx->enc;
+    DevBuf *eb[] = {&E.keys_in, &E.keys_out, &E.vals_in, &E.vals_out, &E.cub_tmp, &E.cx, &E.cy, &E.cz, &E.cvx, &E.cvy,
+                    &E.cvz, &E.crenc, &E.sx, &E.sy, &E.sz, &E.svx, &E.svy, &E.svz, &E.srenc, &E.sbody, &E.ibeg, &E.iend,
+                    &E.nchunk, &E.choff, &E.cand, &E.cand_sorted, &E.uniq, &E.counters, &E.out1, &E.out2, &E.merged};
+    for (DevBuf *b : eb) b->release();
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    for (int f = 0; f < FAM_COUNT; ++f) {
+        cudaEventDestroy(ctx->fam_ev0[f]);
+        cudaEventDestroy(ctx->fam_ev1[f]);
+    }
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return SWCU_OK;
+}
+
+extern "C" const char *swcu_last_error(const swcu_context *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+extern "C" int swcu_set_stream(swcu_context *ctx, void *cuda_stream)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_synchronize(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_device_info(swcu_context *ctx, int32_t *sm_count, int32_t *cc, int64_t *mem_bytes)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc) *cc = ctx->prop.major * 10 + ctx->prop.minor;
+    if (mem_bytes) *mem_bytes = (int64_t)ctx->prop.totalGlobalMem;
+    return SWCU_OK;
+}
+
+extern "C" int64_t swcu_launch_count(const swcu_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ======================================================================================================
+// tier 1: host pointers
+// ======================================================================================================
+extern "C" int swcu_kick_getacch_int_all_tri_pl(swcu_context *ctx, int32_t npl, int32_t nplm, const double *r,
+                                                const double *Gmass, const double *radius, double *acc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (npl < 0 || nplm < 0 || nplm > npl) return fail(ctx, SWCU_ERR_ARG, "tri_pl: bad npl=%d nplm=%d", npl, nplm);
+    if (npl == 0) return SWCU_OK;
+    if (!r || !Gmass || !acc) return fail(ctx, SWCU_ERR_ARG, "tri_pl: null array");
+    Body &b = ctx->s_pl;
+    SWCU_TRY(ensure_body(ctx, b, npl));
+    b.n = npl;
+    b.nplm = nplm;
+    SWCU_TRY(upload_vec3(ctx, r, npl, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(upload_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+    SWCU_TRY(put_or_fill(ctx, Gmass, npl, b.Gm, 0.0));
+    if (radius) SWCU_TRY(put_or_fill(ctx, radius, npl, b.radius, 0.0));
+    SWCU_TRY(kick_pl_tri(ctx, b, radius != nullptr, 0, npl));
+    SWCU_TRY(download_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_kick_getacch_int_all_flat_pl(swcu_context *ctx, int32_t npl, int64_t nplpl, const int32_t *k_plpl,
+                                                 const double *r, const double *Gmass, const double *radius, double *acc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (npl < 0 || nplpl < 0) return fail(ctx, SWCU_ERR_ARG, "flat_pl: bad npl=%d nplpl=%lld", npl, (long long)nplpl);
+    if (npl == 0 || nplpl == 0) return SWCU_OK;
+    if (!r || !Gmass || !acc) return fail(ctx, SWCU_ERR_ARG, "flat_pl: null array");
+    Body &b = ctx->s_pl;
+    SWCU_TRY(ensure_body(ctx, b, npl));
+    b.n = npl;
+    SWCU_TRY(upload_vec3(ctx, r, npl, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(put_or_fill(ctx, Gmass, npl, b.Gm, 0.0));
+    if (radius) SWCU_TRY(put_or_fill(ctx, radius, npl, b.radius, 0.0));
+
+    if (k_plpl == nullptr) {
+        // canonical flattened upper triangle: nplpl = nplm*npl - nplm*(nplm+1)/2 (symba_util.f90:202)
+        int64_t nplm = -1;
+        {
+            // smallest nplm in [0,npl] whose pair count equals nplpl (count is strictly increasing on [0,npl-1])
+            int64_t lo = 0, hi = npl;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) / 2;
+                const int64_t cnt = mid * npl - mid * (mid + 1) / 2;
+                if (cnt < nplpl) lo = mid + 1; else hi = mid;
+            }
+            if (lo * (int64_t)npl - lo * (lo + 1) / 2 == nplpl) nplm = lo;
+        }
+        if (nplm < 0)
+            return fail(ctx, SWCU_ERR_ARG,
+                        "flat_pl: nplpl=%lld is not nplm*npl-nplm*(nplm+1)/2 for any nplm (npl=%d); pass k_plpl",
+                        (long long)nplpl, npl);
+        if (nplm == npl - 1) nplm = npl;  // all pairs: the last body has no extra row of its own
+        b.nplm = (int)nplm;
+        SWCU_TRY(upload_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+        SWCU_TRY(kick_pl_flat(ctx, b, radius != nullptr, (int)nplm));
+        SWCU_TRY(download_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+    } else {
+        // explicit pair table: ahi/ahj accumulate from zero, then acc = acc + (ahi + ahj) (kick.f90:92-112)
+        SWCU_CUDA(ctx, ctx->istage[0].ensure(sizeof(int32_t) * 2 * (size_t)nplpl));
+        SWCU_CUDA(ctx, ctx->istage[1].ensure(sizeof(int32_t) * 2 * (size_t)nplpl));
+        // de-interleave k_plpl(2,nplpl) on the host side of the copy: two strided copies
+        SWCU_CUDA(ctx, cudaMemcpy2DAsync(ctx->istage[0].p, sizeof(int32_t), k_plpl, 2 * sizeof(int32_t), sizeof(int32_t),
+                                         (size_t)nplpl, cudaMemcpyHostToDevice, ctx->stream));
+        SWCU_CUDA(ctx, cudaMemcpy2DAsync(ctx->istage[1].p, sizeof(int32_t), k_plpl + 1, 2 * sizeof(int32_t),
+                                         sizeof(int32_t), (size_t)nplpl, cudaMemcpyHostToDevice, ctx->stream));
+        SWCU_TRY(fill_f64(ctx, b.vx.as<double>(), 0.0, npl));
+        SWCU_TRY(fill_f64(ctx, b.vy.as<double>(), 0.0, npl));
+        SWCU_TRY(fill_f64(ctx, b.vz.as<double>(), 0.0, npl));
+        SWCU_TRY(kick_pair_list(ctx, b, radius != nullptr, nplpl, ctx->istage[0].as<int32_t>(), ctx->istage[1].as<int32_t>(),
+                                b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>()));
+        SWCU_TRY(upload_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+        SWCU_TRY(axpy3(ctx, 1.0, b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>(), b.ax.as<double>(),
+                       b.ay.as<double>(), b.az.as<double>(), nullptr, npl));
+        SWCU_TRY(download_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
+    }
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_symba_kick_subtract_encounters(swcu_context *ctx, int32_t npl, int64_t nenc, const int32_t *index1,
+                                                   const int32_t *index2, const double *rh, const double *Gmass,
+                                                   const double *radius, double *ah)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (npl <= 0 || nenc <= 0) return SWCU_OK;  // symba_kick.f90:54,59
+    if (!index1 || !index2 || !rh || !Gmass || !radius || !ah) return fail(ctx, SWCU_ERR_ARG, "symba subtract: null array");
+    Body &b = ctx->s_pl;
+    SWCU_TRY(ensure_body(ctx, b, npl));
+    b.n = npl;
+    SWCU_TRY(upload_vec3(ctx, rh, npl, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(upload_vec3(ctx, ah, npl, 1, b.ax, b.ay, b.az));
+    SWCU_TRY(put_or_fill(ctx, Gmass, npl, b.Gm, 0.0));
+    SWCU_TRY(put_or_fill(ctx, radius, npl, b.radius, 0.0));
+    SWCU_TRY(upload_arr(ctx, index1, sizeof(int32_t) * (size_t)nenc, ctx->istage[0]));
+    SWCU_TRY(upload_arr(ctx, index2, sizeof(int32_t) * (size_t)nenc, ctx->istage[1]));
+    SWCU_TRY(fill_f64(ctx, b.vx.as<double>(), 0.0, npl));  // ah_enc(:,:) = 0
+    SWCU_TRY(fill_f64(ctx, b.vy.as<double>(), 0.0, npl));
+    SWCU_TRY(fill_f64(ctx, b.vz.as<double>(), 0.0, npl));
+    SWCU_TRY(kick_pair_list(ctx, b, true, nenc, ctx->istage[0].as<int32_t>(), ctx->istage[1].as<int32_t>(),
+                            b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>()));
+    SWCU_TRY(axpy3(ctx, -1.0, b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>(), b.ax.as<double>(),
+                   b.ay.as<double>(), b.az.as<double>(), nullptr, npl));  // ah = ah - ah_enc
+    SWCU_TRY(download_vec3(ctx, ah, npl, 1, b.ax, b.ay, b.az));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_kick_getacch_int_all_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double *rtp,
+                                            const double *rpl, const double *GMpl, const int32_t *lmask, double *acc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (ntp < 0 || npl < 0) return fail(ctx, SWCU_ERR_ARG, "all_tp: bad ntp=%d npl=%d", ntp, npl);
+    if (ntp == 0 || npl == 0) return SWCU_OK;  // kick.f90:61
+    if (!rtp || !rpl || !GMpl || !lmask || !acc) return fail(ctx, SWCU_ERR_ARG, "all_tp: null array");
+    Body &t = ctx->s_tp, &p = ctx->s_pl;
+    SWCU_TRY(ensure_body(ctx, t, ntp));
+    SWCU_TRY(ensure_body(ctx, p, npl));
+    t.n = ntp;
+    p.n = npl;
+    SWCU_TRY(upload_vec3(ctx, rtp, ntp, 0, t.rx, t.ry, t.rz));
+    SWCU_TRY(upload_vec3(ctx, acc, ntp, 1, t.ax, t.ay, t.az));
+    SWCU_TRY(upload_arr(ctx, lmask, sizeof(int32_t) * (size_t)ntp, t.lmask));
+    SWCU_TRY(upload_vec3(ctx, rpl, npl, 2, p.rx, p.ry, p.rz));
+    SWCU_TRY(put_or_fill(ctx, GMpl, npl, p.Gm, 0.0));
+    KickProblem k;
+    k.xi = t.rx.as<double>(); k.yi = t.ry.as<double>(); k.zi = t.rz.as<double>(); k.radi = nullptr;
+    k.row0 = 0; k.row1 = ntp;
+    k.xj = p.rx.as<double>(); k.yj = p.ry.as<double>(); k.zj = p.rz.as<double>(); k.gmj = p.Gm.as<double>(); k.radj = nullptr;
+    k.col0 = 0; k.col1 = npl;
+    k.diag = false;
+    k.lmask = t.lmask.as<int32_t>();
+    k.ax = t.ax.as<double>(); k.ay = t.ay.as<double>(); k.az = t.az.as<double>();
+    SWCU_TRY(kick_rows(ctx, k, FAM_PLTP));
+    SWCU_TRY(download_vec3(ctx, acc, ntp, 1, t.ax, t.ay, t.az));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_drift_all(swcu_context *ctx, int32_t n, const double *mu, double *x, double *v, double dt, int32_t lgr,
+                              double inv_c2, const int32_t *lmask, int32_t *iflag)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (n < 0) return fail(ctx, SWCU_ERR_ARG, "drift_all: bad n=%d", n);
+    if (n == 0) return SWCU_OK;  // drift.f90:81
+    if (!mu || !x || !v || !lmask || !iflag) return fail(ctx, SWCU_ERR_ARG, "drift_all: null array");
+    Body &b = ctx->s_tp;
+    SWCU_TRY(ensure_body(ctx, b, n));
+    b.n = n;
+    SWCU_TRY(upload_vec3(ctx, x, n, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(upload_vec3(ctx, v, n, 1, b.vx, b.vy, b.vz));
+    SWCU_TRY(put_or_fill(ctx, mu, n, b.mu, 0.0));
+    SWCU_TRY(upload_arr(ctx, lmask, sizeof(int32_t) * (size_t)n, b.lmask));
+    SWCU_TRY(upload_arr(ctx, iflag, sizeof(int32_t) * (size_t)n, b.iflag));  // entries with lmask false keep their value
+    SWCU_TRY(drift_bodies(ctx, b, 0, n, dt, lgr, inv_c2, nullptr));
+    SWCU_TRY(download_vec3(ctx, x, n, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(download_vec3(ctx, v, n, 1, b.vx, b.vy, b.vz));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(iflag, b.iflag.p, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_encounter_check_all_sort_and_sweep_plpl(swcu_context *ctx, int32_t npl, const double *r,
+                                                            const double *v, const double *renc, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || npl < 0) return fail(ctx, SWCU_ERR_ARG, "sas_plpl: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (npl == 0) return SWCU_OK;
+    if (!r || !v || !renc) return fail(ctx, SWCU_ERR_ARG, "sas_plpl: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, npl, r, v, renc));
+    return encounter_sweep(ctx, sweep_list(ctx->s_pl, 0, npl, true), nullptr, dt, nenc);
+}
+
+extern "C" int swcu_encounter_check_all_sort_and_sweep_pltp(swcu_context *ctx, int32_t npl, int32_t ntp,
+                                                            const double *rpl, const double *vpl, const double *rtp,
+                                                            const double *vtp, const double *rencpl, double dt,
+                                                            int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || npl < 0 || ntp < 0) return fail(ctx, SWCU_ERR_ARG, "sas_pltp: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (npl == 0 || ntp == 0) return SWCU_OK;
+    if (!rpl || !vpl || !rtp || !vtp || !rencpl) return fail(ctx, SWCU_ERR_ARG, "sas_pltp: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, npl, rpl, vpl, rencpl));
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, ntp, rtp, vtp, nullptr));
+    SweepList l2 = sweep_list(ctx->s_tp, 0, ntp, false);
+    return encounter_sweep(ctx, sweep_list(ctx->s_pl, 0, npl, true), &l2, dt, nenc);
+}
+
+extern "C" int swcu_encounter_check_all_sort_and_sweep_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt,
+                                                             const double *rplm, const double *vplm, const double *rplt,
+                                                             const double *vplt, const double *rencm, const double *renct,
+                                                             double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || nplm < 0 || nplt < 0) return fail(ctx, SWCU_ERR_ARG, "sas_plplm: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (nplm == 0 || nplt == 0) return SWCU_OK;
+    if (!rplm || !vplm || !rplt || !vplt || !rencm || !renct) return fail(ctx, SWCU_ERR_ARG, "sas_plplm: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, nplm, rplm, vplm, rencm));
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, nplt, rplt, vplt, renct));
+    SweepList l2 = sweep_list(ctx->s_tp, 0, nplt, true);
+    return encounter_sweep(ctx, sweep_list(ctx->s_pl, 0, nplm, true), &l2, dt, nenc);
+}
+
+extern "C" int swcu_encounter_check_all_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt, const double *rplm,
+                                              const double *vplm, const double *rplt, const double *vplt,
+                                              const double *rencm, const double *renct, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || nplm < 0 || nplt < 0) return fail(ctx, SWCU_ERR_ARG, "all_plplm: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (nplm == 0) return SWCU_OK;
+    if (!rplm || !vplm || !rencm) return fail(ctx, SWCU_ERR_ARG, "all_plplm: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, nplm, rplm, vplm, rencm));
+    if (nplt == 0) return encounter_sweep(ctx, sweep_list(ctx->s_pl, 0, nplm, true), nullptr, dt, nenc);
+    if (!rplt || !vplt || !renct) return fail(ctx, SWCU_ERR_ARG, "all_plplm: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, nplt, rplt, vplt, renct));
+    return encounter_merge_plplm(ctx, sweep_list(ctx->s_pl, 0, nplm, true), sweep_list(ctx->s_tp, 0, nplt, true), dt, nenc);
+}
+
+// ======================================================================================================
+// tier 2: device-resident populations
+// ======================================================================================================
+extern "C" int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_t nplm, const double *r, const double *v,
+                              const double *Gmass, const double *radius, const double *rhill, const double *mu,
+                              const int32_t *lmask, uint64_t generation)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (n < 0 || (kind != SWCU_PL && kind != SWCU_TP)) return fail(ctx, SWCU_ERR_ARG, "body_sync: bad kind/n");
+    Body &b = body_of(ctx, kind);
+    if (kind == SWCU_PL && (nplm < 0 || nplm > n)) return fail(ctx, SWCU_ERR_ARG, "body_sync: bad nplm=%d (npl=%d)", nplm, n);
+    if (b.valid && b.generation == generation && b.n == n) return SWCU_OK;  // nothing changed on the host side
+    SWCU_TRY(ensure_body(ctx, b, n));
+    b.n = n;
+    b.nplm = (kind == SWCU_PL) ? nplm : 0;
+    b.slice0 = 0;
+    b.slice1 = n;
+    SWCU_TRY(put_or_fill_vec3(ctx, r, n, 0, b.rx, b.ry, b.rz));
+    SWCU_TRY(put_or_fill_vec3(ctx, v, n, 1, b.vx, b.vy, b.vz));
+    SWCU_TRY(put_or_fill_vec3(ctx, nullptr, n, 2, b.ax, b.ay, b.az));
+    SWCU_TRY(put_or_fill(ctx, Gmass, n, b.Gm, 0.0));
+    SWCU_TRY(put_or_fill(ctx, radius, n, b.radius, 0.0));
+    SWCU_TRY(put_or_fill(ctx, rhill, n, b.rhill, 0.0));
+    SWCU_TRY(put_or_fill(ctx, mu, n, b.mu, 0.0));
+    SWCU_TRY(fill_f64(ctx, b.renc.as<double>(), 0.0, n));
+    if (lmask)
+        SWCU_TRY(upload_arr(ctx, lmask, sizeof(int32_t) * (size_t)n, b.lmask));
+    else
+        SWCU_TRY(fill_i32(ctx, b.lmask.as<int32_t>(), 1, n));
+    SWCU_TRY(fill_i32(ctx, b.iflag.as<int32_t>(), 0, n));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host arrays may be reused by the caller right away
+    b.generation = generation;
+    b.valid = true;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_put(swcu_context *ctx, int32_t kind, const double *r, const double *v, const double *a,
+                             const int32_t *lmask)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_put: population not resident (call swcu_body_sync first)");
+    if (r) SWCU_TRY(upload_vec3(ctx, r, b.n, 0, b.rx, b.ry, b.rz));
+    if (v) SWCU_TRY(upload_vec3(ctx, v, b.n, 1, b.vx, b.vy, b.vz));
+    if (a) SWCU_TRY(upload_vec3(ctx, a, b.n, 2, b.ax, b.ay, b.az));
+    if (lmask) SWCU_TRY(upload_arr(ctx, lmask, sizeof(int32_t) * (size_t)b.n, b.lmask));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_get(swcu_context *ctx, int32_t kind, double *r, double *v, double *a, int32_t *iflag)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_get: population not resident");
+    if (r) SWCU_TRY(download_vec3(ctx, r, b.n, 0, b.rx, b.ry, b.rz));
+    if (v) SWCU_TRY(download_vec3(ctx, v, b.n, 1, b.vx, b.vy, b.vz));
+    if (a) SWCU_TRY(download_vec3(ctx, a, b.n, 2, b.ax, b.ay, b.az));
+    if (iflag && b.n > 0)
+        SWCU_CUDA(ctx, cudaMemcpyAsync(iflag, b.iflag.p, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_count(swcu_context *ctx, int32_t kind, int32_t *n, int32_t *nplm, uint64_t *generation)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    Body &b = body_of(ctx, kind);
+    if (n) *n = b.valid ? b.n : 0;
+    if (nplm) *nplm = b.valid ? b.nplm : 0;
+    if (generation) *generation = b.generation;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_zero_accel(swcu_context *ctx, int32_t kind)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "zero_accel: population not resident");
+    SWCU_TRY(fill_f64(ctx, b.ax.as<double>(), 0.0, b.n));
+    SWCU_TRY(fill_f64(ctx, b.ay.as<double>(), 0.0, b.n));
+    return fill_f64(ctx, b.az.as<double>(), 0.0, b.n);
+}
+
+extern "C" int swcu_pl_accel_int(swcu_context *ctx, int32_t loop_variant, int32_t lclose)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl;
+    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_accel_int: pl population not resident");
+    if (pl.n == 0) return SWCU_OK;
+    int variant = ctx->tune_variant >= 0 ? ctx->tune_variant : loop_variant;
+    if (variant == SWCU_LOOP_AUTO) variant = SWCU_LOOP_TRIANGULAR;
+    const bool sliced = !(pl.slice0 == 0 && pl.slice1 == pl.n);
+    if (variant == SWCU_LOOP_FLAT && !sliced) return kick_pl_flat(ctx, pl, lclose != 0, pl.nplm);
+    return kick_pl_tri(ctx, pl, lclose != 0, pl.slice0, pl.slice1);
+}
+
+extern "C" int swcu_tp_accel_int(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &tp = ctx->tp, &pl = ctx->pl;
+    if (!tp.valid || !pl.valid) return fail(ctx, SWCU_ERR_STATE, "tp_accel_int: tp and pl populations must be resident");
+    if (tp.n == 0 || pl.n == 0) return SWCU_OK;  // kick.f90:61
+    KickProblem k;
+    k.xi = tp.rx.as<double>(); k.yi = tp.ry.as<double>(); k.zi = tp.rz.as<double>(); k.radi = nullptr;
+    k.row0 = 0; k.row1 = tp.n;
+    k.xj = pl.rx.as<double>(); k.yj = pl.ry.as<double>(); k.zj = pl.rz.as<double>(); k.gmj = pl.Gm.as<double>(); k.radj = nullptr;
+    k.col0 = 0; k.col1 = pl.n;
+    k.diag = false;
+    k.lmask = tp.lmask.as<int32_t>();
+    k.ax = tp.ax.as<double>(); k.ay = tp.ay.as<double>(); k.az = tp.az.as<double>();
+    return kick_rows(ctx, k, FAM_PLTP);
+}
+
+extern "C" int swcu_pl_set_renc(swcu_context *ctx, int32_t irec)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_set_renc: pl population not resident");
+    if (irec < 0) return fail(ctx, SWCU_ERR_ARG, "pl_set_renc: irec=%d", irec);
+    return set_renc(ctx, ctx->pl, irec);
+}
+
+extern "C" int swcu_body_drift(swcu_context *ctx, int32_t kind, double dt, int32_t lgr, double inv_c2, int32_t *nfail)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_drift: population not resident");
+    const int i0 = (kind == SWCU_PL) ? b.slice0 : 0, i1 = (kind == SWCU_PL) ? b.slice1 : b.n;
+    return drift_bodies(ctx, b, i0, i1, dt, lgr, inv_c2, nfail);
+}
+
+extern "C" int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "kick_velocity: population not resident");
+    return axpy3(ctx, dt, b.ax.as<double>(), b.ay.as<double>(), b.az.as<double>(), b.vx.as<double>(), b.vy.as<double>(),
+                 b.vz.as<double>(), b.lmask.as<int32_t>(), b.n);
+}
+
+extern "C" int swcu_pl_encounter_check(swcu_context *ctx, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl;
+    if (!nenc) return fail(ctx, SWCU_ERR_ARG, "pl_encounter_check: null nenc");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_encounter_check: pl population not resident");
+    if (pl.n == 0) return SWCU_OK;
+    const int nplm = pl.nplm, nplt = pl.n - pl.nplm;
+    if (nplt == 0) return encounter_sweep(ctx, sweep_list(pl, 0, pl.n, true), nullptr, dt, nenc);  // symba_encounter_check.f90:45-46
+    if (nplm == 0) return SWCU_OK;
+    return encounter_merge_plplm(ctx, sweep_list(pl, 0, nplm, true), sweep_list(pl, nplm, nplt, true), dt, nenc);
+}
+
+extern "C" int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl, &tp = ctx->tp;
+    if (!nenc) return fail(ctx, SWCU_ERR_ARG, "tp_encounter_check: null nenc");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (!pl.valid || !tp.valid) return fail(ctx, SWCU_ERR_STATE, "tp_encounter_check: populations not resident");
+    if (pl.n == 0 || tp.n == 0) return SWCU_OK;
+    SweepList l2 = sweep_list(tp, 0, tp.n, false);
+    return encounter_sweep(ctx, sweep_list(pl, 0, pl.n, true), &l2, dt, nenc);
+}
+
+// ======================================================================================================
+// measurement helpers
+// ======================================================================================================
+extern "C" int swcu_timer_start(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_timer_stop(swcu_context *ctx, double *elapsed_ms)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    SWCU_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    SWCU_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (elapsed_ms) *elapsed_ms = ms;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    ctx->kernel_timing = (on != 0);
+    return SWCU_OK;
+}
+
+extern "C" int swcu_last_kernel_ms(swcu_context *ctx, int32_t family, double *ms)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (family < 0 || family >= FAM_COUNT || !ms) return fail(ctx, SWCU_ERR_ARG, "last_kernel_ms: bad family");
+    if (ctx->fam_pending[family]) {
+        SWCU_CUDA(ctx, cudaEventSynchronize(ctx->fam_ev1[family]));
+        float t = 0.f;
+        SWCU_CUDA(ctx, cudaEventElapsedTime(&t, ctx->fam_ev0[family], ctx->fam_ev1[family]));
+        ctx->fam_ms[family] = t;
+        ctx->fam_pending[family] = false;
+    }
+    *ms = ctx->fam_ms[family];
+    return SWCU_OK;
+}
+
+extern "C" int swcu_probe_fp64_peak(swcu_context *ctx, double *tflops)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!tflops) return SWCU_ERR_ARG;
+    const int blocks = ctx->prop.multiProcessorCount * 8, threads = 256, iters = 20000;
+    SWCU_CUDA(ctx, ctx->flush.ensure(sizeof(double) * (size_t)blocks * threads));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        SWCU_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->flush.as<double>(), iters, 1.0 + rep);
+        SWCU_KERNEL_CHECK(ctx);
+        SWCU_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SWCU_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        SWCU_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double flops = 2.0 * 16.0 * (double)iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    *tflops = best;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_probe_hbm_copy(swcu_context *ctx, int64_t bytes, double *gbs)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!gbs || bytes <= 0) return SWCU_ERR_ARG;
+    DevBuf a, b;
+    SWCU_CUDA(ctx, a.ensure((size_t)bytes));
+    SWCU_CUDA(ctx, b.ensure((size_t)bytes));
+    SWCU_CUDA(ctx, cudaMemsetAsync(a.p, 1, (size_t)bytes, ctx->stream));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        SWCU_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        SWCU_CUDA(ctx, cudaMemcpyAsync(b.p, a.p, (size_t)bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        SWCU_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SWCU_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        SWCU_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0) best = std::max(best, 2.0 * (double)bytes / (ms * 1e-3) / 1e9);
+    }
+    a.release();
+    b.release();
+    *gbs = best;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_flush_l2(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    const size_t bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    SWCU_CUDA(ctx, ctx->flush.ensure(bytes));
+    flush_kernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, ctx->stream>>>(ctx->flush.as<double>(), bytes / sizeof(double), 0.0);
+    SWCU_KERNEL_CHECK(ctx);
+    return SWCU_OK;
+}

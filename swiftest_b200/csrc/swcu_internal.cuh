@@ -1,0 +1,213 @@
+// swcu_internal.cuh -- context, device buffers and launch helpers shared by the translation units of
+// libswiftest_cuda.so.  Nothing here is visible through the C ABI (include/swiftest_cuda.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/swiftest_cuda.h"
+
+namespace swcu {
+
+// Growable device allocation.  Capacity only grows; every array is padded so that bulk (TMA) copies rounded
+// up to 16 bytes and clamped row loads never leave the allocation.
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        bytes += 256;
+        if (bytes <= cap) return cudaSuccess;
+        size_t want = bytes + bytes / 4;
+        want = (want + 255) & ~size_t(255);
+        if (p) {
+            cudaError_t e = cudaFree(p);
+            p = nullptr;
+            cap = 0;
+            if (e != cudaSuccess) return e;
+        }
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) return e;
+        cap = want;
+        return cudaSuccess;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// One resident body population, structure-of-arrays in HBM.
+struct Body {
+    int n = 0;
+    int nplm = 0;
+    uint64_t generation = ~uint64_t(0);
+    bool valid = false;
+    int slice0 = 0, slice1 = 0;  // rows this rank owns (multi-GPU); [0,n) on one GPU
+    DevBuf rx, ry, rz, vx, vy, vz, ax, ay, az;
+    DevBuf Gm, radius, rhill, renc, mu;
+    DevBuf lmask, iflag;  // int32
+    void release()
+    {
+        DevBuf *all[] = {&rx, &ry, &rz, &vx, &vy, &vz, &ax, &ay, &az, &Gm, &radius, &rhill, &renc, &mu, &lmask, &iflag};
+        for (DevBuf *b : all) b->release();
+        valid = false;
+        n = 0;
+    }
+};
+
+enum KernelFamily { FAM_PLPL = 0, FAM_PLTP = 1, FAM_DRIFT = 2, FAM_SWEEP = 3, FAM_ALLGATHER = 4, FAM_COUNT = 5 };
+
+struct NcclApi;  // comm.cu
+
+}  // namespace swcu
+
+struct swcu_context {
+    int device = 0;
+    cudaDeviceProp prop;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    swcu::Body pl, tp;
+
+    // scratch populations for the tier-1 (host pointer) entry points, kept apart from the resident ones
+    swcu::Body s_pl, s_tp;
+
+    // staging (AoS images of host arrays) and generic scratch
+    swcu::DevBuf stage[6];
+    swcu::DevBuf istage[2];
+    swcu::DevBuf partial;  // j-split partial accelerations
+    swcu::DevBuf scratch64;
+
+    // encounter state (persists across calls like the reference's `save`d bounding box, encounter_check.f90:163)
+    struct Enc {
+        swcu::DevBuf keys_in, keys_out, vals_in, vals_out, cub_tmp;
+        swcu::DevBuf cx, cy, cz, cvx, cvy, cvz, crenc;          // concatenated sweep population (double list)
+        swcu::DevBuf sx, sy, sz, svx, svy, svz, srenc, sbody;   // gathered into sorted-endpoint order
+        swcu::DevBuf ibeg, iend, nchunk, choff;
+        swcu::DevBuf cand, cand_sorted, uniq, counters;
+        swcu::DevBuf out1, out2;
+        size_t cand_cap = 0;   // pairs
+        int64_t nenc = -1;     // result of the last check (-1: none pending)
+        int64_t nbox_total = 0, nemitted = 0;
+        // second result buffer for the plplm merge
+        swcu::DevBuf merged;
+        const unsigned long long *result = nullptr;  // device pointer to the final sorted unique keys
+    } enc;
+
+    // timing
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool kernel_timing = false;
+    cudaEvent_t fam_ev0[swcu::FAM_COUNT] = {}, fam_ev1[swcu::FAM_COUNT] = {};
+    bool fam_pending[swcu::FAM_COUNT] = {};
+    double fam_ms[swcu::FAM_COUNT] = {};
+
+    swcu::DevBuf flush;
+
+    // multi-GPU
+    swcu::NcclApi *nccl = nullptr;
+    void *comm = nullptr;
+    int nranks = 1, rank = 0;
+    swcu::DevBuf sendbuf, recvbuf;
+
+    // tuning overrides (environment: SWCU_KICK_IB, SWCU_KICK_NSPLIT, SWCU_KICK_VARIANT)
+    int tune_ib = 0, tune_nsplit = 0, tune_variant = -1;
+};
+
+namespace swcu {
+
+int fail(swcu_context *ctx, int code, const char *fmt, ...);
+
+#define SWCU_CUDA(ctx, call)                                                                       \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return swcu::fail((ctx), SWCU_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, \
+                              cudaGetErrorString(e__));                                            \
+    } while (0)
+
+#define SWCU_TRY(expr)                 \
+    do {                               \
+        int rc__ = (expr);             \
+        if (rc__ != SWCU_OK) return rc__; \
+    } while (0)
+
+#define SWCU_KERNEL_CHECK(ctx)                 \
+    do {                                       \
+        (ctx)->launches++;                     \
+        SWCU_CUDA((ctx), cudaGetLastError());  \
+    } while (0)
+
+struct FamTimer {  // brackets a launch group with events when kernel timing is enabled
+    swcu_context *c;
+    int fam;
+    FamTimer(swcu_context *ctx, int family) : c(ctx), fam(family)
+    {
+        if (c->kernel_timing) cudaEventRecord(c->fam_ev0[fam], c->stream);
+    }
+    ~FamTimer()
+    {
+        if (c->kernel_timing) {
+            cudaEventRecord(c->fam_ev1[fam], c->stream);
+            c->fam_pending[fam] = true;
+        }
+    }
+};
+
+inline int cdiv(int64_t a, int64_t b) { return int((a + b - 1) / b); }
+
+// ---- layout conversion (host Fortran AoS r(3,n)  <->  device SoA) : layout_kernels.cu ----
+int aos_to_soa3(swcu_context *ctx, const double *d_aos, double *x, double *y, double *z, int n);
+int soa_to_aos3(swcu_context *ctx, const double *x, const double *y, const double *z, double *d_aos, int n);
+int upload_vec3(swcu_context *ctx, const double *h_aos, int n, int stage_slot, DevBuf &x, DevBuf &y, DevBuf &z);
+int download_vec3(swcu_context *ctx, double *h_aos, int n, int stage_slot, const DevBuf &x, const DevBuf &y,
+                  const DevBuf &z);
+int upload_arr(swcu_context *ctx, const void *h, size_t bytes, DevBuf &d);
+int fill_f64(swcu_context *ctx, double *d, double value, int n);
+int fill_i32(swcu_context *ctx, int32_t *d, int32_t value, int n);
+int ensure_body(swcu_context *ctx, Body &b, int n);
+
+// ---- gravity : kick_kernels.cu ----
+struct KickProblem {
+    // rows (bodies that receive acceleration)
+    const double *xi, *yi, *zi, *radi;
+    int row0, row1;  // half-open
+    // columns (bodies that exert it)
+    const double *xj, *yj, *zj, *gmj, *radj;
+    int col0, col1;
+    bool diag;             // rows and columns index the same population: skip i == j
+    const int32_t *lmask;  // optional row mask
+    double *ax, *ay, *az;  // accumulated in place (+=)
+};
+int kick_rows(swcu_context *ctx, const KickProblem &p, int family);
+int kick_pl_tri(swcu_context *ctx, Body &pl, bool lrad, int row0, int row1);
+int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows);
+int kick_pair_list(swcu_context *ctx, const Body &pl, bool lrad, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2,
+                   double *ex, double *ey, double *ez);
+int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, const double *x2, double *y0,
+          double *y1, double *y2, const int32_t *lmask, int n);
+
+// ---- drift : drift_kernels.cu ----
+int drift_bodies(swcu_context *ctx, Body &b, int i0, int i1, double dt, int lgr, double inv_c2, int32_t *nfail);
+
+// ---- encounters : encounter_kernels.cu ----
+struct SweepList {
+    const double *x, *y, *z, *vx, *vy, *vz, *renc;  // renc may be null (test particles: 0)
+    int n;
+};
+int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc);
+int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc);
+int set_renc(swcu_context *ctx, Body &pl, int irec);
+
+// ---- comm : comm.cu ----
+int comm_allgather_pl(swcu_context *ctx, int with_v);
+void comm_release(swcu_context *ctx);
+
+}  // namespace swcu

@@ -1,0 +1,70 @@
+"""CPU checks of the drop-in boundary: the shared library loads, exports every symbol include/swiftest_cuda.h
+declares, refuses to run without a GPU (no fallback), and its GPU-free helpers agree with the host logic."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+from swiftest_b200 import _lib, shard
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.load()
+    names = _lib.declared_symbols()
+    assert len(names) >= 40
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "swiftest_cuda.h"\nint main(void){return SWCU_OK;}\n')
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["/usr/bin/gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, "-c", str(src), "-o",
+                           str(tmp_path / "t.o")])
+
+
+def test_no_cpu_fallback_without_gpu():
+    """On a box without a GPU creating a context must fail loudly (SWCU_ERR_NOGPU), never fall back."""
+    L = _lib.load()
+    h = C.c_void_p()
+    rc = L.swcu_create(0, C.byref(h))
+    if rc == 0:  # running on the GPU box
+        L.swcu_destroy(h)
+        pytest.skip("GPU present")
+    assert rc == 5 and not h.value
+    from swiftest_b200 import Context, SwcuError
+    with pytest.raises(SwcuError):
+        Context(0)
+
+
+def test_product_package_never_imports_oracle():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "swiftest_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text and "swiftest_oracle" not in text, f
+
+
+@pytest.mark.parametrize("n,nranks", [(100000, 8), (12, 5), (3, 8), (0, 2), (1000001, 4)])
+def test_partition_matches_c_abi(n, nranks):
+    L = _lib.load()
+    covered = 0
+    for r in range(nranks):
+        i0, i1 = C.c_int32(), C.c_int32()
+        assert L.swcu_partition(n, nranks, r, C.byref(i0), C.byref(i1)) == 0
+        assert (i0.value, i1.value) == shard.partition(n, nranks, r)
+        assert i0.value == covered
+        covered = i1.value
+    assert covered == n
+    sizes = [shard.partition(n, nranks, r)[1] - shard.partition(n, nranks, r)[0] for r in range(nranks)]
+    assert max(sizes) - min(sizes) <= 1
+
+
+def test_tp_block_partition_is_coarray_shape():
+    # swiftest_coarray.f90:705-711: ceil(ntot/nimages) per image, last image takes the remainder
+    assert [shard.tp_block_partition(10, 4, k) for k in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert [shard.tp_block_partition(2, 4, k) for k in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]

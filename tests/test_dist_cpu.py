@@ -1,0 +1,79 @@
+"""world_size-2 gloo test of the multi-GPU host logic on CPU: i-sliced pl-pl gravity with an allgather of the
+drifted positions, and block-partitioned test particles against a replicated pl array.  The per-slice compute
+is done by the oracle here (CPU box); on the GPU box tests/test_gpu_multi.py runs the same decomposition through
+the C ABI + NCCL."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, ntp, out):
+    sys.path.insert(0, ROOT)
+    from oracle import load
+    from swiftest_b200 import shard, workloads as W
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = load()
+    d = W.disk(n, seed=42)
+    rh, vb = d["rh"].copy(), d["vh"].copy()
+    dt = d["dt"]
+    i0, i1 = shard.partition(n, world, rank)
+    for _ in range(2):  # kick - drift - allgather, twice
+        # rows [i0,i1): full-row sums over ALL columns, i.e. the tri kernel restricted to a row slice
+        ah = np.zeros((n, 3))
+        o.omp_kick_tri_rad_pl_rows(rh, d["Gmass"], d["radius"], ah, n, i0, i1)
+        vb[i0:i1] += ah[i0:i1] * dt
+        x, v, fl = o.drift_all(d["mu"][i0:i1], rh[i0:i1], vb[i0:i1], dt)
+        assert not fl.any()
+        # allgather of (possibly unequal) slices through padded buffers, like swcu_pl_allgather
+        maxc = -(-n // world)
+        send = torch.zeros(6, maxc, dtype=torch.float64)
+        send[:3, : i1 - i0] = torch.from_numpy(x.T.copy())
+        send[3:, : i1 - i0] = torch.from_numpy(v.T.copy())
+        recv = [torch.zeros_like(send) for _ in range(world)]
+        dist.all_gather(recv, send)
+        for r in range(world):
+            j0, j1 = shard.partition(n, world, r)
+            rh[j0:j1] = recv[r][:3, : j1 - j0].numpy().T
+            vb[j0:j1] = recv[r][3:, : j1 - j0].numpy().T
+    # test particles: block partition, replicated planets, no communication until the final gather
+    tp = W.tp_cloud(ntp, seed=5)
+    t0, t1 = shard.tp_block_partition(ntp, world, rank)
+    acc = o.kick_all_tp(tp["rh"][t0:t1], rh, d["Gmass"], np.ones(t1 - t0, np.int32), np.zeros((t1 - t0, 3)))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (t0, t1, acc))
+    if rank == 0:
+        full = np.zeros((ntp, 3))
+        for (a, b, blk) in gathered:
+            full[a:b] = blk
+        np.savez(out, rh=rh, vb=vb, tp_acc=full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_slices_match_single_process(tmp_path, oracle):
+    from swiftest_b200 import workloads as W
+    n, ntp, world = 301, 57, 2
+    out = str(tmp_path / "res.npz")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, n, ntp, out), nprocs=world, join=True)
+    res = np.load(out)
+    d = W.disk(n, seed=42)
+    rh, vb = d["rh"].copy(), d["vh"].copy()
+    for _ in range(2):
+        ah = oracle.kick_tri_pl(rh, d["Gmass"], d["radius"], np.zeros((n, 3)))
+        vb += ah * d["dt"]
+        rh, vb, fl = oracle.drift_all(d["mu"], rh, vb, d["dt"])
+    assert np.array_equal(res["rh"], rh) and np.array_equal(res["vb"], vb)  # same row order => bit-identical
+    tp = W.tp_cloud(ntp, seed=5)
+    ref = oracle.kick_all_tp(tp["rh"], rh, d["Gmass"], np.ones(ntp, np.int32), np.zeros((ntp, 3)))
+    assert np.array_equal(res["tp_acc"], ref)
