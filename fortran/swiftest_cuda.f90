@@ -1,0 +1,157 @@
+!! swiftest_cuda.f90 -- iso_c_binding interface module over libswiftest_cuda.so (include/swiftest_cuda.h).
+!!
+!! This is the file a Swiftest maintainer adds as src/cuda/swiftest_cuda.f90 (INTEGRATION.md).  It could NOT be compiled
+!! in the build container (no Fortran compiler in the image, SURVEY.md section 8c); every interface below is a literal
+!! transcription of the C prototypes, which ARE exercised from Python/ctypes by tests/.
+!!
+!! Conventions: scalars by value, arrays by reference (assumed-size, contiguous), logical masks converted with
+!! merge(1_c_int, 0_c_int, lmask), nplpl/nenc as integer(c_int64_t), status /= 0 -> base_util_exit(FAILURE).
+module swiftest_cuda
+   use, intrinsic :: iso_c_binding
+   implicit none
+   public
+
+   integer(c_int), parameter :: SWCU_OK = 0
+   integer(c_int), parameter :: SWCU_PL = 0, SWCU_TP = 1
+   integer(c_int), parameter :: SWCU_LOOP_TRIANGULAR = 0, SWCU_LOOP_FLAT = 1, SWCU_LOOP_AUTO = 2
+
+   type(c_ptr), save  :: swcu_ctx = c_null_ptr      !! one context per process / coarray image
+   integer(c_int64_t), save :: swcu_generation_pl = 0_c_int64_t !! bumped in rearray_pl, pl%flatten (Fraggle), restart read-in
+   integer(c_int64_t), save :: swcu_generation_tp = 0_c_int64_t !! bumped in tp%spill / rearray
+
+   interface
+      integer(c_int) function swcu_create(device, ctx) bind(C, name="swcu_create")
+         import :: c_int, c_ptr
+         integer(c_int), value :: device
+         type(c_ptr), intent(out) :: ctx
+      end function
+      integer(c_int) function swcu_destroy(ctx) bind(C, name="swcu_destroy")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      type(c_ptr) function swcu_last_error(ctx) bind(C, name="swcu_last_error")
+         import :: c_ptr
+         type(c_ptr), value :: ctx
+      end function
+
+      ! ---- tier 1: array-level, host arrays ----
+      integer(c_int) function swcu_kick_getacch_int_all_flat_pl(ctx, npl, nplpl, k_plpl, r, Gmass, radius, acc) &
+            bind(C, name="swcu_kick_getacch_int_all_flat_pl")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl
+         integer(c_int64_t), value :: nplpl
+         type(c_ptr), value :: k_plpl           !! c_null_ptr: canonical flattened pairs; else c_loc(k_plpl_enc)
+         real(c_double), intent(in) :: r(3,*), Gmass(*)
+         type(c_ptr), value :: radius           !! c_null_ptr selects the norad variant
+         real(c_double), intent(inout) :: acc(3,*)
+      end function
+      integer(c_int) function swcu_kick_getacch_int_all_tri_pl(ctx, npl, nplm, r, Gmass, radius, acc) &
+            bind(C, name="swcu_kick_getacch_int_all_tri_pl")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl, nplm
+         real(c_double), intent(in) :: r(3,*), Gmass(*)
+         type(c_ptr), value :: radius
+         real(c_double), intent(inout) :: acc(3,*)
+      end function
+      integer(c_int) function swcu_kick_getacch_int_all_tp(ctx, ntp, npl, rtp, rpl, GMpl, lmask, acc) &
+            bind(C, name="swcu_kick_getacch_int_all_tp")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: ntp, npl
+         real(c_double), intent(in) :: rtp(3,*), rpl(3,*), GMpl(*)
+         integer(c_int), intent(in) :: lmask(*)
+         real(c_double), intent(inout) :: acc(3,*)
+      end function
+      integer(c_int) function swcu_symba_kick_subtract_encounters(ctx, npl, nenc, index1, index2, rh, Gmass, radius, ah) &
+            bind(C, name="swcu_symba_kick_subtract_encounters")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*)
+         real(c_double), intent(in) :: rh(3,*), Gmass(*), radius(*)
+         real(c_double), intent(inout) :: ah(3,*)
+      end function
+      integer(c_int) function swcu_drift_all(ctx, n, mu, x, v, dt, lgr, inv_c2, lmask, iflag) bind(C, name="swcu_drift_all")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: n, lgr
+         real(c_double), value :: dt, inv_c2
+         real(c_double), intent(in) :: mu(*)
+         real(c_double), intent(inout) :: x(3,*), v(3,*)
+         integer(c_int), intent(in) :: lmask(*)
+         integer(c_int), intent(inout) :: iflag(*)
+      end function
+      integer(c_int) function swcu_encounter_check_all_sort_and_sweep_plpl(ctx, npl, r, v, renc, dt, nenc) &
+            bind(C, name="swcu_encounter_check_all_sort_and_sweep_plpl")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl
+         real(c_double), intent(in) :: r(3,*), v(3,*), renc(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_check_all_sort_and_sweep_pltp(ctx, npl, ntp, rpl, vpl, rtp, vtp, rencpl, dt, nenc) &
+            bind(C, name="swcu_encounter_check_all_sort_and_sweep_pltp")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl, ntp
+         real(c_double), intent(in) :: rpl(3,*), vpl(3,*), rtp(3,*), vtp(3,*), rencpl(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_check_all_plplm(ctx, nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt, nenc) &
+            bind(C, name="swcu_encounter_check_all_plplm")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nplm, nplt
+         real(c_double), intent(in) :: rplm(3,*), vplm(3,*), rplt(3,*), vplt(3,*), rencm(*), renct(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_fetch(ctx, nenc, index1, index2, lvdotr) bind(C, name="swcu_encounter_fetch")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(out) :: index1(*), index2(*), lvdotr(*)
+      end function
+
+      ! ---- tier 2: device-resident populations (see include/swiftest_cuda.h for the full list) ----
+      integer(c_int) function swcu_body_sync(ctx, kind, n, nplm, r, v, Gmass, radius, rhill, mu, lmask, generation) &
+            bind(C, name="swcu_body_sync")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, n, nplm
+         type(c_ptr), value :: r, v, Gmass, radius, rhill, mu, lmask   !! c_loc(array) or c_null_ptr
+         integer(c_int64_t), value :: generation
+      end function
+      integer(c_int) function swcu_pl_accel_int(ctx, loop_variant, lclose) bind(C, name="swcu_pl_accel_int")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: loop_variant, lclose
+      end function
+      integer(c_int) function swcu_body_drift(ctx, kind, dt, lgr, inv_c2, nfail) bind(C, name="swcu_body_drift")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, lgr
+         real(c_double), value :: dt, inv_c2
+         integer(c_int), intent(out) :: nfail
+      end function
+   end interface
+
+contains
+
+   subroutine swcu_check(status, where)
+      !! Maps a nonzero status to the reference's fatal-error convention (base_util_exit(FAILURE), base_module.f90:589)
+      use base, only : base_util_exit, FAILURE
+      integer(c_int),   intent(in) :: status
+      character(len=*), intent(in) :: where
+      if (status /= SWCU_OK) then
+         write(*,*) "swiftest_cuda: ", where, " failed with status ", status
+         call base_util_exit(FAILURE)
+      end if
+   end subroutine swcu_check
+
+end module swiftest_cuda

@@ -17,6 +17,7 @@
 //   * columns are split over gridDim.y to fill 148 SMs evenly; partial sums are reduced in a fixed order
 //     (deterministic, no atomics).
 #include "swcu_internal.cuh"
+#include "kick_math.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -76,55 +77,66 @@ struct KickArgs {
     int64_t pstride;
 };
 
-// One column body against the IB row bodies of this thread.
+// One column body against the IB row bodies of this thread.  Branch-free: evaluations whose r^2 cannot use the FP32
+// seed (r^2 == 0 on the diagonal, denormal or > FLT_MAX) contribute zero here and raise `bad`; the caller redoes those
+// few with the IEEE expression once per tile (redo_tile), so the hot loop stays one basic block.
 template <int IB, bool RAD, bool DIAG>
 __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double (&yi)[IB], const double (&zi)[IB],
                                             const double (&radi)[IB], const int (&rowid)[IB], double xj, double yj,
                                             double zj, double gmj, double radj, int jglob, double (&ax)[IB],
-                                            double (&ay)[IB], double (&az)[IB])
+                                            double (&ay)[IB], double (&az)[IB], bool &bad)
 {
-    double dx[IB], dy[IB], dz[IB], r2[IB], f[IB];
-    unsigned bad = 0;
 #pragma unroll
     for (int b = 0; b < IB; ++b) {
-        dx[b] = xj - xi[b];
-        dy[b] = yj - yi[b];
-        dz[b] = zj - zi[b];
-        r2[b] = fma(dz[b], dz[b], fma(dy[b], dy[b], dx[b] * dx[b]));
-        const float r2f = __double2float_rn(r2[b]);
-        float y0f;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(r2f));
-        const double y0 = (double)y0f;
-        // third-order Newton step for y = r2^-1/2:  e = 1 - r2*y0^2,  y = y0*(1 + e/2 + 3e^2/8)
-        const double t = r2[b] * y0;
-        const double e = fma(-t, y0, 1.0);
-        const double p = fma(0.375, e, 0.5);
-        const double ye = y0 * e;
-        const double y = fma(ye, p, y0);
+        const double dx = xj - xi[b];
+        const double dy = yj - yi[b];
+        const double dz = zj - zi[b];
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        bool ok;
+        const double y = rsqrt_newton(r2, ok);
         const double g = gmj * y;
         const double y2 = y * y;
-        f[b] = g * y2;
-        // float(r2) must be a normal finite positive number for the seed to be usable
-        const bool ok = (__float_as_uint(r2f) - 0x00800000u) < 0x7f000000u;
-        bad |= (ok ? 0u : 1u) << b;
-    }
-    if (__builtin_expect(bad != 0u, 0)) {
-#pragma unroll
-        for (int b = 0; b < IB; ++b)
-            if ((bad >> b) & 1u) f[b] = gmj / (r2[b] * sqrt(r2[b]));  // the reference's own expression
-    }
-#pragma unroll
-    for (int b = 0; b < IB; ++b) {
-        bool use = true;
-        if (DIAG) use = (rowid[b] != jglob);
+        const double f = g * y2;
+        bad = bad || !ok;
+        bool use = ok;
+        if (DIAG) use = use && (rowid[b] != jglob);
         if (RAD) {
             const double rl = radi[b] + radj;
-            use = use && (r2[b] > rl * rl);
+            use = use && (r2 > rl * rl);
         }
-        const double fb = use ? f[b] : 0.0;
-        ax[b] = fma(fb, dx[b], ax[b]);
-        ay[b] = fma(fb, dy[b], ay[b]);
-        az[b] = fma(fb, dz[b], az[b]);
+        const double fb = use ? f : 0.0;
+        ax[b] = fma(fb, dx, ax[b]);
+        ay[b] = fma(fb, dy, ay[b]);
+        az[b] = fma(fb, dz, az[b]);
+    }
+}
+
+// Rare path: add the evaluations of one tile that the FP32-seeded path had to skip, with the reference's own IEEE
+// expression fac = Gm_j / (r2*sqrt(r2)) (kick.f90:233).
+template <int IB, bool RAD, bool DIAG>
+__device__ __noinline__ void redo_tile(const double *sx, const double *sy, const double *sz, const double *sg,
+                                       const double *sr, int cnt, int jbase, const double (&xi)[IB],
+                                       const double (&yi)[IB], const double (&zi)[IB], const double (&radi)[IB],
+                                       const int (&rowid)[IB], double (&ax)[IB], double (&ay)[IB], double (&az)[IB])
+{
+    for (int jj = 0; jj < cnt; ++jj) {
+#pragma unroll
+        for (int b = 0; b < IB; ++b) {
+            const double dx = sx[jj] - xi[b], dy = sy[jj] - yi[b], dz = sz[jj] - zi[b];
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            bool ok;
+            (void)rsqrt_newton(r2, ok);
+            if (ok) continue;
+            if (DIAG && rowid[b] == jbase + jj) continue;
+            if (RAD) {
+                const double rl = radi[b] + sr[jj];
+                if (!(r2 > rl * rl)) continue;
+            }
+            const double fac = sg[jj] / (r2 * sqrt(r2));
+            ax[b] = fma(fac, dx, ax[b]);
+            ay[b] = fma(fac, dy, ay[b]);
+            az[b] = fma(fac, dz, az[b]);
+        }
     }
 }
 
@@ -188,6 +200,7 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
         const int jbase = a.col0 + t * KTJ;
         const int cnt = min(KTJ, a.col1 - jbase);
         const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sg = sm[s][3], *sr = sm[s][4];
+        bool bad = false;
         int jj = 0;
 #pragma unroll 1
         for (; jj + 1 < cnt; jj += 2) {
@@ -197,13 +210,16 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
             const double2 g2 = *reinterpret_cast<const double2 *>(sg + jj);
             double2 r2 = make_double2(0.0, 0.0);
             if (RAD) r2 = *reinterpret_cast<const double2 *>(sr + jj);
-            eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, x2.x, y2.x, z2.x, g2.x, r2.x, jbase + jj, ax, ay, az);
+            eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, x2.x, y2.x, z2.x, g2.x, r2.x, jbase + jj, ax, ay, az,
+                                       bad);
             eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, x2.y, y2.y, z2.y, g2.y, r2.y, jbase + jj + 1, ax, ay,
-                                       az);
+                                       az, bad);
         }
         if (jj < cnt)
             eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, sx[jj], sy[jj], sz[jj], sg[jj], RAD ? sr[jj] : 0.0,
-                                       jbase + jj, ax, ay, az);
+                                       jbase + jj, ax, ay, az, bad);
+        if (__builtin_expect(bad, 0))
+            redo_tile<IB, RAD, DIAG>(sx, sy, sz, sg, sr, cnt, jbase, xi, yi, zi, radi, rowid, ax, ay, az);
         __syncthreads();
     }
 
@@ -404,17 +420,6 @@ int kick_pl_tri(swcu_context *ctx, Body &pl, bool lrad, int row0, int row1)
     p.col1 = nplm;
     if (p.row1 > p.row0 && nplm > 0) SWCU_TRY(kick_rows(ctx, p, FAM_PLPL));
     return SWCU_OK;
-}
-
-// Flat (pair-order) variant over the canonical flattened triangle restricted to i <= nplm_rows.  The set of
-// interactions is identical to the triangular variant with (npl, nplm_rows).
-int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
-{
-    const int saved = pl.nplm;
-    pl.nplm = nplm_rows;
-    const int rc = kick_pl_tri(ctx, pl, lrad, 0, pl.n);
-    pl.nplm = saved;
-    return rc;
 }
 
 int kick_pair_list(swcu_context *ctx, const Body &pl, bool lrad, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2,

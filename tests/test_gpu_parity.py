@@ -81,6 +81,25 @@ def test_kick_flat_canonical_pairs(ctx, oracle, lrad):
         assert _scaled(got, ref, scale) < ACC_TOL
 
 
+@pytest.mark.parametrize("n,nplm", [(2, 2), (127, 127), (128, 128), (129, 129), (256, 100), (1024, 1024), (1025, 512),
+                                    (4099, 4099), (4224, 4224), (4224, 129), (5000, 1), (9000, 8999)])
+def test_kick_flat_third_law_block_coverage(ctx, oracle, n, nplm):
+    """Every block-pair shape of the third-law kernel: odd/even block counts, ragged last block, nplm on and off
+    block boundaries, a single owner block."""
+    d = W.disk(n, seed=n + nplm)
+    nplpl = oracle.nplplm(n, nplm)
+    acc0 = np.random.default_rng(n).normal(scale=1e-5, size=(n, 3))
+    ref = oracle.kick_tri_pl(d["rh"], d["Gmass"], d["radius"], acc0, nplm=nplm)
+    got = acc0.copy()
+    ctx.kick_getacch_int_all_flat_pl(n, nplpl, None, d["rh"], d["Gmass"], d["radius"], got)
+    scale = oracle.kick_tri_abs_scale(d["rh"], d["Gmass"], d["radius"], nplm=nplm) + np.abs(acc0)
+    assert _scaled(got, ref, scale) < ACC_TOL
+    # momentum conservation: the third-law kernel applies equal and opposite kicks
+    if nplm == n:
+        p = (d["Gmass"][:, None] * (got - acc0)).sum(0)
+        assert np.max(np.abs(p)) < 1e-11 * np.abs(d["Gmass"][:, None] * (got - acc0)).sum()
+
+
 def test_kick_flat_rejects_non_canonical_count(ctx):
     from swiftest_b200 import SwcuError
     d = W.disk(50, seed=1)
