@@ -3,14 +3,15 @@
 
   python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA through the C ABI)
   python bench.py --impl reference --steps K --warmup W    reference arm: the CPU path on the host cores
-  torchrun ... bench.py --gpus N ...                        N>1: one rank per GPU, i-sliced pl-pl + NCCL allgather
+  torchrun ... bench.py --gpus N ...                        N>1: one rank per GPU, NCCL inside the library
 
 Metric: FP64 pair-interactions/s of the SyMBA planetesimal disk, npl = 1e5 fully interacting massive bodies
 (BASELINE.json configs[3]; fits one GPU).  One STEP = one pass of the hot path over the resident system:
    ah = 0 ; pl%accel_int (pl-pl gravity, radius-checked, all N(N-1)/2 pairs) ; vb += ah*dt ; pl%drift (Kepler drift)
-   ; [N>1: allgather of the drifted slices] .
+   ; [N>1: third-law kernel: allreduce of the partial ah inside accel_int; full-row kernel: allgather of the drifted
+   slices] .
 `value` = N(N-1)/2 pairs per step / step time with everything resident in HBM (strong scaling: the system is fixed,
-rows are sliced over the ranks).  `e2e` = the same step with that step's positions and velocities copied from pinned
+block pairs -- or rows -- are split over the ranks).  `e2e` = the same step with that step's positions and velocities copied from pinned
 host memory and the accelerations/positions/velocities read back, every step.
 The sort-and-sweep encounter check and the WHM test-particle configuration (8 planets + 1e6 tp: pl->tp gravity and tp
 drift) are HBM-bound side legs of the same path; they are timed outside the K steps and reported under "extra" with
@@ -224,9 +225,13 @@ def run_ours(args):
     pairs = n * (n - 1) / 2.0
     ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
                   mu=d["mu"], generation=1)
+    # auto = the third-law (flat) kernel: measured 1.43x faster than the full-row kernel at npl = 1e5
+    variant = {"auto": LOOP_FLAT, "tri": LOOP_TRIANGULAR, "flat": LOOP_FLAT}[args.variant]
     i0, i1 = shard.partition(n, world, rank)
-    ctx.pl_set_slice(i0, i1)
-    variant = {"auto": LOOP_TRIANGULAR, "tri": LOOP_TRIANGULAR, "flat": LOOP_FLAT}[args.variant]
+    if variant == LOOP_TRIANGULAR:
+        ctx.pl_set_slice(i0, i1)   # full-row kernel: balanced i-slices, allgather of the drifted slices
+    # flat kernel: balanced runs of block pairs per rank, allreduce of the partial accelerations inside
+    # swcu_pl_accel_int; every rank then kicks and drifts all bodies (O(N), identical results), no allgather
 
     def step():
         ctx.flush_l2()
@@ -234,7 +239,7 @@ def run_ours(args):
         ctx.pl_accel_int(variant, True)
         ctx.body_kick_velocity(PL, dt)
         ctx.body_drift(PL, dt, want_nfail=False)
-        if world > 1:
+        if world > 1 and variant == LOOP_TRIANGULAR:
             ctx.pl_allgather(with_v=True)
 
     def reset_state():
@@ -288,15 +293,17 @@ def run_ours(args):
            "path": "swcu_body_put(r,v) -> zero/accel_int/kick/drift[/allgather] -> swcu_body_get(r,v,a), pinned host arrays"}
 
     hbm_peak, peak_src = peaks()
-    rows_local = i1 - i0
-    flops_kernel = FLOP_PER_PAIR_RAD * (rows_local * (n - 1) / 2.0)  # algorithmic flop of this rank's launch
+    flops_kernel = FLOP_PER_PAIR_RAD * pairs / world  # algorithmic flop of one rank's launch (balanced shares)
     achieved = flops_kernel / (kick_ms_avg * 1e-3) / 1e12
-    roofline = {"bound": "fp64", "kernel": "kick_rows_kernel (pl-pl gravity)", "achieved": achieved, "peak": fp64_peak,
+    kname = "kick_flat_kernel (third-law pl-pl gravity)" if variant == LOOP_FLAT else "kick_rows_kernel (full-row pl-pl gravity)"
+    roofline = {"bound": "fp64", "kernel": kname, "achieved": achieved, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
                 "peak_source": "DFMA microbenchmark run in this process (swcu_probe_fp64_peak); MEASURED_PEAKS.json holds "
                                "no FP64 figure",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR_RAD, "kernel_ms": kick_ms_avg,
-                "executed_flop_per_pair_full_row": 40.0}
+                "note": "kernel_ms brackets the gravity launch group (memset/max-radius, kernel, +allreduce at N>1, +ah update); "
+                        "FP64 instructions hold the B200 issue port 2 cycles and nothing co-issues, so the bound is "
+                        "2*N_fp64 + N_other issue cycles per pair, not the DFMA peak (profiles/r01_fp64_pipe.md)"}
 
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
@@ -317,8 +324,12 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n, "nplm": n,
                        "loop": "triangular full-row" if variant == LOOP_TRIANGULAR else "flat third-law",
-                       "lclose": True, "step": "zero_accel+accel_int+kick_velocity+drift" + ("+allgather(r,v)" if world > 1 else ""),
-                       "sharding": f"i-slices over {world} rank(s)", "l2": "flushed between steps (256 MiB write inside the timed region)",
+                       "lclose": True,
+                       "step": "zero_accel+accel_int+kick_velocity+drift" +
+                               (("+allreduce(ah)" if variant == LOOP_FLAT else "+allgather(r,v)") if world > 1 else ""),
+                       "sharding": (f"block-pair runs over {world} rank(s), allreduce of partial ah" if variant == LOOP_FLAT
+                                    else f"i-slices over {world} rank(s), allgather of drifted r,v"),
+                       "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "seed": 3031179},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "peaks": {"fp64_tflops_measured": fp64_peak, "hbm_gbs": hbm_peak, "hbm_source": peak_src},

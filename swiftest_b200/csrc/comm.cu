@@ -23,6 +23,7 @@ struct NcclApi {
     NcclResult (*CommInitRank)(NcclComm *, int, NcclUniqueId, int) = nullptr;
     NcclResult (*CommDestroy)(NcclComm) = nullptr;
     NcclResult (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    NcclResult (*AllReduce)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(NcclResult) = nullptr;
 };
 
@@ -45,8 +46,10 @@ int load_nccl(swcu_context *ctx)
     api->CommDestroy = (NcclResult(*)(NcclComm))dlsym(h, "ncclCommDestroy");
     api->AllGather =
         (NcclResult(*)(const void *, void *, size_t, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
+    api->AllReduce =
+        (NcclResult(*)(const void *, void *, size_t, int, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllReduce");
     api->GetErrorString = (const char *(*)(NcclResult))dlsym(h, "ncclGetErrorString");
-    if (!api->GetUniqueId || !api->CommInitRank || !api->CommDestroy || !api->AllGather || !api->GetErrorString) {
+    if (!api->GetUniqueId || !api->CommInitRank || !api->CommDestroy || !api->AllGather || !api->AllReduce || !api->GetErrorString) {
         delete api;
         return fail(ctx, SWCU_ERR_NCCL, "libnccl is missing a required symbol");
     }
@@ -120,6 +123,16 @@ int comm_allgather_pl(swcu_context *ctx, int with_v)
         narr, pl.n, ctx->nranks, ctx->rank, maxcount, ctx->recvbuf.as<double>(), pl.rx.as<double>(), pl.ry.as<double>(),
         pl.rz.as<double>(), pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>());
     SWCU_KERNEL_CHECK(ctx);
+    return SWCU_OK;
+}
+
+// in-place sum over ranks (ncclSum == 0) of a device buffer; used by the third-law kernel's pair slices
+int comm_allreduce_sum(swcu_context *ctx, double *buf, size_t count)
+{
+    if (ctx->nranks <= 1) return SWCU_OK;
+    if (!ctx->comm) return fail(ctx, SWCU_ERR_STATE, "allreduce: communicator not initialised");
+    FamTimer ft(ctx, FAM_ALLGATHER);
+    SWCU_NCCL(ctx, ctx->nccl->AllReduce(buf, buf, count, NCCL_FLOAT64, 0, (NcclComm)ctx->comm, ctx->stream));
     return SWCU_OK;
 }
 

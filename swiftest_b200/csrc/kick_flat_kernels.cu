@@ -5,20 +5,22 @@
 // (nplplm, symba/symba_util.f90:202), and the lmtiny branch of the triangular variants (kick.f90:189-217).
 // The 8-byte-per-pair k_plpl table (40 GB at npl = 1e5) is never built: (i,j) come from tile coordinates.
 //
-// Design: each unordered pair is evaluated ONCE (26 FP64-pipe instructions instead of 2 x 22 for the full-row
-// kernel).  Bodies are cut into blocks of 128.  A warp keeps one block resident -- every lane owns 4 "i" bodies
-// (position, Gm, radius, accumulators) in registers -- and meets another block 32 bodies at a time: each lane also
-// holds ONE travelling "j" body with its own accumulator, and the 32 travelling bodies rotate around the warp with
-// SHFL so that after 32 steps every j has met all 128 i.  The j-side sums then leave the warp with 3 coalesced FP64
-// RED.ADD per body.  (A broadcast + butterfly-reduction variant was measured 30% slower: 10 SHFL + 3.8 extra DADD per
-// warp-level pair evaluation against 4 SHFL here.)  Block pairs are assigned cyclically (block I meets I+1 .. I+(nb-1)/2 mod nb) so every block
-// owns the same amount of work, and the (I,k) items are cut into equal consecutive runs, one per resident warp.
-// Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is not fixed (FP64 atomics); the full-row
-// kernel (kick_kernels.cu) is the bitwise-reproducible variant.
+// Design: each unordered pair is evaluated ONCE (21 FP64 instructions instead of 2 x 17 for the full-row kernel).
+// Bodies are cut into blocks of 128.  A warp keeps one block resident -- every lane owns 4 "i" bodies (position, Gm,
+// accumulators) in registers -- and meets another block 32 "j" bodies at a time.  The chunk is staged in the warp's
+// private shared-memory tile; at step s lane l works on column body (l+s) mod 32, so all 32 lanes read different
+// words (conflict free) and no two lanes ever update the same j in the same step.  The reaction on j is kept in a
+// travelling accumulator that moves to the neighbouring lane after every step (3 SHFL.64), or in the shared tile
+// (template switch, chosen by measurement); after 32 steps every j has met all 128 i and the chunk ends with one
+// coalesced RED.ADD.F64 per component.  Block pairs are assigned cyclically (block I meets I+1 .. I+(nb-1)/2 mod nb)
+// so every block owns the same amount of work, and the (I,k) items are cut into equal consecutive runs, one per
+// resident warp.  Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is not fixed (FP64 atomics);
+// the full-row kernel (kick_kernels.cu) is the bitwise-reproducible variant.
 #include "swcu_internal.cuh"
 #include "kick_math.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace swcu {
 namespace {
@@ -29,11 +31,20 @@ constexpr int FWARPS = 4;       // warps (independent work units) per CTA
 
 struct FlatArgs {
     const double *x, *y, *z, *gm, *rad;
+    const double *radmax;  // device scalar: max radius over all bodies (rad variant)
     int n, nplm;
     int nb, nbm;          // blocks in total / blocks that own rows (cover [0,nplm))
     int Km, evenm;        // cyclic half-range among the owner blocks, and whether nbm is even
     long long total_items, items_per_unit;
+    long long item0, item1;  // the run of items this rank owns (multi-GPU: pair slices), [0,total) on one GPU
     double *fx, *fy, *fz; // zero-initialised accumulation target
+};
+
+struct __align__(16) WarpTile {
+    double2 xy[32];
+    double2 zg[32];   // z, Gm
+    double2 axy[32];  // reaction accumulators (ACC_SMEM variant)
+    double az[32];
 };
 
 // number of items owned by block I: diagonal + cyclic partners among owner blocks + all non-owner blocks
@@ -70,29 +81,28 @@ __device__ __forceinline__ void item_decode(long long t, const FlatArgs &a, int 
         J = a.nbm + (k - 1 - kmI);
 }
 
-// Rare path of block_pair: the pairs of one 32-body chunk that the FP32-seeded evaluation skipped (r^2 == 0, denormal
-// or > FLT_MAX), with the reference's IEEE expression irij3 = 1/(r2*sqrt(r2)) (kick.f90:435); all index masks applied.
+// Rare path: the pairs of one 32-body chunk that the seeded evaluation skipped (r^2 == 0, denormal, > FLT_MAX or not
+// safely outside the radii), with the reference's IEEE expression irij3 = 1/(r2*sqrt(r2)) (kick.f90:435), the exact
+// radius test (kick.f90:106-107) and all index masks.
 template <bool RAD>
 __device__ __noinline__ void redo_chunk(const FlatArgs &a, int jbase, bool diag, int lane, const double (&xi)[FIB],
                                         const double (&yi)[FIB], const double (&zi)[FIB], const double (&gmi)[FIB],
-                                        const double (&radi)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
-                                        double (&ayi)[FIB], double (&azi)[FIB])
+                                        const unsigned (&thr)[FIB], const unsigned (&span)[FIB], const int (&idx_i)[FIB],
+                                        double (&axi)[FIB], double (&ayi)[FIB], double (&azi)[FIB])
 {
     for (int s = 0; s < 32; ++s) {
         const int jcur = jbase + ((lane + s) & 31);
         if (jcur >= a.n) continue;
         const double xj = a.x[jcur], yj = a.y[jcur], zj = a.z[jcur], gmj = a.gm[jcur];
-        const double radj = RAD ? a.rad[jcur] : 0.0;
 #pragma unroll
         for (int b = 0; b < FIB; ++b) {
             const double dx = xj - xi[b], dy = yj - yi[b], dz = zj - zi[b];
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            bool ok;
-            (void)rsqrt_newton(r2, ok);
-            if (ok || idx_i[b] == jcur || idx_i[b] >= a.n) continue;
+            if (seed_ok(r2, thr[b], span[b])) continue;  // already done by the fast path
+            if (idx_i[b] == jcur || idx_i[b] >= a.n) continue;
             if (!((idx_i[b] < a.nplm) || (jcur < a.nplm))) continue;
             if (RAD) {
-                const double rl = radi[b] + radj;
+                const double rl = a.rad[idx_i[b]] + a.rad[jcur];
                 if (!(r2 > rl * rl)) continue;
             }
             const double irij3 = 1.0 / (r2 * sqrt(r2));
@@ -109,102 +119,128 @@ __device__ __noinline__ void redo_chunk(const FlatArgs &a, int jbase, bool diag,
     }
 }
 
-// One block pair: block I resident in registers (4 bodies per lane), block J streamed 32 bodies at a time.
-// The 32 column bodies of a chunk are loaded coalesced, one per lane, and then TRAVEL: every lane evaluates its 4
-// pairs against the body it currently holds, adds the reaction to that body's travelling accumulator, and passes
-// body + accumulator to its neighbour (SHFL).  After 32 steps every column body has met all 128 row bodies and is
-// back in the lane that loaded it, so the chunk ends with one coalesced RED.ADD.F64 per component.
+// One block pair: block I resident in registers, block J streamed through the warp's shared tile 32 bodies at a time.
 // CHECKED adds the index masks needed by diagonal blocks, the ragged last block and blocks that straddle nplm.
-template <bool RAD, bool CHECKED>
-__device__ __forceinline__ void block_pair(const FlatArgs &a, int J, bool diag, int lane, const double (&xi)[FIB],
-                                           const double (&yi)[FIB], const double (&zi)[FIB], const double (&gmi)[FIB],
-                                           const double (&radi)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
+template <bool RAD, bool CHECKED, bool ACC_SMEM, int UNR>
+__device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J, bool diag, int lane,
+                                           const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
+                                           const double (&gmi)[FIB], const unsigned (&thr)[FIB],
+                                           const unsigned (&span)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
                                            double (&ayi)[FIB], double (&azi)[FIB])
 {
     const int src = (lane + 1) & 31;
+    // prefetch the first chunk
+    int jc = min(J * FT + lane, a.n - 1);
+    double nx = a.x[jc], ny = a.y[jc], nz = a.z[jc], ng = a.gm[jc];
 #pragma unroll 1
     for (int c = 0; c < FIB; ++c) {
         const int jbase = J * FT + c * 32;
         const int jidx = jbase + lane;
-        const int jc = min(jidx, a.n - 1);
-        double xj = a.x[jc], yj = a.y[jc], zj = a.z[jc], gmj = a.gm[jc];
-        double radj = RAD ? a.rad[jc] : 0.0;
+        __syncwarp();  // every lane is done reading the previous chunk
+        w.xy[lane] = make_double2(nx, ny);
+        w.zg[lane] = make_double2(nz, ng);
+        if (ACC_SMEM) {
+            w.axy[lane] = make_double2(0.0, 0.0);
+            w.az[lane] = 0.0;
+        }
+        __syncwarp();
+        if (c + 1 < FIB) {  // next chunk's loads fly while this one is computed
+            jc = min(jbase + 32 + lane, a.n - 1);
+            nx = a.x[jc];
+            ny = a.y[jc];
+            nz = a.z[jc];
+            ng = a.gm[jc];
+        }
         double ajx = 0.0, ajy = 0.0, ajz = 0.0;
         bool bad = false;
-#pragma unroll 2
+        double2 pxy = w.xy[lane], pzg = w.zg[lane];  // register prefetch of the next step's column body
+#pragma unroll(UNR)
         for (int s = 0; s < 32; ++s) {
-            const int jcur = jbase + ((lane + s) & 31);  // index of the body this lane currently holds
-            double dx[FIB], dy[FIB], dz[FIB], r2[FIB], y3[FIB];
-            bool okb[FIB];
-#pragma unroll
-            for (int b = 0; b < FIB; ++b) {
-                dx[b] = xj - xi[b];
-                dy[b] = yj - yi[b];
-                dz[b] = zj - zi[b];
-                r2[b] = fma(dz[b], dz[b], fma(dy[b], dy[b], dx[b] * dx[b]));
-                const double y = rsqrt_newton(r2[b], okb[b]);
-                const double y2 = y * y;
-                y3[b] = y * y2;
-                bad = bad || !okb[b];
+            const int slot = (lane + s) & 31;
+            const int jcur = jbase + slot;
+            const double2 xy = pxy;
+            const double2 zg = pzg;
+            pxy = w.xy[(slot + 1) & 31];
+            pzg = w.zg[(slot + 1) & 31];
+            if (ACC_SMEM) {
+                const double2 t2 = w.axy[slot];
+                ajx = t2.x;
+                ajy = t2.y;
+                ajz = w.az[slot];
             }
-            // the travelling position can move on as soon as the differences are formed
-            const double xn = __shfl_sync(0xffffffffu, xj, src);
-            const double yn = __shfl_sync(0xffffffffu, yj, src);
-            const double zn = __shfl_sync(0xffffffffu, zj, src);
 #pragma unroll
             for (int b = 0; b < FIB; ++b) {
-                bool use = okb[b];
-                if (RAD) {
-                    const double rl = radi[b] + radj;
-                    use = use && (r2[b] > rl * rl);
-                }
+                const double dx = xy.x - xi[b];
+                const double dy = xy.y - yi[b];
+                const double dz = zg.x - zi[b];
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                bool ok;
+                double y;
                 if (CHECKED) {
-                    use = use && (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
-                          ((idx_i[b] < a.nplm) || (jcur < a.nplm));
+                    const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
+                                   ((idx_i[b] < a.nplm) || (jcur < a.nplm));
+                    // a masked pair must neither contribute nor be redone: give it an always-failing test
+                    y = rsqrt_seeded(r2, thr[b], m ? span[b] : 0u, ok);
+                    bad = bad || (m && !ok);
+                } else {
+                    y = rsqrt_seeded(r2, thr[b], span[b], ok);
+                    bad = bad || !ok;
                 }
-                const double w = use ? y3[b] : 0.0;
-                const double fj = gmj * w;          // acts on i
-                double fi = gmi[b] * w;             // acts on j
+                const double y2 = y * y;
+                const double y3 = y * y2;
+                const double fj = zg.y * y3;  // acts on i
+                double fi = gmi[b] * y3;      // acts on j
                 if (CHECKED) fi = diag ? 0.0 : fi;  // a diagonal block visits (i,j) and (j,i)
-                axi[b] = fma(fj, dx[b], axi[b]);
-                ayi[b] = fma(fj, dy[b], ayi[b]);
-                azi[b] = fma(fj, dz[b], azi[b]);
-                ajx = fma(-fi, dx[b], ajx);
-                ajy = fma(-fi, dy[b], ajy);
-                ajz = fma(-fi, dz[b], ajz);
+                axi[b] = fma(fj, dx, axi[b]);
+                ayi[b] = fma(fj, dy, ayi[b]);
+                azi[b] = fma(fj, dz, azi[b]);
+                ajx = fma(-fi, dx, ajx);
+                ajy = fma(-fi, dy, ajy);
+                ajz = fma(-fi, dz, ajz);
             }
-            xj = xn;
-            yj = yn;
-            zj = zn;
-            gmj = __shfl_sync(0xffffffffu, gmj, src);
-            if (RAD) radj = __shfl_sync(0xffffffffu, radj, src);
-            ajx = __shfl_sync(0xffffffffu, ajx, src);
-            ajy = __shfl_sync(0xffffffffu, ajy, src);
-            ajz = __shfl_sync(0xffffffffu, ajz, src);
+            if (ACC_SMEM) {
+                w.axy[slot] = make_double2(ajx, ajy);
+                w.az[slot] = ajz;
+                __syncwarp();  // the neighbour lane reads this slot in the next step
+            } else {
+                ajx = __shfl_sync(0xffffffffu, ajx, src);
+                ajy = __shfl_sync(0xffffffffu, ajy, src);
+                ajz = __shfl_sync(0xffffffffu, ajz, src);
+            }
         }
-        // 32 rotations: every travelling body is back in the lane that loaded it
+        if (ACC_SMEM) {
+            const double2 t2 = w.axy[lane];
+            ajx = t2.x;
+            ajy = t2.y;
+            ajz = w.az[lane];
+        }
+        // the accumulator of column body jbase+lane is now in this lane
         if (!diag && jidx < a.n) {
             atomicAdd(a.fx + jidx, ajx);
             atomicAdd(a.fy + jidx, ajy);
             atomicAdd(a.fz + jidx, ajz);
         }
-        // rare: pairs whose r^2 could not use the FP32 seed (skipped above) are added with the IEEE expression
-        if (__builtin_expect(bad, 0)) redo_chunk<RAD>(a, jbase, diag, lane, xi, yi, zi, gmi, radi, idx_i, axi, ayi, azi);
+        if (__builtin_expect(bad, 0))
+            redo_chunk<RAD>(a, jbase, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
     }
 }
 
-template <bool RAD>
+template <bool RAD, bool ACC_SMEM, int UNR>
 __global__ void __launch_bounds__(32 * FWARPS) kick_flat_kernel(const FlatArgs a)
 {
+    __shared__ WarpTile tiles[FWARPS];
     const int lane = threadIdx.x & 31;
+    WarpTile &w = tiles[threadIdx.x >> 5];
     const long long unit = (long long)blockIdx.x * FWARPS + (threadIdx.x >> 5);
-    long long t = unit * a.items_per_unit;
-    const long long t_end = min(a.total_items, t + a.items_per_unit);
+    long long t = a.item0 + unit * a.items_per_unit;
+    const long long t_end = min(a.item1, t + a.items_per_unit);
     if (t >= t_end) return;
 
-    double xi[FIB], yi[FIB], zi[FIB], gmi[FIB], radi[FIB], axi[FIB], ayi[FIB], azi[FIB];
+    double xi[FIB], yi[FIB], zi[FIB], gmi[FIB], axi[FIB], ayi[FIB], azi[FIB];
+    unsigned thr[FIB], span[FIB];
     int idx_i[FIB];
     int Icur = -1;
+    const double radmax = RAD ? a.radmax[0] : 0.0;
 
     auto flush = [&]() {
         if (Icur < 0) return;
@@ -233,22 +269,53 @@ __global__ void __launch_bounds__(32 * FWARPS) kick_flat_kernel(const FlatArgs a
                 yi[b] = a.y[ic];
                 zi[b] = a.z[ic];
                 gmi[b] = a.gm[ic];
-                radi[b] = RAD ? a.rad[ic] : 0.0;
+                double rl2 = 0.0;
+                if (RAD) {
+                    const double rl = a.rad[ic] + radmax;
+                    rl2 = rl * rl;
+                }
+                seed_threshold(rl2, thr[b], span[b]);
                 axi[b] = ayi[b] = azi[b] = 0.0;
             }
         }
         const bool checked = diag || I == a.nb - 1 || J == a.nb - 1 || (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
         if (checked)
-            block_pair<RAD, true>(a, J, diag, lane, xi, yi, zi, gmi, radi, idx_i, axi, ayi, azi);
+            block_pair<RAD, true, ACC_SMEM, UNR>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
         else
-            block_pair<RAD, false>(a, J, diag, lane, xi, yi, zi, gmi, radi, idx_i, axi, ayi, azi);
+            block_pair<RAD, false, ACC_SMEM, UNR>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
     }
     flush();
 }
 
+// max over an array of non-negative doubles (their bit patterns order like unsigned integers)
+__global__ void max_nonneg_kernel(const double *v, int n, unsigned long long *out)
+{
+    unsigned long long m = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        m = max(m, (unsigned long long)__double_as_longlong(fabs(v[i])));
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+}
+
 }  // namespace
 
+// device scalar max |v[i]| into ctx->scratch64[8..15]; returns the device pointer
+int max_radius(swcu_context *ctx, const double *radius, int n, const double **d_out)
+{
+    SWCU_CUDA(ctx, ctx->scratch64.ensure(64));
+    unsigned long long *d = ctx->scratch64.as<unsigned long long>() + 1;
+    SWCU_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+    if (n > 0) {
+        max_nonneg_kernel<<<std::min(cdiv(n, 256), 512), 256, 0, ctx->stream>>>(radius, n, d);
+        SWCU_KERNEL_CHECK(ctx);
+    }
+    *d_out = reinterpret_cast<const double *>(d);
+    return SWCU_OK;
+}
+
 // Flat (third-law) variant over the canonical flattened triangle restricted to i < nplm_rows (0-based).
+// With several ranks every rank evaluates an equal run of the (I,k) items, the partial accelerations are summed with
+// one allreduce of 3*npl doubles and added to ah on every rank (all ranks then hold the same ah for all bodies).
 int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
 {
     const int n = pl.n;
@@ -260,6 +327,8 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     a.z = pl.rz.as<double>();
     a.gm = pl.Gm.as<double>();
     a.rad = lrad ? pl.radius.as<double>() : nullptr;
+    a.radmax = nullptr;
+    if (lrad) SWCU_TRY(max_radius(ctx, a.rad, n, &a.radmax));
     a.n = n;
     a.nplm = std::min(nplm_rows, n);
     a.nb = cdiv(n, FT);
@@ -278,23 +347,39 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     a.fz = a.fy + stride;
     SWCU_CUDA(ctx, cudaMemsetAsync(a.fx, 0, sizeof(double) * 3 * stride, ctx->stream));
 
+    // measured on B200 at npl = 1e5 (profiles/r01_kick_notes.md): shared-memory accumulators, no unrolling of the step loop
+    static const bool acc_smem = getenv("SWCU_FLAT_ACC_SMEM") ? atoi(getenv("SWCU_FLAT_ACC_SMEM")) != 0 : true;
+    static const int unr = getenv("SWCU_FLAT_UNROLL") ? atoi(getenv("SWCU_FLAT_UNROLL")) : 1;
+    void (*kern)(const FlatArgs);
+    if (unr == 1)
+        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 1> : kick_flat_kernel<true, false, 1>)
+                    : (acc_smem ? kick_flat_kernel<false, true, 1> : kick_flat_kernel<false, false, 1>);
+    else if (unr == 4)
+        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 4> : kick_flat_kernel<true, false, 4>)
+                    : (acc_smem ? kick_flat_kernel<false, true, 4> : kick_flat_kernel<false, false, 4>);
+    else
+        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 2> : kick_flat_kernel<true, false, 2>)
+                    : (acc_smem ? kick_flat_kernel<false, true, 2> : kick_flat_kernel<false, false, 2>);
     int occ = 1;
-    if (lrad)
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kick_flat_kernel<true>, 32 * FWARPS, 0);
-    else
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kick_flat_kernel<false>, 32 * FWARPS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * FWARPS, 0);
     occ = std::max(1, occ);
+    a.item0 = 0;
+    a.item1 = total;
+    if (ctx->nranks > 1) {  // balanced consecutive runs, like swcu_partition
+        const long long q = total / ctx->nranks, r = total % ctx->nranks;
+        a.item0 = ctx->rank * q + std::min<long long>(ctx->rank, r);
+        a.item1 = a.item0 + q + (ctx->rank < r ? 1 : 0);
+    }
+    const long long mine = a.item1 - a.item0;
     const long long max_units = (long long)ctx->prop.multiProcessorCount * occ * FWARPS;  // one resident wave
-    long long units = std::min(max_units, total);
-    if (ctx->tune_nsplit > 0) units = std::min<long long>(total, (long long)ctx->tune_nsplit * FWARPS);
-    a.items_per_unit = (total + units - 1) / units;
-    units = (total + a.items_per_unit - 1) / a.items_per_unit;
+    long long units = std::max<long long>(1, std::min(max_units, mine));
+    if (ctx->tune_nsplit > 0) units = std::max<long long>(1, std::min<long long>(mine, (long long)ctx->tune_nsplit * FWARPS));
+    a.items_per_unit = std::max<long long>(1, (mine + units - 1) / units);
+    units = std::max<long long>(1, (mine + a.items_per_unit - 1) / a.items_per_unit);
     const int grid = cdiv(units, FWARPS);
-    if (lrad)
-        kick_flat_kernel<true><<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
-    else
-        kick_flat_kernel<false><<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
+    kern<<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);
+    if (ctx->nranks > 1) SWCU_TRY(comm_allreduce_sum(ctx, a.fx, 3 * stride));
     return axpy3(ctx, 1.0, a.fx, a.fy, a.fz, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), nullptr, n);
 }
 

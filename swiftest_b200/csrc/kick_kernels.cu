@@ -71,20 +71,23 @@ struct KickArgs {
     int row0, row1;
     const double *xj, *yj, *zj, *gmj, *radj;
     int col0, col1;
+    const double *radmax;     // device scalar: max column radius (radius-checked variants), else nullptr
+    int diag;                 // rows and columns index the same population
     const int32_t *lmask;
     double *ax, *ay, *az;     // final accumulators (used directly when gridDim.y == 1)
     double *px, *py, *pz;     // partial sums [gridDim.y][pstride]
     int64_t pstride;
 };
 
-// One column body against the IB row bodies of this thread.  Branch-free: evaluations whose r^2 cannot use the FP32
-// seed (r^2 == 0 on the diagonal, denormal or > FLT_MAX) contribute zero here and raise `bad`; the caller redoes those
-// few with the IEEE expression once per tile (redo_tile), so the hot loop stays one basic block.
-template <int IB, bool RAD, bool DIAG>
+// One column body against the IB row bodies of this thread: 17 FP64 + ~9 other instructions per evaluation, one
+// basic block.  Pairs the seeded path cannot take (r^2 == 0 on the diagonal, r^2 outside the FP32 exponent range, or
+// not safely outside the sum of radii -- kick_math.cuh) contribute exactly zero and raise `bad`; the caller redoes
+// those few once per tile (redo_tile).
+template <int IB>
 __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double (&yi)[IB], const double (&zi)[IB],
-                                            const double (&radi)[IB], const int (&rowid)[IB], double xj, double yj,
-                                            double zj, double gmj, double radj, int jglob, double (&ax)[IB],
-                                            double (&ay)[IB], double (&az)[IB], bool &bad)
+                                            const unsigned (&thr)[IB], const unsigned (&span)[IB], double xj, double yj,
+                                            double zj, double gmj, double (&ax)[IB], double (&ay)[IB], double (&az)[IB],
+                                            bool &bad)
 {
 #pragma unroll
     for (int b = 0; b < IB; ++b) {
@@ -93,43 +96,35 @@ __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double
         const double dz = zj - zi[b];
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         bool ok;
-        const double y = rsqrt_newton(r2, ok);
+        const double y = rsqrt_seeded(r2, thr[b], span[b], ok);
+        bad = bad || !ok;
         const double g = gmj * y;
         const double y2 = y * y;
         const double f = g * y2;
-        bad = bad || !ok;
-        bool use = ok;
-        if (DIAG) use = use && (rowid[b] != jglob);
-        if (RAD) {
-            const double rl = radi[b] + radj;
-            use = use && (r2 > rl * rl);
-        }
-        const double fb = use ? f : 0.0;
-        ax[b] = fma(fb, dx, ax[b]);
-        ay[b] = fma(fb, dy, ay[b]);
-        az[b] = fma(fb, dz, az[b]);
+        ax[b] = fma(f, dx, ax[b]);
+        ay[b] = fma(f, dy, ay[b]);
+        az[b] = fma(f, dz, az[b]);
     }
 }
 
-// Rare path: add the evaluations of one tile that the FP32-seeded path had to skip, with the reference's own IEEE
-// expression fac = Gm_j / (r2*sqrt(r2)) (kick.f90:233).
-template <int IB, bool RAD, bool DIAG>
-__device__ __noinline__ void redo_tile(const double *sx, const double *sy, const double *sz, const double *sg,
-                                       const double *sr, int cnt, int jbase, const double (&xi)[IB],
-                                       const double (&yi)[IB], const double (&zi)[IB], const double (&radi)[IB],
-                                       const int (&rowid)[IB], double (&ax)[IB], double (&ay)[IB], double (&az)[IB])
+// Rare path: the evaluations of one tile that the seeded path skipped, with the reference's own IEEE expression
+// fac = Gm_j / (r2*sqrt(r2)) and exact radius test rji2 > (radius_i + radius_j)**2 (kick.f90:227-237).
+template <int IB>
+__device__ __noinline__ void redo_tile(const KickArgs &a, const double *sx, const double *sy, const double *sz,
+                                       const double *sg, int cnt, int jbase, const double (&xi)[IB],
+                                       const double (&yi)[IB], const double (&zi)[IB], const unsigned (&thr)[IB],
+                                       const unsigned (&span)[IB], const int (&rowid)[IB], double (&ax)[IB],
+                                       double (&ay)[IB], double (&az)[IB])
 {
     for (int jj = 0; jj < cnt; ++jj) {
 #pragma unroll
         for (int b = 0; b < IB; ++b) {
             const double dx = sx[jj] - xi[b], dy = sy[jj] - yi[b], dz = sz[jj] - zi[b];
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            bool ok;
-            (void)rsqrt_newton(r2, ok);
-            if (ok) continue;
-            if (DIAG && rowid[b] == jbase + jj) continue;
-            if (RAD) {
-                const double rl = radi[b] + sr[jj];
+            if (seed_ok(r2, thr[b], span[b])) continue;  // already added by the fast path
+            if (a.diag && rowid[b] == jbase + jj) continue;
+            if (a.radi != nullptr) {
+                const double rl = a.radi[min(rowid[b], a.row1 - 1)] + a.radj[jbase + jj];
                 if (!(r2 > rl * rl)) continue;
             }
             const double fac = sg[jj] / (r2 * sqrt(r2));
@@ -140,10 +135,10 @@ __device__ __noinline__ void redo_tile(const double *sx, const double *sy, const
     }
 }
 
-template <int IB, bool RAD, bool DIAG>
+template <int IB>
 __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
 {
-    __shared__ __align__(128) double sm[KSTAGES][5][KTJ];
+    __shared__ __align__(128) double sm[KSTAGES][4][KTJ];
     __shared__ __align__(8) uint64_t full[KSTAGES];
 
     const int tid = threadIdx.x;
@@ -152,8 +147,10 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
     const int t0 = (int)blockIdx.y * tiles_per;
     const int t1 = min(ntile_total, t0 + tiles_per);
     const bool direct = (gridDim.y == 1);
+    const double radmax = (a.radmax != nullptr) ? a.radmax[0] : 0.0;
 
-    double xi[IB], yi[IB], zi[IB], radi[IB], ax[IB], ay[IB], az[IB];
+    double xi[IB], yi[IB], zi[IB], ax[IB], ay[IB], az[IB];
+    unsigned thr[IB], span[IB];
     int rowid[IB];
 #pragma unroll
     for (int b = 0; b < IB; ++b) {
@@ -162,7 +159,12 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
         xi[b] = a.xi[ic];
         yi[b] = a.yi[ic];
         zi[b] = a.zi[ic];
-        radi[b] = RAD ? a.radi[ic] : 0.0;
+        double rl2 = 0.0;
+        if (a.radi != nullptr) {
+            const double rl = a.radi[ic] + radmax;
+            rl2 = rl * rl;
+        }
+        seed_threshold(rl2, thr[b], span[b]);
         // one column split: start from the incoming acceleration so the sum runs in the reference's order
         ax[b] = direct ? a.ax[ic] : 0.0;
         ay[b] = direct ? a.ay[ic] : 0.0;
@@ -180,12 +182,11 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
         const int j = a.col0 + t * KTJ;
         const int cnt = min(KTJ, a.col1 - j);
         const uint32_t bytes = (uint32_t)((cnt * 8 + 15) & ~15);
-        mbar_expect_tx(&full[s], bytes * (RAD ? 5u : 4u));
+        mbar_expect_tx(&full[s], bytes * 4u);
         bulk_g2s(&sm[s][0][0], a.xj + j, bytes, &full[s]);
         bulk_g2s(&sm[s][1][0], a.yj + j, bytes, &full[s]);
         bulk_g2s(&sm[s][2][0], a.zj + j, bytes, &full[s]);
         bulk_g2s(&sm[s][3][0], a.gmj + j, bytes, &full[s]);
-        if (RAD) bulk_g2s(&sm[s][4][0], a.radj + j, bytes, &full[s]);
     };
 
     if (tid == 0 && t0 < t1) issue(t0, 0);
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
 
         const int jbase = a.col0 + t * KTJ;
         const int cnt = min(KTJ, a.col1 - jbase);
-        const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sg = sm[s][3], *sr = sm[s][4];
+        const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sg = sm[s][3];
         bool bad = false;
         int jj = 0;
 #pragma unroll 1
@@ -208,18 +209,11 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
             const double2 y2 = *reinterpret_cast<const double2 *>(sy + jj);
             const double2 z2 = *reinterpret_cast<const double2 *>(sz + jj);
             const double2 g2 = *reinterpret_cast<const double2 *>(sg + jj);
-            double2 r2 = make_double2(0.0, 0.0);
-            if (RAD) r2 = *reinterpret_cast<const double2 *>(sr + jj);
-            eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, x2.x, y2.x, z2.x, g2.x, r2.x, jbase + jj, ax, ay, az,
-                                       bad);
-            eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, x2.y, y2.y, z2.y, g2.y, r2.y, jbase + jj + 1, ax, ay,
-                                       az, bad);
+            eval_column<IB>(xi, yi, zi, thr, span, x2.x, y2.x, z2.x, g2.x, ax, ay, az, bad);
+            eval_column<IB>(xi, yi, zi, thr, span, x2.y, y2.y, z2.y, g2.y, ax, ay, az, bad);
         }
-        if (jj < cnt)
-            eval_column<IB, RAD, DIAG>(xi, yi, zi, radi, rowid, sx[jj], sy[jj], sz[jj], sg[jj], RAD ? sr[jj] : 0.0,
-                                       jbase + jj, ax, ay, az, bad);
-        if (__builtin_expect(bad, 0))
-            redo_tile<IB, RAD, DIAG>(sx, sy, sz, sg, sr, cnt, jbase, xi, yi, zi, radi, rowid, ax, ay, az);
+        if (jj < cnt) eval_column<IB>(xi, yi, zi, thr, span, sx[jj], sy[jj], sz[jj], sg[jj], ax, ay, az, bad);
+        if (__builtin_expect(bad, 0)) redo_tile<IB>(a, sx, sy, sz, sg, cnt, jbase, xi, yi, zi, thr, span, rowid, ax, ay, az);
         __syncthreads();
     }
 
@@ -343,16 +337,11 @@ int launch_rows(swcu_context *ctx, const KickProblem &p, int nsplit_override)
         a.pz = a.py + stride * ns;
         a.pstride = stride;
     }
+    a.diag = p.diag ? 1 : 0;
+    a.radmax = nullptr;
+    if (p.radi != nullptr) SWCU_TRY(max_radius(ctx, p.radj + p.col0, ncols, &a.radmax));
     const dim3 grid(nrb, ns), block(KNT);
-    const bool rad = (p.radi != nullptr);
-    if (rad && p.diag)
-        kick_rows_kernel<IB, true, true><<<grid, block, 0, ctx->stream>>>(a);
-    else if (rad)
-        kick_rows_kernel<IB, true, false><<<grid, block, 0, ctx->stream>>>(a);
-    else if (p.diag)
-        kick_rows_kernel<IB, false, true><<<grid, block, 0, ctx->stream>>>(a);
-    else
-        kick_rows_kernel<IB, false, false><<<grid, block, 0, ctx->stream>>>(a);
+    kick_rows_kernel<IB><<<grid, block, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);
     if (ns > 1) {
         kick_reduce_partials_kernel<<<cdiv(nrows, 256), 256, 0, ctx->stream>>>(a.px, a.py, a.pz, a.pstride, ns, p.row0,

@@ -1,32 +1,59 @@
-// kick_math.cuh -- FP64 inverse square root from an FP32 MUFU.RSQ seed (shared by the gravity kernels).
+// kick_math.cuh -- the per-pair arithmetic shared by the gravity kernels.
+//
+// Measured on B200 (scripts/fp64_microbench.cu, profiles/r01_fp64_pipe.md): an FP64 instruction holds the SMSP issue
+// port for 2 cycles and nothing co-issues in its shadow, every other instruction costs 1 cycle.  The cost of a pair
+// evaluation is therefore 2*N_fp64 + N_other issue cycles and BOTH counts are minimised here:
+//   * 1/r^3 from an FP32 MUFU.RSQ seed + one third-order Newton step (5 FP64) instead of IEEE sqrt + divide (~60);
+//   * the double<->float conversions are integer moves on the high word (no F2F, which issues at quarter rate);
+//   * ONE unsigned compare on the high word of r^2 decides "usable by the fast path": r^2 is a normal float, nonzero,
+//     finite AND safely outside the sum of radii.  Pairs that fail contribute exactly zero and are redone by the
+//     caller with the reference's IEEE expression and exact radius test (rare: diagonal, overlapping bodies,
+//     coordinates outside the FP32 exponent range).
 #pragma once
+#include <stdint.h>
 
 namespace swcu {
 
-// y = r2^(-1/2) to ~1e-16 relative: seed y0 = rsqrt.approx.f32(float(r2)) (relative error < 2^-22), then one
-// third-order Newton step  e = 1 - r2*y0^2,  y = y0*(1 + e/2 + 3e^2/8)  (error ~ 5/16 e^3).
-// ok == false when float(r2) is not a normal finite positive number (r2 == 0, denormal, > FLT_MAX): the caller must
-// then use the IEEE expression 1/(r2*sqrt(r2)) instead.
-// The double<->float conversions are done with integer bit moves (exponent re-bias + funnel shift) instead of F2F:
-// F2F.F32.F64 / F2F.F64.F32 issue at 1/4 of the DFMA rate and were measured to hold back the FP64 pipe
-// (profiles/r01_kick_notes.md).
-__device__ __forceinline__ double rsqrt_newton(double r2, bool &ok)
+constexpr unsigned SEED_HI_MIN = 0x38100000u;  // high word of the smallest r^2 that maps to a normal float (2^-126)
+constexpr unsigned SEED_HI_MAX = 0x47F00000u;  // high word of 2^128: first r^2 that overflows a float
+
+// Threshold pair for the fast-path test of one row body: ok <=> (hi(r2) - thr) <u span.
+// rlim2 = (radius_i + max radius of any column)^2; pass rlim2 = 0 for the variants without a radius check.
+__device__ __forceinline__ void seed_threshold(double rlim2, unsigned &thr, unsigned &span)
 {
-    const int hi = __double2hiint(r2);
-    const unsigned lo = (unsigned)__double2loint(r2);
-    // float(r2), truncated: exponent re-biased by 1023-127 = 896, top 23 mantissa bits kept
-    const unsigned fb = __funnelshift_l(lo, (unsigned)(hi - 0x38000000), 3);
-    // usable when the double exponent maps to a normal float exponent (1..254) and r2 is positive and finite
-    ok = (unsigned)(hi - 0x38100000) < (unsigned)(0x47F00000 - 0x38100000);
+    unsigned t = (unsigned)__double2hiint(rlim2) + 1u;  // first high word that guarantees r2 > rlim2
+    t = max(t, SEED_HI_MIN);
+    t = min(t, SEED_HI_MAX);
+    thr = t;
+    span = SEED_HI_MAX - t;
+}
+
+// y ~ r2^(-1/2) to ~2e-17 relative when ok; when not, y is a denormal whose cube (all callers use y^3) is exactly 0.
+// Seed: the top 20 mantissa bits of r2 re-biased into a float, MUFU.RSQ, top 20 bits widened back (relative error
+// < 2^-19), then y = y0*(1 + e/2 + 3e^2/8) with e = 1 - r2*y0^2 (error ~ 5/16 e^3 < 2^-55).
+__device__ __forceinline__ double rsqrt_seeded(double r2, unsigned thr, unsigned span, bool &ok)
+{
+    const unsigned hi = (unsigned)__double2hiint(r2);
+    ok = (hi - thr) < span;
+    const unsigned fb = (hi << 3) - 0xC0000000u;  // (hi - 0x38000000) << 3 : exponent re-biased by 1023-127
     float y0f;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(__uint_as_float(fb)));
     const unsigned yb = __float_as_uint(y0f);
-    const double y0 = __hiloint2double((int)((yb >> 3) + 0x38000000u), (int)(yb << 29));  // exact widening
+    const unsigned hy = ok ? ((yb >> 3) + 0x38000000u) : 0u;
+    // the low word is whatever is at hand (the seed bits): it perturbs a valid seed by < 2^-20 and leaves a rejected
+    // one a denormal (< 2^-1042) whose cube underflows to exactly zero -- no register move to build the pair
+    const double y0 = __hiloint2double((int)hy, (int)yb);
     const double t = r2 * y0;
     const double e = fma(-t, y0, 1.0);
     const double p = fma(0.375, e, 0.5);
     const double ye = y0 * e;
     return fma(ye, p, y0);
+}
+
+// Same test as rsqrt_seeded without the arithmetic (used by the redo paths to find the skipped pairs).
+__device__ __forceinline__ bool seed_ok(double r2, unsigned thr, unsigned span)
+{
+    return ((unsigned)__double2hiint(r2) - thr) < span;
 }
 
 }  // namespace swcu

@@ -189,6 +189,7 @@ struct KickProblem {
 int kick_rows(swcu_context *ctx, const KickProblem &p, int family);
 int kick_pl_tri(swcu_context *ctx, Body &pl, bool lrad, int row0, int row1);
 int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows);
+int max_radius(swcu_context *ctx, const double *radius, int n, const double **d_out);
 int kick_pair_list(swcu_context *ctx, const Body &pl, bool lrad, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2,
                    double *ex, double *ey, double *ez);
 int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, const double *x2, double *y0,
@@ -208,6 +209,7 @@ int set_renc(swcu_context *ctx, Body &pl, int irec);
 
 // ---- comm : comm.cu ----
 int comm_allgather_pl(swcu_context *ctx, int with_v);
+int comm_allreduce_sum(swcu_context *ctx, double *buf, size_t count);
 void comm_release(swcu_context *ctx);
 
 }  // namespace swcu
