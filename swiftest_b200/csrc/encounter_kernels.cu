@@ -113,32 +113,41 @@ __global__ void chunk_count_kernel(int ntot, const int *__restrict__ ibeg, const
     if ((threadIdx.x & 31) == 0 && nb > 0) atomicAdd(nbox_total, (unsigned long long)nb);
 }
 
-// encounter_check_one, encounter_check.f90:591-618
+// chunk -> body map for the sweep (bodies own consecutive chunk ids from the prefix sum); chunks beyond the capacity of
+// the map fall back to a binary search in the sweep kernel
+__global__ void chunk_owner_kernel(int ntot, const int *__restrict__ nchunk, const int *__restrict__ choff,
+                                   int *__restrict__ owner, int cap)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ntot) return;
+    const int c0 = choff[i], nc = nchunk[i];
+    for (int q = 0; q < nc && c0 + q < cap; ++q) owner[c0 + q] = i;
+}
+
+// encounter_check_one, encounter_check.f90:591-618.
+// The exact expressions (two IEEE divisions) are only evaluated for pairs that can possibly be an encounter: for
+// vdotr <= 0 both branches of r2min satisfy r2min >= r2 + 2*vdotr*dt (tmin < dt implies vdotr^2/v2 < -vdotr*dt), so
+// r2 + 2*vdotr*dt > r2crit*(1 + 1e-9) proves "no encounter" with a margin 1e7 times the rounding error of either side.
+// The decision is therefore identical to the reference expression for every input.
 __device__ __forceinline__ bool check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr,
                                           double renc, double dt, double vsmall)
 {
     const double r2 = xr * xr + yr * yr + zr * zr;
     const double r2crit = renc * renc;
-    double vdotr, r2min;
-    if (r2 > r2crit) {
-        vdotr = vxr * xr + vyr * yr + vzr * zr;
-        if (vdotr > 0.0) {
-            r2min = r2;
-        } else {
-            const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
-            if (v2 <= vsmall) {
-                r2min = r2;
-            } else {
-                const double tmin = -vdotr / v2;
-                if (tmin < dt)
-                    r2min = r2 - vdotr * vdotr / v2;
-                else
-                    r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
-            }
-        }
-    } else {
-        vdotr = -1.0;
+    if (!(r2 > r2crit)) return true;  // vdotr = -1, r2min = r2 <= r2crit  (:612-615)
+    const double vdotr = vxr * xr + vyr * yr + vzr * zr;
+    if (vdotr > 0.0) return false;    // lvdotr false (:596-597, :617)
+    if (r2 + 2.0 * vdotr * dt > r2crit * 1.000000001) return false;  // conservative: cannot come close enough
+    double r2min;
+    const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
+    if (v2 <= vsmall) {
         r2min = r2;
+    } else {
+        const double tmin = -vdotr / v2;
+        if (tmin < dt)
+            r2min = r2 - vdotr * vdotr / v2;
+        else
+            r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
     }
     const bool lvdotr = (vdotr < 0.0);
     return lvdotr && (r2min <= r2crit);
@@ -146,6 +155,7 @@ __device__ __forceinline__ bool check_one(double xr, double yr, double zr, doubl
 
 // K10: the sweep.  One warp per chunk of one body's interval.
 __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single, const int *__restrict__ choff,
+                                                    const int *__restrict__ owner, int owner_cap,
                                                     const int *__restrict__ ibeg, const int *__restrict__ iend,
                                                     const double *__restrict__ cx, const double *__restrict__ cy,
                                                     const double *__restrict__ cz, const double *__restrict__ cvx,
@@ -164,15 +174,20 @@ __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single
     const int total = choff[ntot];
     for (int c = warp; c < total; c += nwarps) {
         // body i with choff[i] <= c < choff[i+1]
-        int lo = 0, hi = ntot - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (choff[mid + 1] <= c)
-                lo = mid + 1;
-            else
-                hi = mid;
+        int i;
+        if (c < owner_cap) {
+            i = owner[c];
+        } else {
+            int lo = 0, hi = ntot - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (choff[mid + 1] <= c)
+                    lo = mid + 1;
+                else
+                    hi = mid;
+            }
+            i = lo;
         }
-        const int i = lo;
         const int kb = ibeg[i] + 1 + (c - choff[i]) * SWEEP_CHUNK;
         const int ke = min(kb + SWEEP_CHUNK, iend[i]);
         const double xi = cx[i], yi = cy[i], zi = cz[i];
@@ -332,15 +347,24 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
                                                  ctx->stream));
     ctx->launches += 1;
 
+    // chunk -> body map, sized from the previous call (grown after this one if it was too small)
+    if (E.owner_cap < (size_t)ntot + 1024) E.owner_cap = (size_t)ntot + 1024;
+    SWCU_CUDA(ctx, E.owner.ensure(ib * E.owner_cap));
+    const int owner_cap = (int)std::min<size_t>(E.owner_cap, 0x7fffffff);
+    chunk_owner_kernel<<<cdiv(ntot, 256), 256, 0, ctx->stream>>>(ntot, E.nchunk.as<int>(), E.choff.as<int>(),
+                                                                E.owner.as<int>(), owner_cap);
+    SWCU_KERNEL_CHECK(ctx);
+
     if (E.cand_cap < (size_t)4 * ntot + 65536) E.cand_cap = (size_t)4 * ntot + 65536;
     const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
     const int sweep_blocks = ctx->prop.multiProcessorCount * 8;
     unsigned long long h_counts[2] = {0, 0};
+    int h_total_chunks = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
         SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
         SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
         sweep_kernel<<<sweep_blocks, 128, 0, ctx->stream>>>(
-            ntot, n1, single ? 1 : 0, E.choff.as<int>(), E.ibeg.as<int>(), E.iend.as<int>(), E.cx.as<double>(),
+            ntot, n1, single ? 1 : 0, E.choff.as<int>(), E.owner.as<int>(), owner_cap, E.ibeg.as<int>(), E.iend.as<int>(), E.cx.as<double>(),
             E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(), E.cvz.as<double>(),
             E.crenc.as<double>(), E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(),
             E.svy.as<double>(), E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>(), dt, vsmall,
@@ -348,11 +372,14 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
         SWCU_KERNEL_CHECK(ctx);
         SWCU_CUDA(ctx, cudaMemcpyAsync(h_counts, d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                        ctx->stream));
+        SWCU_CUDA(ctx, cudaMemcpyAsync(&h_total_chunks, E.choff.as<int>() + ntot, sizeof(int), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
         SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (h_counts[0] <= E.cand_cap) break;
         E.cand_cap = (size_t)(h_counts[0] + h_counts[0] / 4 + 1024);  // overflow: grow and sweep again
         if (attempt == 2) return fail(ctx, SWCU_ERR_STATE, "encounter sweep: candidate buffer overflow persists");
     }
+    if ((size_t)h_total_chunks > E.owner_cap) E.owner_cap = (size_t)h_total_chunks + (size_t)h_total_chunks / 4;
     E.nbox_total = (int64_t)h_counts[1];
     E.nemitted = (int64_t)h_counts[0];
     const long long ncand = (long long)h_counts[0];

@@ -136,7 +136,7 @@ __device__ __noinline__ void redo_tile(const KickArgs &a, const double *sx, cons
 }
 
 template <int IB>
-__global__ void __launch_bounds__(KNT) kick_rows_kernel(const KickArgs a)
+__global__ void __launch_bounds__(KNT) kick_rows_kernel(const __grid_constant__ KickArgs a)
 {
     __shared__ __align__(128) double sm[KSTAGES][4][KTJ];
     __shared__ __align__(8) uint64_t full[KSTAGES];

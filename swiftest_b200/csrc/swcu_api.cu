@@ -170,7 +170,7 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     auto &E = ctx->enc;
     DevBuf *eb[] = {&E.keys_in, &E.keys_out, &E.vals_in, &E.vals_out, &E.cub_tmp, &E.cx, &E.cy, &E.cz, &E.cvx, &E.cvy,
                     &E.cvz, &E.crenc, &E.sx, &E.sy, &E.sz, &E.svx, &E.svy, &E.svz, &E.srenc, &E.sbody, &E.ibeg, &E.iend,
-                    &E.nchunk, &E.choff, &E.cand, &E.cand_sorted, &E.uniq, &E.counters, &E.out1, &E.out2, &E.merged};
+                    &E.nchunk, &E.choff, &E.owner, &E.cand, &E.cand_sorted, &E.uniq, &E.counters, &E.out1, &E.out2, &E.merged};
     for (DevBuf *b : eb) b->release();
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);

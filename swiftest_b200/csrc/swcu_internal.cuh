@@ -91,7 +91,8 @@ struct swcu_context {
         swcu::DevBuf keys_in, keys_out, vals_in, vals_out, cub_tmp;
         swcu::DevBuf cx, cy, cz, cvx, cvy, cvz, crenc;          // concatenated sweep population (double list)
         swcu::DevBuf sx, sy, sz, svx, svy, svz, srenc, sbody;   // gathered into sorted-endpoint order
-        swcu::DevBuf ibeg, iend, nchunk, choff;
+        swcu::DevBuf ibeg, iend, nchunk, choff, owner;
+        size_t owner_cap = 0;  // entries of the chunk -> body map
         swcu::DevBuf cand, cand_sorted, uniq, counters;
         swcu::DevBuf out1, out2;
         size_t cand_cap = 0;   // pairs
