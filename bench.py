@@ -393,6 +393,25 @@ def side_legs(ctx, args, d, hbm_peak, peak_src):
                               "roofline": {"bound": "hbm", "achieved": DRIFT_BYTES_PER_BODY * ntp / td / 1e9,
                                            "peak": hbm_peak, "unit": "GB/s",
                                            "frac": DRIFT_BYTES_PER_BODY * ntp / td / 1e9 / hbm_peak}}}
+    # next row: the fused WHM tp step (kick dt/2, drift, new ah, kick dt/2 in one pass: 152 B per tp)
+    fms = []
+    ah0 = np.zeros(3)
+    for i in range(8):
+        r2 = float(p["rh"][i] @ p["rh"][i])
+        ah0 -= p["Gmass"][i] / (r2 * np.sqrt(r2)) * p["rh"][i]
+    ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
+    ctx.body_zero_accel(TP)
+    ctx.tp_accel_int()
+    for it in range(8):
+        ctx.flush_l2()
+        ctx.whm_tp_step(0.01, ah0, want_nfail=False)
+        if it >= 3:
+            fms.append(ctx.last_kernel_ms(FAM_DRIFT))
+    tf = float(np.mean(fms)) * 1e-3
+    ex["whm_tp"]["fused_step"] = {"ms": tf * 1e3, "tp_steps_per_s": ntp / tf, "unfused_ms": (tk + td) * 1e3 + 2 * 0.02,
+                                  "roofline": {"bound": "hbm", "achieved": 152.0 * ntp / tf / 1e9, "peak": hbm_peak,
+                                               "unit": "GB/s", "frac": 152.0 * ntp / tf / 1e9 / hbm_peak,
+                                               "bytes_per_tp": 152}}
     ms = []
     ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
     ctx.pl_set_renc(0)

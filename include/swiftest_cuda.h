@@ -151,6 +151,12 @@ int swcu_body_drift(swcu_context *ctx, int32_t kind, double dt, int32_t lgr, dou
 /* v += a*dt for masked bodies (helio_kick_vb_pl/tp, helio_kick.f90:113-128,157-165) -- O(N) glue kept on the
  * device so a kick-drift sequence needs no host round trip */
 int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt);
+/* NEXT ROW: the whole WHM test-particle step whm_step_tp (whm/whm_step.f90:72-100) in one kernel:
+ * vh += ah*dt/2 with the accelerations kept from the previous end of step (whm_kick_vh_tp, whm_kick.f90:265-314),
+ * Kepler drift over dt, ah = ah0 + direct terms of the resident planets (their end-of-step positions; ah0(3) is
+ * whm_kick_getacch_ah0, whm_kick.f90:124-149, computed by the caller), vh += ah*dt/2.  Requires npl <= 64 and no GR.
+ * On the first step call swcu_body_zero_accel(TP) + swcu_tp_accel_int() with the begin-of-step planets (lfirst). */
+int swcu_whm_tp_step(swcu_context *ctx, double dt, const double *ah0, int32_t *nfail);
 /* pl%encounter_check / tp%encounter_check on resident r,v,renc (symba_encounter_check.f90:14-87,238-296);
  * nplm<npl uses the plplm path.  Results via swcu_encounter_fetch. */
 int swcu_pl_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);

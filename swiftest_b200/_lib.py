@@ -62,6 +62,7 @@ def load():
         "swcu_pl_set_renc": [p, i32],
         "swcu_body_drift": [p, i32, d, i32, d, p],
         "swcu_body_kick_velocity": [p, i32, d],
+        "swcu_whm_tp_step": [p, d, p, p],
         "swcu_pl_encounter_check": [p, d, p],
         "swcu_tp_encounter_check": [p, d, p],
         "swcu_comm_unique_id": [p, p],

@@ -240,6 +240,14 @@ class Context:
                                          C.byref(nf) if want_nfail else None))
         return nf.value
 
+    def whm_tp_step(self, dt, ah0, want_nfail=True):
+        """Fused whm_step_tp on the resident test particles (kick dt/2 with the kept ah, drift dt, new ah at the resident
+        planets' positions + ah0, kick dt/2).  Returns the number of particles whose drift failed."""
+        ah0 = _vec(ah0, 3, name="ah0")
+        nf = C.c_int32()
+        self._ck(self._L.swcu_whm_tp_step(self._h, float(dt), _ptr(ah0), C.byref(nf) if want_nfail else None))
+        return nf.value
+
     def body_kick_velocity(self, kind, dt):
         self._ck(self._L.swcu_body_kick_velocity(self._h, kind, float(dt)))
 

@@ -13,8 +13,8 @@
 // travelling accumulator that moves to the neighbouring lane after every step (3 SHFL.64), or in the shared tile
 // (template switch, chosen by measurement); after 32 steps every j has met all 128 i and the chunk ends with one
 // coalesced RED.ADD.F64 per component.  Block pairs are assigned cyclically (block I meets I+1 .. I+(nb-1)/2 mod nb)
-// so every block owns the same amount of work, and the (I,k) items are cut into equal consecutive runs, one per
-// resident warp.  Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is not fixed (FP64 atomics);
+// so every block owns the same amount of work; a persistent grid of warps claims runs of 2 consecutive (I,k) items
+// from a global counter (dynamic scheduling; a static one-wave split proved fragile, see kick_flat_kernel).  Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is not fixed (FP64 atomics);
 // the full-row kernel (kick_kernels.cu) is the bitwise-reproducible variant.
 #include "swcu_internal.cuh"
 #include "kick_math.cuh"
@@ -29,22 +29,29 @@ constexpr int FIB = 4;          // i bodies per lane
 constexpr int FT = 32 * FIB;    // bodies per block
 constexpr int FWARPS = 4;       // warps (independent work units) per CTA
 
+// ordering of a lane's accumulator store before its neighbour's load of the same slot in the next step
+// (a compiler-only fence was tried and is NOT sufficient: it produced wrong sums in blocks that take the masked path)
+#define FLAT_STEP_FENCE() __syncwarp()
+
 struct FlatArgs {
     const double *x, *y, *z, *gm, *rad;
     const double *radmax;  // device scalar: max radius over all bodies (rad variant)
     int n, nplm;
     int nb, nbm;          // blocks in total / blocks that own rows (cover [0,nplm))
     int Km, evenm;        // cyclic half-range among the owner blocks, and whether nbm is even
-    long long total_items, items_per_unit;
+    long long total_items;
     long long item0, item1;  // the run of items this rank owns (multi-GPU: pair slices), [0,total) on one GPU
+    int quantum;             // items a warp claims per visit to the work counter
+    unsigned long long *counter;  // zero-initialised work counter (dynamic scheduling)
     double *fx, *fy, *fz; // zero-initialised accumulation target
 };
 
+// every array has the same 16-byte stride so one byte offset addresses all four
 struct __align__(16) WarpTile {
     double2 xy[32];
     double2 zg[32];   // z, Gm
     double2 axy[32];  // reaction accumulators (ACC_SMEM variant)
-    double az[32];
+    double2 az[32];   // .x used
 };
 
 // number of items owned by block I: diagonal + cyclic partners among owner blocks + all non-owner blocks
@@ -119,9 +126,72 @@ __device__ __noinline__ void redo_chunk(const FlatArgs &a, int jbase, bool diag,
     }
 }
 
+// One step of block_pair: lane l meets column body `slot`; everything in the warp tile is addressed with the single byte
+// offset off = 16*slot.  The column body of the NEXT step is fetched first so its LDS latency hides behind the math.
+template <bool RAD, bool CHECKED, bool ACC_SMEM>
+__device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned off, unsigned off_next, const double2 xy,
+                                          const double2 zg, double2 &nxy, double2 &nzg, int jbase, bool diag, int src,
+                                          const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
+                                          const double (&gmi)[FIB], const unsigned (&thr)[FIB],
+                                          const unsigned (&span)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
+                                          double (&ayi)[FIB], double (&azi)[FIB], double &ajx, double &ajy, double &ajz,
+                                          unsigned &hymin)
+{
+    nxy = *reinterpret_cast<const double2 *>(wb + off_next);
+    nzg = *reinterpret_cast<const double2 *>(wb + 512 + off_next);
+    if (ACC_SMEM) {
+        const double2 t2 = *reinterpret_cast<const double2 *>(wb + 1024 + off);
+        ajx = t2.x;
+        ajy = t2.y;
+        ajz = *reinterpret_cast<const double *>(wb + 1536 + off);
+    }
+    const int jcur = jbase + (int)(off >> 4);
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) {
+        const double dx = xy.x - xi[b];
+        const double dy = xy.y - yi[b];
+        const double dz = zg.x - zi[b];
+        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        unsigned hy;
+        double y;
+        if (CHECKED) {
+            const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
+                           ((idx_i[b] < a.nplm) || (jcur < a.nplm));
+            // a masked pair never contributes (always-failing test); redo_chunk applies the masks again
+            y = rsqrt_seeded(r2, thr[b], m ? span[b] : 0u, hy);
+        } else {
+            y = rsqrt_seeded(r2, thr[b], span[b], hy);
+        }
+        hymin = min(hymin, hy);
+        const double y2 = y * y;
+        const double y3 = y * y2;
+        const double fj = zg.y * y3;  // acts on i
+        double fi = gmi[b] * y3;      // acts on j
+        if (CHECKED) fi = diag ? 0.0 : fi;  // a diagonal block visits (i,j) and (j,i)
+        axi[b] = fma(fj, dx, axi[b]);
+        ayi[b] = fma(fj, dy, ayi[b]);
+        azi[b] = fma(fj, dz, azi[b]);
+        ajx = fma(-fi, dx, ajx);
+        ajy = fma(-fi, dy, ajy);
+        ajz = fma(-fi, dz, ajz);
+    }
+    if (ACC_SMEM) {
+        *reinterpret_cast<double2 *>(wb + 1024 + off) = make_double2(ajx, ajy);
+        *reinterpret_cast<double *>(wb + 1536 + off) = ajz;
+        // The neighbour lane reads this slot in the next step.  The warp is converged here (no divergent branch inside
+        // the chunk loop) and a warp's shared-memory accesses are performed in program order, so a compiler-level fence
+        // is sufficient; the full __syncwarp() stays at the chunk boundaries.
+        FLAT_STEP_FENCE();
+    } else {
+        ajx = __shfl_sync(0xffffffffu, ajx, src);
+        ajy = __shfl_sync(0xffffffffu, ajy, src);
+        ajz = __shfl_sync(0xffffffffu, ajz, src);
+    }
+}
+
 // One block pair: block I resident in registers, block J streamed through the warp's shared tile 32 bodies at a time.
 // CHECKED adds the index masks needed by diagonal blocks, the ragged last block and blocks that straddle nplm.
-template <bool RAD, bool CHECKED, bool ACC_SMEM, int UNR>
+template <bool RAD, bool CHECKED, bool ACC_SMEM>
 __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J, bool diag, int lane,
                                            const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
                                            const double (&gmi)[FIB], const unsigned (&thr)[FIB],
@@ -141,7 +211,7 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
         w.zg[lane] = make_double2(nz, ng);
         if (ACC_SMEM) {
             w.axy[lane] = make_double2(0.0, 0.0);
-            w.az[lane] = 0.0;
+            w.az[lane] = make_double2(0.0, 0.0);
         }
         __syncwarp();
         if (c + 1 < FIB) {  // next chunk's loads fly while this one is computed
@@ -152,67 +222,28 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
             ng = a.gm[jc];
         }
         double ajx = 0.0, ajy = 0.0, ajz = 0.0;
-        bool bad = false;
-        double2 pxy = w.xy[lane], pzg = w.zg[lane];  // register prefetch of the next step's column body
-#pragma unroll(UNR)
-        for (int s = 0; s < 32; ++s) {
-            const int slot = (lane + s) & 31;
-            const int jcur = jbase + slot;
-            const double2 xy = pxy;
-            const double2 zg = pzg;
-            pxy = w.xy[(slot + 1) & 31];
-            pzg = w.zg[(slot + 1) & 31];
-            if (ACC_SMEM) {
-                const double2 t2 = w.axy[slot];
-                ajx = t2.x;
-                ajy = t2.y;
-                ajz = w.az[slot];
-            }
-#pragma unroll
-            for (int b = 0; b < FIB; ++b) {
-                const double dx = xy.x - xi[b];
-                const double dy = xy.y - yi[b];
-                const double dz = zg.x - zi[b];
-                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-                bool ok;
-                double y;
-                if (CHECKED) {
-                    const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
-                                   ((idx_i[b] < a.nplm) || (jcur < a.nplm));
-                    // a masked pair must neither contribute nor be redone: give it an always-failing test
-                    y = rsqrt_seeded(r2, thr[b], m ? span[b] : 0u, ok);
-                    bad = bad || (m && !ok);
-                } else {
-                    y = rsqrt_seeded(r2, thr[b], span[b], ok);
-                    bad = bad || !ok;
-                }
-                const double y2 = y * y;
-                const double y3 = y * y2;
-                const double fj = zg.y * y3;  // acts on i
-                double fi = gmi[b] * y3;      // acts on j
-                if (CHECKED) fi = diag ? 0.0 : fi;  // a diagonal block visits (i,j) and (j,i)
-                axi[b] = fma(fj, dx, axi[b]);
-                ayi[b] = fma(fj, dy, ayi[b]);
-                azi[b] = fma(fj, dz, azi[b]);
-                ajx = fma(-fi, dx, ajx);
-                ajy = fma(-fi, dy, ajy);
-                ajz = fma(-fi, dz, ajz);
-            }
-            if (ACC_SMEM) {
-                w.axy[slot] = make_double2(ajx, ajy);
-                w.az[slot] = ajz;
-                __syncwarp();  // the neighbour lane reads this slot in the next step
-            } else {
-                ajx = __shfl_sync(0xffffffffu, ajx, src);
-                ajy = __shfl_sync(0xffffffffu, ajy, src);
-                ajz = __shfl_sync(0xffffffffu, ajz, src);
-            }
+        unsigned hymin = 0xffffffffu;  // running minimum of the seed words: 0 <=> some pair was rejected
+        char *wb = reinterpret_cast<char *>(&w);
+        // two steps per iteration with two named register sets (A, B): no register copies for the prefetch
+        unsigned off = (unsigned)lane << 4;
+        double2 axy_ = *reinterpret_cast<const double2 *>(wb + off);
+        double2 azg_ = *reinterpret_cast<const double2 *>(wb + 512 + off);
+        double2 bxy_, bzg_;
+#pragma unroll 1
+        for (int s = 0; s < 32; s += 2) {
+            const unsigned off1 = (off + 16u) & 0x1f0u, off2 = (off + 32u) & 0x1f0u;
+            flat_step<RAD, CHECKED, ACC_SMEM>(a, wb, off, off1, axy_, azg_, bxy_, bzg_, jbase, diag, src, xi, yi, zi, gmi,
+                                              thr, span, idx_i, axi, ayi, azi, ajx, ajy, ajz, hymin);
+            flat_step<RAD, CHECKED, ACC_SMEM>(a, wb, off1, off2, bxy_, bzg_, axy_, azg_, jbase, diag, src, xi, yi, zi, gmi,
+                                              thr, span, idx_i, axi, ayi, azi, ajx, ajy, ajz, hymin);
+            off = off2;
         }
+        const bool bad = (hymin == 0u);
         if (ACC_SMEM) {
             const double2 t2 = w.axy[lane];
             ajx = t2.x;
             ajy = t2.y;
-            ajz = w.az[lane];
+            ajz = w.az[lane].x;
         }
         // the accumulator of column body jbase+lane is now in this lane
         if (!diag && jidx < a.n) {
@@ -225,17 +256,12 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
     }
 }
 
-template <bool RAD, bool ACC_SMEM, int UNR>
+template <bool RAD, bool ACC_SMEM>
 __global__ void __launch_bounds__(32 * FWARPS) kick_flat_kernel(const FlatArgs a)
 {
     __shared__ WarpTile tiles[FWARPS];
     const int lane = threadIdx.x & 31;
     WarpTile &w = tiles[threadIdx.x >> 5];
-    const long long unit = (long long)blockIdx.x * FWARPS + (threadIdx.x >> 5);
-    long long t = a.item0 + unit * a.items_per_unit;
-    const long long t_end = min(a.item1, t + a.items_per_unit);
-    if (t >= t_end) return;
-
     double xi[FIB], yi[FIB], zi[FIB], gmi[FIB], axi[FIB], ayi[FIB], azi[FIB];
     unsigned thr[FIB], span[FIB];
     int idx_i[FIB];
@@ -254,35 +280,47 @@ __global__ void __launch_bounds__(32 * FWARPS) kick_flat_kernel(const FlatArgs a
         }
     };
 
-    for (; t < t_end; ++t) {
-        int I, J;
-        bool diag;
-        item_decode(t, a, I, J, diag);
-        if (I != Icur) {
-            flush();
-            Icur = I;
+    // Dynamic scheduling: a warp claims `quantum` consecutive items at a time from a global counter.  (A static split
+    // sized to exactly one resident wave was measured to be fragile: when the tail of the previous kernel still
+    // occupies an SM at launch, one CTA is left over, runs alone after the others and doubles the kernel time.)
+    for (;;) {
+        unsigned long long q = 0;
+        if (lane == 0) q = atomicAdd(a.counter, 1ull);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        long long t = a.item0 + (long long)q * a.quantum;
+        if (t >= a.item1) break;
+        const long long t_end = min(a.item1, t + a.quantum);
+        for (; t < t_end; ++t) {
+            int I, J;
+            bool diag;
+            item_decode(t, a, I, J, diag);
+            if (I != Icur) {
+                flush();
+                Icur = I;
 #pragma unroll
-            for (int b = 0; b < FIB; ++b) {
-                idx_i[b] = I * FT + b * 32 + lane;
-                const int ic = min(idx_i[b], a.n - 1);
-                xi[b] = a.x[ic];
-                yi[b] = a.y[ic];
-                zi[b] = a.z[ic];
-                gmi[b] = a.gm[ic];
-                double rl2 = 0.0;
-                if (RAD) {
-                    const double rl = a.rad[ic] + radmax;
-                    rl2 = rl * rl;
+                for (int b = 0; b < FIB; ++b) {
+                    idx_i[b] = I * FT + b * 32 + lane;
+                    const int ic = min(idx_i[b], a.n - 1);
+                    xi[b] = a.x[ic];
+                    yi[b] = a.y[ic];
+                    zi[b] = a.z[ic];
+                    gmi[b] = a.gm[ic];
+                    double rl2 = 0.0;
+                    if (RAD) {
+                        const double rl = a.rad[ic] + radmax;
+                        rl2 = rl * rl;
+                    }
+                    seed_threshold(rl2, thr[b], span[b]);
+                    axi[b] = ayi[b] = azi[b] = 0.0;
                 }
-                seed_threshold(rl2, thr[b], span[b]);
-                axi[b] = ayi[b] = azi[b] = 0.0;
             }
+            const bool checked =
+                diag || I == a.nb - 1 || J == a.nb - 1 || (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
+            if (checked)
+                block_pair<RAD, true, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
+            else
+                block_pair<RAD, false, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
         }
-        const bool checked = diag || I == a.nb - 1 || J == a.nb - 1 || (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
-        if (checked)
-            block_pair<RAD, true, ACC_SMEM, UNR>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
-        else
-            block_pair<RAD, false, ACC_SMEM, UNR>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
     }
     flush();
 }
@@ -347,19 +385,10 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     a.fz = a.fy + stride;
     SWCU_CUDA(ctx, cudaMemsetAsync(a.fx, 0, sizeof(double) * 3 * stride, ctx->stream));
 
-    // measured on B200 at npl = 1e5 (profiles/r01_kick_notes.md): shared-memory accumulators, no unrolling of the step loop
+    // measured on B200 at npl = 1e5 (profiles/r01_fp64_pipe.md): shared-memory accumulators beat the SHFL-travelling ones
     static const bool acc_smem = getenv("SWCU_FLAT_ACC_SMEM") ? atoi(getenv("SWCU_FLAT_ACC_SMEM")) != 0 : true;
-    static const int unr = getenv("SWCU_FLAT_UNROLL") ? atoi(getenv("SWCU_FLAT_UNROLL")) : 1;
-    void (*kern)(const FlatArgs);
-    if (unr == 1)
-        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 1> : kick_flat_kernel<true, false, 1>)
-                    : (acc_smem ? kick_flat_kernel<false, true, 1> : kick_flat_kernel<false, false, 1>);
-    else if (unr == 4)
-        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 4> : kick_flat_kernel<true, false, 4>)
-                    : (acc_smem ? kick_flat_kernel<false, true, 4> : kick_flat_kernel<false, false, 4>);
-    else
-        kern = lrad ? (acc_smem ? kick_flat_kernel<true, true, 2> : kick_flat_kernel<true, false, 2>)
-                    : (acc_smem ? kick_flat_kernel<false, true, 2> : kick_flat_kernel<false, false, 2>);
+    void (*kern)(const FlatArgs) = lrad ? (acc_smem ? kick_flat_kernel<true, true> : kick_flat_kernel<true, false>)
+                                        : (acc_smem ? kick_flat_kernel<false, true> : kick_flat_kernel<false, false>);
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * FWARPS, 0);
     occ = std::max(1, occ);
@@ -371,11 +400,13 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
         a.item1 = a.item0 + q + (ctx->rank < r ? 1 : 0);
     }
     const long long mine = a.item1 - a.item0;
-    const long long max_units = (long long)ctx->prop.multiProcessorCount * occ * FWARPS;  // one resident wave
-    long long units = std::max<long long>(1, std::min(max_units, mine));
-    if (ctx->tune_nsplit > 0) units = std::max<long long>(1, std::min<long long>(mine, (long long)ctx->tune_nsplit * FWARPS));
-    a.items_per_unit = std::max<long long>(1, (mine + units - 1) / units);
-    units = std::max<long long>(1, (mine + a.items_per_unit - 1) / a.items_per_unit);
+    a.quantum = ctx->tune_nsplit > 0 ? ctx->tune_nsplit : 2;  // measured: 1..2 best at npl = 1e5 (7.9 ms), 8: 8.3, 32: 9.8
+    SWCU_CUDA(ctx, ctx->scratch64.ensure(64));
+    a.counter = ctx->scratch64.as<unsigned long long>() + 2;
+    SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
+    // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work)
+    const long long nquanta = (mine + a.quantum - 1) / a.quantum;
+    const long long units = std::max<long long>(1, std::min<long long>((long long)ctx->prop.multiProcessorCount * occ * FWARPS, nquanta));
     const int grid = cdiv(units, FWARPS);
     kern<<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);

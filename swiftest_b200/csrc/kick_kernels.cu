@@ -87,7 +87,7 @@ template <int IB>
 __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double (&yi)[IB], const double (&zi)[IB],
                                             const unsigned (&thr)[IB], const unsigned (&span)[IB], double xj, double yj,
                                             double zj, double gmj, double (&ax)[IB], double (&ay)[IB], double (&az)[IB],
-                                            bool &bad)
+                                            unsigned &hymin)
 {
 #pragma unroll
     for (int b = 0; b < IB; ++b) {
@@ -95,9 +95,9 @@ __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double
         const double dy = yj - yi[b];
         const double dz = zj - zi[b];
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        bool ok;
-        const double y = rsqrt_seeded(r2, thr[b], span[b], ok);
-        bad = bad || !ok;
+        unsigned hy;
+        const double y = rsqrt_seeded(r2, thr[b], span[b], hy);
+        if (hy == 0u) hymin = 0u;  // (a predicate OR measured 4 % faster here than an integer min)
         const double g = gmj * y;
         const double y2 = y * y;
         const double f = g * y2;
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const __grid_constant__ 
         const int jbase = a.col0 + t * KTJ;
         const int cnt = min(KTJ, a.col1 - jbase);
         const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sg = sm[s][3];
-        bool bad = false;
+        unsigned bad = 0xffffffffu;  // running minimum of the seed words: 0 <=> some evaluation was rejected
         int jj = 0;
 #pragma unroll 1
         for (; jj + 1 < cnt; jj += 2) {
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const __grid_constant__ 
             eval_column<IB>(xi, yi, zi, thr, span, x2.y, y2.y, z2.y, g2.y, ax, ay, az, bad);
         }
         if (jj < cnt) eval_column<IB>(xi, yi, zi, thr, span, sx[jj], sy[jj], sz[jj], sg[jj], ax, ay, az, bad);
-        if (__builtin_expect(bad, 0)) redo_tile<IB>(a, sx, sy, sz, sg, cnt, jbase, xi, yi, zi, thr, span, rowid, ax, ay, az);
+        if (__builtin_expect(bad == 0u, 0)) redo_tile<IB>(a, sx, sy, sz, sg, cnt, jbase, xi, yi, zi, thr, span, rowid, ax, ay, az);
         __syncthreads();
     }
 
@@ -291,6 +291,78 @@ __global__ void axpy3_kernel(double alpha, const double *x0, const double *x1, c
     y2[i] = fma(alpha, x2[i], y2[i]);
 }
 
+// pl -> tp with a handful of planets (swiftest_kick_getacch_int_all_tp, kick.f90:394-412): pure streaming over the
+// test particles, HBM bound (76 B per tp).  The planets (<= TP_SMALL_NPL) sit in shared memory; one thread per tp, two
+// tps in flight per thread for memory-level parallelism; no tile pipeline, no barrier after the prologue.
+constexpr int TP_SMALL_NPL = 64;
+__global__ void __launch_bounds__(256) kick_tp_small_kernel(int ntp, int npl, const double *__restrict__ xt,
+                                                            const double *__restrict__ yt, const double *__restrict__ zt,
+                                                            const double *__restrict__ xp, const double *__restrict__ yp,
+                                                            const double *__restrict__ zp, const double *__restrict__ gp,
+                                                            const int32_t *__restrict__ lmask, double *__restrict__ ax,
+                                                            double *__restrict__ ay, double *__restrict__ az)
+{
+    __shared__ double4 pl[TP_SMALL_NPL];
+    if (threadIdx.x < npl) pl[threadIdx.x] = make_double4(xp[threadIdx.x], yp[threadIdx.x], zp[threadIdx.x], gp[threadIdx.x]);
+    __syncthreads();
+    unsigned thr, span;
+    seed_threshold(0.0, thr, span);
+    const int i0 = blockIdx.x * 512 + threadIdx.x;
+    int idx[2] = {i0, i0 + 256};
+    double x[2], y[2], z[2], a0[2], a1[2], a2[2];
+    bool on[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        on[q] = idx[q] < ntp && lmask[idx[q]] != 0;
+        const int ic = min(idx[q], ntp - 1);
+        x[q] = xt[ic];
+        y[q] = yt[ic];
+        z[q] = zt[ic];
+        a0[q] = ax[ic];
+        a1[q] = ay[ic];
+        a2[q] = az[ic];
+    }
+    unsigned hymin = 0xffffffffu;
+    for (int j = 0; j < npl; ++j) {
+        const double4 p = pl[j];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const double dx = p.x - x[q], dy = p.y - y[q], dz = p.z - z[q];
+            const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            unsigned hy;
+            const double yv = rsqrt_seeded(r2, thr, span, hy);
+            hymin = min(hymin, hy);
+            const double f = (p.w * yv) * (yv * yv);
+            a0[q] = fma(f, dx, a0[q]);
+            a1[q] = fma(f, dy, a1[q]);
+            a2[q] = fma(f, dz, a2[q]);
+        }
+    }
+    if (__builtin_expect(hymin == 0u, 0)) {  // a tp on top of a planet or coordinates outside the FP32 exponent range
+        for (int j = 0; j < npl; ++j) {
+            const double4 p = pl[j];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const double dx = p.x - x[q], dy = p.y - y[q], dz = p.z - z[q];
+                const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                if (seed_ok(r2, thr, span)) continue;
+                const double f = p.w / (r2 * sqrt(r2));  // kick.f90:464
+                a0[q] = fma(f, dx, a0[q]);
+                a1[q] = fma(f, dy, a1[q]);
+                a2[q] = fma(f, dz, a2[q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        if (on[q]) {
+            ax[idx[q]] = a0[q];
+            ay[idx[q]] = a1[q];
+            az[idx[q]] = a2[q];
+        }
+    }
+}
+
 int choose_nsplit(int nrowblocks, int ntiles, int nsm)
 {
     int best = 1;
@@ -359,6 +431,13 @@ int kick_rows(swcu_context *ctx, const KickProblem &p, int family)
     if (nrows <= 0 || ncols <= 0) return SWCU_OK;
     if (p.col0 % 2 != 0) return fail(ctx, SWCU_ERR_ARG, "kick_rows: column range must start at an even index");
     FamTimer ft(ctx, family);
+    if (!p.diag && p.radi == nullptr && ncols <= TP_SMALL_NPL && p.lmask != nullptr && p.row0 == 0 && ctx->tune_ib == 0) {
+        kick_tp_small_kernel<<<cdiv(nrows, 512), 256, 0, ctx->stream>>>(nrows, ncols, p.xi, p.yi, p.zi, p.xj + p.col0,
+                                                                       p.yj + p.col0, p.zj + p.col0, p.gmj + p.col0,
+                                                                       p.lmask, p.ax, p.ay, p.az);
+        SWCU_KERNEL_CHECK(ctx);
+        return SWCU_OK;
+    }
     int ib = ctx->tune_ib;
     if (ib != 1 && ib != 2 && ib != 4) {
         const double work = (double)nrows * (double)ncols;

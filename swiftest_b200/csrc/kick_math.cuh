@@ -31,15 +31,18 @@ __device__ __forceinline__ void seed_threshold(double rlim2, unsigned &thr, unsi
 // y ~ r2^(-1/2) to ~2e-17 relative when ok; when not, y is a denormal whose cube (all callers use y^3) is exactly 0.
 // Seed: the top 20 mantissa bits of r2 re-biased into a float, MUFU.RSQ, top 20 bits widened back (relative error
 // < 2^-19), then y = y0*(1 + e/2 + 3e^2/8) with e = 1 - r2*y0^2 (error ~ 5/16 e^3 < 2^-55).
-__device__ __forceinline__ double rsqrt_seeded(double r2, unsigned thr, unsigned span, bool &ok)
+// `hy` returns the selected high word of the seed (0 when the pair was rejected): callers that only need to know whether
+// ANY pair of a tile was rejected keep the running minimum of hy (one 3-input integer min per two pairs) instead of a
+// predicate per pair.
+__device__ __forceinline__ double rsqrt_seeded(double r2, unsigned thr, unsigned span, unsigned &hy)
 {
     const unsigned hi = (unsigned)__double2hiint(r2);
-    ok = (hi - thr) < span;
+    const bool ok = (hi - thr) < span;
     const unsigned fb = (hi << 3) - 0xC0000000u;  // (hi - 0x38000000) << 3 : exponent re-biased by 1023-127
     float y0f;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(__uint_as_float(fb)));
     const unsigned yb = __float_as_uint(y0f);
-    const unsigned hy = ok ? ((yb >> 3) + 0x38000000u) : 0u;
+    hy = ok ? ((yb >> 3) + 0x38000000u) : 0u;
     // the low word is whatever is at hand (the seed bits): it perturbs a valid seed by < 2^-20 and leaves a rejected
     // one a denormal (< 2^-1042) whose cube underflows to exactly zero -- no register move to build the pair
     const double y0 = __hiloint2double((int)hy, (int)yb);

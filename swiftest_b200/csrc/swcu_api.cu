@@ -576,6 +576,15 @@ extern "C" int swcu_body_drift(swcu_context *ctx, int32_t kind, double dt, int32
     return drift_bodies(ctx, b, i0, i1, dt, lgr, inv_c2, nfail);
 }
 
+extern "C" int swcu_whm_tp_step(swcu_context *ctx, double dt, const double *ah0, int32_t *nfail)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->tp.valid || !ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "whm_tp_step: tp and pl populations must be resident");
+    if (!ah0) return fail(ctx, SWCU_ERR_ARG, "whm_tp_step: null ah0");
+    if (ctx->tp.n == 0 || ctx->pl.n == 0) return SWCU_OK;  // whm_kick.f90:91
+    return whm_tp_step(ctx, ctx->tp, ctx->pl, dt, ah0, nfail);
+}
+
 extern "C" int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt)
 {
     SWCU_TRY(check_ctx(ctx));

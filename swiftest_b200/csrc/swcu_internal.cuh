@@ -198,6 +198,7 @@ int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, c
 
 // ---- drift : drift_kernels.cu ----
 int drift_bodies(swcu_context *ctx, Body &b, int i0, int i1, double dt, int lgr, double inv_c2, int32_t *nfail);
+int whm_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double dt, const double ah0[3], int32_t *nfail);
 
 // ---- encounters : encounter_kernels.cu ----
 struct SweepList {

@@ -443,6 +443,56 @@ def test_resident_tp_kick_drift_and_encounter(ctx, oracle):
     _same_pairs(got, oracle.encounter_pltp(p["rh"], p["vh"], tp["rh"], tp["vh"], p["rhill"] * 6.5, 0.05))
 
 
+def test_fused_whm_tp_step_matches_unfused_oracle_sequence(ctx, oracle):
+    """Next row: whm_step_tp as one kernel vs kick/drift/kick built from oracle calls
+    (whm_step.f90:72-100, whm_kick.f90:70-149,265-314)."""
+    p = W.planets8_year_units()
+    ntp, dt = 30000, 0.01
+    tp = W.tp_cloud(ntp, seed=5)
+    rng = np.random.default_rng(5)
+    mask = (rng.uniform(size=ntp) > 0.05).astype(np.int32)
+    on = mask.astype(bool)
+
+    def ah0_of(rpl):  # whm_kick_getacch_ah0
+        a = np.zeros(3)
+        for i in range(len(p["Gmass"])):
+            r2 = float(rpl[i] @ rpl[i])
+            a = a - p["Gmass"][i] * (1.0 / (r2 * np.sqrt(r2))) * rpl[i]
+        return a
+
+    rbeg = p["rh"]
+    rend = p["rh"] + p["vh"] * dt  # any end-of-step planet positions will do for the comparison
+    mu = np.full(ntp, p["cb_Gmass"])
+    # reference sequence: lfirst accel at rbeg, kick, drift, accel at rend, kick
+    ah = np.zeros((ntp, 3))
+    ah[on] += ah0_of(rbeg)
+    ah = oracle.kick_all_tp(tp["rh"], rbeg, p["Gmass"], mask, ah)
+    v = tp["vh"].copy()
+    v[on] = v[on] + ah[on] * (0.5 * dt)
+    x, v, fl = oracle.drift_all(mu, tp["rh"], v, dt, lmask=mask)
+    ah2 = np.zeros((ntp, 3))
+    ah2[on] += ah0_of(rend)
+    ah2 = oracle.kick_all_tp(x, rend, p["Gmass"], mask, ah2)
+    v[on] = v[on] + ah2[on] * (0.5 * dt)
+    # device: resident populations, first-step accelerations through the unfused calls, then the fused step
+    ctx.body_sync(PL, 8, nplm=8, r=rbeg, v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=p["cb_Gmass"] + p["Gmass"], generation=31)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=mu, lmask=mask, generation=32)
+    a_first = np.zeros((ntp, 3))
+    a_first[on] += ah0_of(rbeg)
+    ctx.body_put(TP, a=a_first)
+    ctx.tp_accel_int()
+    ctx.body_put(PL, r=rend)
+    assert ctx.whm_tp_step(dt, ah0_of(rend)) == 0
+    out = ctx.body_get(TP, iflag=True)
+    assert np.array_equal(out["iflag"][on], fl[on])
+    assert np.max(np.abs(out["r"] - x) / np.linalg.norm(x, axis=1, keepdims=True)) < 1e-12
+    assert np.max(np.abs(out["v"] - v) / np.linalg.norm(v, axis=1, keepdims=True)) < 1e-12
+    assert np.max(np.abs(out["a"][on] - ah2[on])) <= 1e-12 * np.abs(ah2).max()
+    off = ~on
+    assert np.array_equal(out["r"][off], tp["rh"][off]) and np.array_equal(out["v"][off], tp["vh"][off])
+
+
 # ---------------------------------------------------------------------------------------------- system level
 def test_helio_integration_tracks_oracle_run(ctx, oracle):
     """Energy and angular-momentum error of a Sun + 8 planets run must track the CPU run step for step
