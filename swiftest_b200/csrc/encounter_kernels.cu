@@ -194,44 +194,56 @@ __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single
         const double vxi = cvx[i], vyi = cvy[i], vzi = cvz[i];
         const double renci = crenc[i];
         const bool in1 = i < n1;
-        for (int k0 = kb; k0 < ke; k0 += 32) {
-            const int k = k0 + lane;
-            bool hit = false;
-            unsigned long long key = 0ull;
-            if (k < ke) {
-                const int j = sbody[k];
-                bool good = true;
-                if (!single) good = ((j < n1) != in1);  // only bodies of the other list (:873,:890)
-                if (good) {
-                    const double xr = sx[k] - xi, yr = sy[k] - yi, zr = sz[k] - zi;
-                    const double vxr = svx[k] - vxi, vyr = svy[k] - vyi, vzr = svz[k] - vzi;
-                    const double renc12 = renci + srenc[k];
-                    hit = check_one(xr, yr, zr, vxr, vyr, vzr, renc12, dt, vsmall);
-                    if (hit) {
-                        unsigned a, b;
-                        if (single) {  // :976-983 index1 < index2
-                            a = (unsigned)min(i, j) + 1u;
-                            b = (unsigned)max(i, j) + 1u;
-                        } else if (in1) {  // index1 = list-1 body, index2 = list-2 body
-                            a = (unsigned)i + 1u;
-                            b = (unsigned)(j - n1) + 1u;
-                        } else {
-                            a = (unsigned)j + 1u;
-                            b = (unsigned)(i - n1) + 1u;
+        // two candidates per lane per iteration: their eight streams of loads are issued together
+        for (int k0 = kb; k0 < ke; k0 += 64) {
+            bool hit[2];
+            unsigned long long key[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const int k = k0 + 32 * u + lane;
+                hit[u] = false;
+                key[u] = 0ull;
+                if (k < ke) {
+                    const int j = sbody[k];
+                    bool good = true;
+                    if (!single) good = ((j < n1) != in1);  // only bodies of the other list (:873,:890)
+                    if (good) {
+                        const double xr = sx[k] - xi, yr = sy[k] - yi, zr = sz[k] - zi;
+                        const double vxr = svx[k] - vxi, vyr = svy[k] - vyi, vzr = svz[k] - vzi;
+                        const double renc12 = renci + srenc[k];
+                        hit[u] = check_one(xr, yr, zr, vxr, vyr, vzr, renc12, dt, vsmall);
+                        if (hit[u]) {
+                            unsigned a, b;
+                            if (single) {  // :976-983 index1 < index2
+                                a = (unsigned)min(i, j) + 1u;
+                                b = (unsigned)max(i, j) + 1u;
+                            } else if (in1) {  // index1 = list-1 body, index2 = list-2 body
+                                a = (unsigned)i + 1u;
+                                b = (unsigned)(j - n1) + 1u;
+                            } else {
+                                a = (unsigned)j + 1u;
+                                b = (unsigned)(i - n1) + 1u;
+                            }
+                            key[u] = ((unsigned long long)a << 32) | b;
                         }
-                        key = ((unsigned long long)a << 32) | b;
                     }
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, hit[0]);
+            const unsigned m1 = __ballot_sync(0xffffffffu, hit[1]);
+            if (m0 | m1) {
                 unsigned long long base = 0ull;
-                const int leader = __ffs(m) - 1;
-                if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (hit) {
-                    const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < cap) cand[pos] = key;
+                const int n0 = __popc(m0);
+                if (lane == 0) base = atomicAdd(count, (unsigned long long)(n0 + __popc(m1)));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (hit[0]) {
+                    const unsigned long long pos = base + __popc(m0 & below);
+                    if (pos < cap) cand[pos] = key[0];
+                }
+                if (hit[1]) {
+                    const unsigned long long pos = base + n0 + __popc(m1 & below);
+                    if (pos < cap) cand[pos] = key[1];
                 }
             }
         }

@@ -28,6 +28,9 @@ namespace {
 constexpr int FIB = 4;          // i bodies per lane
 constexpr int FT = 32 * FIB;    // bodies per block
 constexpr int FWARPS = 4;       // warps (independent work units) per CTA
+#ifndef FLAT_MIN_CTAS
+#define FLAT_MIN_CTAS 3
+#endif
 
 // ordering of a lane's accumulator store before its neighbour's load of the same slot in the next step
 // (a compiler-only fence was tried and is NOT sufficient: it produced wrong sums in blocks that take the masked path)
@@ -257,7 +260,7 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
 }
 
 template <bool RAD, bool ACC_SMEM>
-__global__ void __launch_bounds__(32 * FWARPS) kick_flat_kernel(const FlatArgs a)
+__global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(const FlatArgs a)
 {
     __shared__ WarpTile tiles[FWARPS];
     const int lane = threadIdx.x & 31;
