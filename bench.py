@@ -246,7 +246,6 @@ def run_ours(args):
         ctx.body_put(PL, r=d["rh"], v=d["vh"])
 
     # ---------------- device-resident timing ----------------
-    ctx.enable_kernel_timing(True)
     for _ in range(args.warmup):
         step()
     barrier()
@@ -254,19 +253,22 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    kick_ms = []
     barrier()
+    ctx.enable_kernel_timing(2)  # an event pair per launch group, read after the loop: nothing stalls the stream
     ctx.timer_start()
     for _ in range(args.steps):
         step()
-        kick_ms.append(ctx.last_kernel_ms(FAM_PLPL))
     ms_total = ctx.timer_stop()
     barrier()
+    fam_ms = {name: ctx.kernel_ms_accumulated(f) for name, f in
+              (("gravity", FAM_PLPL), ("drift", FAM_DRIFT), ("collective", FAM_ALLGATHER))}
+    ctx.enable_kernel_timing(0)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(ms_total / args.steps)
     value = pairs / (ms_step * 1e-3)
-    kick_ms_avg = max_over_ranks(float(np.mean(kick_ms)))
+    kick_ms_avg = max_over_ranks(fam_ms["gravity"][0] / max(1, fam_ms["gravity"][1]))
+    breakdown = {k: (max_over_ranks(v[0] / args.steps) if v[1] else 0.0) for k, v in fam_ms.items()}
     fp64_peak = ctx.probe_fp64_peak()
 
     # ---------------- end-to-end: host buffers in, results out, every step ----------------
@@ -279,7 +281,6 @@ def run_ours(args):
         step()
         ctx.body_get(PL, out=out)
 
-    ctx.enable_kernel_timing(False)
     for _ in range(max(1, args.warmup)):
         step_e2e()
     barrier()
@@ -296,8 +297,15 @@ def run_ours(args):
     flops_kernel = FLOP_PER_PAIR_RAD * pairs / world  # algorithmic flop of one rank's launch (balanced shares)
     achieved = flops_kernel / (kick_ms_avg * 1e-3) / 1e12
     kname = "kick_flat_kernel (third-law pl-pl gravity)" if variant == LOOP_FLAT else "kick_rows_kernel (full-row pl-pl gravity)"
+    traffic = None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if variant == LOOP_FLAT and n == 100000 and world == 1:
+            traffic = tj["kick_flat_kernel"]["dram_bytes_read"] + tj["kick_flat_kernel"]["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "fp64", "kernel": kname, "achieved": achieved, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fp64_peak, "traffic": traffic,
                 "peak_source": "DFMA microbenchmark run in this process (swcu_probe_fp64_peak); MEASURED_PEAKS.json holds "
                                "no FP64 figure",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR_RAD, "kernel_ms": kick_ms_avg,
@@ -332,6 +340,7 @@ def run_ours(args):
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "seed": 3031179},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "breakdown_ms_per_step": breakdown,
             "peaks": {"fp64_tflops_measured": fp64_peak, "hbm_gbs": hbm_peak, "hbm_source": peak_src},
             "extra": extra}
         print(json.dumps(line))

@@ -193,7 +193,10 @@ int swcu_flush_l2(swcu_context *ctx);
 /* duration in ms of the most recent launch group of a kernel family, measured with CUDA events inside the
  * library: 0 = pl-pl gravity, 1 = pl-tp gravity, 2 = drift, 3 = sweep (sort..compaction), 4 = allgather */
 int swcu_last_kernel_ms(swcu_context *ctx, int32_t family, double *ms);
+/* on = 0 off; 1 keep the last launch group per family (swcu_last_kernel_ms); 2 log an event pair for EVERY launch group
+ * since this call, read later with swcu_kernel_ms_accumulated (no stream synchronisation inside the timed region) */
 int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on);
+int swcu_kernel_ms_accumulated(swcu_context *ctx, int32_t family, double *total_ms, int32_t *count);
 
 #ifdef __cplusplus
 }

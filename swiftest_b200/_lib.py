@@ -78,6 +78,7 @@ def load():
         "swcu_flush_l2": [p],
         "swcu_last_kernel_ms": [p, i32, p],
         "swcu_enable_kernel_timing": [p, i32],
+        "swcu_kernel_ms_accumulated": [p, i32, p, p],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -290,7 +290,13 @@ class Context:
         return ms.value
 
     def enable_kernel_timing(self, on=True):
-        self._ck(self._L.swcu_enable_kernel_timing(self._h, int(bool(on))))
+        """False/0 off, True/1 last launch group per family, 2 accumulate every launch group (kernel_ms_accumulated)."""
+        self._ck(self._L.swcu_enable_kernel_timing(self._h, int(on)))
+
+    def kernel_ms_accumulated(self, family):
+        ms, n = C.c_double(), C.c_int32()
+        self._ck(self._L.swcu_kernel_ms_accumulated(self._h, family, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
 
     def last_kernel_ms(self, family):
         ms = C.c_double()

@@ -175,6 +175,10 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int f = 0; f < FAM_COUNT; ++f) {
+        for (cudaEvent_t e : ctx->fam_log0[f]) cudaEventDestroy(e);
+        for (cudaEvent_t e : ctx->fam_log1[f]) cudaEventDestroy(e);
+    }
+    for (int f = 0; f < FAM_COUNT; ++f) {
         cudaEventDestroy(ctx->fam_ev0[f]);
         cudaEventDestroy(ctx->fam_ev1[f]);
     }
@@ -648,7 +652,26 @@ extern "C" int swcu_timer_stop(swcu_context *ctx, double *elapsed_ms)
 extern "C" int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on)
 {
     if (!ctx) return SWCU_ERR_ARG;
-    ctx->kernel_timing = (on != 0);
+    ctx->kernel_timing = on;
+    if (on == 2)
+        for (int f = 0; f < FAM_COUNT; ++f) ctx->fam_log_used[f] = 0;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_kernel_ms_accumulated(swcu_context *ctx, int32_t family, double *total_ms, int32_t *count)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (family < 0 || family >= FAM_COUNT || !total_ms) return fail(ctx, SWCU_ERR_ARG, "kernel_ms_accumulated: bad family");
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    const size_t n = ctx->fam_log_used[family];
+    for (size_t k = 0; k < n; ++k) {
+        float t = 0.f;
+        SWCU_CUDA(ctx, cudaEventElapsedTime(&t, ctx->fam_log0[family][k], ctx->fam_log1[family][k]));
+        sum += t;
+    }
+    *total_ms = sum;
+    if (count) *count = (int32_t)n;
     return SWCU_OK;
 }
 

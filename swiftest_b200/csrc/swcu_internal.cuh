@@ -105,10 +105,13 @@ struct swcu_context {
 
     // timing
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool kernel_timing = false;
+    int kernel_timing = 0;  // 0 off, 1 last launch group per family, 2 accumulate every launch group
     cudaEvent_t fam_ev0[swcu::FAM_COUNT] = {}, fam_ev1[swcu::FAM_COUNT] = {};
     bool fam_pending[swcu::FAM_COUNT] = {};
     double fam_ms[swcu::FAM_COUNT] = {};
+    // accumulating mode (kernel_timing == 2): one event pair per launch group, read without stalling the stream
+    std::vector<cudaEvent_t> fam_log0[swcu::FAM_COUNT], fam_log1[swcu::FAM_COUNT];
+    size_t fam_log_used[swcu::FAM_COUNT] = {};
 
     swcu::DevBuf flush;
 
@@ -149,15 +152,30 @@ int fail(swcu_context *ctx, int code, const char *fmt, ...);
 struct FamTimer {  // brackets a launch group with events when kernel timing is enabled
     swcu_context *c;
     int fam;
+    size_t slot = 0;
     FamTimer(swcu_context *ctx, int family) : c(ctx), fam(family)
     {
-        if (c->kernel_timing) cudaEventRecord(c->fam_ev0[fam], c->stream);
+        if (c->kernel_timing == 1) {
+            cudaEventRecord(c->fam_ev0[fam], c->stream);
+        } else if (c->kernel_timing == 2) {
+            slot = c->fam_log_used[fam]++;
+            if (slot >= c->fam_log0[fam].size()) {
+                cudaEvent_t a, b;
+                cudaEventCreate(&a);
+                cudaEventCreate(&b);
+                c->fam_log0[fam].push_back(a);
+                c->fam_log1[fam].push_back(b);
+            }
+            cudaEventRecord(c->fam_log0[fam][slot], c->stream);
+        }
     }
     ~FamTimer()
     {
-        if (c->kernel_timing) {
+        if (c->kernel_timing == 1) {
             cudaEventRecord(c->fam_ev1[fam], c->stream);
             c->fam_pending[fam] = true;
+        } else if (c->kernel_timing == 2) {
+            cudaEventRecord(c->fam_log1[fam][slot], c->stream);
         }
     }
 };
