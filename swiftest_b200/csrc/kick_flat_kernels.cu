@@ -38,7 +38,7 @@ constexpr int FWARPS = 4;       // warps (independent work units) per CTA
 
 struct FlatArgs {
     const double *x, *y, *z, *gm, *rad;
-    const double *radmax;  // device scalar: max radius over all bodies (rad variant)
+    const double *radmax;  // device scalars: [0] max radius over all bodies, [1] max |coordinate|
     int n, nplm;
     int nb, nbm;          // blocks in total / blocks that own rows (cover [0,nplm))
     int Km, evenm;        // cyclic half-range among the owner blocks, and whether nbm is even
@@ -149,23 +149,22 @@ __device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned 
         ajz = *reinterpret_cast<const double *>(wb + 1536 + off);
     }
     const int jcur = jbase + (int)(off >> 4);
+    unsigned hy[FIB];
 #pragma unroll
     for (int b = 0; b < FIB; ++b) {
         const double dx = xy.x - xi[b];
         const double dy = xy.y - yi[b];
         const double dz = zg.x - zi[b];
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        unsigned hy;
         double y;
         if (CHECKED) {
             const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
                            ((idx_i[b] < a.nplm) || (jcur < a.nplm));
             // a masked pair never contributes (always-failing test); redo_chunk applies the masks again
-            y = rsqrt_seeded(r2, thr[b], m ? span[b] : 0u, hy);
+            y = rsqrt_seeded<true>(r2, thr[b], m ? span[b] : 0u, hy[b]);
         } else {
-            y = rsqrt_seeded(r2, thr[b], span[b], hy);
+            y = rsqrt_seeded<false>(r2, thr[b], span[b], hy[b]);  // the caller guarantees |coordinates| < 2^62
         }
-        hymin = min(hymin, hy);
         const double y2 = y * y;
         const double y3 = y * y2;
         const double fj = zg.y * y3;  // acts on i
@@ -178,6 +177,8 @@ __device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned 
         ajy = fma(-fi, dy, ajy);
         ajz = fma(-fi, dz, ajz);
     }
+    static_assert(FIB == 4, "the seed-word minimum below is written for 4 row bodies per lane");
+    hymin = __vimin3_u32(__vimin3_u32(hymin, hy[0], hy[1]), hy[2], hy[3]);  // 2 x VIMNMX3 for 4 pairs
     if (ACC_SMEM) {
         *reinterpret_cast<double2 *>(wb + 1024 + off) = make_double2(ajx, ajy);
         *reinterpret_cast<double *>(wb + 1536 + off) = ajz;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
     int idx_i[FIB];
     int Icur = -1;
     const double radmax = RAD ? a.radmax[0] : 0.0;
+    const bool coords_safe = a.radmax[1] < COORD_SAFE_MAX;  // else every block pair takes the fully checked path
 
     auto flush = [&]() {
         if (Icur < 0) return;
@@ -317,8 +319,8 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
                     axi[b] = ayi[b] = azi[b] = 0.0;
                 }
             }
-            const bool checked =
-                diag || I == a.nb - 1 || J == a.nb - 1 || (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
+            const bool checked = !coords_safe || diag || I == a.nb - 1 || J == a.nb - 1 ||
+                                 (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
             if (checked)
                 block_pair<RAD, true, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
             else
@@ -328,26 +330,38 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
     flush();
 }
 
-// max over an array of non-negative doubles (their bit patterns order like unsigned integers)
-__global__ void max_nonneg_kernel(const double *v, int n, unsigned long long *out)
+// out[0] = max |radius[i]| (0 when radius == nullptr), out[1] = max over bodies of max(|x|,|y|,|z|); the bit patterns of
+// non-negative doubles order like unsigned integers, so one integer atomicMax per warp does the reduction
+__global__ void max_radius_coord_kernel(const double *radius, const double *x, const double *y, const double *z, int n,
+                                        unsigned long long *out)
 {
-    unsigned long long m = 0ull;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        m = max(m, (unsigned long long)__double_as_longlong(fabs(v[i])));
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) atomicMax(out, m);
+    unsigned long long mr = 0ull, mc = 0ull;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (radius != nullptr) mr = max(mr, (unsigned long long)__double_as_longlong(fabs(radius[i])));
+        const double c = fmax(fabs(x[i]), fmax(fabs(y[i]), fabs(z[i])));
+        mc = max(mc, (unsigned long long)__double_as_longlong(c));  // NaN orders above every finite value: unsafe
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mr = max(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+        mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, mr);
+        atomicMax(out + 1, mc);
+    }
 }
 
 }  // namespace
 
-// device scalar max |v[i]| into ctx->scratch64[8..15]; returns the device pointer
-int max_radius(swcu_context *ctx, const double *radius, int n, const double **d_out)
+// device scalars {max radius, max |coordinate|} of a population into two 8-byte slots of ctx->scratch64
+int max_radius(swcu_context *ctx, const double *radius, const double *x, const double *y, const double *z, int n,
+               int slot, const double **d_out)
 {
-    SWCU_CUDA(ctx, ctx->scratch64.ensure(64));
-    unsigned long long *d = ctx->scratch64.as<unsigned long long>() + 1;
-    SWCU_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+    SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
+    unsigned long long *d = ctx->scratch64.as<unsigned long long>() + slot;  // slot 1: columns / whole population, 4: rows
+    SWCU_CUDA(ctx, cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (n > 0) {
-        max_nonneg_kernel<<<std::min(cdiv(n, 256), 512), 256, 0, ctx->stream>>>(radius, n, d);
+        max_radius_coord_kernel<<<std::min(cdiv(n, 256), 512), 256, 0, ctx->stream>>>(radius, x, y, z, n, d);
         SWCU_KERNEL_CHECK(ctx);
     }
     *d_out = reinterpret_cast<const double *>(d);
@@ -368,8 +382,7 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     a.z = pl.rz.as<double>();
     a.gm = pl.Gm.as<double>();
     a.rad = lrad ? pl.radius.as<double>() : nullptr;
-    a.radmax = nullptr;
-    if (lrad) SWCU_TRY(max_radius(ctx, a.rad, n, &a.radmax));
+    SWCU_TRY(max_radius(ctx, a.rad, a.x, a.y, a.z, n, 1, &a.radmax));
     a.n = n;
     a.nplm = std::min(nplm_rows, n);
     a.nb = cdiv(n, FT);
@@ -404,8 +417,8 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     }
     const long long mine = a.item1 - a.item0;
     a.quantum = ctx->tune_nsplit > 0 ? ctx->tune_nsplit : 2;  // measured: 1..2 best at npl = 1e5 (7.9 ms), 8: 8.3, 32: 9.8
-    SWCU_CUDA(ctx, ctx->scratch64.ensure(64));
-    a.counter = ctx->scratch64.as<unsigned long long>() + 2;
+    SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
+    a.counter = ctx->scratch64.as<unsigned long long>() + 3;
     SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
     // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work)
     const long long nquanta = (mine + a.quantum - 1) / a.quantum;

@@ -71,7 +71,8 @@ struct KickArgs {
     int row0, row1;
     const double *xj, *yj, *zj, *gmj, *radj;
     int col0, col1;
-    const double *radmax;     // device scalar: max column radius (radius-checked variants), else nullptr
+    const double *radmax;     // device scalars of the columns: [0] max radius, [1] max |coordinate|
+    const double *rowmax;     // same for the rows ([1] used)
     int diag;                 // rows and columns index the same population
     const int32_t *lmask;
     double *ax, *ay, *az;     // final accumulators (used directly when gridDim.y == 1)
@@ -83,7 +84,7 @@ struct KickArgs {
 // basic block.  Pairs the seeded path cannot take (r^2 == 0 on the diagonal, r^2 outside the FP32 exponent range, or
 // not safely outside the sum of radii -- kick_math.cuh) contribute exactly zero and raise `bad`; the caller redoes
 // those few once per tile (redo_tile).
-template <int IB>
+template <int IB, bool UPPER>
 __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double (&yi)[IB], const double (&zi)[IB],
                                             const unsigned (&thr)[IB], const unsigned (&span)[IB], double xj, double yj,
                                             double zj, double gmj, double (&ax)[IB], double (&ay)[IB], double (&az)[IB],
@@ -96,7 +97,7 @@ __device__ __forceinline__ void eval_column(const double (&xi)[IB], const double
         const double dz = zj - zi[b];
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
         unsigned hy;
-        const double y = rsqrt_seeded(r2, thr[b], span[b], hy);
+        const double y = rsqrt_seeded<UPPER>(r2, thr[b], span[b], hy);
         if (hy == 0u) hymin = 0u;  // (a predicate OR measured 4 % faster here than an integer min)
         const double g = gmj * y;
         const double y2 = y * y;
@@ -147,7 +148,9 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const __grid_constant__ 
     const int t0 = (int)blockIdx.y * tiles_per;
     const int t1 = min(ntile_total, t0 + tiles_per);
     const bool direct = (gridDim.y == 1);
-    const double radmax = (a.radmax != nullptr) ? a.radmax[0] : 0.0;
+    const double radmax = (a.radi != nullptr) ? a.radmax[0] : 0.0;
+    // rows and columns all below 2^62 in magnitude: r^2 cannot overflow a float and the range test loses its upper end
+    const bool coords_safe = a.radmax[1] < COORD_SAFE_MAX && a.rowmax[1] < COORD_SAFE_MAX;
 
     double xi[IB], yi[IB], zi[IB], ax[IB], ay[IB], az[IB];
     unsigned thr[IB], span[IB];
@@ -201,18 +204,20 @@ __global__ void __launch_bounds__(KNT) kick_rows_kernel(const __grid_constant__ 
         const int jbase = a.col0 + t * KTJ;
         const int cnt = min(KTJ, a.col1 - jbase);
         const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sg = sm[s][3];
-        unsigned bad = 0xffffffffu;  // running minimum of the seed words: 0 <=> some evaluation was rejected
+        unsigned bad = 0xffffffffu;  // 0 <=> some evaluation of this tile was rejected by the fast-path test
         int jj = 0;
+        if (coords_safe) {
 #pragma unroll 1
-        for (; jj + 1 < cnt; jj += 2) {
-            const double2 x2 = *reinterpret_cast<const double2 *>(sx + jj);
-            const double2 y2 = *reinterpret_cast<const double2 *>(sy + jj);
-            const double2 z2 = *reinterpret_cast<const double2 *>(sz + jj);
-            const double2 g2 = *reinterpret_cast<const double2 *>(sg + jj);
-            eval_column<IB>(xi, yi, zi, thr, span, x2.x, y2.x, z2.x, g2.x, ax, ay, az, bad);
-            eval_column<IB>(xi, yi, zi, thr, span, x2.y, y2.y, z2.y, g2.y, ax, ay, az, bad);
+            for (; jj + 1 < cnt; jj += 2) {
+                const double2 x2 = *reinterpret_cast<const double2 *>(sx + jj);
+                const double2 y2 = *reinterpret_cast<const double2 *>(sy + jj);
+                const double2 z2 = *reinterpret_cast<const double2 *>(sz + jj);
+                const double2 g2 = *reinterpret_cast<const double2 *>(sg + jj);
+                eval_column<IB, false>(xi, yi, zi, thr, span, x2.x, y2.x, z2.x, g2.x, ax, ay, az, bad);
+                eval_column<IB, false>(xi, yi, zi, thr, span, x2.y, y2.y, z2.y, g2.y, ax, ay, az, bad);
+            }
         }
-        if (jj < cnt) eval_column<IB>(xi, yi, zi, thr, span, sx[jj], sy[jj], sz[jj], sg[jj], ax, ay, az, bad);
+        for (; jj < cnt; ++jj) eval_column<IB, true>(xi, yi, zi, thr, span, sx[jj], sy[jj], sz[jj], sg[jj], ax, ay, az, bad);
         if (__builtin_expect(bad == 0u, 0)) redo_tile<IB>(a, sx, sy, sz, sg, cnt, jbase, xi, yi, zi, thr, span, rowid, ax, ay, az);
         __syncthreads();
     }
@@ -410,8 +415,12 @@ int launch_rows(swcu_context *ctx, const KickProblem &p, int nsplit_override)
         a.pstride = stride;
     }
     a.diag = p.diag ? 1 : 0;
-    a.radmax = nullptr;
-    if (p.radi != nullptr) SWCU_TRY(max_radius(ctx, p.radj + p.col0, ncols, &a.radmax));
+    // {max radius, max |coordinate|} of the columns and, when they are a different population (pl -> tp), of the rows
+    SWCU_TRY(max_radius(ctx, p.radj ? p.radj + p.col0 : nullptr, p.xj + p.col0, p.yj + p.col0, p.zj + p.col0, ncols, 1,
+                        &a.radmax));
+    a.rowmax = a.radmax;
+    if (p.xi != p.xj)
+        SWCU_TRY(max_radius(ctx, nullptr, p.xi + p.row0, p.yi + p.row0, p.zi + p.row0, nrows, 4, &a.rowmax));
     const dim3 grid(nrb, ns), block(KNT);
     kick_rows_kernel<IB><<<grid, block, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);

@@ -34,10 +34,17 @@ __device__ __forceinline__ void seed_threshold(double rlim2, unsigned &thr, unsi
 // `hy` returns the selected high word of the seed (0 when the pair was rejected): callers that only need to know whether
 // ANY pair of a tile was rejected keep the running minimum of hy (one 3-input integer min per two pairs) instead of a
 // predicate per pair.
+//
+// UPPER = false drops the upper end of the range test (r2 < 2^128), saving the subtract: one compare hi >= thr.  It may
+// only be used when the caller has established that no r2 can reach 2^128, i.e. every |coordinate| < 2^62
+// (COORD_SAFE_MAX; the gravity launchers compute max|coordinate| on the device next to the max radius).
+constexpr double COORD_SAFE_MAX = 4611686018427387904.0;  // 2^62: r2 <= 3*(2*2^62)^2 < 2^128
+
+template <bool UPPER = true>
 __device__ __forceinline__ double rsqrt_seeded(double r2, unsigned thr, unsigned span, unsigned &hy)
 {
     const unsigned hi = (unsigned)__double2hiint(r2);
-    const bool ok = (hi - thr) < span;
+    const bool ok = UPPER ? ((hi - thr) < span) : (hi >= thr);
     const unsigned fb = (hi << 3) - 0xC0000000u;  // (hi - 0x38000000) << 3 : exponent re-biased by 1023-127
     float y0f;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(__uint_as_float(fb)));

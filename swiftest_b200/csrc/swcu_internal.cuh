@@ -208,7 +208,8 @@ struct KickProblem {
 int kick_rows(swcu_context *ctx, const KickProblem &p, int family);
 int kick_pl_tri(swcu_context *ctx, Body &pl, bool lrad, int row0, int row1);
 int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows);
-int max_radius(swcu_context *ctx, const double *radius, int n, const double **d_out);
+int max_radius(swcu_context *ctx, const double *radius, const double *x, const double *y, const double *z, int n,
+               int slot, const double **d_out);
 int kick_pair_list(swcu_context *ctx, const Body &pl, bool lrad, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2,
                    double *ex, double *ey, double *ez);
 int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, const double *x2, double *y0,

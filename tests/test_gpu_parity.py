@@ -145,6 +145,27 @@ def test_kick_extreme_separations_take_ieee_path(ctx, oracle):
     assert _scaled(got, ref, scale) < ACC_TOL
 
 
+@pytest.mark.parametrize("far", [1e15, 1e20, 1e30])
+def test_kick_coordinate_guard_for_both_kernels(ctx, oracle, far):
+    """The fast path drops the r^2 < 2^128 test only when every |coordinate| < 2^62; a body beyond that (or r^2 beyond
+    the FP32 exponent range) must send the pairs through the checked / IEEE paths in both kernels."""
+    n = 700
+    d = W.disk(n, seed=3)
+    r = d["rh"].copy()
+    r[17] = [far, -0.5 * far, 0.25 * far]
+    r[400] = [-far, far, far]
+    for flat in (False, True):
+        ref = oracle.kick_tri_pl(r, d["Gmass"], d["radius"], np.zeros((n, 3)))
+        got = np.zeros((n, 3))
+        if flat:
+            ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, r, d["Gmass"], d["radius"], got)
+        else:
+            ctx.kick_getacch_int_all_tri_pl(n, n, r, d["Gmass"], d["radius"], got)
+        assert np.all(np.isfinite(got))
+        scale = oracle.kick_tri_abs_scale(r, d["Gmass"], d["radius"])
+        assert _scaled(got, ref, scale) < ACC_TOL
+
+
 @pytest.mark.parametrize("ntp,npl", [(50, 108), (1000, 8), (100000, 8), (3000, 700)])
 def test_kick_tp(ctx, oracle, ntp, npl):
     rng = np.random.default_rng(ntp + npl)
