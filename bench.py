@@ -46,6 +46,9 @@ def parse_args():
     ap.add_argument("--npl", type=int, default=100000)
     ap.add_argument("--ntp", type=int, default=1000000)
     ap.add_argument("--variant", default="auto", choices=["auto", "tri", "flat"])
+    ap.add_argument("--collective", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1, third-law kernel: fused reduce+update+allgather over NVLink peer memory (p2p) or "
+                         "ncclAllReduce of the partial accelerations (nccl)")
     ap.add_argument("--no-extra", action="store_true", help="skip the sweep / tp side legs and the CPU baseline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
     ap.add_argument("--conservation", type=int, default=0, help="run an n-step energy/L tracking run (extra)")
@@ -233,8 +236,20 @@ def run_ours(args):
     # flat kernel: balanced runs of block pairs per rank, allreduce of the partial accelerations inside
     # swcu_pl_accel_int; every rank then kicks and drifts all bodies (O(N), identical results), no allgather
 
+    use_p2p = world > 1 and variant == LOOP_FLAT and args.collective == "p2p"
+    if use_p2p:
+        # CUDA-IPC handles of every rank's exchange buffers, gathered with torch.distributed (host plumbing only)
+        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        allh = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        ctx.p2p_import(world, rank, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        dist.barrier()
+
     def step():
         ctx.flush_l2()
+        if use_p2p:
+            ctx.pl_kick_drift_p2p(dt, True, want_nfail=False)
+            return
         ctx.body_zero_accel(PL)
         ctx.pl_accel_int(variant, True)
         ctx.body_kick_velocity(PL, dt)
@@ -334,9 +349,11 @@ def run_ours(args):
                        "loop": "triangular full-row" if variant == LOOP_TRIANGULAR else "flat third-law",
                        "lclose": True,
                        "step": "zero_accel+accel_int+kick_velocity+drift" +
-                               (("+allreduce(ah)" if variant == LOOP_FLAT else "+allgather(r,v)") if world > 1 else ""),
-                       "sharding": (f"block-pair runs over {world} rank(s), allreduce of partial ah" if variant == LOOP_FLAT
+                               ((("[reduce-scatter+kick+drift+allgather fused over NVLink peer memory]" if use_p2p
+                                  else "+ncclAllReduce(ah)") if variant == LOOP_FLAT else "+allgather(r,v)") if world > 1 else ""),
+                       "sharding": (f"block-pair runs over {world} rank(s)" if variant == LOOP_FLAT
                                     else f"i-slices over {world} rank(s), allgather of drifted r,v"),
+                       "collective": ("p2p-fused" if use_p2p else ("nccl" if world > 1 else "none")),
                        "l2": "flushed between steps (256 MiB write inside the timed region)",
                        "seed": 3031179},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -346,6 +363,8 @@ def run_ours(args):
         print(json.dumps(line))
     if dist:
         dist.barrier()
+        if use_p2p:
+            ctx.p2p_close()
         ctx.comm_finalize()
         dist.destroy_process_group()
     ctx.close()

@@ -179,6 +179,22 @@ int swcu_pl_allgather(swcu_context *ctx, int32_t with_v);
 /* balanced contiguous partition of n units over nranks: counts differ by at most one, big ranks first */
 int swcu_partition(int32_t n, int32_t nranks, int32_t rank, int32_t *i0, int32_t *i1);
 
+/* Fused step over NVLink peer memory (no NCCL on the data path).  Each rank exports CUDA-IPC handles of its partial-
+ * acceleration buffer, its resident pl r,v arrays and a flag block (swcu_p2p_export, after swcu_body_sync); the host
+ * side gathers the handles of all ranks (any transport: torch.distributed, MPI, a file) and hands the table to
+ * swcu_p2p_import.  swcu_pl_kick_drift_p2p then runs one step of the pl population:
+ *   third-law gravity on this rank's run of block pairs -> signal/wait across GPUs -> ONE kernel that sums this rank's
+ *   slice of the partial accelerations straight out of the peers' memory (fixed rank order), applies vb += ah*dt and the
+ *   Kepler drift to the slice, and stores the new r,v slice into every peer's resident arrays -> wait for all slices.
+ * The reduce-scatter, the O(N) update and the allgather are one kernel; flags in peer memory are the only sync. */
+#define SWCU_P2P_NBUF 8
+#define SWCU_IPC_HANDLE_BYTES 64
+int swcu_p2p_export(swcu_context *ctx, void *handles /* SWCU_P2P_NBUF * SWCU_IPC_HANDLE_BYTES */);
+int swcu_p2p_import(swcu_context *ctx, int32_t nranks, int32_t rank,
+                    const void *all_handles /* nranks * SWCU_P2P_NBUF * SWCU_IPC_HANDLE_BYTES, rank-major */);
+int swcu_p2p_close(swcu_context *ctx);
+int swcu_pl_kick_drift_p2p(swcu_context *ctx, int32_t lclose, double dt, int32_t *nfail);
+
 /* ------------------------------------------------------------------------------------------------------
  * Measurement helpers (CUDA events on the library's stream; probes for the roofline denominators)
  * ---------------------------------------------------------------------------------------------------- */

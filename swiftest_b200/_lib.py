@@ -71,6 +71,10 @@ def load():
         "swcu_pl_set_slice": [p, i32, i32],
         "swcu_pl_allgather": [p, i32],
         "swcu_partition": [i32, i32, i32, p, p],
+        "swcu_p2p_export": [p, p],
+        "swcu_p2p_import": [p, i32, i32, p],
+        "swcu_p2p_close": [p],
+        "swcu_pl_kick_drift_p2p": [p, i32, d, p],
         "swcu_timer_start": [p],
         "swcu_timer_stop": [p, p],
         "swcu_probe_fp64_peak": [p, p],

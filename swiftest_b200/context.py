@@ -280,6 +280,31 @@ class Context:
     def pl_allgather(self, with_v=False):
         self._ck(self._L.swcu_pl_allgather(self._h, int(bool(with_v))))
 
+    # peer-memory (CUDA IPC) fused step
+    P2P_HANDLE_BYTES = 8 * 64
+
+    def p2p_export(self):
+        buf = (C.c_char * self.P2P_HANDLE_BYTES)()
+        self._ck(self._L.swcu_p2p_export(self._h, buf))
+        return bytes(buf)
+
+    def p2p_import(self, nranks, rank, all_handles):
+        """all_handles: the concatenation of every rank's p2p_export() bytes, in rank order."""
+        if len(all_handles) != nranks * self.P2P_HANDLE_BYTES:
+            raise ValueError("all_handles must hold nranks * 512 bytes")
+        buf = (C.c_char * len(all_handles)).from_buffer_copy(all_handles)
+        self._ck(self._L.swcu_p2p_import(self._h, nranks, rank, buf))
+
+    def p2p_close(self):
+        self._ck(self._L.swcu_p2p_close(self._h))
+
+    def pl_kick_drift_p2p(self, dt, lclose=True, want_nfail=True):
+        """One fused multi-GPU step of the resident pl population (third-law gravity on this rank's block pairs, then
+        reduce-scatter + vb += ah*dt + Kepler drift + allgather in one kernel over NVLink peer memory)."""
+        nf = C.c_int32()
+        self._ck(self._L.swcu_pl_kick_drift_p2p(self._h, int(bool(lclose)), float(dt), C.byref(nf) if want_nfail else None))
+        return nf.value
+
     # ---- measurement ----
     def timer_start(self):
         self._ck(self._L.swcu_timer_start(self._h))

@@ -214,3 +214,88 @@ extern "C" int swcu_pl_allgather(swcu_context *ctx, int32_t with_v)
     if (!ctx) return SWCU_ERR_ARG;
     return comm_allgather_pl(ctx, with_v);
 }
+
+// ======================================================================================================
+// Peer-memory exchange: CUDA-IPC export/import of the buffers the fused step touches on every rank
+//   buffer 0: F (partial accelerations, 3*stride doubles)   buffers 1..6: pl rx,ry,rz,vx,vy,vz   buffer 7: flags
+// ======================================================================================================
+extern "C" int swcu_p2p_export(swcu_context *ctx, void *handles)
+{
+    if (!ctx || !handles) return SWCU_ERR_ARG;
+    SWCU_CUDA(ctx, cudaSetDevice(ctx->device));
+    Body &pl = ctx->pl;
+    if (!pl.valid || pl.n <= 0) return fail(ctx, SWCU_ERR_STATE, "swcu_p2p_export: pl population not resident");
+    auto &P = ctx->p2p;
+    P.stride = ((size_t)pl.n + 31) & ~size_t(31);
+    SWCU_CUDA(ctx, P.F.ensure(sizeof(double) * 3 * P.stride));
+    SWCU_CUDA(ctx, P.flags.ensure(sizeof(unsigned long long) * 64));
+    SWCU_CUDA(ctx, cudaMemsetAsync(P.flags.p, 0, sizeof(unsigned long long) * 64, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemsetAsync(P.F.p, 0, sizeof(double) * 3 * P.stride, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    void *bufs[SWCU_P2P_NBUF] = {P.F.p, pl.rx.p, pl.ry.p, pl.rz.p, pl.vx.p, pl.vy.p, pl.vz.p, P.flags.p};
+    static_assert(sizeof(cudaIpcMemHandle_t) == SWCU_IPC_HANDLE_BYTES, "IPC handle size");
+    for (int b = 0; b < SWCU_P2P_NBUF; ++b) {
+        cudaIpcMemHandle_t h;
+        SWCU_CUDA(ctx, cudaIpcGetMemHandle(&h, bufs[b]));
+        memcpy((char *)handles + (size_t)b * SWCU_IPC_HANDLE_BYTES, &h, SWCU_IPC_HANDLE_BYTES);
+    }
+    return SWCU_OK;
+}
+
+extern "C" int swcu_p2p_import(swcu_context *ctx, int32_t nranks, int32_t rank, const void *all_handles)
+{
+    if (!ctx || !all_handles || nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return SWCU_ERR_ARG;
+    SWCU_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto &P = ctx->p2p;
+    Body &pl = ctx->pl;
+    if (!pl.valid || P.F.p == nullptr) return fail(ctx, SWCU_ERR_STATE, "swcu_p2p_import: call swcu_p2p_export first");
+    void *own[SWCU_P2P_NBUF] = {P.F.p, pl.rx.p, pl.ry.p, pl.rz.p, pl.vx.p, pl.vy.p, pl.vz.p, P.flags.p};
+    for (int r = 0; r < nranks; ++r) {
+        for (int b = 0; b < SWCU_P2P_NBUF; ++b) {
+            if (r == rank) {
+                P.peer[r][b] = own[b];
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, (const char *)all_handles + ((size_t)r * SWCU_P2P_NBUF + b) * SWCU_IPC_HANDLE_BYTES,
+                   SWCU_IPC_HANDLE_BYTES);
+            void *p = nullptr;
+            SWCU_CUDA(ctx, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+            P.peer[r][b] = p;
+        }
+    }
+    P.nranks = nranks;
+    P.rank = rank;
+    P.epoch = 0;
+    P.ready = true;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_p2p_close(swcu_context *ctx)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    auto &P = ctx->p2p;
+    if (P.ready) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (int r = 0; r < P.nranks; ++r)
+            if (r != P.rank)
+                for (int b = 0; b < SWCU_P2P_NBUF; ++b)
+                    if (P.peer[r][b]) cudaIpcCloseMemHandle(P.peer[r][b]);
+    }
+    P.ready = false;
+    P.nranks = 1;
+    P.rank = 0;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_pl_kick_drift_p2p(swcu_context *ctx, int32_t lclose, double dt, int32_t *nfail)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    SWCU_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->p2p.ready) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_kick_drift_p2p: peer buffers not imported");
+    Body &pl = ctx->pl;
+    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_kick_drift_p2p: pl population not resident");
+    SWCU_TRY(kick_pl_flat(ctx, pl, lclose != 0, pl.nplm, /*reduce=*/false));
+    return p2p_step_after_kick(ctx, dt, nfail);
+}

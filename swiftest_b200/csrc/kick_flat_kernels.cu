@@ -45,7 +45,10 @@ struct FlatArgs {
     long long total_items;
     long long item0, item1;  // the run of items this rank owns (multi-GPU: pair slices), [0,total) on one GPU
     int quantum;             // items a warp claims per visit to the work counter
-    unsigned long long *counter;  // zero-initialised work counter (dynamic scheduling)
+    unsigned long long *counter;  // work counter (dynamic scheduling); in peer-memory mode ONE counter shared by all GPUs
+    unsigned long long counter_base;  // value of the counter at which this launch's first quantum sits
+    int system_scope;             // 1: the counter lives in (possibly remote) peer memory -> system-scope atomics
+    long long first_warp, total_warps;  // this launch's first global warp id and the warps of all sharers together
     double *fx, *fy, *fz; // zero-initialised accumulation target
 };
 
@@ -288,12 +291,30 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
     // Dynamic scheduling: a warp claims `quantum` consecutive items at a time from a global counter.  (A static split
     // sized to exactly one resident wave was measured to be fragile: when the tail of the previous kernel still
     // occupies an SM at launch, one CTA is left over, runs alone after the others and doubles the kernel time.)
+    // The first quantum of every warp is static (its global warp id): no claim storm on the counter at launch, which
+    // with eight GPUs sharing one counter cost ~0.1 ms.  Claimed values then map to quanta total_warps, total_warps+1, ...
+    // The claim for the NEXT quantum is issued before the current one is processed, so the round trip of the atomic
+    // (a couple of microseconds over NVLink when the counter lives on another GPU) hides behind ~15 us of arithmetic.
+    auto claim = [&]() -> unsigned long long {
+        unsigned long long c = 0;
+        if (lane == 0)
+            c = (a.system_scope ? atomicAdd_system(a.counter, 1ull) : atomicAdd(a.counter, 1ull)) - a.counter_base +
+                (unsigned long long)a.total_warps;
+        return c;  // valid in lane 0 only; broadcast when it is consumed
+    };
+    unsigned long long q = (unsigned long long)(a.first_warp + (long long)blockIdx.x * FWARPS + (threadIdx.x >> 5));
+    unsigned long long qnext = claim();
     for (;;) {
-        unsigned long long q = 0;
-        if (lane == 0) q = atomicAdd(a.counter, 1ull);
-        q = __shfl_sync(0xffffffffu, q, 0);
         long long t = a.item0 + (long long)q * a.quantum;
-        if (t >= a.item1) break;
+        if (t >= a.item1) {
+            if (q >= (unsigned long long)a.total_warps) break;  // the failed claim that ends this warp
+            // (a warp whose static quantum lies beyond the range falls through to its prefetched claim)
+            q = __shfl_sync(0xffffffffu, qnext, 0);
+            qnext = ~0ull;
+            if (q >= (unsigned long long)a.total_warps && a.item0 + (long long)q * a.quantum >= a.item1) break;
+            qnext = claim();
+            continue;
+        }
         const long long t_end = min(a.item1, t + a.quantum);
         for (; t < t_end; ++t) {
             int I, J;
@@ -326,6 +347,9 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
             else
                 block_pair<RAD, false, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
         }
+        q = __shfl_sync(0xffffffffu, qnext, 0);
+        if (a.item0 + (long long)q * a.quantum >= a.item1) break;  // that was this warp's one failed claim
+        qnext = claim();
     }
     flush();
 }
@@ -371,7 +395,7 @@ int max_radius(swcu_context *ctx, const double *radius, const double *x, const d
 // Flat (third-law) variant over the canonical flattened triangle restricted to i < nplm_rows (0-based).
 // With several ranks every rank evaluates an equal run of the (I,k) items, the partial accelerations are summed with
 // one allreduce of 3*npl doubles and added to ah on every rank (all ranks then hold the same ah for all bodies).
-int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
+int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool reduce)
 {
     const int n = pl.n;
     if (n <= 1 || nplm_rows <= 0) return SWCU_OK;
@@ -395,8 +419,13 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
 
     // zeroed accumulation target, then acc += F
     const size_t stride = ((size_t)n + 31) & ~size_t(31);
-    SWCU_CUDA(ctx, ctx->partial.ensure(sizeof(double) * 3 * stride));
-    a.fx = ctx->partial.as<double>();
+    if (!reduce) {  // peer-memory mode: accumulate into the exported buffer, the caller reduces across ranks
+        if (!ctx->p2p.ready || ctx->p2p.stride != stride) return fail(ctx, SWCU_ERR_STATE, "kick_pl_flat: p2p buffers not set up for npl=%d", n);
+        a.fx = ctx->p2p.F.as<double>();
+    } else {
+        SWCU_CUDA(ctx, ctx->partial.ensure(sizeof(double) * 3 * stride));
+        a.fx = ctx->partial.as<double>();
+    }
     a.fy = a.fx + stride;
     a.fz = a.fy + stride;
     SWCU_CUDA(ctx, cudaMemsetAsync(a.fx, 0, sizeof(double) * 3 * stride, ctx->stream));
@@ -410,22 +439,46 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows)
     occ = std::max(1, occ);
     a.item0 = 0;
     a.item1 = total;
-    if (ctx->nranks > 1) {  // balanced consecutive runs, like swcu_partition
-        const long long q = total / ctx->nranks, r = total % ctx->nranks;
-        a.item0 = ctx->rank * q + std::min<long long>(ctx->rank, r);
-        a.item1 = a.item0 + q + (ctx->rank < r ? 1 : 0);
+    // NCCL mode: balanced consecutive runs of items per rank.  Peer-memory mode: all ranks claim quanta from ONE counter
+    // in rank 0's memory (system-scope atomics over NVLink), so the GPUs finish together whatever their speed.
+    const int nr = reduce ? ctx->nranks : 1, rk = reduce ? ctx->rank : 0;
+    if (nr > 1) {  // balanced consecutive runs, like swcu_partition
+        const long long q = total / nr, r = total % nr;
+        a.item0 = rk * q + std::min<long long>(rk, r);
+        a.item1 = a.item0 + q + (rk < r ? 1 : 0);
     }
     const long long mine = a.item1 - a.item0;
+    const long long warps_max = (long long)ctx->prop.multiProcessorCount * occ * FWARPS;
     a.quantum = ctx->tune_nsplit > 0 ? ctx->tune_nsplit : 2;  // measured: 1..2 best at npl = 1e5 (7.9 ms), 8: 8.3, 32: 9.8
+    const int sharers = reduce ? 1 : ctx->p2p.nranks;
+    if (ctx->tune_nsplit <= 0 && mine / a.quantum < 40 * warps_max * sharers) a.quantum = 1;  // few quanta per warp: finer tail
     SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
     a.counter = ctx->scratch64.as<unsigned long long>() + 3;
-    SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
+    a.counter_base = 0;
+    a.system_scope = 0;
     // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work)
     const long long nquanta = (mine + a.quantum - 1) / a.quantum;
-    const long long units = std::max<long long>(1, std::min<long long>((long long)ctx->prop.multiProcessorCount * occ * FWARPS, nquanta));
+    long long units = std::max<long long>(1, std::min<long long>(warps_max, nquanta));
+    if (!reduce && ctx->p2p.nranks > 1) {
+        // shared counter: never reset (a fast rank must not see a stale zero); every launch consumes exactly
+        // max(nquanta - total_warps, 0) successful claims + one failed claim per warp of every rank, so all ranks agree
+        // on the base of each epoch
+        units = warps_max;  // identical grids on all ranks keep that sum predictable
+        const unsigned long long per_epoch = (unsigned long long)std::max<long long>(nquanta, units * ctx->p2p.nranks);
+        a.counter = reinterpret_cast<unsigned long long *>(ctx->p2p.peer[0][7]) + 40;
+        a.counter_base = ctx->p2p.epoch * per_epoch;  // epoch counts completed steps (incremented after the kick)
+        a.system_scope = 1;
+        a.first_warp = units * ctx->p2p.rank;
+        a.total_warps = units * ctx->p2p.nranks;
+    } else {
+        a.first_warp = 0;
+        a.total_warps = units;
+        SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
+    }
     const int grid = cdiv(units, FWARPS);
     kern<<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);
+    if (!reduce) return SWCU_OK;
     if (ctx->nranks > 1) SWCU_TRY(comm_allreduce_sum(ctx, a.fx, 3 * stride));
     return axpy3(ctx, 1.0, a.fx, a.fy, a.fz, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), nullptr, n);
 }

@@ -155,6 +155,9 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     if (!ctx) return SWCU_ERR_ARG;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    swcu_p2p_close(ctx);
+    ctx->p2p.F.release();
+    ctx->p2p.flags.release();
     comm_release(ctx);
     ctx->pl.release();
     ctx->tp.release();

@@ -121,6 +121,16 @@ struct swcu_context {
     int nranks = 1, rank = 0;
     swcu::DevBuf sendbuf, recvbuf;
 
+    // peer-memory exchange (fused reduce + update + allgather over NVLink, comm_p2p / drift_kernels.cu)
+    struct P2P {
+        bool ready = false;
+        int nranks = 1, rank = 0;
+        size_t stride = 0;              // doubles per component in F
+        swcu::DevBuf F, flags;          // local: partial accelerations [3][stride]; flags [2][16] u64 + error word
+        void *peer[8][SWCU_P2P_NBUF];   // mapped pointers of every rank's exported buffers (own rank: local pointers)
+        unsigned long long epoch = 0;
+    } p2p;
+
     // tuning overrides (environment: SWCU_KICK_IB, SWCU_KICK_NSPLIT, SWCU_KICK_VARIANT)
     int tune_ib = 0, tune_nsplit = 0, tune_variant = -1;
 };
@@ -207,7 +217,7 @@ struct KickProblem {
 };
 int kick_rows(swcu_context *ctx, const KickProblem &p, int family);
 int kick_pl_tri(swcu_context *ctx, Body &pl, bool lrad, int row0, int row1);
-int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows);
+int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool reduce = true);
 int max_radius(swcu_context *ctx, const double *radius, const double *x, const double *y, const double *z, int n,
                int slot, const double **d_out);
 int kick_pair_list(swcu_context *ctx, const Body &pl, bool lrad, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2,
@@ -231,6 +241,7 @@ int set_renc(swcu_context *ctx, Body &pl, int irec);
 // ---- comm : comm.cu ----
 int comm_allgather_pl(swcu_context *ctx, int with_v);
 int comm_allreduce_sum(swcu_context *ctx, double *buf, size_t count);
+int p2p_step_after_kick(swcu_context *ctx, double dt, int32_t *nfail);  // drift_kernels.cu
 void comm_release(swcu_context *ctx);
 
 }  // namespace swcu

@@ -42,6 +42,19 @@ def _worker(rank, world, port, n, out):
                 c.pl_allgather(with_v=True)
         g = c.body_get(PL)
         res[name + "_r"], res[name + "_v"] = g["r"], g["v"]
+    # fused peer-memory step (CUDA IPC, no NCCL on the data path)
+    c.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                mu=d["mu"], generation=777)
+    handles = [None] * world
+    dist.all_gather_object(handles, c.p2p_export())
+    c.p2p_import(world, rank, b"".join(handles))
+    dist.barrier()
+    for _ in range(2):
+        assert c.pl_kick_drift_p2p(dt, True) == 0
+    g = c.body_get(PL)
+    res["p2p_r"], res["p2p_v"] = g["r"], g["v"]
+    dist.barrier()
+    c.p2p_close()
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     if rank == 0:
@@ -71,6 +84,6 @@ def test_two_gpu_slices_and_pair_slices_match_oracle(tmp_path, oracle):
         ah = oracle.kick_tri_pl(rh, d["Gmass"], d["radius"], np.zeros((n, 3)))
         vb = vb + ah * d["dt"]
         rh, vb, fl = oracle.drift_all(d["mu"], rh, vb, d["dt"])
-    for name in ("tri", "flat"):
+    for name in ("tri", "flat", "p2p"):
         assert np.max(np.abs(res[name + "_r"] - rh) / np.linalg.norm(rh, axis=1, keepdims=True)) < 1e-12
         assert np.max(np.abs(res[name + "_v"] - vb) / np.linalg.norm(vb, axis=1, keepdims=True)) < 1e-12
