@@ -64,50 +64,97 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md).  NVML is polled from a thread every
+    few milliseconds (an nvidia-smi child process takes longer to start than a short timed region lasts); nvidia-smi
+    -lms is the fallback when pynvml is missing."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.thread, self.mode = index, [], False, None, None
+        self.proc = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([q.strip() for q in line.split(",")])
-
-    def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
+            pass
         try:
-            self.proc.wait(timeout=5)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                                         text=True)
+            self.mode = "smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
+            t0 = time.time()
+            while not self.rows and time.time() - t0 < 3.0:  # wait for the first sample before timing starts
+                time.sleep(0.02)
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        for r in self.rows:
+            self.mode = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2])); pw.append(float(r[3]))
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                try:
+                    watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    watts = 0.0
+                self.rows.append((mhz, self.max_mhz, watts, mask))
             except Exception:
                 pass
-        if not sm:
+            time.sleep(0.004)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            r = [q.strip() for q in line.split(",")]
+            try:
+                mask = 0
+                for bit, val in zip((0x8, 0x40, 0x20, 0x4), r[3:7]):
+                    if val.lower().startswith("active"):
+                        mask |= bit
+                self.rows.append((float(r[0]), float(r[1]), float(r[2]), mask))
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"]}
+        if self.mode == "nvml":
+            time.sleep(0.01)
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+        else:
+            time.sleep(0.12)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+        sm = [r[0] for r in self.rows]
+        mask = 0
+        for r in self.rows:
+            mask |= r[3]
+        return {"sm_mhz": float(np.median(sm)), "sm_min_mhz": float(min(sm)), "sm_max_mhz": float(max(r[1] for r in self.rows)),
+                "power_w_max": float(max(r[2] for r in self.rows)), "samples": len(sm), "source": self.mode,
+                "reasons": sorted(n for b, n in self.REASONS.items() if mask & b)}
 
 
 # =====================================================================================================================
@@ -239,10 +286,21 @@ def run_ours(args):
     use_p2p = world > 1 and variant == LOOP_FLAT and args.collective == "p2p"
     if use_p2p:
         # CUDA-IPC handles of every rank's exchange buffers, gathered with torch.distributed (host plumbing only)
-        mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        ok = torch.ones(1, device="cuda")
+        try:
+            mine = torch.frombuffer(bytearray(ctx.p2p_export()), dtype=torch.uint8).cuda()
+        except Exception:
+            mine, ok = torch.zeros(512, dtype=torch.uint8, device="cuda"), torch.zeros(1, device="cuda")
         allh = [torch.zeros_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
-        ctx.p2p_import(world, rank, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+        if ok.item():
+            try:
+                ctx.p2p_import(world, rank, b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
+            except Exception:
+                ok = torch.zeros(1, device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not ok.item():  # peer mapping unavailable on this box: every rank falls back to the NCCL collective
+            use_p2p = False
         dist.barrier()
 
     def step():
@@ -340,6 +398,9 @@ def run_ours(args):
     if args.conservation and rank == 0 and world == 1:
         extra["conservation"] = conservation_run(ctx, args.conservation)
 
+    if world > 1 and not args.no_extra:
+        extra["whm_tp_sharded"] = tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak)
+
     if rank == 0:
         line = {
             "metric": "FP64 pair-interactions/s (pl-pl N=1e5)", "value": value, "unit": "pair-interactions/s",
@@ -368,6 +429,38 @@ def run_ours(args):
         ctx.comm_finalize()
         dist.destroy_process_group()
     ctx.close()
+
+
+def tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak):
+    """WHM test particles over several GPUs: block partition like swiftest_coarray_distribute_system
+    (swiftest_coarray.f90:705-711), planets replicated, no per-step communication.  Fused tp step, all ranks."""
+    from swiftest_b200 import PL, TP, shard, workloads as W
+    p = W.planets8_year_units()
+    ntp = args.ntp
+    tp = W.tp_cloud(ntp, seed=123)
+    t0, t1 = shard.tp_block_partition(ntp, world, rank)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=p["cb_Gmass"] + p["Gmass"], generation=902)
+    ctx.body_sync(TP, t1 - t0, r=tp["rh"][t0:t1], v=tp["vh"][t0:t1], mu=np.full(t1 - t0, p["cb_Gmass"]), generation=903)
+    ah0 = np.zeros(3)
+    for i in range(8):
+        r2 = float(p["rh"][i] @ p["rh"][i])
+        ah0 -= p["Gmass"][i] / (r2 * np.sqrt(r2)) * p["rh"][i]
+    ctx.body_zero_accel(TP)
+    ctx.tp_accel_int()
+    for _ in range(3):
+        ctx.whm_tp_step(0.01, ah0, want_nfail=False)
+    nsteps = 20
+    barrier()
+    ctx.timer_start()
+    for _ in range(nsteps):
+        ctx.flush_l2()
+        ctx.whm_tp_step(0.01, ah0, want_nfail=False)
+    ms = max_over_ranks(ctx.timer_stop() / nsteps)
+    barrier()
+    return {"ntp_total": ntp, "ranks": world, "ms_per_step": ms, "tp_steps_per_s": ntp / (ms * 1e-3),
+            "partition": "block (coarray_distribute shape), planets replicated, no per-step communication",
+            "note": "includes the 256 MiB L2 flush between steps"}
 
 
 def side_legs(ctx, args, d, hbm_peak, peak_src):

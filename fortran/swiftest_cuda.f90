@@ -132,6 +132,78 @@ module swiftest_cuda
          type(c_ptr), value :: ctx
          integer(c_int), value :: loop_variant, lclose
       end function
+      integer(c_int) function swcu_tp_accel_int(ctx) bind(C, name="swcu_tp_accel_int")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_body_zero_accel(ctx, kind) bind(C, name="swcu_body_zero_accel")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+      end function
+      integer(c_int) function swcu_body_kick_velocity(ctx, kind, dt) bind(C, name="swcu_body_kick_velocity")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         real(c_double), value :: dt
+      end function
+      integer(c_int) function swcu_pl_set_renc(ctx, irec) bind(C, name="swcu_pl_set_renc")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: irec
+      end function
+      integer(c_int) function swcu_pl_encounter_check(ctx, dt, nenc) bind(C, name="swcu_pl_encounter_check")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_tp_encounter_check(ctx, dt, nenc) bind(C, name="swcu_tp_encounter_check")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_body_put(ctx, kind, r, v, a, lmask) bind(C, name="swcu_body_put")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         type(c_ptr), value :: r, v, a, lmask      !! c_loc(array) or c_null_ptr
+      end function
+      integer(c_int) function swcu_body_get(ctx, kind, r, v, a, iflag) bind(C, name="swcu_body_get")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         type(c_ptr), value :: r, v, a, iflag
+      end function
+      !! whm_step_tp in one kernel (whm/whm_step.f90:72-100); ah0 = whm_kick_getacch_ah0 at the end-of-step planets
+      integer(c_int) function swcu_whm_tp_step(ctx, dt, ah0, nfail) bind(C, name="swcu_whm_tp_step")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         real(c_double), intent(in) :: ah0(3)
+         integer(c_int), intent(out) :: nfail
+      end function
+      !! multi-GPU (one image / process per GPU): NCCL id exchange or CUDA-IPC handle exchange is done by the host
+      !! (co_broadcast of the byte buffers in a Coarray build), see include/swiftest_cuda.h
+      integer(c_int) function swcu_p2p_export(ctx, handles) bind(C, name="swcu_p2p_export")
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: ctx
+         character(kind=c_char), intent(out) :: handles(512)
+      end function
+      integer(c_int) function swcu_p2p_import(ctx, nranks, rank, all_handles) bind(C, name="swcu_p2p_import")
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nranks, rank
+         character(kind=c_char), intent(in) :: all_handles(*)
+      end function
+      integer(c_int) function swcu_pl_kick_drift_p2p(ctx, lclose, dt, nfail) bind(C, name="swcu_pl_kick_drift_p2p")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: lclose
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: nfail
+      end function
       integer(c_int) function swcu_body_drift(ctx, kind, dt, lgr, inv_c2, nfail) bind(C, name="swcu_body_drift")
          import :: c_int, c_ptr, c_double
          type(c_ptr), value :: ctx

@@ -68,3 +68,35 @@ def test_tp_block_partition_is_coarray_shape():
     # swiftest_coarray.f90:705-711: ceil(ntot/nimages) per image, last image takes the remainder
     assert [shard.tp_block_partition(10, 4, k) for k in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
     assert [shard.tp_block_partition(2, 4, k) for k in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+
+
+def test_null_context_and_bad_arguments_are_rejected_without_a_gpu():
+    """Argument validation happens before any CUDA call: status codes, never a crash, never a silent success."""
+    L = _lib.load()
+    assert L.swcu_last_error(None) == b"null context"
+    assert L.swcu_destroy(None) == 2                       # SWCU_ERR_ARG
+    assert L.swcu_encounter_fetch(None, 0, None, None, None) == 2
+    assert L.swcu_encounter_stats(None, None, None) == 2
+    assert L.swcu_body_count(None, 0, None, None, None) == 2
+    assert L.swcu_create(0, None) == 2
+    i0, i1 = C.c_int32(), C.c_int32()
+    assert L.swcu_partition(10, 0, 0, C.byref(i0), C.byref(i1)) == 2
+    assert L.swcu_partition(10, 4, 4, C.byref(i0), C.byref(i1)) == 2
+    assert L.swcu_partition(-1, 4, 0, C.byref(i0), C.byref(i1)) == 2
+    assert L.swcu_version() == 100
+    assert L.swcu_launch_count(None) == 0
+
+
+def test_python_harness_validates_shapes_before_calling_the_library():
+    import numpy as np
+    from swiftest_b200.context import Context, _vec, _vec3
+    with pytest.raises(ValueError):
+        _vec3(np.zeros((4, 2)))
+    with pytest.raises(ValueError):
+        _vec3(np.zeros((4, 3)), n=5)
+    with pytest.raises(ValueError):
+        _vec(np.zeros(3), n=4)
+    with pytest.raises(ValueError):
+        Context._inplace3(np.zeros((4, 3), dtype=np.float32), 4)
+    with pytest.raises(ValueError):
+        Context._inplace3(np.zeros((3, 4)).T, 4)  # not C-contiguous

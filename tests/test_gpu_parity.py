@@ -532,3 +532,34 @@ def test_helio_integration_tracks_oracle_run(ctx, oracle):
     assert abs((Eb - Ea) / E0) < 1e-11
     assert np.linalg.norm(Lb - La) / np.linalg.norm(L0) < 1e-12
     assert np.max(np.abs(a.rh - b.rh)) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------- error behaviour
+def test_error_paths_return_status_and_message(ctx):
+    """The reference's conventions: early returns for empty populations, fatal status for inconsistent calls."""
+    from swiftest_b200 import Context, SwcuError
+    d = W.disk(64, seed=1)
+    with Context(0) as c:  # a fresh context: nothing resident
+        with pytest.raises(SwcuError, match="not resident"):
+            c.pl_accel_int(LOOP_TRIANGULAR, True)
+        with pytest.raises(SwcuError, match="not resident"):
+            c.body_drift(PL, 0.01)
+        with pytest.raises(SwcuError, match="not resident"):
+            c.body_get(PL)
+        with pytest.raises(SwcuError, match="not imported"):
+            c.pl_kick_drift_p2p(0.01)
+        with pytest.raises(SwcuError, match="bad npl"):
+            c.kick_getacch_int_all_tri_pl(64, 65, d["rh"], d["Gmass"], d["radius"], np.zeros((64, 3)))
+        with pytest.raises(SwcuError, match="bad nplm"):
+            c.body_sync(PL, 64, nplm=70, r=d["rh"])
+        # fetch must match the count of the last check
+        n = c.encounter_check_all_sort_and_sweep_plpl(64, d["rh"], d["vh"], d["rhill"] * 100, d["dt"])[0]
+        import ctypes as C
+        i1 = np.zeros(n + 5, np.int32)
+        rc = c._L.swcu_encounter_fetch(c._h, n + 1, i1.ctypes.data, i1.ctypes.data, None)
+        assert rc == 2 and b"last check found" in c._L.swcu_last_error(c._h)
+        assert C.sizeof(C.c_void_p) == 8
+    # no-ops of the reference: npl == 0 or ntp == 0 return without touching acc (kick.f90:61, drift.f90:81)
+    acc = np.full((5, 3), 7.0)
+    ctx.kick_getacch_int_all_tp(5, 0, np.zeros((5, 3)), np.zeros((0, 3)), np.zeros(0), np.ones(5, np.int32), acc)
+    assert np.all(acc == 7.0)
