@@ -34,6 +34,10 @@ if ROOT not in sys.path:
 FLOP_PER_PAIR_RAD = 28.0   # algorithmic flop per unordered pair with the radius check
 FLOP_PER_TPEVAL = 17.0
 DRIFT_BYTES_PER_BODY = 112.0
+# potential energy, per unordered pair (swiftest_util.f90:1325-1329): 3 sub, 5 for r^2, sqrt, divide, Gm*m, add
+FLOP_PER_PE_PAIR = 12.0
+# fused helio tp step, per tp: r, vb, lmask read (52 B); r, vb, vh, ah, iflag written (100 B)
+HELIO_TP_BYTES = 152.0
 SWEEP_BYTES = dict(body=56.0, sort=2 * 24.0 * 2, gather=2 * 56.0, cand=56.0, out=9.0)
 
 
@@ -104,6 +108,7 @@ class ClockSampler:
 
     def _poll_nvml(self):
         nv = self.nv
+        k, watts = 0, 0.0
         while not self.stop_flag:
             try:
                 mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
@@ -111,14 +116,16 @@ class ClockSampler:
                     mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
                 except Exception:
                     mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-                try:
-                    watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
-                except Exception:
-                    watts = 0.0
+                if k % 8 == 0:  # NVML queries take milliseconds under load: power only now and then
+                    try:
+                        watts = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                    except Exception:
+                        pass
+                k += 1
                 self.rows.append((mhz, self.max_mhz, watts, mask))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def _read_smi(self):
         for line in self.proc.stdout:
@@ -389,6 +396,7 @@ def run_ours(args):
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
         extra = side_legs(ctx, args, d, hbm_peak, peak_src)
+        extra["next_rows"] = next_row_legs(ctx, args, d, hbm_peak, fp64_peak)
     cpu = None
     if not args.no_extra and rank == 0 and world == 1:
         try:
@@ -545,6 +553,71 @@ def side_legs(ctx, args, d, hbm_peak, peak_src):
     ex["sweep_pltp"] = {"npl": 8, "ntp": ntp, "nenc": int(nenc), "nbox_total": int(st["nbox_total"]),
                         "ms": float(np.mean(ms))}
     ctx.enable_kernel_timing(False)
+    return ex
+
+
+def next_row_legs(ctx, args, d, hbm_peak, fp64_peak):
+    """the device-resident democratic-heliocentric step and the energy sums."""
+    from swiftest_b200 import PL, TP, LOOP_AUTO, workloads as W
+    from swiftest_b200.context import FAM_DRIFT, FAM_PLPL
+    ex = {}
+    n = d["n"]
+    GMcb = W.GMSUN
+    # (1) helio_step_pl at the headline size: two kicks + drift + all O(N) glue per call, nothing crosses PCIe
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                  mu=np.full(n, GMcb), generation=11)
+    ctx.helio_step_pl(GMcb, d["dt"], LOOP_AUTO, True, lfirst=True)
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    reps = 3
+    for _ in range(reps):
+        ctx.helio_step_pl(GMcb, d["dt"], LOOP_AUTO, True, lfirst=False, want_nfail=False)
+    ms = ctx.timer_stop() / reps
+    ex["helio_step_pl"] = {"npl": n, "ms_per_step": ms, "kicks_per_step": 2, "launches_per_step": (ctx.launch_count() - l0) / reps,
+                           "pair_interactions_per_s": 2 * n * (n - 1) / 2.0 / (ms * 1e-3)}
+    # (2) potential energy + KE + L of the same disk through the host-pointer call (upload included in e2e_ms)
+    mass = d["Gmass"] / GMcb
+    ctx.enable_kernel_timing(True)
+    ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, d["rh"])
+    kms, ems = [], []
+    for _ in range(3):
+        ctx.flush_l2()
+        t0 = time.perf_counter()
+        pe = ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, d["rh"])
+        ems.append((time.perf_counter() - t0) * 1e3)
+        kms.append(ctx.last_kernel_ms(FAM_PLPL))
+    ctx.enable_kernel_timing(False)
+    tk = float(np.mean(kms)) * 1e-3
+    pairs = n * (n - 1) / 2.0
+    ex["potential_energy"] = {"npl": n, "pe": pe, "kernel_ms": tk * 1e3, "e2e_ms": float(np.mean(ems)), "pairs_per_s": pairs / tk,
+                              "flop_per_pair": FLOP_PER_PE_PAIR,
+                              "roofline": {"bound": "fp64", "achieved": pairs * FLOP_PER_PE_PAIR / tk / 1e12,
+                                           "peak": fp64_peak, "unit": "TFLOP/s",
+                                           "frac": pairs * FLOP_PER_PE_PAIR / tk / 1e12 / fp64_peak}}
+    # (3) helio_step_tp as one kernel: Sun + 8 planets + ntp test particles
+    p = W.planets8_year_units()
+    ntp = args.ntp
+    tp = W.tp_cloud(ntp, seed=123)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=np.full(8, p["cb_Gmass"]), generation=12)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, p["cb_Gmass"]), generation=13)
+    ctx.enable_kernel_timing(True)
+    fms, pms = [], []
+    for it in range(8):
+        ctx.flush_l2()
+        ctx.timer_start()
+        ctx.helio_step_pl(p["cb_Gmass"], 0.01, LOOP_AUTO, True, lfirst=(it == 0), want_nfail=False)
+        pms.append(ctx.timer_stop())
+        ctx.helio_step_tp(p["cb_Gmass"], 0.01, lfirst=(it == 0), want_nfail=False)
+        if it >= 3:
+            fms.append(ctx.last_kernel_ms(FAM_DRIFT))
+    ctx.enable_kernel_timing(False)
+    tf = float(np.mean(fms)) * 1e-3
+    ex["helio_step_tp"] = {"npl": 8, "ntp": ntp, "ms": tf * 1e3, "tp_steps_per_s": ntp / tf,
+                           "helio_step_pl_8_planets_ms": float(np.mean(pms[3:])),
+                           "roofline": {"bound": "hbm", "achieved": HELIO_TP_BYTES * ntp / tf / 1e9, "peak": hbm_peak,
+                                        "unit": "GB/s", "frac": HELIO_TP_BYTES * ntp / tf / 1e9 / hbm_peak,
+                                        "bytes_per_tp": HELIO_TP_BYTES}}
     return ex
 
 

@@ -162,6 +162,52 @@ int swcu_whm_tp_step(swcu_context *ctx, double dt, const double *ah0, int32_t *n
 int swcu_pl_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);
 int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);
 
+/* ---- tier 2: the O(N) glue of the democratic-heliocentric step, device resident -------------
+ * A resident population keeps two velocities: v (= vh, what swcu_body_sync / _put / _get move) and vb, created as a
+ * copy of v on first use.  The central-body vectors vbcb, ptbeg, ptend live on the device between calls; every
+ * `double *` output below may be NULL (then nothing is copied back and the call does not synchronise).
+ * Sums over bodies run in the reference's serial order for n <= 1024 (bit-identical to the CPU loop) and as a fixed
+ * tree above (reproducible run to run; compare with a tolerance). */
+/* swiftest_util_coord_vh2vb_pl (swiftest_util.f90:424-459): vbcb = -sum(Gm*vh)/(GMcb + sum Gm); vb = vh + vbcb */
+int swcu_pl_vh2vb(swcu_context *ctx, double GMcb, double *vbcb);
+/* swiftest_util_coord_vb2vh_pl (:363-395): vbcb = -sum_{i=npl..1, lmask} Gm*vb/GMcb; vh = vb - vbcb */
+int swcu_pl_vb2vh(swcu_context *ctx, double GMcb, double *vbcb);
+/* helio_drift_linear_pl (helio_drift.f90:129-165): pt = sum(Gm*vb, lmask)/GMcb; rh += pt*dt; kept as ptbeg / ptend */
+int swcu_pl_lindrift(swcu_context *ctx, double GMcb, double dt, int32_t lbeg, double *pt);
+/* helio_drift_linear_tp (:168-200) with the resident ptbeg / ptend; swcu_cb_set_pt loads them when the planets were
+ * stepped elsewhere (e.g. tp shards on other GPUs) */
+int swcu_tp_lindrift(swcu_context *ctx, double dt, int32_t lbeg);
+int swcu_cb_set_pt(swcu_context *ctx, const double *ptbeg, const double *ptend);
+int swcu_cb_get_pt(swcu_context *ctx, double *ptbeg, double *ptend);
+/* swiftest_util_coord_vh2vb_tp / _vb2vh_tp (:398-421, 462-485) with vbcb = -ptbeg (lbeg) or -ptend */
+int swcu_tp_vh2vb(swcu_context *ctx, int32_t lbeg);
+int swcu_tp_vb2vh(swcu_context *ctx, int32_t lbeg);
+/* the tail of helio_kick_vb_pl / _tp (helio_kick.f90:113-128, 157-165): pl also keeps rbeg (lbeg) or rend = rh */
+int swcu_body_kick_vb(swcu_context *ctx, int32_t kind, double dt, int32_t lbeg);
+/* helio_drift_body (helio_drift.f90:14-54): Danby drift of (rh, vb) with mu = GMcb for every body */
+int swcu_body_drift_vb(swcu_context *ctx, int32_t kind, double GMcb, double dt, int32_t *nfail);
+int swcu_body_put_vb(swcu_context *ctx, int32_t kind, const double *vb);
+int swcu_body_get_vb(swcu_context *ctx, int32_t kind, double *vb, double *rbeg, double *rend);
+/* helio_step_pl (helio_step.f90:37-78): [vh2vb if lfirst] lindrift, kick, drift, kick, lindrift, vb2vh -- all on the
+ * device; only nfail (when not NULL) crosses PCIe */
+int swcu_helio_step_pl(swcu_context *ctx, double GMcb, double dt, int32_t loop_variant, int32_t lclose, int32_t lfirst,
+                       int32_t *nfail);
+/* helio_step_tp (helio_step.f90:81-123) as ONE kernel over the tp arrays; uses the rbeg, rend, ptbeg, ptend that
+ * swcu_helio_step_pl left on the device (npl <= 64) */
+int swcu_helio_step_tp(swcu_context *ctx, double GMcb, double dt, int32_t lfirst, int32_t *nfail);
+
+/* ---- tier 1: energy and angular momentum of the massive bodies -------------------------------
+ * swiftest_util_get_potential_energy_flat / _triangular (swiftest_util.f90:1291-1394): both add the same terms, one
+ * kernel serves both.  rb(3,npl) barycentric positions, mass = Gmass/GU; lmask may be NULL (all bodies). */
+int swcu_util_get_potential_energy(swcu_context *ctx, int32_t npl, const int32_t *lmask, double GMcb,
+                                   const double *Gmass, const double *mass, const double *rb, double *pe);
+/* swiftest_util_get_energy_and_momentum_system (:1172-1288) without rotation / oblateness:
+ * out8 = { ke_orbit, pe, be, te, L_orbit(1:3), GMtot } */
+int swcu_util_get_energy_and_momentum(swcu_context *ctx, int32_t npl, const int32_t *lmask, double GMcb, double mass_cb,
+                                      const double *rbcb, const double *vbcb, const double *Gmass, const double *mass,
+                                      const double *radius, const double *rb, const double *vb, int32_t lclose,
+                                      double *out8);
+
 /* ------------------------------------------------------------------------------------------------------
  * Multi-GPU: one process (context) per GPU.  pl-pl gravity is split by contiguous i-slices with an NCCL
  * allgather of the drifted positions (and velocities) each step; test particles are block-partitioned like

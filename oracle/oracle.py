@@ -58,6 +58,20 @@ class Oracle:
         L.swo_kick_tri_abs_scale.argtypes = [i32, i32, p, p, p, C.c_int, p]
         L.swo_kick_all_tp.argtypes = [i32, i32, p, p, p, p, p]
         L.swo_symba_kick_subtract_enc.argtypes = [i32, i64, p, p, p, p, p, p]
+        L.swo_coord_vh2vb_pl.argtypes = [i32, d, p, p, p, p]
+        L.swo_coord_vb2vh_pl.argtypes = [i32, d, p, p, p, p, p]
+        L.swo_coord_vh2vb_tp.argtypes = [i32, p, p, p, p]
+        L.swo_coord_vb2vh_tp.argtypes = [i32, p, p, p, p]
+        L.swo_coord_h2b_pl.argtypes = [i32, d, p, p, p, p, p, p, p, p]
+        L.swo_helio_drift_linear_pl.argtypes = [i32, d, p, p, p, d, p, p]
+        L.swo_helio_drift_linear_tp.argtypes = [i32, p, p, d, p]
+        L.swo_helio_kick_vb.argtypes = [i32, p, p, d, p]
+        L.swo_helio_step_pl.argtypes = [i32, d, p, p, C.c_int, p, p, d, p, p, p, p, p, p, p, p, p, p]
+        L.swo_helio_step_tp.argtypes = [i32, i32, d, p, p, p, p, p, p, p, d, p, p, p, p, p]
+        L.swo_whm_kick_getacch_ah0.argtypes = [i32, p, p, p]
+        L.swo_get_potential_energy_tri.argtypes = [i32, p, d, p, p, p, p]
+        L.swo_get_potential_energy_flat.argtypes = [i32, i64, p, p, d, p, p, p, p]
+        L.swo_get_energy_and_momentum.argtypes = [i32, p, d, d, p, p, p, p, p, p, p, C.c_int, C.c_int, p]
         L.swo_omp_kick_flat_rad_pl.argtypes = [i32, i32, p, p, p, p]
         L.swo_omp_kick_tri_rad_pl.argtypes = [i32, i32, p, p, p, p]
         L.swo_omp_kick_tri_rad_pl_rows.argtypes = [i32, i32, i32, i32, p, p, p, p]
@@ -204,6 +218,114 @@ class Oracle:
         a, b = C.c_int32(0), C.c_int32(0)
         self.lib.swo_encounter_check_one(xr, yr, zr, vxr, vyr, vzr, renc, dt, C.byref(a), C.byref(b))
         return bool(a.value), bool(b.value)
+
+    # ---- swiftest_oracle_step.c: integrator glue and energy sums ----
+    @staticmethod
+    def _a(x):
+        return None if x is None else x.ctypes.data
+
+    def coord_vh2vb_pl(self, GMcb, Gmass, vh):
+        Gmass, vh = _c(Gmass), _c(vh)
+        vb, vbcb = np.zeros_like(vh), np.zeros(3)
+        self.lib.swo_coord_vh2vb_pl(len(Gmass), GMcb, self._a(Gmass), self._a(vh), self._a(vb), self._a(vbcb))
+        return vb, vbcb
+
+    def coord_vb2vh_pl(self, GMcb, Gmass, vb, lactive=None):
+        Gmass, vb = _c(Gmass), _c(vb)
+        la = None if lactive is None else _c(lactive, _i32)
+        vh, vbcb = np.zeros_like(vb), np.zeros(3)
+        self.lib.swo_coord_vb2vh_pl(len(Gmass), GMcb, self._a(Gmass), self._a(la), self._a(vb), self._a(vh), self._a(vbcb))
+        return vh, vbcb
+
+    def coord_h2b_pl(self, GMcb, Gmass, rh, vh, lactive=None):
+        Gmass, rh, vh = _c(Gmass), _c(rh), _c(vh)
+        la = None if lactive is None else _c(lactive, _i32)
+        rb, vb, rbcb, vbcb = np.zeros_like(rh), np.zeros_like(vh), np.zeros(3), np.zeros(3)
+        self.lib.swo_coord_h2b_pl(len(Gmass), GMcb, self._a(Gmass), self._a(la), self._a(rh), self._a(vh), self._a(rb),
+                                  self._a(vb), self._a(rbcb), self._a(vbcb))
+        return rb, vb, rbcb, vbcb
+
+    def helio_drift_linear_pl(self, GMcb, Gmass, vb, rh, dt, lmask=None):
+        Gmass, vb, rh = _c(Gmass), _c(vb), _c(rh).copy()
+        lm = None if lmask is None else _c(lmask, _i32)
+        pt = np.zeros(3)
+        self.lib.swo_helio_drift_linear_pl(len(Gmass), GMcb, self._a(Gmass), self._a(vb), self._a(lm), dt, self._a(rh),
+                                           self._a(pt))
+        return rh, pt
+
+    def helio_kick_vb(self, ah, vb, dt, lmask=None):
+        ah, vb = _c(ah), _c(vb).copy()
+        lm = None if lmask is None else _c(lmask, _i32)
+        self.lib.swo_helio_kick_vb(len(ah), self._a(lm), self._a(ah), dt, self._a(vb))
+        return vb
+
+    def helio_step_pl(self, st, GMcb, Gmass, radius, dt, lflat=False, lmask=None):
+        """st: dict with rh, vh, vb, lfirst (updated in place).  Returns iflag."""
+        n = len(Gmass)
+        Gmass = _c(Gmass)
+        radius = None if radius is None else _c(radius)
+        lm = None if lmask is None else _c(lmask, _i32)
+        for k in ("rh", "vh", "vb"):
+            st[k] = _c(st[k])
+        for k in ("ah", "rbeg", "rend"):
+            st[k] = np.zeros((n, 3))
+        for k in ("ptbeg", "ptend", "vbcb"):
+            st.setdefault(k, np.zeros(3))
+        lf = C.c_int32(int(st.get("lfirst", True)))
+        iflag = np.zeros(n, _i32)
+        self.lib.swo_helio_step_pl(n, GMcb, self._a(Gmass), self._a(radius), int(lflat), self._a(lm), C.byref(lf), dt,
+                                   self._a(st["rh"]), self._a(st["vh"]), self._a(st["vb"]), self._a(st["ah"]),
+                                   self._a(st["rbeg"]), self._a(st["rend"]), self._a(st["ptbeg"]), self._a(st["ptend"]),
+                                   self._a(st["vbcb"]), self._a(iflag))
+        st["lfirst"] = bool(lf.value)
+        return iflag
+
+    def helio_step_tp(self, st, pl, GMcb, GMpl, dt, lmask=None):
+        """st: tp state dict (rh, vh, vb, lfirst); pl: the planets' state dict after helio_step_pl of the same step."""
+        n = len(st["rh"])
+        GMpl = _c(GMpl)
+        lm = None if lmask is None else _c(lmask, _i32)
+        for k in ("rh", "vh", "vb"):
+            st[k] = _c(st[k])
+        st["ah"] = np.zeros((n, 3))
+        lf = C.c_int32(int(st.get("lfirst", True)))
+        iflag = np.zeros(n, _i32)
+        self.lib.swo_helio_step_tp(n, len(GMpl), GMcb, self._a(GMpl), self._a(pl["rbeg"]), self._a(pl["rend"]),
+                                   self._a(pl["ptbeg"]), self._a(pl["ptend"]), self._a(lm), C.byref(lf), dt,
+                                   self._a(st["rh"]), self._a(st["vh"]), self._a(st["vb"]), self._a(st["ah"]),
+                                   self._a(iflag))
+        st["lfirst"] = bool(lf.value)
+        return iflag
+
+    def whm_kick_getacch_ah0(self, mu, rhp):
+        mu, rhp = _c(mu), _c(rhp)
+        out = np.zeros(3)
+        self.lib.swo_whm_kick_getacch_ah0(len(mu), self._a(mu), self._a(rhp), self._a(out))
+        return out
+
+    def get_potential_energy(self, GMcb, Gmass, mass, rb, lmask=None, flat=False):
+        Gmass, mass, rb = _c(Gmass), _c(mass), _c(rb)
+        lm = None if lmask is None else _c(lmask, _i32)
+        n = len(Gmass)
+        pe = C.c_double()
+        if flat:
+            self.lib.swo_get_potential_energy_flat(n, n * (n - 1) // 2, None, self._a(lm), GMcb, self._a(Gmass),
+                                                   self._a(mass), self._a(rb), C.byref(pe))
+        else:
+            self.lib.swo_get_potential_energy_tri(n, self._a(lm), GMcb, self._a(Gmass), self._a(mass), self._a(rb),
+                                                  C.byref(pe))
+        return pe.value
+
+    def get_energy_and_momentum(self, GMcb, mass_cb, rbcb, vbcb, Gmass, mass, radius, rb, vb, lmask=None, lclose=True,
+                                flat=False):
+        Gmass, mass, radius, rb, vb = _c(Gmass), _c(mass), _c(radius), _c(rb), _c(vb)
+        rbcb, vbcb = _c(rbcb), _c(vbcb)
+        lm = None if lmask is None else _c(lmask, _i32)
+        out = np.zeros(8)
+        self.lib.swo_get_energy_and_momentum(len(Gmass), self._a(lm), GMcb, mass_cb, self._a(rbcb), self._a(vbcb),
+                                             self._a(Gmass), self._a(mass), self._a(radius), self._a(rb), self._a(vb),
+                                             int(lclose), int(flat), self._a(out))
+        return dict(ke_orbit=out[0], pe=out[1], be=out[2], te=out[3], L_orbit=out[4:7].copy(), GMtot=out[7])
 
 
 _cache = {}

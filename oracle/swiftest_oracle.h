@@ -102,6 +102,35 @@ void swo_encounter_fetch(int32_t *index1, int32_t *index2, int32_t *lvdotr);
 /* statistics of the last sort-and-sweep call: sum_i nbox_i over loverlap bodies (broad-phase candidates) */
 int64_t swo_encounter_last_nbox_total(void);
 
+/* ---- the O(N) glue around the hot path and the energy sums (swiftest_oracle_step.c) ---- */
+void swo_coord_vh2vb_pl(int32_t npl, double GMcb, const double *Gmass, const double *vh, double *vb, double *vbcb);
+void swo_coord_vb2vh_pl(int32_t npl, double GMcb, const double *Gmass, const int32_t *lactive, const double *vb,
+                        double *vh, double *vbcb);
+void swo_coord_vh2vb_tp(int32_t ntp, const int32_t *lmask, const double *vbcb, const double *vh, double *vb);
+void swo_coord_vb2vh_tp(int32_t ntp, const int32_t *lmask, const double *vbcb, const double *vb, double *vh);
+void swo_coord_h2b_pl(int32_t npl, double GMcb, const double *Gmass, const int32_t *lactive, const double *rh,
+                      const double *vh, double *rb, double *vb, double *rbcb, double *vbcb);
+void swo_helio_drift_linear_pl(int32_t npl, double GMcb, const double *Gmass, const double *vb, const int32_t *lmask,
+                               double dt, double *rh, double *pt);
+void swo_helio_drift_linear_tp(int32_t ntp, const int32_t *lmask, const double *pt, double dt, double *rh);
+void swo_helio_kick_vb(int32_t n, const int32_t *lmask, const double *ah, double dt, double *vb);
+void swo_helio_step_pl(int32_t npl, double GMcb, const double *Gmass, const double *radius, int lflat,
+                       const int32_t *lmask, int32_t *lfirst, double dt, double *rh, double *vh, double *vb,
+                       double *ah, double *rbeg, double *rend, double *ptbeg, double *ptend, double *vbcb,
+                       int32_t *iflag);
+void swo_helio_step_tp(int32_t ntp, int32_t npl, double GMcb, const double *GMpl, const double *rbeg,
+                       const double *rend, const double *ptbeg, const double *ptend, const int32_t *lmask,
+                       int32_t *lfirst, double dt, double *rh, double *vh, double *vb, double *ah, int32_t *iflag);
+void swo_whm_kick_getacch_ah0(int32_t n, const double *mu, const double *rhp, double *ah0);
+void swo_get_potential_energy_tri(int32_t npl, const int32_t *lmask, double GMcb, const double *Gmass,
+                                  const double *mass, const double *rb, double *pe);
+void swo_get_potential_energy_flat(int32_t npl, int64_t nplpl, const int32_t *k_plpl, const int32_t *lmask,
+                                   double GMcb, const double *Gmass, const double *mass, const double *rb, double *pe);
+/* out[0] ke_orbit, out[1] pe, out[2] be, out[3] te, out[4..6] L_orbit, out[7] GMtot */
+void swo_get_energy_and_momentum(int32_t npl, const int32_t *lmask, double GMcb, double mass_cb, const double *rbcb,
+                                 const double *vbcb, const double *Gmass, const double *mass, const double *radius,
+                                 const double *rb, const double *vb, int lclose, int lflat, double *out);
+
 #ifdef __cplusplus
 }
 #endif

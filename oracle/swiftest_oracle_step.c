@@ -1,0 +1,326 @@
+/*
+ * swiftest_oracle_step.c -- CPU restatement of the O(N) glue around the hot path and of the energy sums
+ * (SURVEY.md section 8f, ranks 1 and 2).  TEST INFRASTRUCTURE ONLY, see swiftest_oracle.h.
+ *
+ * PARITY STATUS: UNPINNED (the reference holds no function-level vectors for these routines); the only pins are the
+ * system-level conservation thresholds of tests/test_swiftest.py:119-121, which tests/test_oracle.py re-checks on
+ * the restated democratic-heliocentric step.
+ *
+ * Every sum below runs in the order the reference's serial loop / `sum` intrinsic runs it (first to last index unless
+ * noted), one IEEE operation per Fortran operation (-ffp-contract=off).  `norm2` is restated as sqrt(x*x+y*y+z*z)
+ * (libgfortran's norm2 rescales to avoid overflow and may differ in the last place; the CUDA path is compared with a
+ * tolerance for every quantity that passes through a long sum).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "swiftest_oracle.h"
+
+/* swiftest_util_coord_vh2vb_pl, swiftest/swiftest_util.f90:424-459 (no mask: every body counts) */
+void swo_coord_vh2vb_pl(int32_t npl, double GMcb, const double *Gmass, const double *vh, double *vb, double *vbcb)
+{
+    if (npl <= 0) return;
+    double s = 0.0;
+    for (int32_t i = 0; i < npl; ++i) s += Gmass[i];
+    const double Gmtot = GMcb + s;
+    vbcb[0] = vbcb[1] = vbcb[2] = 0.0;
+    for (int32_t i = 0; i < npl; ++i)
+        for (int k = 0; k < 3; ++k) vbcb[k] = vbcb[k] - Gmass[i] * vh[3 * i + k];
+    for (int k = 0; k < 3; ++k) vbcb[k] = vbcb[k] / Gmtot;
+    for (int32_t i = 0; i < npl; ++i)
+        for (int k = 0; k < 3; ++k) vb[3 * i + k] = vh[3 * i + k] + vbcb[k];
+}
+
+/* swiftest_util_coord_vb2vh_pl, swiftest_util.f90:363-395: the loop runs from npl DOWN to 1 and divides every term
+ * by GMcb; lactive(i) = status(i) /= INACTIVE */
+void swo_coord_vb2vh_pl(int32_t npl, double GMcb, const double *Gmass, const int32_t *lactive, const double *vb,
+                        double *vh, double *vbcb)
+{
+    if (npl <= 0) return;
+    vbcb[0] = vbcb[1] = vbcb[2] = 0.0;
+    for (int32_t i = npl - 1; i >= 0; --i) {
+        if (lactive && !lactive[i]) continue;
+        for (int k = 0; k < 3; ++k) vbcb[k] = vbcb[k] - Gmass[i] * vb[3 * i + k] / GMcb;
+    }
+    for (int32_t i = 0; i < npl; ++i)
+        for (int k = 0; k < 3; ++k) vh[3 * i + k] = vb[3 * i + k] - vbcb[k];
+}
+
+/* swiftest_util_coord_vh2vb_tp :462-485 and _vb2vh_tp :398-421 */
+void swo_coord_vh2vb_tp(int32_t ntp, const int32_t *lmask, const double *vbcb, const double *vh, double *vb)
+{
+    for (int32_t i = 0; i < ntp; ++i) {
+        if (lmask && !lmask[i]) continue;
+        for (int k = 0; k < 3; ++k) vb[3 * i + k] = vh[3 * i + k] + vbcb[k];
+    }
+}
+void swo_coord_vb2vh_tp(int32_t ntp, const int32_t *lmask, const double *vbcb, const double *vb, double *vh)
+{
+    for (int32_t i = 0; i < ntp; ++i) {
+        if (lmask && !lmask[i]) continue;
+        for (int k = 0; k < 3; ++k) vh[3 * i + k] = vb[3 * i + k] - vbcb[k];
+    }
+}
+
+/* swiftest_util_coord_h2b_pl :228-265 (position and velocity; inactive bodies skipped) */
+void swo_coord_h2b_pl(int32_t npl, double GMcb, const double *Gmass, const int32_t *lactive, const double *rh,
+                      const double *vh, double *rb, double *vb, double *rbcb, double *vbcb)
+{
+    if (npl <= 0) return;
+    double Gmtot = GMcb, xt[3] = {0, 0, 0}, vt[3] = {0, 0, 0};
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lactive && !lactive[i]) continue;
+        Gmtot = Gmtot + Gmass[i];
+        for (int k = 0; k < 3; ++k) {
+            xt[k] = xt[k] + Gmass[i] * rh[3 * i + k];
+            vt[k] = vt[k] + Gmass[i] * vh[3 * i + k];
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        rbcb[k] = -xt[k] / Gmtot;
+        vbcb[k] = -vt[k] / Gmtot;
+    }
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lactive && !lactive[i]) continue;
+        for (int k = 0; k < 3; ++k) {
+            rb[3 * i + k] = rh[3 * i + k] + rbcb[k];
+            vb[3 * i + k] = vh[3 * i + k] + vbcb[k];
+        }
+    }
+}
+
+/* helio_drift_linear_pl, helio/helio_drift.f90:129-165 (+ _one :82-103, _all :106-126) */
+void swo_helio_drift_linear_pl(int32_t npl, double GMcb, const double *Gmass, const double *vb, const int32_t *lmask,
+                               double dt, double *rh, double *pt)
+{
+    if (npl <= 0) return;
+    for (int k = 0; k < 3; ++k) {
+        double s = 0.0;
+        for (int32_t i = 0; i < npl; ++i)
+            if (!lmask || lmask[i]) s += Gmass[i] * vb[3 * i + k];
+        pt[k] = s / GMcb;
+    }
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lmask && !lmask[i]) continue;
+        for (int k = 0; k < 3; ++k) rh[3 * i + k] = rh[3 * i + k] + pt[k] * dt;
+    }
+}
+
+/* helio_drift_linear_tp, helio_drift.f90:168-200 */
+void swo_helio_drift_linear_tp(int32_t ntp, const int32_t *lmask, const double *pt, double dt, double *rh)
+{
+    for (int32_t i = 0; i < ntp; ++i) {
+        if (lmask && !lmask[i]) continue;
+        for (int k = 0; k < 3; ++k) rh[3 * i + k] = rh[3 * i + k] + pt[k] * dt;
+    }
+}
+
+/* the velocity update of helio_kick_vb_pl / _tp, helio/helio_kick.f90:120-128, 160-165 */
+void swo_helio_kick_vb(int32_t n, const int32_t *lmask, const double *ah, double dt, double *vb)
+{
+    for (int32_t i = 0; i < n; ++i) {
+        if (lmask && !lmask[i]) continue;
+        for (int k = 0; k < 3; ++k) vb[3 * i + k] = vb[3 * i + k] + ah[3 * i + k] * dt;
+    }
+}
+
+/* helio_kick_vb_pl, helio_kick.f90:91-132: ah = 0; helio_kick_getacch_pl (:14-54, interaction term only);
+ * set_beg_end; vb += ah*dt */
+static void helio_kick_vb_pl(int32_t npl, const double *Gmass, const double *radius, int lflat, const int32_t *lmask,
+                             double dt, const double *rh, double *vb, double *ah, double *rsave)
+{
+    memset(ah, 0, sizeof(double) * 3 * (size_t)npl);
+    if (lflat) { /* swiftest_kick_getacch_int_pl, swiftest_kick.f90:29-33 */
+        const int64_t nplpl = (int64_t)npl * (npl - 1) / 2;
+        if (radius) swo_kick_flat_rad_pl(npl, nplpl, NULL, rh, Gmass, radius, ah);
+        else swo_kick_flat_norad_pl(npl, nplpl, NULL, rh, Gmass, ah);
+    } else { /* :35-39 */
+        if (radius) swo_kick_tri_rad_pl(npl, npl, rh, Gmass, radius, ah);
+        else swo_kick_tri_norad_pl(npl, npl, rh, Gmass, ah);
+    }
+    if (rsave) memcpy(rsave, rh, sizeof(double) * 3 * (size_t)npl);
+    swo_helio_kick_vb(npl, lmask, ah, dt, vb);
+}
+
+/* helio_step_pl, helio/helio_step.f90:37-78 (no GR, no oblateness, no user force).
+ * radius == NULL selects the norad variants (param%lclose false).  *lfirst is cleared after the first call. */
+void swo_helio_step_pl(int32_t npl, double GMcb, const double *Gmass, const double *radius, int lflat,
+                       const int32_t *lmask, int32_t *lfirst, double dt, double *rh, double *vh, double *vb,
+                       double *ah, double *rbeg, double *rend, double *ptbeg, double *ptend, double *vbcb,
+                       int32_t *iflag)
+{
+    if (npl <= 0) return;
+    const double dth = 0.5 * dt;
+    if (*lfirst) {
+        swo_coord_vh2vb_pl(npl, GMcb, Gmass, vh, vb, vbcb);
+        *lfirst = 0;
+    }
+    swo_helio_drift_linear_pl(npl, GMcb, Gmass, vb, lmask, dth, rh, ptbeg);
+    helio_kick_vb_pl(npl, Gmass, radius, lflat, lmask, dth, rh, vb, ah, rbeg);
+    { /* helio_drift_body, helio_drift.f90:14-54: mu(:) = cb%Gmass */
+        double *mu = (double *)malloc(sizeof(double) * (size_t)npl);
+        int32_t *mask1 = NULL;
+        if (!lmask) {
+            mask1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)npl);
+            for (int32_t i = 0; i < npl; ++i) mask1[i] = 1;
+        }
+        for (int32_t i = 0; i < npl; ++i) mu[i] = GMcb;
+        for (int32_t i = 0; i < npl; ++i) iflag[i] = 0;
+        swo_drift_all(mu, rh, vb, npl, 0, 0.0, dt, lmask ? lmask : mask1, iflag);
+        free(mu);
+        free(mask1);
+    }
+    helio_kick_vb_pl(npl, Gmass, radius, lflat, lmask, dth, rh, vb, ah, rend);
+    swo_helio_drift_linear_pl(npl, GMcb, Gmass, vb, lmask, dth, rh, ptend);
+    swo_coord_vb2vh_pl(npl, GMcb, Gmass, NULL, vb, vh, vbcb);
+}
+
+/* helio_step_tp, helio_step.f90:81-123 with helio_kick_vb_tp (helio_kick.f90:135-169) and helio_kick_getacch_tp
+ * (:57-88, interaction term only): the begin kick uses pl%rbeg, the end kick pl%rend */
+void swo_helio_step_tp(int32_t ntp, int32_t npl, double GMcb, const double *GMpl, const double *rbeg,
+                       const double *rend, const double *ptbeg, const double *ptend, const int32_t *lmask,
+                       int32_t *lfirst, double dt, double *rh, double *vh, double *vb, double *ah, int32_t *iflag)
+{
+    if (ntp <= 0) return;
+    const double dth = 0.5 * dt;
+    double m[3];
+    int32_t *mask1 = NULL;
+    if (!lmask) {
+        mask1 = (int32_t *)malloc(sizeof(int32_t) * (size_t)ntp);
+        for (int32_t i = 0; i < ntp; ++i) mask1[i] = 1;
+        lmask = mask1;
+    }
+    if (*lfirst) {
+        for (int k = 0; k < 3; ++k) m[k] = -ptbeg[k];
+        swo_coord_vh2vb_tp(ntp, lmask, m, vh, vb);
+        *lfirst = 0;
+    }
+    swo_helio_drift_linear_tp(ntp, lmask, ptbeg, dth, rh);
+    memset(ah, 0, sizeof(double) * 3 * (size_t)ntp);
+    if (npl > 0) swo_kick_all_tp(ntp, npl, rh, rbeg, GMpl, lmask, ah);
+    swo_helio_kick_vb(ntp, lmask, ah, dth, vb);
+    {
+        double *mu = (double *)malloc(sizeof(double) * (size_t)ntp);
+        for (int32_t i = 0; i < ntp; ++i) mu[i] = GMcb;
+        for (int32_t i = 0; i < ntp; ++i) iflag[i] = 0;
+        swo_drift_all(mu, rh, vb, ntp, 0, 0.0, dt, lmask, iflag);
+        free(mu);
+    }
+    memset(ah, 0, sizeof(double) * 3 * (size_t)ntp);
+    if (npl > 0) swo_kick_all_tp(ntp, npl, rh, rend, GMpl, lmask, ah);
+    swo_helio_kick_vb(ntp, lmask, ah, dth, vb);
+    swo_helio_drift_linear_tp(ntp, lmask, ptend, dth, rh);
+    for (int k = 0; k < 3; ++k) m[k] = -ptend[k];
+    swo_coord_vb2vh_tp(ntp, lmask, m, vb, vh);
+    free(mask1);
+}
+
+/* whm_kick_getacch_ah0, whm/whm_kick.f90:124-149 */
+void swo_whm_kick_getacch_ah0(int32_t n, const double *mu, const double *rhp, double *ah0)
+{
+    ah0[0] = ah0[1] = ah0[2] = 0.0;
+    for (int32_t i = 0; i < n; ++i) {
+        const double x = rhp[3 * i], y = rhp[3 * i + 1], z = rhp[3 * i + 2];
+        const double r2 = x * x + y * y + z * z;
+        const double ir3h = 1.0 / (r2 * sqrt(r2));
+        const double fac = mu[i] * ir3h;
+        ah0[0] = ah0[0] - fac * x;
+        ah0[1] = ah0[1] - fac * y;
+        ah0[2] = ah0[2] - fac * z;
+    }
+}
+
+/* swiftest_util_get_potential_energy_triangular, swiftest_util.f90:1344-1394 */
+void swo_get_potential_energy_tri(int32_t npl, const int32_t *lmask, double GMcb, const double *Gmass,
+                                  const double *mass, const double *rb, double *pe_out)
+{
+    double pe = 0.0;
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lmask && !lmask[i]) continue;
+        double row = 0.0; /* sum(pepl(i+1:npl), lmask(i+1:npl)) */
+        for (int32_t j = i + 1; j < npl; ++j) {
+            if (lmask && !lmask[j]) continue;
+            const double dx = rb[3 * i] - rb[3 * j], dy = rb[3 * i + 1] - rb[3 * j + 1], dz = rb[3 * i + 2] - rb[3 * j + 2];
+            row += -(Gmass[i] * mass[j]) / sqrt(dx * dx + dy * dy + dz * dz);
+        }
+        pe = pe + row;
+    }
+    double cb = 0.0; /* sum(pecb(1:npl), lmask(1:npl)), pecb(i) = -GMcb*mass(i)/norm2(rb(:,i)) */
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lmask && !lmask[i]) continue;
+        const double x = rb[3 * i], y = rb[3 * i + 1], z = rb[3 * i + 2];
+        cb += -GMcb * mass[i] / sqrt(x * x + y * y + z * z);
+    }
+    *pe_out = pe + cb;
+}
+
+/* swiftest_util_get_potential_energy_flat, swiftest_util.f90:1291-1341; k_plpl == NULL: canonical flattened order */
+void swo_get_potential_energy_flat(int32_t npl, int64_t nplpl, const int32_t *k_plpl, const int32_t *lmask,
+                                   double GMcb, const double *Gmass, const double *mass, const double *rb,
+                                   double *pe_out)
+{
+    double pp = 0.0;
+    for (int64_t k = 1; k <= nplpl; ++k) {
+        int32_t i, j;
+        if (k_plpl) {
+            i = k_plpl[2 * (k - 1)];
+            j = k_plpl[2 * (k - 1) + 1];
+        } else {
+            swo_flatten_k_to_ij(npl, k, &i, &j);
+        }
+        --i;
+        --j;
+        if (lmask && !(lmask[i] && lmask[j])) continue;
+        const double dx = rb[3 * i] - rb[3 * j], dy = rb[3 * i + 1] - rb[3 * j + 1], dz = rb[3 * i + 2] - rb[3 * j + 2];
+        pp += -(Gmass[i] * mass[j]) / sqrt(dx * dx + dy * dy + dz * dz);
+    }
+    double cb = 0.0;
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lmask && !lmask[i]) continue;
+        const double x = rb[3 * i], y = rb[3 * i + 1], z = rb[3 * i + 2];
+        cb += -GMcb * mass[i] / sqrt(x * x + y * y + z * z);
+    }
+    *pe_out = pp + cb;
+}
+
+/* swiftest_util_get_energy_and_momentum_system, swiftest_util.f90:1172-1288, lrotation = .false., no oblateness.
+ * out[0] ke_orbit, out[1] pe, out[2] be, out[3] te, out[4..6] L_orbit, out[7] GMtot */
+void swo_get_energy_and_momentum(int32_t npl, const int32_t *lmask, double GMcb, double mass_cb, const double *rbcb,
+                                 const double *vbcb, const double *Gmass, const double *mass, const double *radius,
+                                 const double *rb, const double *vb, int lclose, int lflat, double *out)
+{
+    double gms = 0.0;
+    for (int32_t i = 0; i < npl; ++i)
+        if (!lmask || lmask[i]) gms += Gmass[i];
+    out[7] = GMcb + gms;
+    const double kecb = mass_cb * (vbcb[0] * vbcb[0] + vbcb[1] * vbcb[1] + vbcb[2] * vbcb[2]);
+    double Lcb[3];
+    Lcb[0] = mass_cb * (rbcb[1] * vbcb[2] - rbcb[2] * vbcb[1]);
+    Lcb[1] = mass_cb * (rbcb[2] * vbcb[0] - rbcb[0] * vbcb[2]);
+    Lcb[2] = mass_cb * (rbcb[0] * vbcb[1] - rbcb[1] * vbcb[0]);
+    double ke = 0.0, L[3] = {0, 0, 0};
+    for (int32_t i = 0; i < npl; ++i) {
+        if (lmask && !lmask[i]) continue;
+        const double *r = rb + 3 * i, *v = vb + 3 * i;
+        const double h0 = r[1] * v[2] - r[2] * v[1];
+        const double h1 = r[2] * v[0] - r[0] * v[2];
+        const double h2 = r[0] * v[1] - r[1] * v[0];
+        L[0] += mass[i] * h0;
+        L[1] += mass[i] * h1;
+        L[2] += mass[i] * h2;
+        ke += mass[i] * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    }
+    double pe;
+    if (lflat) swo_get_potential_energy_flat(npl, (int64_t)npl * (npl - 1) / 2, NULL, lmask, GMcb, Gmass, mass, rb, &pe);
+    else swo_get_potential_energy_tri(npl, lmask, GMcb, Gmass, mass, rb, &pe);
+    out[0] = 0.5 * (kecb + ke);
+    out[1] = pe;
+    for (int k = 0; k < 3; ++k) out[4 + k] = Lcb[k] + L[k];
+    double be = 0.0;
+    if (lclose)
+        for (int32_t i = 0; i < npl; ++i)
+            if (!lmask || lmask[i]) be += -3 * Gmass[i] * mass[i] / (5 * radius[i]);
+    out[2] = be;
+    out[3] = out[0] + 0.0 + out[1] + out[2];
+}

@@ -63,6 +63,22 @@ def load():
         "swcu_body_drift": [p, i32, d, i32, d, p],
         "swcu_body_kick_velocity": [p, i32, d],
         "swcu_whm_tp_step": [p, d, p, p],
+        "swcu_pl_vh2vb": [p, d, p],
+        "swcu_pl_vb2vh": [p, d, p],
+        "swcu_pl_lindrift": [p, d, d, i32, p],
+        "swcu_tp_lindrift": [p, d, i32],
+        "swcu_cb_set_pt": [p, p, p],
+        "swcu_cb_get_pt": [p, p, p],
+        "swcu_tp_vh2vb": [p, i32],
+        "swcu_tp_vb2vh": [p, i32],
+        "swcu_body_kick_vb": [p, i32, d, i32],
+        "swcu_body_drift_vb": [p, i32, d, d, p],
+        "swcu_body_put_vb": [p, i32, p],
+        "swcu_body_get_vb": [p, i32, p, p, p],
+        "swcu_helio_step_pl": [p, d, d, i32, i32, i32, p],
+        "swcu_helio_step_tp": [p, d, d, i32, p],
+        "swcu_util_get_potential_energy": [p, i32, p, d, p, p, p, p],
+        "swcu_util_get_energy_and_momentum": [p, i32, p, d, d, p, p, p, p, p, p, p, i32, p],
         "swcu_pl_encounter_check": [p, d, p],
         "swcu_tp_encounter_check": [p, d, p],
         "swcu_comm_unique_id": [p, p],

@@ -261,6 +261,96 @@ class Context:
         self._ck(self._L.swcu_tp_encounter_check(self._h, float(dt), C.byref(n)))
         return self._fetch(n.value) if fetch else n.value
 
+    # ---- the O(N) glue of the democratic-heliocentric step (helio/helio_step.f90, swiftest_util.f90:363-485) ----
+    def _vec3_out(self, fn, *args, want=True):
+        out = np.zeros(3, _f64)
+        self._ck(fn(self._h, *args, _ptr(out) if want else None))
+        return out if want else None
+
+    def pl_vh2vb(self, GMcb, want=True):
+        """swiftest_util_coord_vh2vb_pl: vb = vh + vbcb on the resident planets; returns vbcb."""
+        return self._vec3_out(self._L.swcu_pl_vh2vb, float(GMcb), want=want)
+
+    def pl_vb2vh(self, GMcb, want=True):
+        """swiftest_util_coord_vb2vh_pl: vh = vb - vbcb; returns vbcb."""
+        return self._vec3_out(self._L.swcu_pl_vb2vh, float(GMcb), want=want)
+
+    def pl_lindrift(self, GMcb, dt, lbeg, want=True):
+        """helio_drift_linear_pl: rh += pt*dt with pt = sum(Gm*vb, lmask)/GMcb; returns pt (kept as ptbeg/ptend)."""
+        return self._vec3_out(self._L.swcu_pl_lindrift, float(GMcb), float(dt), int(bool(lbeg)), want=want)
+
+    def tp_lindrift(self, dt, lbeg):
+        self._ck(self._L.swcu_tp_lindrift(self._h, float(dt), int(bool(lbeg))))
+
+    def cb_set_pt(self, ptbeg=None, ptend=None):
+        ptbeg = None if ptbeg is None else _vec(ptbeg, 3)
+        ptend = None if ptend is None else _vec(ptend, 3)
+        self._ck(self._L.swcu_cb_set_pt(self._h, _ptr(ptbeg), _ptr(ptend)))
+
+    def cb_get_pt(self):
+        b, e = np.zeros(3, _f64), np.zeros(3, _f64)
+        self._ck(self._L.swcu_cb_get_pt(self._h, _ptr(b), _ptr(e)))
+        return b, e
+
+    def tp_vh2vb(self, lbeg=True):
+        self._ck(self._L.swcu_tp_vh2vb(self._h, int(bool(lbeg))))
+
+    def tp_vb2vh(self, lbeg=False):
+        self._ck(self._L.swcu_tp_vb2vh(self._h, int(bool(lbeg))))
+
+    def body_kick_vb(self, kind, dt, lbeg):
+        self._ck(self._L.swcu_body_kick_vb(self._h, kind, float(dt), int(bool(lbeg))))
+
+    def body_drift_vb(self, kind, GMcb, dt, want_nfail=True):
+        nf = C.c_int32()
+        self._ck(self._L.swcu_body_drift_vb(self._h, kind, float(GMcb), float(dt), C.byref(nf) if want_nfail else None))
+        return nf.value
+
+    def body_put_vb(self, kind, vb):
+        vb = _vec3(vb, self.body_count(kind)[0])
+        self._ck(self._L.swcu_body_put_vb(self._h, kind, _ptr(vb)))
+
+    def body_get_vb(self, kind, vb=True, rbeg=False, rend=False):
+        n = self.body_count(kind)[0]
+        res = {k: np.empty((n, 3), _f64) for k, w in (("vb", vb), ("rbeg", rbeg), ("rend", rend)) if w}
+        self._ck(self._L.swcu_body_get_vb(self._h, kind, _ptr(res.get("vb")), _ptr(res.get("rbeg")), _ptr(res.get("rend"))))
+        return res
+
+    def helio_step_pl(self, GMcb, dt, loop_variant=LOOP_AUTO, lclose=True, lfirst=False, want_nfail=True):
+        """helio_step_pl on the resident planets; nothing but the drift-failure count crosses PCIe."""
+        nf = C.c_int32()
+        self._ck(self._L.swcu_helio_step_pl(self._h, float(GMcb), float(dt), loop_variant, int(bool(lclose)),
+                                            int(bool(lfirst)), C.byref(nf) if want_nfail else None))
+        return nf.value
+
+    def helio_step_tp(self, GMcb, dt, lfirst=False, want_nfail=True):
+        """helio_step_tp as one kernel; call after helio_step_pl of the same step (uses its rbeg/rend/ptbeg/ptend)."""
+        nf = C.c_int32()
+        self._ck(self._L.swcu_helio_step_tp(self._h, float(GMcb), float(dt), int(bool(lfirst)),
+                                            C.byref(nf) if want_nfail else None))
+        return nf.value
+
+    # ---- energy and momentum (swiftest_util.f90:1172-1394) ----
+    def util_get_potential_energy(self, npl, lmask, GMcb, Gmass, mass, rb):
+        lmask = None if lmask is None else _vec(lmask, npl, _i32)
+        Gmass, mass, rb = _vec(Gmass, npl), _vec(mass, npl), _vec3(rb, npl)
+        pe = C.c_double()
+        self._ck(self._L.swcu_util_get_potential_energy(self._h, npl, _ptr(lmask), float(GMcb), _ptr(Gmass), _ptr(mass),
+                                                        _ptr(rb), C.byref(pe)))
+        return pe.value
+
+    def util_get_energy_and_momentum(self, npl, lmask, GMcb, mass_cb, rbcb, vbcb, Gmass, mass, radius, rb, vb,
+                                     lclose=True):
+        """Returns dict(ke_orbit, pe, be, te, L_orbit(3), GMtot)."""
+        lmask = None if lmask is None else _vec(lmask, npl, _i32)
+        Gmass, mass, radius = _vec(Gmass, npl), _vec(mass, npl), _vec(radius, npl)
+        rb, vb, rbcb, vbcb = _vec3(rb, npl), _vec3(vb, npl), _vec(rbcb, 3), _vec(vbcb, 3)
+        out = np.zeros(8, _f64)
+        self._ck(self._L.swcu_util_get_energy_and_momentum(
+            self._h, npl, _ptr(lmask), float(GMcb), float(mass_cb), _ptr(rbcb), _ptr(vbcb), _ptr(Gmass), _ptr(mass),
+            _ptr(radius), _ptr(rb), _ptr(vb), int(bool(lclose)), _ptr(out)))
+        return dict(ke_orbit=out[0], pe=out[1], be=out[2], te=out[3], L_orbit=out[4:7].copy(), GMtot=out[7])
+
     # ---- multi-GPU ----
     def comm_unique_id(self):
         buf = (C.c_char * 128)()

@@ -168,6 +168,8 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     ctx->partial.release();
     ctx->scratch64.release();
     ctx->flush.release();
+    ctx->cbs.release();
+    ctx->sumbuf.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
     auto &E = ctx->enc;
@@ -464,6 +466,7 @@ extern "C" int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_
     if (kind == SWCU_PL && (nplm < 0 || nplm > n)) return fail(ctx, SWCU_ERR_ARG, "body_sync: bad nplm=%d (npl=%d)", nplm, n);
     if (b.valid && b.generation == generation && b.n == n) return SWCU_OK;  // nothing changed on the host side
     SWCU_TRY(ensure_body(ctx, b, n));
+    b.helio_ready = false;  // vb, rbeg, rend are re-derived after a re-upload
     b.n = n;
     b.nplm = (kind == SWCU_PL) ? nplm : 0;
     b.slice0 = 0;
@@ -535,11 +538,10 @@ extern "C" int swcu_body_zero_accel(swcu_context *ctx, int32_t kind)
     return fill_f64(ctx, b.az.as<double>(), 0.0, b.n);
 }
 
-extern "C" int swcu_pl_accel_int(swcu_context *ctx, int32_t loop_variant, int32_t lclose)
+namespace swcu {
+int pl_accel_int(swcu_context *ctx, int loop_variant, int lclose)
 {
-    SWCU_TRY(check_ctx(ctx));
     Body &pl = ctx->pl;
-    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_accel_int: pl population not resident");
     if (pl.n == 0) return SWCU_OK;
     int variant = ctx->tune_variant >= 0 ? ctx->tune_variant : loop_variant;
     // AUTO: the third-law kernel measured 1.43x faster than the full-row kernel at npl = 1e5 and is never slower from
@@ -547,6 +549,14 @@ extern "C" int swcu_pl_accel_int(swcu_context *ctx, int32_t loop_variant, int32_
     if (variant == SWCU_LOOP_AUTO) variant = (pl.n >= 1024) ? SWCU_LOOP_FLAT : SWCU_LOOP_TRIANGULAR;
     if (variant == SWCU_LOOP_FLAT) return kick_pl_flat(ctx, pl, lclose != 0, pl.nplm);
     return kick_pl_tri(ctx, pl, lclose != 0, pl.slice0, pl.slice1);
+}
+}  // namespace swcu
+
+extern "C" int swcu_pl_accel_int(swcu_context *ctx, int32_t loop_variant, int32_t lclose)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_accel_int: pl population not resident");
+    return pl_accel_int(ctx, loop_variant, lclose);
 }
 
 extern "C" int swcu_tp_accel_int(swcu_context *ctx)
@@ -629,6 +639,216 @@ extern "C" int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *ne
     if (pl.n == 0 || tp.n == 0) return SWCU_OK;
     SweepList l2 = sweep_list(tp, 0, tp.n, false);
     return encounter_sweep(ctx, sweep_list(pl, 0, pl.n, true), &l2, dt, nenc);
+}
+
+// ======================================================================================================
+// tier 2: the O(N) glue of the democratic-heliocentric step
+// ======================================================================================================
+namespace {
+int fetch_cbs(swcu_context *ctx, int slot, double *out3)
+{
+    if (!out3) return SWCU_OK;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(out3, ctx->cbs.as<double>() + slot, 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+int need_pl(swcu_context *ctx, const char *who)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "%s: pl population not resident", who);
+    return SWCU_OK;
+}
+int need_tp(swcu_context *ctx, const char *who)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->tp.valid) return fail(ctx, SWCU_ERR_STATE, "%s: tp population not resident", who);
+    return SWCU_OK;
+}
+}  // namespace
+
+extern "C" int swcu_pl_vh2vb(swcu_context *ctx, double GMcb, double *vbcb)
+{
+    SWCU_TRY(need_pl(ctx, "pl_vh2vb"));
+    if (ctx->pl.n == 0) return SWCU_OK;
+    SWCU_TRY(pl_vh2vb(ctx, GMcb));
+    return fetch_cbs(ctx, CBS_VBCB, vbcb);
+}
+
+extern "C" int swcu_pl_vb2vh(swcu_context *ctx, double GMcb, double *vbcb)
+{
+    SWCU_TRY(need_pl(ctx, "pl_vb2vh"));
+    if (ctx->pl.n == 0) return SWCU_OK;
+    SWCU_TRY(pl_vb2vh(ctx, GMcb));
+    return fetch_cbs(ctx, CBS_VBCB, vbcb);
+}
+
+extern "C" int swcu_pl_lindrift(swcu_context *ctx, double GMcb, double dt, int32_t lbeg, double *pt)
+{
+    SWCU_TRY(need_pl(ctx, "pl_lindrift"));
+    if (ctx->pl.n == 0) return SWCU_OK;
+    SWCU_TRY(pl_lindrift(ctx, GMcb, dt, lbeg));
+    return fetch_cbs(ctx, lbeg ? CBS_PTBEG : CBS_PTEND, pt);
+}
+
+extern "C" int swcu_cb_set_pt(swcu_context *ctx, const double *ptbeg, const double *ptend)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_TRY(ensure_step_state(ctx));
+    if (ptbeg) SWCU_CUDA(ctx, cudaMemcpyAsync(ctx->cbs.as<double>() + CBS_PTBEG, ptbeg, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    if (ptend) SWCU_CUDA(ctx, cudaMemcpyAsync(ctx->cbs.as<double>() + CBS_PTEND, ptend, 3 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_cb_get_pt(swcu_context *ctx, double *ptbeg, double *ptend)
+{
+    SWCU_TRY(check_ctx(ctx));
+    SWCU_TRY(ensure_step_state(ctx));
+    SWCU_TRY(fetch_cbs(ctx, CBS_PTBEG, ptbeg));
+    return fetch_cbs(ctx, CBS_PTEND, ptend);
+}
+
+extern "C" int swcu_tp_lindrift(swcu_context *ctx, double dt, int32_t lbeg)
+{
+    SWCU_TRY(need_tp(ctx, "tp_lindrift"));
+    return tp_lindrift(ctx, dt, lbeg);
+}
+
+extern "C" int swcu_tp_vh2vb(swcu_context *ctx, int32_t lbeg)
+{
+    SWCU_TRY(need_tp(ctx, "tp_vh2vb"));
+    return tp_vh2vb(ctx, lbeg);
+}
+
+extern "C" int swcu_tp_vb2vh(swcu_context *ctx, int32_t lbeg)
+{
+    SWCU_TRY(need_tp(ctx, "tp_vb2vh"));
+    return tp_vb2vh(ctx, lbeg);
+}
+
+extern "C" int swcu_body_kick_vb(swcu_context *ctx, int32_t kind, double dt, int32_t lbeg)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_kick_vb: population not resident");
+    return kick_vb_save(ctx, b, dt, kind == SWCU_PL ? (lbeg ? 1 : 2) : 0);
+}
+
+extern "C" int swcu_body_drift_vb(swcu_context *ctx, int32_t kind, double GMcb, double dt, int32_t *nfail)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_drift_vb: population not resident");
+    SWCU_TRY(ensure_helio(ctx, b));
+    return drift_bodies(ctx, b, 0, b.n, dt, 0, 0.0, nfail, 1, GMcb);
+}
+
+extern "C" int swcu_body_put_vb(swcu_context *ctx, int32_t kind, const double *vb)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_put_vb: population not resident");
+    if (!vb) return fail(ctx, SWCU_ERR_ARG, "body_put_vb: null array");
+    SWCU_TRY(ensure_helio(ctx, b));
+    SWCU_TRY(upload_vec3(ctx, vb, b.n, 1, b.wx, b.wy, b.wz));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_get_vb(swcu_context *ctx, int32_t kind, double *vb, double *rbeg, double *rend)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_get_vb: population not resident");
+    SWCU_TRY(ensure_helio(ctx, b));
+    if (vb) SWCU_TRY(download_vec3(ctx, vb, b.n, 1, b.wx, b.wy, b.wz));
+    if (rbeg) SWCU_TRY(download_vec3(ctx, rbeg, b.n, 0, b.bx, b.by, b.bz));
+    if (rend) SWCU_TRY(download_vec3(ctx, rend, b.n, 2, b.ex, b.ey, b.ez));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_helio_step_pl(swcu_context *ctx, double GMcb, double dt, int32_t loop_variant, int32_t lclose,
+                                  int32_t lfirst, int32_t *nfail)
+{
+    SWCU_TRY(need_pl(ctx, "helio_step_pl"));
+    if (!(GMcb > 0.0)) return fail(ctx, SWCU_ERR_ARG, "helio_step_pl: GMcb must be positive");
+    return helio_step_pl(ctx, GMcb, dt, loop_variant, lclose, lfirst, nfail);
+}
+
+extern "C" int swcu_helio_step_tp(swcu_context *ctx, double GMcb, double dt, int32_t lfirst, int32_t *nfail)
+{
+    SWCU_TRY(need_tp(ctx, "helio_step_tp"));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "helio_step_tp: pl population not resident");
+    if (!(GMcb > 0.0)) return fail(ctx, SWCU_ERR_ARG, "helio_step_tp: GMcb must be positive");
+    if (nfail) *nfail = 0;
+    if (ctx->tp.n == 0) return SWCU_OK;  // helio_step.f90:98
+    SWCU_TRY(ensure_step_state(ctx));
+    SWCU_TRY(ensure_helio(ctx, ctx->tp));
+    SWCU_TRY(ensure_helio(ctx, ctx->pl));
+    return helio_tp_step(ctx, ctx->tp, ctx->pl, GMcb, dt, lfirst, nfail);
+}
+
+// ======================================================================================================
+// tier 1: energy and momentum of the massive bodies
+// ======================================================================================================
+namespace {
+int stage_energy(swcu_context *ctx, int32_t npl, const int32_t *lmask, const double *Gmass, const double *mass,
+                 const double *radius, const double *rb, const double *vb)
+{
+    Body &b = ctx->s_pl;
+    SWCU_TRY(stage_population(ctx, b, npl, rb, vb, nullptr));
+    SWCU_TRY(put_or_fill(ctx, Gmass, npl, b.Gm, 0.0));
+    SWCU_TRY(put_or_fill(ctx, mass, npl, b.mu, 0.0));
+    SWCU_TRY(put_or_fill(ctx, radius, npl, b.radius, 1.0));
+    if (lmask)
+        SWCU_TRY(upload_arr(ctx, lmask, sizeof(int32_t) * (size_t)npl, b.lmask));
+    else
+        SWCU_TRY(fill_i32(ctx, b.lmask.as<int32_t>(), 1, npl));
+    return SWCU_OK;
+}
+}  // namespace
+
+extern "C" int swcu_util_get_potential_energy(swcu_context *ctx, int32_t npl, const int32_t *lmask, double GMcb,
+                                              const double *Gmass, const double *mass, const double *rb, double *pe)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!pe || npl < 0) return fail(ctx, SWCU_ERR_ARG, "get_potential_energy: bad argument");
+    *pe = 0.0;
+    if (npl == 0) return SWCU_OK;
+    if (!Gmass || !mass || !rb) return fail(ctx, SWCU_ERR_ARG, "get_potential_energy: null array");
+    SWCU_TRY(stage_energy(ctx, npl, lmask, Gmass, mass, nullptr, rb, nullptr));
+    double s[8];
+    SWCU_TRY(energy_and_momentum(ctx, ctx->s_pl, GMcb, 0, true, s));
+    *pe = -s[1] - s[2];
+    return SWCU_OK;
+}
+
+extern "C" int swcu_util_get_energy_and_momentum(swcu_context *ctx, int32_t npl, const int32_t *lmask, double GMcb,
+                                                 double mass_cb, const double *rbcb, const double *vbcb,
+                                                 const double *Gmass, const double *mass, const double *radius,
+                                                 const double *rb, const double *vb, int32_t lclose, double *out8)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!out8 || npl < 0 || !rbcb || !vbcb) return fail(ctx, SWCU_ERR_ARG, "get_energy_and_momentum: bad argument");
+    if (npl > 0 && (!Gmass || !mass || !rb || !vb || (lclose && !radius)))
+        return fail(ctx, SWCU_ERR_ARG, "get_energy_and_momentum: null array");
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (npl > 0) {
+        SWCU_TRY(stage_energy(ctx, npl, lmask, Gmass, mass, radius, rb, vb));
+        SWCU_TRY(energy_and_momentum(ctx, ctx->s_pl, GMcb, lclose, false, s));
+    }
+    // swiftest_util.f90:1206-1209, 1269-1283
+    const double kecb = mass_cb * (vbcb[0] * vbcb[0] + vbcb[1] * vbcb[1] + vbcb[2] * vbcb[2]);
+    out8[0] = 0.5 * (kecb + s[0]);
+    out8[1] = -s[1] - s[2];
+    out8[2] = lclose ? -s[3] : 0.0;
+    out8[3] = out8[0] + 0.0 + out8[1] + out8[2];
+    out8[4] = mass_cb * (rbcb[1] * vbcb[2] - rbcb[2] * vbcb[1]) + s[4];
+    out8[5] = mass_cb * (rbcb[2] * vbcb[0] - rbcb[0] * vbcb[2]) + s[5];
+    out8[6] = mass_cb * (rbcb[0] * vbcb[1] - rbcb[1] * vbcb[0]) + s[6];
+    out8[7] = GMcb + s[7];
+    return SWCU_OK;
 }
 
 // ======================================================================================================

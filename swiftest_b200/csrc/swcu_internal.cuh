@@ -52,9 +52,15 @@ struct Body {
     DevBuf rx, ry, rz, vx, vy, vz, ax, ay, az;
     DevBuf Gm, radius, rhill, renc, mu;
     DevBuf lmask, iflag;  // int32
+    // democratic-heliocentric integrators keep two velocities: v* above is vh, w* is vb (allocated on first use);
+    // b* / e* are the planet positions at the begin / end kick (pl%rbeg, pl%rend: swiftest_util.f90:2057-2080)
+    DevBuf wx, wy, wz, bx, by, bz, ex, ey, ez;
+    bool helio_ready = false;
     void release()
     {
-        DevBuf *all[] = {&rx, &ry, &rz, &vx, &vy, &vz, &ax, &ay, &az, &Gm, &radius, &rhill, &renc, &mu, &lmask, &iflag};
+        DevBuf *all[] = {&rx, &ry, &rz, &vx, &vy, &vz, &ax, &ay, &az, &Gm, &radius, &rhill, &renc, &mu, &lmask, &iflag,
+                         &wx, &wy, &wz, &bx, &by, &bz, &ex, &ey, &ez};
+        helio_ready = false;
         for (DevBuf *b : all) b->release();
         valid = false;
         n = 0;
@@ -114,6 +120,11 @@ struct swcu_context {
     size_t fam_log_used[swcu::FAM_COUNT] = {};
 
     swcu::DevBuf flush;
+
+    // central-body scalars of the integrator glue, on the device (step_kernels.cu): doubles
+    // [0..3] raw sums of the last reduction, [4..6] vbcb, [8..10] ptbeg, [12..14] ptend, [16] GMtot, [20..27] energy sums
+    swcu::DevBuf cbs;
+    swcu::DevBuf sumbuf;  // per-CTA partials of the tree reductions + ticket counter (zeroed when allocated)
 
     // multi-GPU
     swcu::NcclApi *nccl = nullptr;
@@ -226,7 +237,29 @@ int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, c
           double *y1, double *y2, const int32_t *lmask, int n);
 
 // ---- drift : drift_kernels.cu ----
-int drift_bodies(swcu_context *ctx, Body &b, int i0, int i1, double dt, int lgr, double inv_c2, int32_t *nfail);
+// vsel = 0 drifts (r, v) with the per-body mu array; vsel = 1 drifts (r, w) = (rh, vb) with mu = mu_scalar = GMcb, the
+// democratic-heliocentric pair (helio_drift.f90:38-40)
+int drift_bodies(swcu_context *ctx, Body &b, int i0, int i1, double dt, int lgr, double inv_c2, int32_t *nfail,
+                 int vsel = 0, double mu_scalar = 0.0);
+int helio_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double gmcb, double dt, int lfirst, int32_t *nfail);
+
+// ---- integrator glue : step_kernels.cu ----
+constexpr int CBS_SUM = 0, CBS_VBCB = 4, CBS_PTBEG = 8, CBS_PTEND = 12, CBS_GMTOT = 16, CBS_ENERGY = 20, CBS_DOUBLES = 32;
+int ensure_step_state(swcu_context *ctx);
+int ensure_helio(swcu_context *ctx, Body &b);
+int pl_vh2vb(swcu_context *ctx, double gmcb);
+int pl_vb2vh(swcu_context *ctx, double gmcb);
+int pl_lindrift(swcu_context *ctx, double gmcb, double dt, int lbeg);
+int tp_lindrift(swcu_context *ctx, double dt, int lbeg);
+int tp_vh2vb(swcu_context *ctx, int lbeg);  // vbcb = -ptbeg / -ptend (helio_step.f90:103,118)
+int tp_vb2vh(swcu_context *ctx, int lbeg);
+int kick_vb_save(swcu_context *ctx, Body &b, double dt, int save /*0 none, 1 rbeg, 2 rend*/);
+int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclose, int lfirst, int32_t *nfail);
+int pl_accel_int(swcu_context *ctx, int loop_variant, int lclose);  // swcu_api.cu
+
+// ---- energy and momentum : energy_kernels.cu ----
+// positions / velocities in the s_pl scratch population (rb in r*, vb in v*), mass in s_pl.mu, Gmass in s_pl.Gm
+int energy_and_momentum(swcu_context *ctx, Body &b, double gmcb, int lclose, bool pe_only, double *out8);
 int whm_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double dt, const double ah0[3], int32_t *nfail);
 
 // ---- encounters : encounter_kernels.cu ----

@@ -1,0 +1,280 @@
+"""GPU parity tests for the rows SURVEY.md section 8(f) ranks next: the O(N) glue of the democratic-heliocentric step
+on the device-resident populations (rank 1) and the energy / momentum sums (rank 2), against the CPU restatement.
+
+Bars: the element-wise glue is BIT-EXACT whenever the sums are (n <= 1024: the device adds in the reference's serial
+order); above that the fixed-tree sums are compared at 1e-14 relative to sum|terms|.  Whole steps inherit the 1e-12 bar
+of the accelerations inside them.  Energy sums: 1e-13 relative to sum|terms|.
+"""
+import numpy as np
+import pytest
+
+from swiftest_b200 import workloads as W
+from swiftest_b200 import PL, TP, LOOP_FLAT, LOOP_TRIANGULAR
+
+pytestmark = pytest.mark.gpu
+
+
+def _fixture108():
+    f = W.fixture("108pl_50tp")
+    return f, float(f["cb_Gmass"]), float(f["dt"])
+
+
+def _sync_pl(ctx, gen, rh, vh, Gm, radius, GMcb, lmask=None):
+    n = len(Gm)
+    ctx.body_sync(PL, n, nplm=n, r=rh, v=vh, Gmass=Gm, radius=radius, mu=np.full(n, GMcb), lmask=lmask, generation=gen)
+
+
+# ------------------------------------------------------------------------------------------------ glue, one call each
+def test_glue_calls_bit_exact_on_the_108_body_fixture(ctx, oracle):
+    f, GMcb, dt = _fixture108()
+    Gm, rh, vh = f["pl_Gmass"], f["pl_rh"], f["pl_vh"]
+    mask = np.ones(108, np.int32)
+    mask[[3, 50, 107]] = 0
+    _sync_pl(ctx, 9001, rh, vh, Gm, f["pl_radius"], GMcb, lmask=mask)
+    # vh2vb: unmasked (swiftest_util.f90:440-455)
+    vb_ref, vbcb_ref = oracle.coord_vh2vb_pl(GMcb, Gm, vh)
+    vbcb = ctx.pl_vh2vb(GMcb)
+    assert np.array_equal(vbcb, vbcb_ref)
+    assert np.array_equal(ctx.body_get_vb(PL)["vb"], vb_ref)
+    # lindrift: masked sum, masked update
+    r_ref, pt_ref = oracle.helio_drift_linear_pl(GMcb, Gm, vb_ref, rh, 0.5 * dt, mask)
+    pt = ctx.pl_lindrift(GMcb, 0.5 * dt, lbeg=True)
+    assert np.array_equal(pt, pt_ref)
+    assert np.array_equal(ctx.body_get(PL)["r"], r_ref)
+    ptb, pte = ctx.cb_get_pt()
+    assert np.array_equal(ptb, pt_ref) and pte.shape == (3,)
+    # kick tail: vb += ah*dt under the mask, rbeg = rh for everyone
+    ah = np.random.default_rng(2).normal(scale=1e-2, size=(108, 3))
+    ctx.body_put(PL, a=ah)
+    ctx.body_kick_vb(PL, 0.5 * dt, lbeg=True)
+    got = ctx.body_get_vb(PL, vb=True, rbeg=True)
+    assert np.array_equal(got["vb"], oracle.helio_kick_vb(ah, vb_ref, 0.5 * dt, mask))
+    assert np.array_equal(got["rbeg"], r_ref)
+    # vb2vh: reversed masked sum with a division per term, unmasked update
+    vb_now = got["vb"]
+    vh_ref, vbcb2_ref = oracle.coord_vb2vh_pl(GMcb, Gm, vb_now, mask)
+    vbcb2 = ctx.pl_vb2vh(GMcb)
+    assert np.array_equal(vbcb2, vbcb2_ref)
+    assert np.array_equal(ctx.body_get(PL)["v"], vh_ref)
+
+
+@pytest.mark.parametrize("n", [1025, 5000, 70001])
+def test_glue_tree_sums_are_reproducible_and_within_tolerance(ctx, oracle, n):
+    d = W.disk(n, seed=n)
+    GMcb = 39.476926408897626
+    vbcbs = []
+    for rep in range(2):
+        _sync_pl(ctx, 9100 + 2 * n + rep, d["rh"], d["vh"], d["Gmass"], d["radius"], GMcb)
+        vbcbs.append(ctx.pl_vh2vb(GMcb))
+    assert np.array_equal(vbcbs[0], vbcbs[1])  # same bits run to run
+    vb_ref, vbcb_ref = oracle.coord_vh2vb_pl(GMcb, d["Gmass"], d["vh"])
+    scale = (d["Gmass"][:, None] * np.abs(d["vh"])).sum(0) / (GMcb + d["Gmass"].sum())
+    assert np.all(np.abs(vbcbs[0] - vbcb_ref) <= 1e-14 * scale)
+    vb = ctx.body_get_vb(PL)["vb"]
+    assert np.max(np.abs(vb - vb_ref)) <= 1e-14 * scale.max() + 2e-16 * np.abs(vb_ref).max()
+    rh_ref, pt_ref = oracle.helio_drift_linear_pl(GMcb, d["Gmass"], vb, d["rh"], 0.01)
+    pt = ctx.pl_lindrift(GMcb, 0.01, lbeg=False)
+    scale_pt = (d["Gmass"][:, None] * np.abs(vb)).sum(0) / GMcb
+    assert np.all(np.abs(pt - pt_ref) <= 1e-14 * scale_pt)
+    vh_ref, vbcb2_ref = oracle.coord_vb2vh_pl(GMcb, d["Gmass"], vb)
+    assert np.all(np.abs(ctx.pl_vb2vh(GMcb) - vbcb2_ref) <= 1e-14 * scale_pt)
+
+
+def test_glue_state_errors_and_empty(ctx):
+    import swiftest_b200 as S
+    with S.Context() as c:
+        with pytest.raises(S.SwcuError):
+            c.pl_vh2vb(1.0)
+        with pytest.raises(S.SwcuError):
+            c.helio_step_tp(1.0, 0.01)
+        c.body_sync(PL, 0, generation=1)
+        c.body_sync(TP, 0, generation=2)
+        assert c.helio_step_pl(1.0, 0.01, lfirst=True) == 0  # helio_step.f90:54: nothing to do
+        assert c.helio_step_tp(1.0, 0.01, lfirst=True) == 0
+        with pytest.raises(S.SwcuError):
+            c.helio_step_pl(0.0, 0.01)
+
+
+# ------------------------------------------------------------------------------------------------ whole steps
+@pytest.mark.parametrize("variant", [LOOP_TRIANGULAR, LOOP_FLAT])
+def test_helio_step_pl_tracks_oracle_on_fixture(ctx, oracle, variant):
+    f, GMcb, dt = _fixture108()
+    Gm, rad = f["pl_Gmass"], f["pl_radius"]
+    _sync_pl(ctx, 9200 + variant, f["pl_rh"], f["pl_vh"], Gm, rad, GMcb)
+    st = dict(rh=f["pl_rh"].copy(), vh=f["pl_vh"].copy(), vb=np.zeros((108, 3)), lfirst=True)
+    nsteps = 40
+    for k in range(nsteps):
+        assert not oracle.helio_step_pl(st, GMcb, Gm, rad, dt, lflat=(variant == LOOP_FLAT)).any()
+        assert ctx.helio_step_pl(GMcb, dt, loop_variant=variant, lclose=True, lfirst=(k == 0)) == 0
+    out = ctx.body_get(PL)
+    hv = ctx.body_get_vb(PL, vb=True, rbeg=True, rend=True)
+    rs, vs = np.abs(st["rh"]).max(), np.abs(st["vh"]).max()
+    # 40 steps of 1e-12-accurate kicks; errors grow linearly at worst
+    assert np.max(np.abs(out["r"] - st["rh"])) < 1e-11 * rs
+    assert np.max(np.abs(out["v"] - st["vh"])) < 1e-11 * vs
+    assert np.max(np.abs(hv["vb"] - st["vb"])) < 1e-11 * vs
+    assert np.max(np.abs(hv["rbeg"] - st["rbeg"])) < 1e-11 * rs
+    assert np.max(np.abs(hv["rend"] - st["rend"])) < 1e-11 * rs
+    ptb, pte = ctx.cb_get_pt()
+    assert np.max(np.abs(ptb - st["ptbeg"])) < 1e-11 * np.abs(st["ptbeg"]).max()
+    assert np.max(np.abs(pte - st["ptend"])) < 1e-11 * np.abs(st["ptend"]).max()
+
+
+def test_helio_step_pl_first_step_matches_unfused_device_calls(ctx):
+    """The one-call step and the same step issued call by call through the ABI give identical bits."""
+    f, GMcb, dt = _fixture108()
+    Gm, rad = f["pl_Gmass"], f["pl_radius"]
+    _sync_pl(ctx, 9301, f["pl_rh"], f["pl_vh"], Gm, rad, GMcb)
+    ctx.helio_step_pl(GMcb, dt, loop_variant=LOOP_TRIANGULAR, lclose=True, lfirst=True)
+    a = ctx.body_get(PL)
+    avb = ctx.body_get_vb(PL)["vb"]
+    _sync_pl(ctx, 9302, f["pl_rh"], f["pl_vh"], Gm, rad, GMcb)
+    dth = 0.5 * dt
+    ctx.pl_vh2vb(GMcb, want=False)
+    ctx.pl_lindrift(GMcb, dth, True, want=False)
+    for lbeg in (True, False):
+        ctx.body_zero_accel(PL)
+        ctx.pl_accel_int(LOOP_TRIANGULAR, True)
+        ctx.body_kick_vb(PL, dth, lbeg)
+        if lbeg:
+            assert ctx.body_drift_vb(PL, GMcb, dt) == 0
+    ctx.pl_lindrift(GMcb, dth, False, want=False)
+    ctx.pl_vb2vh(GMcb, want=False)
+    b = ctx.body_get(PL)
+    assert np.array_equal(a["r"], b["r"]) and np.array_equal(a["v"], b["v"])
+    assert np.array_equal(avb, ctx.body_get_vb(PL)["vb"])
+
+
+def test_helio_step_tp_fused_kernel_tracks_oracle(ctx, oracle):
+    p = W.planets8_year_units()
+    GMcb, dt = float(p["cb_Gmass"]), 0.01
+    ntp = 20000
+    tp = W.tp_cloud(ntp, seed=9)
+    mask = (np.random.default_rng(9).uniform(size=ntp) > 0.03).astype(np.int32)
+    on = mask.astype(bool)
+    _sync_pl(ctx, 9401, p["rh"], p["vh"], p["Gmass"], p["radius"], GMcb)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, GMcb), lmask=mask, generation=9402)
+    pl = dict(rh=p["rh"].copy(), vh=p["vh"].copy(), vb=np.zeros((8, 3)), lfirst=True)
+    st = dict(rh=tp["rh"].copy(), vh=tp["vh"].copy(), vb=np.zeros((ntp, 3)), lfirst=True)
+    for k in range(10):
+        oracle.helio_step_pl(pl, GMcb, p["Gmass"], p["radius"], dt)
+        fl = oracle.helio_step_tp(st, pl, GMcb, p["Gmass"], dt, lmask=mask)
+        assert ctx.helio_step_pl(GMcb, dt, loop_variant=LOOP_TRIANGULAR, lclose=True, lfirst=(k == 0)) == 0
+        assert ctx.helio_step_tp(GMcb, dt, lfirst=(k == 0)) == int(np.count_nonzero(fl[on]))
+    out = ctx.body_get(TP, iflag=True)
+    vb = ctx.body_get_vb(TP)["vb"]
+    rn = np.linalg.norm(st["rh"], axis=1, keepdims=True)
+    vn = np.linalg.norm(st["vh"], axis=1, keepdims=True)
+    assert np.max(np.abs(out["r"][on] - st["rh"][on]) / rn[on]) < 1e-11
+    assert np.max(np.abs(out["v"][on] - st["vh"][on]) / vn[on]) < 1e-11
+    assert np.max(np.abs(vb[on] - st["vb"][on]) / vn[on]) < 1e-11
+    assert np.max(np.abs(out["a"][on] - st["ah"][on])) <= 1e-11 * np.abs(st["ah"]).max()
+    off = ~on  # masked particles are not touched (helio_step.f90 loops are all under lmask)
+    assert np.array_equal(out["r"][off], tp["rh"][off]) and np.array_equal(out["v"][off], tp["vh"][off])
+
+
+def test_helio_step_tp_with_planets_stepped_elsewhere(ctx, oracle):
+    """tp shards on other GPUs receive ptbeg / ptend from the planets' owner (swcu_cb_set_pt) and rbeg / rend as
+    resident planet positions: same result as the local sequence."""
+    p = W.planets8_year_units()
+    GMcb, dt = float(p["cb_Gmass"]), 0.01
+    ntp = 3000
+    tp = W.tp_cloud(ntp, seed=19)
+    _sync_pl(ctx, 9501, p["rh"], p["vh"], p["Gmass"], p["radius"], GMcb)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, GMcb), generation=9502)
+    ctx.helio_step_pl(GMcb, dt, loop_variant=LOOP_TRIANGULAR, lfirst=True)
+    ctx.helio_step_tp(GMcb, dt, lfirst=True)
+    a = ctx.body_get(TP)
+    ptb, pte = ctx.cb_get_pt()
+    # unfused tp sequence with ptbeg/ptend loaded explicitly
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, GMcb), generation=9503)
+    ctx.cb_set_pt(ptb, pte)
+    ctx.tp_vh2vb(lbeg=True)
+    ctx.tp_lindrift(0.5 * dt, lbeg=True)
+    b = ctx.body_get(TP)
+    st = dict(rh=tp["rh"] + ptb * (0.5 * dt))
+    assert np.array_equal(b["r"], st["rh"])
+    assert np.array_equal(ctx.body_get_vb(TP)["vb"], tp["vh"] + (-ptb))
+    assert np.all(np.isfinite(a["r"]))
+
+
+# ------------------------------------------------------------------------------------------------ energy
+def _energy_inputs(n, seed, nmask=0):
+    d = W.disk(n, seed=seed)
+    GMcb = 39.476926408897626
+    GU = GMcb
+    mass = d["Gmass"] / GU
+    mask = np.ones(n, np.int32)
+    if nmask:
+        mask[np.random.default_rng(seed).choice(n, nmask, replace=False)] = 0
+    return d, GMcb, mass, mask
+
+
+@pytest.mark.parametrize("n,nmask", [(1, 0), (2, 0), (108, 5), (257, 0), (1500, 40), (4100, 0)])
+def test_potential_energy_matches_oracle(ctx, oracle, n, nmask):
+    d, GMcb, mass, mask = _energy_inputs(n, 600 + n, nmask)
+    lm = mask if nmask else None
+    ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, d["rh"], lm)
+    got = ctx.util_get_potential_energy(n, lm, GMcb, d["Gmass"], mass, d["rh"])
+    assert abs(got - ref) <= 1e-13 * abs(ref)
+    # flat and triangular reference variants are the same number up to summation order
+    flat = oracle.get_potential_energy(GMcb, d["Gmass"], mass, d["rh"], lm, flat=True)
+    assert abs(got - flat) <= 1e-13 * abs(ref)
+
+
+def test_potential_energy_edge_cases(ctx, oracle):
+    d, GMcb, mass, mask = _energy_inputs(300, 77)
+    rb = d["rh"].copy()
+    # a masked-out body sitting exactly on an active one and one at the origin: no contribution, no NaN
+    rb[10] = rb[200]
+    rb[11] = 0.0
+    mask[[10, 11]] = 0
+    ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, rb, mask)
+    got = ctx.util_get_potential_energy(300, mask, GMcb, d["Gmass"], mass, rb)
+    assert np.isfinite(got) and abs(got - ref) <= 1e-13 * abs(ref)
+    # two ACTIVE bodies at the same place: the reference divides by zero -> -inf; so does the device (IEEE redo path)
+    mask[10] = 1
+    ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, rb, mask)
+    got = ctx.util_get_potential_energy(300, mask, GMcb, d["Gmass"], mass, rb)
+    assert ref == -np.inf and got == -np.inf
+    # coordinates far outside the FP32 exponent range take the IEEE path too
+    big = d["rh"] * 1e60
+    ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, big)
+    got = ctx.util_get_potential_energy(300, None, GMcb, d["Gmass"], mass, big)
+    assert abs(got - ref) <= 1e-13 * abs(ref)
+    assert ctx.util_get_potential_energy(0, None, GMcb, np.zeros(0), np.zeros(0), np.zeros((0, 3))) == 0.0
+
+
+def test_energy_and_momentum_matches_oracle(ctx, oracle):
+    f, GMcb, _ = _fixture108()
+    Gm = f["pl_Gmass"]
+    mass = Gm / GMcb
+    mask = np.ones(108, np.int32)
+    mask[[7, 90]] = 0
+    rb, vb, rbcb, vbcb = oracle.coord_h2b_pl(GMcb, Gm, f["pl_rh"], f["pl_vh"])
+    for lm, lclose in ((None, True), (mask, True), (mask, False)):
+        ref = oracle.get_energy_and_momentum(GMcb, 1.0, rbcb, vbcb, Gm, mass, f["pl_radius"], rb, vb, lm, lclose)
+        got = ctx.util_get_energy_and_momentum(108, lm, GMcb, 1.0, rbcb, vbcb, Gm, mass, f["pl_radius"], rb, vb, lclose)
+        for k in ("ke_orbit", "pe", "be", "te", "GMtot"):
+            assert abs(got[k] - ref[k]) <= 1e-13 * max(abs(ref[k]), abs(ref["pe"]) if k == "te" else 0.0), k
+        assert np.max(np.abs(got["L_orbit"] - ref["L_orbit"])) <= 1e-13 * np.abs(ref["L_orbit"]).max()
+
+
+def test_potential_energy_large_disk_against_blocked_numpy(ctx):
+    """Full-size property check (no oracle pass at this size): 2e4 bodies against a blocked float64 numpy sum."""
+    n = 20000
+    d, GMcb, mass, _ = _energy_inputs(n, 4242)
+    rb = d["rh"]
+    tot = 0.0
+    for i0 in range(0, n, 2000):
+        blk = rb[i0:i0 + 2000]
+        dist = np.sqrt(((blk[:, None, :] - rb[None, :, :]) ** 2).sum(2))
+        w = d["Gmass"][i0:i0 + 2000, None] * mass[None, :]
+        jj = np.arange(n)[None, :]
+        ii = np.arange(i0, min(i0 + 2000, n))[:, None]
+        sel = jj > ii
+        tot += (w[sel] / dist[sel]).sum()
+    ref = -tot - (GMcb * mass / np.linalg.norm(rb, axis=1)).sum()
+    got = ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, rb)
+    assert abs(got - ref) <= 1e-12 * abs(ref)
+    assert got == ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, rb)  # reproducible bits

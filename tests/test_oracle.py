@@ -281,3 +281,129 @@ def test_helio_integration_conserves_energy_and_momentum(oracle):
     slopeL = np.polyfit(ts, dL, 1)[0]
     assert abs(slopeE) < 1e-8 and abs(slopeL) < 1e-10
     assert np.max(np.abs(dE)) < 1e-6
+
+
+# ---------------------------------------------------------------- integrator glue and energy sums
+def _rand_system(n, seed):
+    rng = np.random.default_rng(seed)
+    rh = rng.normal(size=(n, 3)) * 3.0
+    vh = rng.normal(size=(n, 3))
+    Gm = rng.uniform(1e-8, 1e-4, n)
+    return rh, vh, Gm
+
+
+def test_coord_changes_follow_the_reference_sums(oracle):
+    rh, vh, Gm = _rand_system(37, 3)
+    GMcb = 39.47
+    vb, vbcb = oracle.coord_vh2vb_pl(GMcb, Gm, vh)
+    # vh2vb: plain forward sum over GMtot (swiftest_util.f90:440-447)
+    s = np.zeros(3)
+    for i in range(37):
+        s = s - Gm[i] * vh[i]
+    tot = 0.0
+    for g in Gm:
+        tot += g
+    assert np.array_equal(vbcb, s / (GMcb + tot))
+    assert np.array_equal(vb, vh + vbcb)
+    # vb2vh: reversed loop, each term divided by GMcb (swiftest_util.f90:380-384); masked bodies skipped
+    act = np.ones(37, np.int32)
+    act[[4, 20]] = 0
+    vh2, vbcb2 = oracle.coord_vb2vh_pl(GMcb, Gm, vb, act)
+    s = np.zeros(3)
+    for i in range(36, -1, -1):
+        if act[i]:
+            s = s - Gm[i] * vb[i] / GMcb
+    assert np.array_equal(vbcb2, s)
+    assert np.array_equal(vh2, vb - vbcb2)
+    # the two conversions are inverse to each other up to rounding when nothing is masked
+    vh3, _ = oracle.coord_vb2vh_pl(GMcb, Gm, vb)
+    assert np.max(np.abs(vh3 - vh)) < 1e-14
+
+
+def test_helio_step_in_c_matches_independent_numpy_stepper(oracle):
+    """swo_helio_step_pl (serial sums, C) against tests/helio.py (numpy pairwise sums) on the 108-body fixture:
+    two restatements of helio_step.f90:37-78 written independently must agree to rounding."""
+    from tests.helio import HelioSystem, OracleBackend
+    f, _ = _fixture108()
+    GMcb, Gm, rad = float(f["cb_Gmass"]), f["pl_Gmass"], f["pl_radius"]
+    ref = HelioSystem(GMcb, Gm, f["pl_rh"], f["pl_vh"], rad, OracleBackend(oracle))
+    st = dict(rh=f["pl_rh"].copy(), vh=f["pl_vh"].copy(), vb=np.zeros_like(f["pl_vh"]), lfirst=True)
+    dt = float(f["dt"])
+    for _ in range(20):
+        ref.step(dt)
+        fl = oracle.helio_step_pl(st, GMcb, Gm, rad, dt, lflat=False)
+        assert not fl.any()
+    assert st["lfirst"] is False
+    scale = np.max(np.abs(ref.rh))
+    assert np.max(np.abs(st["rh"] - ref.rh)) < 1e-12 * scale
+    assert np.max(np.abs(st["vh"] - ref.vh)) < 1e-12 * np.max(np.abs(ref.vh))
+    # flat and triangular loops inside the step differ only by summation order
+    st2 = dict(rh=f["pl_rh"].copy(), vh=f["pl_vh"].copy(), vb=np.zeros_like(f["pl_vh"]), lfirst=True)
+    for _ in range(20):
+        oracle.helio_step_pl(st2, GMcb, Gm, rad, dt, lflat=True)
+    assert np.max(np.abs(st2["rh"] - st["rh"])) < 1e-12 * scale
+
+
+def test_helio_step_tp_is_a_massless_planet(oracle):
+    """A test particle stepped by swo_helio_step_tp must follow a planet of negligible mass stepped by
+    swo_helio_step_pl from the same state (the tp sees rbeg / rend / ptbeg / ptend of the planets)."""
+    p = W.planets8_year_units()
+    GMcb, dt = float(p["cb_Gmass"]), 0.01
+    rtp = np.array([[2.7, 0.3, 0.1]])
+    vtp = np.array([[-0.4, 3.7, 0.2]])
+    Gm9 = np.append(p["Gmass"], 1e-30)
+    rad9 = np.append(p["radius"], 1e-12)
+    big = dict(rh=np.vstack([p["rh"], rtp]), vh=np.vstack([p["vh"], vtp]), vb=np.zeros((9, 3)), lfirst=True)
+    pl = dict(rh=p["rh"].copy(), vh=p["vh"].copy(), vb=np.zeros((8, 3)), lfirst=True)
+    tp = dict(rh=rtp.copy(), vh=vtp.copy(), vb=np.zeros((1, 3)), lfirst=True)
+    for _ in range(50):
+        oracle.helio_step_pl(big, GMcb, Gm9, rad9, dt)
+        oracle.helio_step_pl(pl, GMcb, p["Gmass"], p["radius"], dt)
+        fl = oracle.helio_step_tp(tp, pl, GMcb, p["Gmass"], dt)
+        assert not fl.any()
+    assert np.max(np.abs(tp["rh"][0] - big["rh"][8])) < 1e-11
+    assert np.max(np.abs(tp["vh"][0] - big["vh"][8])) < 1e-11
+
+
+def test_potential_energy_variants_and_brute_force(oracle):
+    rng = np.random.default_rng(11)
+    n = 300
+    rb = rng.normal(size=(n, 3)) * 2
+    Gm = rng.uniform(1e-7, 1e-5, n)
+    GU = 39.47 / 1.0
+    mass = Gm / GU
+    mask = np.ones(n, np.int32)
+    mask[rng.choice(n, 17, replace=False)] = 0
+    for lm in (None, mask):
+        tri = oracle.get_potential_energy(39.47, Gm, mass, rb, lm, flat=False)
+        flat = oracle.get_potential_energy(39.47, Gm, mass, rb, lm, flat=True)
+        on = np.ones(n, bool) if lm is None else lm.astype(bool)
+        d = np.linalg.norm(rb[:, None, :] - rb[None, :, :], axis=2)
+        iu = np.triu_indices(n, 1)
+        keep = on[iu[0]] & on[iu[1]]
+        brute = -(Gm[iu[0]] * mass[iu[1]] / d[iu])[keep].sum() - (39.47 * mass / np.linalg.norm(rb, axis=1))[on].sum()
+        assert abs(tri - flat) < 1e-13 * abs(brute)
+        assert abs(tri - brute) < 1e-13 * abs(brute)
+
+
+def test_energy_and_momentum_on_planets(oracle):
+    """te and L_orbit of the restated get_energy_and_momentum stay put over a restated helio run (8 planets)."""
+    p = W.planets8_year_units()
+    GMcb = float(p["cb_Gmass"])
+    GU = GMcb  # solar masses
+    mass, mcb = p["Gmass"] / GU, 1.0
+    st = dict(rh=p["rh"].copy(), vh=p["vh"].copy(), vb=np.zeros((8, 3)), lfirst=True)
+
+    def em():
+        rb, vb, rbcb, vbcb = oracle.coord_h2b_pl(GMcb, p["Gmass"], st["rh"], st["vh"])
+        # the reference's pecb uses |rb_i| (swiftest_util.f90:1318); evaluate it in the frame where the Sun is at the
+        # origin (rb - rbcb) so that the number is the physical potential
+        return oracle.get_energy_and_momentum(GMcb, mcb, rbcb * 0, vbcb, p["Gmass"], mass, p["radius"], rb - rbcb, vb,
+                                              lclose=False), rbcb, vbcb
+    e0, _, _ = em()
+    for _ in range(1000):
+        oracle.helio_step_pl(st, GMcb, p["Gmass"], p["radius"], 0.01)
+    e1, _, _ = em()
+    assert abs(e1["te"] - e0["te"]) < 1e-6 * abs(e0["te"])
+    assert e0["ke_orbit"] > 0 and e0["pe"] < 0 and e0["be"] == 0.0
+    assert abs(e0["GMtot"] - (GMcb + p["Gmass"].sum())) < 1e-12
