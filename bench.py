@@ -423,7 +423,7 @@ def run_ours(args):
                        "sharding": (f"block-pair runs over {world} rank(s)" if variant == LOOP_FLAT
                                     else f"i-slices over {world} rank(s), allgather of drifted r,v"),
                        "collective": ("p2p-fused" if use_p2p else ("nccl" if world > 1 else "none")),
-                       "l2": "flushed between steps (256 MiB write inside the timed region)",
+                       "l2": "flushed between steps (160 MiB write = 1.33 x L2, inside the timed region)",
                        "seed": 3031179},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "breakdown_ms_per_step": breakdown,
@@ -468,7 +468,7 @@ def tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak):
     barrier()
     return {"ntp_total": ntp, "ranks": world, "ms_per_step": ms, "tp_steps_per_s": ntp / (ms * 1e-3),
             "partition": "block (coarray_distribute shape), planets replicated, no per-step communication",
-            "note": "includes the 256 MiB L2 flush between steps"}
+            "note": "includes the 160 MiB L2 flush between steps"}
 
 
 def side_legs(ctx, args, d, hbm_peak, peak_src):

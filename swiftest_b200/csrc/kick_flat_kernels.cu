@@ -44,12 +44,17 @@ struct FlatArgs {
     int Km, evenm;        // cyclic half-range among the owner blocks, and whether nbm is even
     long long total_items;
     long long item0, item1;  // the run of items this rank owns (multi-GPU: pair slices), [0,total) on one GPU
-    int quantum;             // items a warp claims per visit to the work counter
+    int quantum;             // items a warp claims per visit to the work counter (coarse phase)
+    // graded schedule: claims [ph_q[k], ph_q[k+1]) take ph_sz[k] consecutive 32-column chunks each, starting at chunk
+    // ph_u[k] of this launch's run; sizes shrink towards the end of the run (whole items ... one chunk)
+    long long ph_q[6], ph_u[6];
+    int ph_sz[5];
     unsigned long long *counter;  // work counter (dynamic scheduling); in peer-memory mode ONE counter shared by all GPUs
     unsigned long long counter_base;  // value of the counter at which this launch's first quantum sits
     int system_scope;             // 1: the counter lives in (possibly remote) peer memory -> system-scope atomics
     long long first_warp, total_warps;  // this launch's first global warp id and the warps of all sharers together
     double *fx, *fy, *fz; // zero-initialised accumulation target
+    unsigned long long *trace;  // development aid (SWCU_FLAT_TRACE): per warp {start, end} %globaltimer, items done
 };
 
 // every array has the same 16-byte stride so one byte offset addresses all four
@@ -163,8 +168,10 @@ __device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned 
         if (CHECKED) {
             const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
                            ((idx_i[b] < a.nplm) || (jcur < a.nplm));
-            // a masked pair never contributes (always-failing test); redo_chunk applies the masks again
+            // a masked pair never contributes (always-failing test: y^3 underflows to exactly zero) and must not send
+            // the chunk to redo_chunk either: every chunk of a diagonal block holds a self pair per lane
             y = rsqrt_seeded<true>(r2, thr[b], m ? span[b] : 0u, hy[b]);
+            hy[b] = m ? hy[b] : 0xffffffffu;
         } else {
             y = rsqrt_seeded<false>(r2, thr[b], span[b], hy[b]);  // the caller guarantees |coordinates| < 2^62
         }
@@ -203,14 +210,14 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
                                            const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
                                            const double (&gmi)[FIB], const unsigned (&thr)[FIB],
                                            const unsigned (&span)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
-                                           double (&ayi)[FIB], double (&azi)[FIB])
+                                           double (&ayi)[FIB], double (&azi)[FIB], int c0 = 0, int c1 = FIB)
 {
     const int src = (lane + 1) & 31;
     // prefetch the first chunk
-    int jc = min(J * FT + lane, a.n - 1);
+    int jc = min(J * FT + c0 * 32 + lane, a.n - 1);
     double nx = a.x[jc], ny = a.y[jc], nz = a.z[jc], ng = a.gm[jc];
 #pragma unroll 1
-    for (int c = 0; c < FIB; ++c) {
+    for (int c = c0; c < c1; ++c) {
         const int jbase = J * FT + c * 32;
         const int jidx = jbase + lane;
         __syncwarp();  // every lane is done reading the previous chunk
@@ -221,7 +228,7 @@ __device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J
             w.az[lane] = make_double2(0.0, 0.0);
         }
         __syncwarp();
-        if (c + 1 < FIB) {  // next chunk's loads fly while this one is computed
+        if (c + 1 < c1) {  // next chunk's loads fly while this one is computed
             jc = min(jbase + 32 + lane, a.n - 1);
             nx = a.x[jc];
             ny = a.y[jc];
@@ -275,6 +282,13 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
     int Icur = -1;
     const double radmax = RAD ? a.radmax[0] : 0.0;
     const bool coords_safe = a.radmax[1] < COORD_SAFE_MAX;  // else every block pair takes the fully checked path
+    unsigned long long *tr = a.trace ? a.trace + 4 * ((size_t)blockIdx.x * FWARPS + (threadIdx.x >> 5)) : nullptr;
+    unsigned long long ndone = 0;
+    if (tr && lane == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        tr[0] = t0;
+    }
 
     auto flush = [&]() {
         if (Icur < 0) return;
@@ -302,21 +316,39 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
                 (unsigned long long)a.total_warps;
         return c;  // valid in lane 0 only; broadcast when it is consumed
     };
+    // Claim q covers chunk units [u0, u1) of this launch's run (4 units = the 32-column chunks of one block pair).  The
+    // bulk of the run goes out in whole items; towards the end the claims shrink (4, 2, 1 chunks) so that the kernel
+    // does not end on a ragged edge: three warps share an SMSP and the scheduler does not serve them equally (traced:
+    // 361..987 chunks per warp over one launch), so a block pair claimed late by a slow warp can take 100-200 us.
+    // Measured idle at the end of the launch: 76 us per warp without the grading; that is 7 % of the kernel once eight
+    // GPUs share the work.
+    const long long unit0 = a.item0 * FIB, unit1 = a.item1 * FIB;
+    auto range = [&](unsigned long long qq, long long &u0, long long &u1) -> bool {
+        if (qq >= (unsigned long long)a.ph_q[5]) return false;
+        int k = 0;
+#pragma unroll
+        for (int j = 1; j < 5; ++j) k += (qq >= (unsigned long long)a.ph_q[j]) ? 1 : 0;
+        u0 = unit0 + a.ph_u[k] + (long long)(qq - (unsigned long long)a.ph_q[k]) * a.ph_sz[k];
+        u1 = min(u0 + a.ph_sz[k], unit0 + a.ph_u[k + 1]);  // the last claim of a phase may be short
+        return u0 < unit1;
+    };
     unsigned long long q = (unsigned long long)(a.first_warp + (long long)blockIdx.x * FWARPS + (threadIdx.x >> 5));
     unsigned long long qnext = claim();
     for (;;) {
-        long long t = a.item0 + (long long)q * a.quantum;
-        if (t >= a.item1) {
+        long long u, u_end;
+        if (!range(q, u, u_end)) {
             if (q >= (unsigned long long)a.total_warps) break;  // the failed claim that ends this warp
             // (a warp whose static quantum lies beyond the range falls through to its prefetched claim)
             q = __shfl_sync(0xffffffffu, qnext, 0);
-            qnext = ~0ull;
-            if (q >= (unsigned long long)a.total_warps && a.item0 + (long long)q * a.quantum >= a.item1) break;
+            if (!range(q, u, u_end)) break;
             qnext = claim();
-            continue;
         }
-        const long long t_end = min(a.item1, t + a.quantum);
-        for (; t < t_end; ++t) {
+        while (u < u_end) {
+            const long long t = u / FIB;
+            const int c0 = (int)(u - t * FIB);
+            const int c1 = (int)min((long long)FIB, c0 + (u_end - u));
+            u += c1 - c0;
+            ndone += c1 - c0;
             int I, J;
             bool diag;
             item_decode(t, a, I, J, diag);
@@ -343,15 +375,27 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
             const bool checked = !coords_safe || diag || I == a.nb - 1 || J == a.nb - 1 ||
                                  (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
             if (checked)
-                block_pair<RAD, true, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
+                block_pair<RAD, true, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi, c0, c1);
             else
-                block_pair<RAD, false, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
+                block_pair<RAD, false, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi, c0, c1);
         }
         q = __shfl_sync(0xffffffffu, qnext, 0);
-        if (a.item0 + (long long)q * a.quantum >= a.item1) break;  // that was this warp's one failed claim
+        long long dummy0, dummy1;
+        if (!range(q, dummy0, dummy1)) break;  // that was this warp's one failed claim
         qnext = claim();
     }
+    if (tr && lane == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        tr[1] = t1;
+        tr[2] = ndone;
+    }
     flush();
+    if (tr && lane == 0) {
+        unsigned long long t2;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
+        tr[3] = t2;
+    }
 }
 
 // out[0] = max |radius[i]| (0 when radius == nullptr), out[1] = max over bodies of max(|x|,|y|,|z|); the bit patterns of
@@ -449,15 +493,56 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     }
     const long long mine = a.item1 - a.item0;
     const long long warps_max = (long long)ctx->prop.multiProcessorCount * occ * FWARPS;
-    a.quantum = ctx->tune_nsplit > 0 ? ctx->tune_nsplit : 2;  // measured: 1..2 best at npl = 1e5 (7.9 ms), 8: 8.3, 32: 9.8
+    // Items per coarse claim.  Every claim switches the resident row block (12 REDs + 20 loads + thresholds, with only
+    // three warps per SMSP to hide it): measured at npl = 1e5 with the graded end of the schedule, 1 item 7.90 ms,
+    // 2 items 7.73, 4 items 7.67, 6 items 7.65 (but slower at 7e4 bodies).  Fewer items per warp -> smaller claims.
     const int sharers = reduce ? 1 : ctx->p2p.nranks;
-    if (ctx->tune_nsplit <= 0 && mine / a.quantum < 40 * warps_max * sharers) a.quantum = 1;  // few quanta per warp: finer tail
+    a.quantum = 4;
+    if (mine < 32 * warps_max * sharers) a.quantum = 2;
+    if (mine < 16 * warps_max * sharers) a.quantum = 1;
+    if (ctx->tune_nsplit > 0) a.quantum = ctx->tune_nsplit;
     SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
     a.counter = ctx->scratch64.as<unsigned long long>() + 3;
     a.counter_base = 0;
     a.system_scope = 0;
-    // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work)
-    const long long nquanta = (mine + a.quantum - 1) / a.quantum;
+    // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work).  The last
+    // `fine` chunks per warp (of all sharers) are handed out one 32-column chunk at a time (see the kernel's `range`).
+    // chunks per warp (of all sharers) handed out in 1-, 2-, 4- and 8-chunk claims at the end of the run.  A claim of s
+    // chunks can take ~2 s chunk-times on a warp the scheduler disfavours, so everything finer than s has to last that
+    // long: 2 s chunks per warp for size s.
+    static int fine[4] = {2, 4, 8, 16};
+    static bool fine_read = false;
+    if (!fine_read) {
+        fine_read = true;
+        if (const char *e = getenv("SWCU_FLAT_FINE")) sscanf(e, "%d,%d,%d,%d", &fine[0], &fine[1], &fine[2], &fine[3]);
+    }
+    auto split_quanta = [&](long long items, long long warps_all) -> long long {
+        const long long U = items * FIB, G = (long long)a.quantum * FIB;
+        long long left = U;
+        long long nq[5] = {0, 0, 0, 0, 0};  // phases in run order: G, 8, 4, 2, 1 chunks
+        const int sz[5] = {(int)G, 8, 4, 2, 1};
+        for (int k = 4; k >= 1; --k) {  // carve the fine phases off the end of the run
+            if (sz[k] >= G) continue;
+            long long want = std::min<long long>(left, warps_all * fine[4 - k]);
+            want -= want % sz[k];
+            nq[k] = want / sz[k];
+            left -= want;
+        }
+        // the coarse phase takes what is left; a remainder that is not a multiple of G goes out as one more claim
+        nq[0] = (left + G - 1) / G;
+        long long qacc = 0, uacc = 0;
+        for (int k = 0; k < 5; ++k) {
+            a.ph_q[k] = qacc;
+            a.ph_u[k] = uacc;
+            a.ph_sz[k] = sz[k];
+            qacc += nq[k];
+            uacc += (k == 0) ? left : nq[k] * sz[k];
+        }
+        a.ph_q[5] = qacc;
+        a.ph_u[5] = uacc;
+        return qacc;
+    };
+    const long long nquanta = split_quanta(mine, warps_max * sharers);
     long long units = std::max<long long>(1, std::min<long long>(warps_max, nquanta));
     if (!reduce && ctx->p2p.nranks > 1) {
         // shared counter: never reset (a fast rank must not see a stale zero); every launch consumes exactly
@@ -476,8 +561,25 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
     }
     const int grid = cdiv(units, FWARPS);
+    a.trace = nullptr;
+    static const char *trace_path = getenv("SWCU_FLAT_TRACE");
+    static DevBuf trace_buf;
+    if (trace_path) {
+        SWCU_CUDA(ctx, trace_buf.ensure(sizeof(unsigned long long) * 4 * (size_t)grid * FWARPS));
+        SWCU_CUDA(ctx, cudaMemsetAsync(trace_buf.p, 0, sizeof(unsigned long long) * 4 * (size_t)grid * FWARPS, ctx->stream));
+        a.trace = trace_buf.as<unsigned long long>();
+    }
     kern<<<grid, 32 * FWARPS, 0, ctx->stream>>>(a);
     SWCU_KERNEL_CHECK(ctx);
+    if (trace_path) {  // development aid: dump the per-warp timeline of this launch (overwrites the file)
+        std::vector<unsigned long long> h((size_t)4 * grid * FWARPS);
+        SWCU_CUDA(ctx, cudaMemcpyAsync(h.data(), trace_buf.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (FILE *f = fopen(trace_path, "wb")) {
+            fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+            fclose(f);
+        }
+    }
     if (!reduce) return SWCU_OK;
     if (ctx->nranks > 1) SWCU_TRY(comm_allreduce_sum(ctx, a.fx, 3 * stride));
     return axpy3(ctx, 1.0, a.fx, a.fy, a.fz, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), nullptr, n);

@@ -37,9 +37,10 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     if (s == 12345.6789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true; keeps the chains alive
 }
 
-__global__ void flush_kernel(double *buf, size_t n, double v)
+__global__ void flush_kernel(double2 *buf, size_t n)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = v;
+    const double2 z = make_double2(0.0, 0.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = z;
 }
 
 __global__ void mask_merge_iflag_kernel(int n, const int32_t *lmask, const int32_t *computed, int32_t *inout)
@@ -962,9 +963,10 @@ extern "C" int swcu_probe_hbm_copy(swcu_context *ctx, int64_t bytes, double *gbs
 extern "C" int swcu_flush_l2(swcu_context *ctx)
 {
     SWCU_TRY(check_ctx(ctx));
-    const size_t bytes = (size_t)256 << 20;  // 256 MiB > 126 MB L2
+    static const int mib = env_int("SWCU_FLUSH_MIB", 160);  // 160 MiB = 168 MB = 1.33 x the 126 MB L2
+    const size_t bytes = (size_t)(mib < 128 ? 128 : mib) << 20;
     SWCU_CUDA(ctx, ctx->flush.ensure(bytes));
-    flush_kernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, ctx->stream>>>(ctx->flush.as<double>(), bytes / sizeof(double), 0.0);
+    flush_kernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, ctx->stream>>>(ctx->flush.as<double2>(), bytes / sizeof(double2));
     SWCU_KERNEL_CHECK(ctx);
     return SWCU_OK;
 }
