@@ -211,6 +211,162 @@ module swiftest_cuda
          real(c_double), value :: dt, inv_c2
          integer(c_int), intent(out) :: nfail
       end function
+
+      ! ---- tier 2: democratic-heliocentric glue on the resident populations (helio/helio_step.f90:37-123) ----
+      !! out-vectors are passed as type(c_ptr): c_loc(vec) to receive the value, c_null_ptr to leave it on the device
+      integer(c_int) function swcu_pl_vh2vb(ctx, GMcb, vbcb) bind(C, name="swcu_pl_vh2vb")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx, vbcb
+         real(c_double), value :: GMcb
+      end function
+      integer(c_int) function swcu_pl_vb2vh(ctx, GMcb, vbcb) bind(C, name="swcu_pl_vb2vh")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx, vbcb
+         real(c_double), value :: GMcb
+      end function
+      integer(c_int) function swcu_pl_lindrift(ctx, GMcb, dt, lbeg, pt) bind(C, name="swcu_pl_lindrift")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx, pt
+         real(c_double), value :: GMcb, dt
+         integer(c_int), value :: lbeg
+      end function
+      integer(c_int) function swcu_tp_lindrift(ctx, dt, lbeg) bind(C, name="swcu_tp_lindrift")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         integer(c_int), value :: lbeg
+      end function
+      integer(c_int) function swcu_cb_set_pt(ctx, ptbeg, ptend) bind(C, name="swcu_cb_set_pt")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx, ptbeg, ptend
+      end function
+      integer(c_int) function swcu_cb_get_pt(ctx, ptbeg, ptend) bind(C, name="swcu_cb_get_pt")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx, ptbeg, ptend
+      end function
+      integer(c_int) function swcu_tp_vh2vb(ctx, lbeg) bind(C, name="swcu_tp_vh2vb")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: lbeg
+      end function
+      integer(c_int) function swcu_tp_vb2vh(ctx, lbeg) bind(C, name="swcu_tp_vb2vh")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: lbeg
+      end function
+      integer(c_int) function swcu_body_kick_vb(ctx, kind, dt, lbeg) bind(C, name="swcu_body_kick_vb")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, lbeg
+         real(c_double), value :: dt
+      end function
+      integer(c_int) function swcu_body_drift_vb(ctx, kind, GMcb, dt, nfail) bind(C, name="swcu_body_drift_vb")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         real(c_double), value :: GMcb, dt
+         integer(c_int), intent(out) :: nfail
+      end function
+      integer(c_int) function swcu_body_put_vb(ctx, kind, vb) bind(C, name="swcu_body_put_vb")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         real(c_double), intent(in) :: vb(3,*)
+      end function
+      integer(c_int) function swcu_body_get_vb(ctx, kind, vb, rbeg, rend) bind(C, name="swcu_body_get_vb")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx, vb, rbeg, rend
+         integer(c_int), value :: kind
+      end function
+      integer(c_int) function swcu_helio_step_pl(ctx, GMcb, dt, loop_variant, lclose, lfirst, nfail) &
+            bind(C, name="swcu_helio_step_pl")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: GMcb, dt
+         integer(c_int), value :: loop_variant, lclose, lfirst
+         integer(c_int), intent(out) :: nfail
+      end function
+      integer(c_int) function swcu_helio_step_tp(ctx, GMcb, dt, lfirst, nfail) bind(C, name="swcu_helio_step_tp")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: GMcb, dt
+         integer(c_int), value :: lfirst
+         integer(c_int), intent(out) :: nfail
+      end function
+
+      ! ---- tier 1: energy sums, triangular encounter checks, pl-tp discard, SyMBA list check ----
+      integer(c_int) function swcu_util_get_potential_energy(ctx, npl, lmask, GMcb, Gmass, mass, rb, pe) &
+            bind(C, name="swcu_util_get_potential_energy")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl
+         integer(c_int), intent(in) :: lmask(*)
+         real(c_double), value :: GMcb
+         real(c_double), intent(in) :: Gmass(*), mass(*), rb(3,*)
+         real(c_double), intent(out) :: pe
+      end function
+      integer(c_int) function swcu_util_get_energy_and_momentum(ctx, npl, lmask, GMcb, mass_cb, rbcb, vbcb, Gmass, mass, &
+            radius, rb, vb, lclose, out8) bind(C, name="swcu_util_get_energy_and_momentum")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl, lclose
+         integer(c_int), intent(in) :: lmask(*)
+         real(c_double), value :: GMcb, mass_cb
+         real(c_double), intent(in) :: rbcb(3), vbcb(3), Gmass(*), mass(*), radius(*), rb(3,*), vb(3,*)
+         real(c_double), intent(out) :: out8(8)   !! ke_orbit, pe, be, te, L_orbit(1:3), GMtot
+      end function
+      integer(c_int) function swcu_encounter_check_all_triangular_plpl(ctx, npl, r, v, renc, dt, nenc) &
+            bind(C, name="swcu_encounter_check_all_triangular_plpl")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl
+         real(c_double), intent(in) :: r(3,*), v(3,*), renc(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_check_all_triangular_pltp(ctx, npl, ntp, rpl, vpl, rtp, vtp, rencpl, dt, nenc) &
+            bind(C, name="swcu_encounter_check_all_triangular_pltp")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: npl, ntp
+         real(c_double), intent(in) :: rpl(3,*), vpl(3,*), rtp(3,*), vtp(3,*), rencpl(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_check_all_triangular_plplm(ctx, nplm, nplt, rplm, vplm, rplt, vplt, rencm, &
+            renct, dt, nenc) bind(C, name="swcu_encounter_check_all_triangular_plplm")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nplm, nplt
+         real(c_double), intent(in) :: rplm(3,*), vplm(3,*), rplt(3,*), vplt(3,*), rencm(*), renct(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_discard_pl_tp(ctx, ntp, npl, rtp, vtp, lactive, rpl, vpl, radius, dt, iplanet, ndiscard) &
+            bind(C, name="swcu_discard_pl_tp")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: ntp, npl
+         real(c_double), intent(in) :: rtp(3,*), vtp(3,*), rpl(3,*), vpl(3,*), radius(*)
+         integer(c_int), intent(in) :: lactive(*)   !! merge(1, 0, tp%status == ACTIVE)
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: iplanet(*), ndiscard
+      end function
+      integer(c_int) function swcu_symba_encounter_check_list(ctx, nenc, index1, index2, lencmask, n1, r1, v1, renc1, &
+            radius1, n2, r2, v2, renc2, radius2, dt, lencounter, lvdotr, nfound) &
+            bind(C, name="swcu_symba_encounter_check_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lencmask(*)
+         integer(c_int), value :: n1, n2
+         real(c_double), intent(in) :: r1(3,*), v1(3,*), renc1(*), radius1(*)
+         type(c_ptr), value :: r2, v2, renc2, radius2   !! c_null_ptr for the pl-pl form / absent arrays
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: lencounter(*)
+         integer(c_int), intent(inout) :: lvdotr(*)
+         integer(c_int64_t), intent(out) :: nfound
+      end function
    end interface
 
 contains

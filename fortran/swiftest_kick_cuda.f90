@@ -104,3 +104,63 @@
 !               call swcu_check(swcu_symba_kick_subtract_encounters(swcu_ctx, npl, int(plpl_encounter%nenc, c_int64_t), &
 !                     plpl_encounter%index1, plpl_encounter%index2, pl%rh, pl%Gmass, pl%radius, pl%ah), "symba subtract")
 !            end if
+
+! ---- in submodule(helio) s_helio_step: the whole democratic-heliocentric step stays on the device (tier 2) ---------
+!    helio_step_pl (helio_step.f90:37-78) and helio_step_tp (:81-123) become one call each.  The resident arrays were
+!    uploaded by swcu_body_sync when swcu_generation_pl / _tp last changed; rh, vh (and vb for output) come back with
+!    swcu_body_get / swcu_body_get_vb only when the driver writes a frame (INTEGRATION.md section 3, hook 3).
+   module subroutine helio_step_pl(self, nbody_system, param, t, dt)
+      use swiftest_cuda
+      implicit none
+      class(helio_pl),              intent(inout) :: self
+      class(swiftest_nbody_system), intent(inout) :: nbody_system
+      class(swiftest_parameters),   intent(inout) :: param
+      real(DP),                     intent(in)    :: t, dt
+      integer(c_int) :: nfail, variant
+      if (self%nbody == 0) return
+      variant = merge(SWCU_LOOP_FLAT, SWCU_LOOP_TRIANGULAR, param%lflatten_interactions)
+      call swcu_check(swcu_helio_step_pl(swcu_ctx, nbody_system%cb%Gmass, dt, variant, &
+                                         merge(1_c_int, 0_c_int, param%lclose), merge(1_c_int, 0_c_int, self%lfirst), nfail), &
+                      "helio_step_pl")
+      self%lfirst = .false.
+      if (nfail > 0) call helio_step_fetch_drift_failures(self)   ! swcu_body_get(iflag) -> DISCARDED_DRIFTERR (helio_drift.f90:41-50)
+   end subroutine
+
+   module subroutine helio_step_tp(self, nbody_system, param, t, dt)
+      use swiftest_cuda
+      implicit none
+      class(helio_tp),              intent(inout) :: self
+      class(swiftest_nbody_system), intent(inout) :: nbody_system
+      class(swiftest_parameters),   intent(inout) :: param
+      real(DP),                     intent(in)    :: t, dt
+      integer(c_int) :: nfail
+      if (self%nbody == 0) return
+      call swcu_check(swcu_helio_step_tp(swcu_ctx, nbody_system%cb%Gmass, dt, merge(1_c_int, 0_c_int, self%lfirst), nfail), &
+                      "helio_step_tp")
+      self%lfirst = .false.
+      if (nfail > 0) call helio_step_fetch_drift_failures(self)
+   end subroutine
+
+! ---- in submodule(swiftest) s_swiftest_util: swiftest_util_get_potential_energy_flat / _triangular -----------------
+   module subroutine swiftest_util_get_potential_energy_triangular(npl, lmask, GMcb, Gmass, mass, rb, pe)
+      use swiftest_cuda
+      implicit none
+      integer(I4B),                 intent(in)  :: npl
+      logical,      dimension(:),   intent(in)  :: lmask
+      real(DP),                     intent(in)  :: GMcb
+      real(DP),     dimension(:),   intent(in)  :: Gmass, mass
+      real(DP),     dimension(:,:), intent(in)  :: rb
+      real(DP),                     intent(out) :: pe
+      integer(c_int), dimension(npl) :: imask
+      imask(:) = merge(1_c_int, 0_c_int, lmask(1:npl))
+      call swcu_check(swcu_util_get_potential_energy(swcu_ctx, npl, imask, GMcb, Gmass, mass, rb, pe), "potential energy")
+   end subroutine
+
+! ---- in submodule(swiftest) s_swiftest_discard: the double loop of swiftest_discard_pl_tp (:261-288) ---------------
+!         call swcu_check(swcu_discard_pl_tp(swcu_ctx, ntp, npl, tp%rh, tp%vh, merge(1_c_int, 0_c_int, tp%status(1:ntp) == ACTIVE), &
+!                                            pl%rh, pl%vh, pl%radius, param%dt, iplanet, ndiscard), "discard_pl_tp")
+!         do i = 1, ntp            ! the bookkeeping (status, ldiscard, log line, info%set_value) stays as it is,
+!            j = iplanet(i)        ! driven by the planet index the kernel found
+!            if (j == 0) cycle
+!            tp%status(i) = DISCARDED_PLR ; tp%lmask(i) = .false. ; pl%ldiscard(j) = .true. ; ...
+!         end do

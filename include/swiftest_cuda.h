@@ -196,6 +196,32 @@ int swcu_helio_step_pl(swcu_context *ctx, double GMcb, double dt, int32_t loop_v
  * swcu_helio_step_pl left on the device (npl <= 64) */
 int swcu_helio_step_tp(swcu_context *ctx, double GMcb, double dt, int32_t lfirst, int32_t *nfail);
 
+/* ---- tier 1: triangular encounter checks, pl-tp discard, SyMBA list check ----------------
+ * encounter_check_all_triangular_plpl / _pltp / _plplm (encounter_check.f90:436-570): the predicate on every pair
+ * (ENCOUNTER_CHECK TRIANGULAR), no broad phase; same two-phase result protocol and canonical order as the sweep. */
+int swcu_encounter_check_all_triangular_plpl(swcu_context *ctx, int32_t npl, const double *r, const double *v,
+                                             const double *renc, double dt, int64_t *nenc);
+int swcu_encounter_check_all_triangular_pltp(swcu_context *ctx, int32_t npl, int32_t ntp, const double *rpl,
+                                             const double *vpl, const double *rtp, const double *vtp,
+                                             const double *rencpl, double dt, int64_t *nenc);
+int swcu_encounter_check_all_triangular_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt, const double *rplm,
+                                              const double *vplm, const double *rplt, const double *vplt,
+                                              const double *rencm, const double *renct, double dt, int64_t *nenc);
+/* swiftest_discard_pl_tp (swiftest_discard.f90:244-337): iplanet(i) = the first planet (1-based, ascending index) that
+ * active test particle i is, or within dt will be, closer to than its radius; 0 = keep.  lactive may be NULL. */
+int swcu_discard_pl_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double *rtp, const double *vtp,
+                       const int32_t *lactive, const double *rpl, const double *vpl, const double *radius, double dt,
+                       int32_t *iplanet, int32_t *ndiscard);
+/* the pair loop of symba_encounter_check_list_plpl / _pltp (symba_encounter_check.f90:122-137, 197-211) over an
+ * existing encounter list: lencounter(k), lvdotr(k) for the pairs of lencmask (lvdotr is left alone elsewhere).
+ * n2 == 0: both indices address list 1 (pl-pl); else index2 addresses list 2 (renc2 / radius2 may be NULL: 0).
+ * The level bookkeeping that follows (:139-153) stays with the caller. */
+int swcu_symba_encounter_check_list(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                                    const int32_t *lencmask, int32_t n1, const double *r1, const double *v1,
+                                    const double *renc1, const double *radius1, int32_t n2, const double *r2,
+                                    const double *v2, const double *renc2, const double *radius2, double dt,
+                                    int32_t *lencounter, int32_t *lvdotr, int64_t *nfound);
+
 /* ---- tier 1: energy and angular momentum of the massive bodies -------------------------------
  * swiftest_util_get_potential_energy_flat / _triangular (swiftest_util.f90:1291-1394): both add the same terms, one
  * kernel serves both.  rb(3,npl) barycentric positions, mass = Gmass/GU; lmask may be NULL (all bodies). */

@@ -46,7 +46,7 @@ class Oracle:
         for n in ("swo_encounter_sas_pltp", "swo_encounter_tri_pltp"):
             getattr(L, n).restype = i64
             getattr(L, n).argtypes = [i32, i32, p, p, p, p, p, d]
-        for n in ("swo_encounter_sas_plplm", "swo_encounter_all_plplm"):
+        for n in ("swo_encounter_sas_plplm", "swo_encounter_all_plplm", "swo_encounter_tri_plplm"):
             getattr(L, n).restype = i64
             getattr(L, n).argtypes = [i32, i32, p, p, p, p, p, p, d]
         L.swo_encounter_last_nbox_total.restype = i64
@@ -69,6 +69,10 @@ class Oracle:
         L.swo_helio_step_pl.argtypes = [i32, d, p, p, C.c_int, p, p, d, p, p, p, p, p, p, p, p, p, p]
         L.swo_helio_step_tp.argtypes = [i32, i32, d, p, p, p, p, p, p, p, d, p, p, p, p, p]
         L.swo_whm_kick_getacch_ah0.argtypes = [i32, p, p, p]
+        L.swo_discard_pl_tp.restype = i32
+        L.swo_discard_pl_tp.argtypes = [i32, i32, p, p, p, p, p, p, d, p]
+        L.swo_symba_encounter_check_list.restype = i64
+        L.swo_symba_encounter_check_list.argtypes = [i64, p, p, p, p, p, p, p, p, p, p, p, d, p, p]
         L.swo_get_potential_energy_tri.argtypes = [i32, p, d, p, p, p, p]
         L.swo_get_potential_energy_flat.argtypes = [i32, i64, p, p, d, p, p, p, p]
         L.swo_get_energy_and_momentum.argtypes = [i32, p, d, d, p, p, p, p, p, p, p, C.c_int, C.c_int, p]
@@ -205,9 +209,11 @@ class Oracle:
                   renc.ctypes.data, float(dt))
         return self._fetch(nenc)
 
-    def encounter_plplm(self, rplm, vplm, rplt, vplt, rencm, renct, dt, merged=False):
+    def encounter_plplm(self, rplm, vplm, rplt, vplt, rencm, renct, dt, merged=False, triangular=False):
         a = [_c(q) for q in (rplm, vplm, rplt, vplt, rencm, renct)]
         fn = self.lib.swo_encounter_all_plplm if merged else self.lib.swo_encounter_sas_plplm
+        if triangular:
+            fn = self.lib.swo_encounter_tri_plplm
         nenc = fn(len(a[4]), len(a[5]), *[q.ctypes.data for q in a], float(dt))
         return self._fetch(nenc)
 
@@ -326,6 +332,33 @@ class Oracle:
                                              self._a(Gmass), self._a(mass), self._a(radius), self._a(rb), self._a(vb),
                                              int(lclose), int(flat), self._a(out))
         return dict(ke_orbit=out[0], pe=out[1], be=out[2], te=out[3], L_orbit=out[4:7].copy(), GMtot=out[7])
+
+    def discard_pl_tp(self, rtp, vtp, lactive, rpl, vpl, radius, dt):
+        rtp, vtp, rpl, vpl, radius = _c(rtp), _c(vtp), _c(rpl), _c(vpl), _c(radius)
+        la = None if lactive is None else _c(lactive, _i32)
+        ipl = np.zeros(len(rtp), _i32)
+        nd = self.lib.swo_discard_pl_tp(len(rtp), len(rpl), self._a(rtp), self._a(vtp), self._a(la), self._a(rpl),
+                                        self._a(vpl), self._a(radius), float(dt), self._a(ipl))
+        return ipl, int(nd)
+
+    def symba_encounter_check_list(self, index1, index2, lencmask, r1, v1, renc1, radius1, dt, r2=None, v2=None,
+                                   renc2=None, radius2=None, lvdotr=None):
+        index1, index2 = _c(index1, _i32), _c(index2, _i32)
+        nenc = len(index1)
+        lm = None if lencmask is None else _c(lencmask, _i32)
+        r1, v1, renc1, radius1 = _c(r1), _c(v1), _c(renc1), _c(radius1)
+        if r2 is None:
+            r2, v2, renc2, radius2 = r1, v1, renc1, radius1
+        else:
+            r2, v2 = _c(r2), _c(v2)
+            renc2 = None if renc2 is None else _c(renc2)
+            radius2 = None if radius2 is None else _c(radius2)
+        lenc = np.zeros(nenc, _i32)
+        lvd = np.zeros(nenc, _i32) if lvdotr is None else _c(lvdotr, _i32).copy()
+        n = self.lib.swo_symba_encounter_check_list(nenc, self._a(index1), self._a(index2), self._a(lm), self._a(r1),
+                                                    self._a(v1), self._a(renc1), self._a(radius1), self._a(r2), self._a(v2),
+                                                    self._a(renc2), self._a(radius2), float(dt), self._a(lenc), self._a(lvd))
+        return lenc, lvd, int(n)
 
 
 _cache = {}

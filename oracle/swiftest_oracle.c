@@ -1082,3 +1082,23 @@ int64_t swo_encounter_tri_pltp(int32_t npl, int32_t ntp, const double *rpl, cons
     }
     return g_nkeys;
 }
+
+/* encounter_check.f90:475-522: plm x plt double loop, index1 = plm index, index2 = plt index (caller shifts by nplm) */
+int64_t swo_encounter_tri_plplm(int32_t nplm, int32_t nplt, const double *rplm, const double *vplm, const double *rplt,
+                                const double *vplt, const double *rencm, const double *renct, double dt)
+{
+    keys_reset();
+    for (int32_t i = 1; i <= nplm; ++i) {
+        const double *ri = rplm + 3 * (size_t)(i - 1), *vi = vplm + 3 * (size_t)(i - 1);
+        for (int32_t j = 1; j <= nplt; ++j) {
+            const double *rj = rplt + 3 * (size_t)(j - 1), *vj = vplt + 3 * (size_t)(j - 1);
+            double xr = rj[0] - ri[0], yr = rj[1] - ri[1], zr = rj[2] - ri[2];
+            double vxr = vj[0] - vi[0], vyr = vj[1] - vi[1], vzr = vj[2] - vi[2];
+            double renc12 = rencm[i - 1] + renct[j - 1];
+            int32_t lenc, lvd;
+            swo_encounter_check_one(xr, yr, zr, vxr, vyr, vzr, renc12, dt, &lenc, &lvd);
+            if (lenc) keys_push(i, j);
+        }
+    }
+    return g_nkeys;
+}

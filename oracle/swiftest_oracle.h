@@ -98,6 +98,8 @@ int64_t swo_encounter_all_plplm(int32_t nplm, int32_t nplt, const double *rplm, 
 int64_t swo_encounter_tri_plpl(int32_t npl, const double *r, const double *v, const double *renc, double dt);
 int64_t swo_encounter_tri_pltp(int32_t npl, int32_t ntp, const double *rpl, const double *vpl, const double *rtp,
                                const double *vtp, const double *rencpl, double dt);
+int64_t swo_encounter_tri_plplm(int32_t nplm, int32_t nplt, const double *rplm, const double *vplm, const double *rplt,
+                                const double *vplt, const double *rencm, const double *renct, double dt);
 void swo_encounter_fetch(int32_t *index1, int32_t *index2, int32_t *lvdotr);
 /* statistics of the last sort-and-sweep call: sum_i nbox_i over loverlap bodies (broad-phase candidates) */
 int64_t swo_encounter_last_nbox_total(void);
@@ -121,6 +123,13 @@ void swo_helio_step_pl(int32_t npl, double GMcb, const double *Gmass, const doub
 void swo_helio_step_tp(int32_t ntp, int32_t npl, double GMcb, const double *GMpl, const double *rbeg,
                        const double *rend, const double *ptbeg, const double *ptend, const int32_t *lmask,
                        int32_t *lfirst, double dt, double *rh, double *vh, double *vb, double *ah, int32_t *iflag);
+void swo_discard_pl_close(const double *dx, const double *dv, double dt, double r2crit, int32_t *iflag, double *r2min);
+int32_t swo_discard_pl_tp(int32_t ntp, int32_t npl, const double *rtp, const double *vtp, const int32_t *lactive,
+                          const double *rpl, const double *vpl, const double *radius, double dt, int32_t *iplanet);
+int64_t swo_symba_encounter_check_list(int64_t nenc, const int32_t *index1, const int32_t *index2,
+                                       const int32_t *lencmask, const double *r1, const double *v1, const double *renc1,
+                                       const double *radius1, const double *r2, const double *v2, const double *renc2,
+                                       const double *radius2, double dt, int32_t *lencounter, int32_t *lvdotr);
 void swo_whm_kick_getacch_ah0(int32_t n, const double *mu, const double *rhp, double *ah0);
 void swo_get_potential_energy_tri(int32_t npl, const int32_t *lmask, double GMcb, const double *Gmass,
                                   const double *mass, const double *rb, double *pe);

@@ -324,3 +324,87 @@ void swo_get_energy_and_momentum(int32_t npl, const int32_t *lmask, double GMcb,
     out[2] = be;
     out[3] = out[0] + 0.0 + out[1] + out[2];
 }
+
+/* swiftest_discard_pl_close, swiftest/swiftest_discard.f90:295-337 */
+void swo_discard_pl_close(const double *dx, const double *dv, double dt, double r2crit, int32_t *iflag, double *r2min)
+{
+    const double r2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+    *r2min = r2;
+    if (r2 <= r2crit) {
+        *iflag = 1;
+    } else {
+        const double vdotr = dx[0] * dv[0] + dx[1] * dv[1] + dx[2] * dv[2];
+        if (vdotr > 0.0) {
+            *iflag = 0;
+        } else {
+            const double v2 = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+            const double tmin = -vdotr / v2;
+            double m;
+            if (tmin < dt) m = r2 - vdotr * vdotr / v2;
+            else m = r2 + 2 * vdotr * dt + v2 * (dt * dt);
+            m = m < r2 ? m : r2; /* min(r2min, r2) */
+            *r2min = m;
+            *iflag = (m <= r2crit) ? 1 : 0;
+        }
+    }
+}
+
+/* swiftest_discard_pl_tp, swiftest_discard.f90:244-292: for every ACTIVE test particle the FIRST planet (ascending j)
+ * whose discard_pl_close test fires; iplanet[i] = that j (1-based) or 0.  Returns the number of particles discarded. */
+int32_t swo_discard_pl_tp(int32_t ntp, int32_t npl, const double *rtp, const double *vtp, const int32_t *lactive,
+                          const double *rpl, const double *vpl, const double *radius, double dt, int32_t *iplanet)
+{
+    int32_t nd = 0;
+    for (int32_t i = 0; i < ntp; ++i) {
+        iplanet[i] = 0;
+        if (lactive && !lactive[i]) continue;
+        for (int32_t j = 0; j < npl; ++j) {
+            double dx[3], dv[3], r2min;
+            int32_t isp;
+            for (int k = 0; k < 3; ++k) {
+                dx[k] = rtp[3 * i + k] - rpl[3 * j + k];
+                dv[k] = vtp[3 * i + k] - vpl[3 * j + k];
+            }
+            swo_discard_pl_close(dx, dv, dt, radius[j] * radius[j], &isp, &r2min);
+            if (isp != 0) {
+                iplanet[i] = j + 1;
+                ++nd;
+                break;
+            }
+        }
+    }
+    return nd;
+}
+
+/* The pair loop of symba_encounter_check_list_plpl / _pltp, symba/symba_encounter_check.f90:122-137 / 197-211:
+ * for the pairs of the mask: xr = r2(j) - r1(i), vr = v2(j) - v1(i), rcrit = renc1(i) + renc2(j) (renc2 == NULL: test
+ * particles, 0), encounter_check_one, then drop physically overlapping pairs (rji2 > (radius1(i) + radius2(j))**2 must
+ * hold; radius2 == NULL: 0).  lencounter[k] is written for every k (0 outside the mask), lvdotr[k] only inside it.
+ * Returns the number of encounters. */
+int64_t swo_symba_encounter_check_list(int64_t nenc, const int32_t *index1, const int32_t *index2,
+                                       const int32_t *lencmask, const double *r1, const double *v1, const double *renc1,
+                                       const double *radius1, const double *r2, const double *v2, const double *renc2,
+                                       const double *radius2, double dt, int32_t *lencounter, int32_t *lvdotr)
+{
+    int64_t n = 0;
+    for (int64_t k = 0; k < nenc; ++k) {
+        lencounter[k] = 0;
+        if (lencmask && !lencmask[k]) continue;
+        const int32_t i = index1[k] - 1, j = index2[k] - 1;
+        const double xr = r2[3 * j] - r1[3 * i], yr = r2[3 * j + 1] - r1[3 * i + 1], zr = r2[3 * j + 2] - r1[3 * i + 2];
+        const double vxr = v2[3 * j] - v1[3 * i], vyr = v2[3 * j + 1] - v1[3 * i + 1], vzr = v2[3 * j + 2] - v1[3 * i + 2];
+        const double rcrit12 = renc1[i] + (renc2 ? renc2[j] : 0.0);
+        int32_t lenc, lvd;
+        swo_encounter_check_one(xr, yr, zr, vxr, vyr, vzr, rcrit12, dt, &lenc, &lvd);
+        lvdotr[k] = lvd;
+        if (lenc) {
+            const double rl = radius1[i] + (radius2 ? radius2[j] : 0.0);
+            const double rlim2 = rl * rl;
+            const double rji2 = xr * xr + yr * yr + zr * zr;
+            lenc = rji2 > rlim2;
+        }
+        lencounter[k] = lenc;
+        n += lenc ? 1 : 0;
+    }
+    return n;
+}

@@ -330,6 +330,68 @@ class Context:
                                             C.byref(nf) if want_nfail else None))
         return nf.value
 
+    # ---- triangular encounter checks, discard, SyMBA list check ----
+    def encounter_check_all_triangular_plpl(self, npl, r, v, renc, dt):
+        r, v, renc = _vec3(r, npl), _vec3(v, npl), _vec(renc, npl)
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_triangular_plpl(self._h, npl, _ptr(r), _ptr(v), _ptr(renc), float(dt),
+                                                                  C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_check_all_triangular_pltp(self, npl, ntp, rpl, vpl, rtp, vtp, rencpl, dt):
+        rpl, vpl, rtp, vtp = _vec3(rpl, npl), _vec3(vpl, npl), _vec3(rtp, ntp), _vec3(vtp, ntp)
+        rencpl = _vec(rencpl, npl)
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_triangular_pltp(self._h, npl, ntp, _ptr(rpl), _ptr(vpl), _ptr(rtp),
+                                                                  _ptr(vtp), _ptr(rencpl), float(dt), C.byref(n)))
+        return self._fetch(n.value)
+
+    def encounter_check_all_triangular_plplm(self, nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt):
+        rplm, vplm, rplt, vplt = _vec3(rplm, nplm), _vec3(vplm, nplm), _vec3(rplt, nplt), _vec3(vplt, nplt)
+        rencm, renct = _vec(rencm, nplm), _vec(renct, nplt)
+        n = C.c_int64()
+        self._ck(self._L.swcu_encounter_check_all_triangular_plplm(self._h, nplm, nplt, _ptr(rplm), _ptr(vplm), _ptr(rplt),
+                                                                   _ptr(vplt), _ptr(rencm), _ptr(renct), float(dt),
+                                                                   C.byref(n)))
+        return self._fetch(n.value)
+
+    def discard_pl_tp(self, rtp, vtp, lactive, rpl, vpl, radius, dt):
+        """swiftest_discard_pl_tp: returns (iplanet[ntp] with the 1-based discarding planet or 0, number discarded)."""
+        rtp, vtp = _vec3(rtp), _vec3(vtp)
+        ntp = rtp.shape[0]
+        rpl, vpl = _vec3(rpl), _vec3(vpl)
+        npl = rpl.shape[0]
+        radius = _vec(radius, npl)
+        lactive = None if lactive is None else _vec(lactive, ntp, _i32)
+        ipl = np.zeros(ntp, _i32)
+        nd = C.c_int32()
+        self._ck(self._L.swcu_discard_pl_tp(self._h, ntp, npl, _ptr(rtp), _ptr(vtp), _ptr(lactive), _ptr(rpl), _ptr(vpl),
+                                            _ptr(radius), float(dt), _ptr(ipl), C.byref(nd)))
+        return ipl, nd.value
+
+    def symba_encounter_check_list(self, index1, index2, lencmask, r1, v1, renc1, radius1, dt, r2=None, v2=None,
+                                   renc2=None, radius2=None, lvdotr=None):
+        """Pair loop of symba_encounter_check_list_plpl (r2 None) / _pltp.  Returns (lencounter, lvdotr, nfound)."""
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lencmask = None if lencmask is None else _vec(lencmask, nenc, _i32)
+        r1, v1 = _vec3(r1), _vec3(v1)
+        n1 = r1.shape[0]
+        renc1, radius1 = _vec(renc1, n1), _vec(radius1, n1)
+        n2 = 0
+        if r2 is not None:
+            r2, v2 = _vec3(r2), _vec3(v2)
+            n2 = r2.shape[0]
+            renc2 = None if renc2 is None else _vec(renc2, n2)
+            radius2 = None if radius2 is None else _vec(radius2, n2)
+        lenc = np.zeros(nenc, _i32)
+        lvd = np.zeros(nenc, _i32) if lvdotr is None else _vec(lvdotr, nenc, _i32).copy()
+        nf = C.c_int64()
+        self._ck(self._L.swcu_symba_encounter_check_list(
+            self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lencmask), n1, _ptr(r1), _ptr(v1), _ptr(renc1), _ptr(radius1),
+            n2, _ptr(r2), _ptr(v2), _ptr(renc2), _ptr(radius2), float(dt), _ptr(lenc), _ptr(lvd), C.byref(nf)))
+        return lenc, lvd, nf.value
+
     # ---- energy and momentum (swiftest_util.f90:1172-1394) ----
     def util_get_potential_energy(self, npl, lmask, GMcb, Gmass, mass, rb):
         lmask = None if lmask is None else _vec(lmask, npl, _i32)

@@ -271,6 +271,193 @@ __global__ void set_renc_kernel(int n, const double *__restrict__ rhill, double 
     if (i < n) renc[i] = rhill[i] * RHSCALE * rshell_irec;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Triangular (all-pairs) variants, encounter_check_all_triangular_plpl / _plplm / _pltp (:436-570) with
+// encounter_check_all_triangular_one (:384-433): the predicate on every pair, no broad phase.  One row body per thread,
+// column bodies staged in shared memory TRI_T at a time, hits appended with a warp-aggregated atomic; the canonical
+// (index1, index2) order comes from the same key sort as the sweep.  O(n1*n2) FP64 compare work: this is the
+// `ENCOUNTER_CHECK TRIANGULAR` option of the reference and the superset checker for the sweep.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TRI_T = 128;
+constexpr int TRI_COLS = 2048;
+
+__global__ void __launch_bounds__(TRI_T) tri_check_kernel(ListDev a, ListDev b, int single, double dt, double vsmall,
+                                                          unsigned long long *__restrict__ cand, unsigned long long cap,
+                                                          unsigned long long *__restrict__ count)
+{
+    __shared__ double sx[TRI_T], sy[TRI_T], sz[TRI_T], svx[TRI_T], svy[TRI_T], svz[TRI_T], sr[TRI_T];
+    const ListDev &c = single ? a : b;
+    const int row0 = blockIdx.x * TRI_T;
+    const int i = row0 + threadIdx.x;
+    const bool ion = i < a.n;
+    const int ic = ion ? i : a.n - 1;
+    const double xi = a.x[ic], yi = a.y[ic], zi = a.z[ic], vxi = a.vx[ic], vyi = a.vy[ic], vzi = a.vz[ic];
+    const double renci = a.renc ? a.renc[ic] : 0.0;
+    const int c0 = blockIdx.y * TRI_COLS, c1 = min(c.n, c0 + TRI_COLS);
+    const int lane = threadIdx.x & 31;
+    for (int t0 = c0; t0 < c1; t0 += TRI_T) {
+        if (single && t0 + TRI_T - 1 <= row0) continue;  // every column of this tile has j <= every row of the CTA
+        __syncthreads();
+        {
+            const int j = min(t0 + (int)threadIdx.x, c.n - 1);
+            sx[threadIdx.x] = c.x[j];
+            sy[threadIdx.x] = c.y[j];
+            sz[threadIdx.x] = c.z[j];
+            svx[threadIdx.x] = c.vx[j];
+            svy[threadIdx.x] = c.vy[j];
+            svz[threadIdx.x] = c.vz[j];
+            sr[threadIdx.x] = c.renc ? c.renc[j] : 0.0;
+        }
+        __syncthreads();
+        const int jn = min(TRI_T, c1 - t0);
+        for (int jj = 0; jj < jn; ++jj) {
+            const int j = t0 + jj;
+            bool hit = false;
+            if (ion && (!single || j > i)) {
+                const double xr = sx[jj] - xi, yr = sy[jj] - yi, zr = sz[jj] - zi;
+                const double vxr = svx[jj] - vxi, vyr = svy[jj] - vyi, vzr = svz[jj] - vzi;
+                const double renc12 = renci + sr[jj];
+                hit = check_one(xr, yr, zr, vxr, vyr, vzr, renc12, dt, vsmall);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                unsigned long long base = 0;
+                if (lane == __ffs(m) - 1) base = atomicAdd(count, (unsigned long long)__popc(m));
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (hit) {
+                    const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < cap) cand[slot] = ((unsigned long long)(unsigned)(i + 1) << 32) | (unsigned)(j + 1);
+                }
+            }
+        }
+    }
+}
+
+// swiftest_discard_pl_close (swiftest/swiftest_discard.f90:295-337)
+__device__ __forceinline__ int discard_pl_close(double dx, double dy, double dz, double dvx, double dvy, double dvz,
+                                                double dt, double r2crit)
+{
+    const double r2 = dx * dx + dy * dy + dz * dz;
+    if (r2 <= r2crit) return 1;
+    const double vdotr = dx * dvx + dy * dvy + dz * dvz;
+    if (vdotr > 0.0) return 0;
+    const double v2 = dvx * dvx + dvy * dvy + dvz * dvz;
+    const double tmin = -vdotr / v2;
+    double r2min;
+    if (tmin < dt)
+        r2min = r2 - vdotr * vdotr / v2;
+    else
+        r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
+    r2min = (r2min < r2) ? r2min : r2;  // min(r2min, r2); a NaN (v2 == 0) falls back to r2 like the intrinsic
+    return (r2min <= r2crit) ? 1 : 0;
+}
+
+// swiftest_discard_pl_tp (swiftest_discard.f90:244-292): for every active test particle the first planet, in ascending
+// index order, that it is or will be too close to within dt.  iplanet = 1-based planet index or 0.
+__global__ void __launch_bounds__(128) discard_pl_tp_kernel(int ntp, int npl, const double *__restrict__ tx,
+                                                            const double *__restrict__ ty, const double *__restrict__ tz,
+                                                            const double *__restrict__ tvx, const double *__restrict__ tvy,
+                                                            const double *__restrict__ tvz, const int32_t *__restrict__ lactive,
+                                                            const double *__restrict__ px, const double *__restrict__ py,
+                                                            const double *__restrict__ pz, const double *__restrict__ pvx,
+                                                            const double *__restrict__ pvy, const double *__restrict__ pvz,
+                                                            const double *__restrict__ radius, double dt,
+                                                            int32_t *__restrict__ iplanet, int *__restrict__ ndiscard)
+{
+    __shared__ double sx[128], sy[128], sz[128], svx[128], svy[128], svz[128], sr2[128];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool on = i < ntp && lactive[i] != 0;
+    const int ic = min(i, ntp - 1);
+    const double xi = tx[ic], yi = ty[ic], zi = tz[ic], vxi = tvx[ic], vyi = tvy[ic], vzi = tvz[ic];
+    int found = 0;
+    for (int t0 = 0; t0 < npl; t0 += 128) {
+        if (__syncthreads_and(found != 0 || !on)) break;  // nobody in this CTA is still looking
+        {
+            const int j = min(t0 + (int)threadIdx.x, npl - 1);
+            sx[threadIdx.x] = px[j];
+            sy[threadIdx.x] = py[j];
+            sz[threadIdx.x] = pz[j];
+            svx[threadIdx.x] = pvx[j];
+            svy[threadIdx.x] = pvy[j];
+            svz[threadIdx.x] = pvz[j];
+            const double r = radius[j];
+            sr2[threadIdx.x] = r * r;
+        }
+        __syncthreads();
+        const int jn = min(128, npl - t0);
+        if (on && found == 0) {
+            for (int jj = 0; jj < jn; ++jj) {
+                if (discard_pl_close(xi - sx[jj], yi - sy[jj], zi - sz[jj], vxi - svx[jj], vyi - svy[jj], vzi - svz[jj], dt,
+                                     sr2[jj])) {
+                    found = t0 + jj + 1;
+                    break;
+                }
+            }
+        }
+    }
+    if (i < ntp) {
+        iplanet[i] = found;
+        if (found) atomicAdd(ndiscard, 1);
+    }
+}
+
+// encounter_check_one with both outputs (lencounter, lvdotr), :573-621
+__device__ __forceinline__ bool check_one_full(double xr, double yr, double zr, double vxr, double vyr, double vzr,
+                                               double renc, double dt, double vsmall, bool &lvdotr)
+{
+    const double r2 = xr * xr + yr * yr + zr * zr;
+    const double r2crit = renc * renc;
+    if (!(r2 > r2crit)) {  // vdotr = -1, r2min = r2
+        lvdotr = true;
+        return true;
+    }
+    const double vdotr = vxr * xr + vyr * yr + vzr * zr;
+    lvdotr = (vdotr < 0.0);
+    if (vdotr > 0.0) return false;
+    double r2min;
+    const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
+    if (v2 <= vsmall) {
+        r2min = r2;
+    } else {
+        const double tmin = -vdotr / v2;
+        if (tmin < dt)
+            r2min = r2 - vdotr * vdotr / v2;
+        else
+            r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
+    }
+    return lvdotr && (r2min <= r2crit);
+}
+
+// the pair loop of symba_encounter_check_list_plpl / _pltp (symba/symba_encounter_check.f90:122-137, 197-211)
+__global__ void symba_check_list_kernel(long long nenc, const int32_t *__restrict__ index1,
+                                        const int32_t *__restrict__ index2, const int32_t *__restrict__ lencmask, ListDev a,
+                                        const double *__restrict__ radius1, ListDev b, const double *__restrict__ radius2,
+                                        double dt, double vsmall, int32_t *__restrict__ lencounter,
+                                        int32_t *__restrict__ lvdotr, unsigned long long *__restrict__ count)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nenc) return;
+    if (lencmask && lencmask[k] == 0) {
+        lencounter[k] = 0;
+        return;
+    }
+    const int i = index1[k] - 1, j = index2[k] - 1;
+    const double xr = b.x[j] - a.x[i], yr = b.y[j] - a.y[i], zr = b.z[j] - a.z[i];
+    const double vxr = b.vx[j] - a.vx[i], vyr = b.vy[j] - a.vy[i], vzr = b.vz[j] - a.vz[i];
+    const double rcrit12 = a.renc[i] + (b.renc ? b.renc[j] : 0.0);
+    bool lvd;
+    bool lenc = check_one_full(xr, yr, zr, vxr, vyr, vzr, rcrit12, dt, vsmall, lvd);
+    lvdotr[k] = lvd ? 1 : 0;
+    if (lenc) {  // physically overlapping bodies are ignored (:131-135)
+        const double rl = radius1[i] + (radius2 ? radius2[j] : 0.0);
+        const double rlim2 = rl * rl;
+        const double rji2 = xr * xr + yr * yr + zr * zr;
+        lenc = rji2 > rlim2;
+    }
+    lencounter[k] = lenc ? 1 : 0;
+    if (lenc) atomicAdd(count, 1ull);
+}
+
 ListDev to_dev(const SweepList &l)
 {
     ListDev d;
@@ -292,6 +479,33 @@ int set_renc(swcu_context *ctx, Body &pl, int irec)
 }
 
 // Sort-and-sweep of one list (l2 == nullptr) or two lists.  Leaves the sorted unique keys in ctx->enc.uniq.
+// K11 canonical order + duplicate removal (:976-985, :703-757) of the ncand keys in E.cand
+int canonical_order(swcu_context *ctx, long long ncand, int64_t *nenc_out)
+{
+    auto &E = ctx->enc;
+    int *d_nuniq = reinterpret_cast<int *>(E.counters.as<unsigned long long>() + 2);
+    SWCU_CUDA(ctx, E.cand_sorted.ensure(sizeof(unsigned long long) * ncand));
+    SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * ncand));
+    size_t tmp_k = 0, tmp_u = 0;
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_k, E.cand.as<unsigned long long>(),
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, tmp_u, E.cand_sorted.as<unsigned long long>(),
+                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
+    SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_k, tmp_u)));
+    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, E.cand.as<unsigned long long>(),
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(E.cub_tmp.p, tmp_u, E.cand_sorted.as<unsigned long long>(),
+                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
+    ctx->launches += 6;
+    int h_nuniq = 0;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    E.nenc = h_nuniq;
+    E.result = E.uniq.as<unsigned long long>();
+    *nenc_out = h_nuniq;
+    return SWCU_OK;
+}
+
 int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out)
 {
     auto &E = ctx->enc;
@@ -397,27 +611,7 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     const long long ncand = (long long)h_counts[0];
     if (ncand == 0) return SWCU_OK;
 
-    // K11 canonical order + duplicate removal (:976-985, :703-757)
-    SWCU_CUDA(ctx, E.cand_sorted.ensure(sizeof(unsigned long long) * ncand));
-    SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * ncand));
-    size_t tmp_k = 0, tmp_u = 0;
-    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_k, E.cand.as<unsigned long long>(),
-                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
-    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, tmp_u, E.cand_sorted.as<unsigned long long>(),
-                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
-    SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_k, tmp_u)));
-    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, E.cand.as<unsigned long long>(),
-                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
-    SWCU_CUDA(ctx, cub::DeviceSelect::Unique(E.cub_tmp.p, tmp_u, E.cand_sorted.as<unsigned long long>(),
-                                             E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
-    ctx->launches += 6;
-    int h_nuniq = 0;
-    SWCU_CUDA(ctx, cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    E.nenc = h_nuniq;
-    E.result = E.uniq.as<unsigned long long>();
-    *nenc_out = h_nuniq;
-    return SWCU_OK;
+    return canonical_order(ctx, ncand, nenc_out);
 }
 
 // encounter_check_all_plplm (:42-109): plpl on the fully interacting block, then plm x plt with index2 shifted
@@ -457,6 +651,97 @@ int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepLi
     SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, m_in, m_out, n, 0, 64, ctx->stream));
     ctx->launches += 4;
     E.result = m_out;
+    return SWCU_OK;
+}
+
+// encounter_check_all_triangular_plpl (l2 == nullptr) / _pltp / _plplm (:436-570); results like encounter_sweep
+int encounter_triangular(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out)
+{
+    auto &E = ctx->enc;
+    E.nenc = 0;
+    E.result = nullptr;
+    E.nbox_total = 0;
+    E.nemitted = 0;
+    *nenc_out = 0;
+    const int n1 = l1.n, n2 = l2 ? l2->n : 0;
+    const bool single = (l2 == nullptr);
+    if (n1 == 0 || (!single && n2 == 0)) return SWCU_OK;
+    FamTimer ft(ctx, FAM_SWEEP);
+    SWCU_CUDA(ctx, E.counters.ensure(64));
+    unsigned long long *d_count = E.counters.as<unsigned long long>();
+    SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, 32, ctx->stream));
+    ListDev a = to_dev(l1), b;
+    if (l2) b = to_dev(*l2); else { b = a; b.n = 0; }
+    const int ncols = single ? n1 : n2;
+    const dim3 grid(cdiv(n1, TRI_T), cdiv(ncols, TRI_COLS));
+    if (E.cand_cap < 65536) E.cand_cap = 65536;
+    const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
+    unsigned long long h_count = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+        tri_check_kernel<<<grid, TRI_T, 0, ctx->stream>>>(a, b, single ? 1 : 0, dt, vsmall, E.cand.as<unsigned long long>(),
+                                                         (unsigned long long)E.cand_cap, d_count);
+        SWCU_KERNEL_CHECK(ctx);
+        SWCU_CUDA(ctx, cudaMemcpyAsync(&h_count, d_count, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h_count <= E.cand_cap) break;
+        E.cand_cap = (size_t)(h_count + h_count / 4 + 1024);  // overflow: grow and run again
+        if (attempt == 2) return fail(ctx, SWCU_ERR_STATE, "triangular encounter check: candidate buffer overflow persists");
+    }
+    E.nemitted = (int64_t)h_count;
+    E.nbox_total = (int64_t)n1 * ncols;
+    if (h_count == 0) return SWCU_OK;
+    return canonical_order(ctx, (long long)h_count, nenc_out);
+}
+
+// swiftest_discard_pl_tp on device arrays (tp: positions/velocities/mask; pl: positions/velocities/radius)
+int discard_pl_tp(swcu_context *ctx, const Body &tp, const Body &pl, const int32_t *d_lactive, double dt,
+                  int32_t *d_iplanet, int32_t *ndiscard)
+{
+    if (ndiscard) *ndiscard = 0;
+    if (tp.n == 0) return SWCU_OK;
+    if (pl.n == 0) return fill_i32(ctx, d_iplanet, 0, tp.n);
+    SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
+    int *d_n = ctx->scratch64.as<int>();
+    SWCU_CUDA(ctx, cudaMemsetAsync(d_n, 0, sizeof(int), ctx->stream));
+    {
+        FamTimer ft(ctx, FAM_PLTP);
+        discard_pl_tp_kernel<<<cdiv(tp.n, 128), 128, 0, ctx->stream>>>(
+            tp.n, pl.n, tp.rx.as<double>(), tp.ry.as<double>(), tp.rz.as<double>(), tp.vx.as<double>(), tp.vy.as<double>(),
+            tp.vz.as<double>(), d_lactive, pl.rx.as<double>(), pl.ry.as<double>(), pl.rz.as<double>(), pl.vx.as<double>(),
+            pl.vy.as<double>(), pl.vz.as<double>(), pl.radius.as<double>(), dt, d_iplanet, d_n);
+        SWCU_KERNEL_CHECK(ctx);
+    }
+    if (ndiscard) {
+        SWCU_CUDA(ctx, cudaMemcpyAsync(ndiscard, d_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return SWCU_OK;
+}
+
+// symba_encounter_check_list_* pair loop on device arrays; radius2 / l2.renc may be null (test particles)
+int symba_check_list(swcu_context *ctx, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2, const int32_t *d_mask,
+                     const SweepList &l1, const double *d_radius1, const SweepList &l2, const double *d_radius2, double dt,
+                     int32_t *d_lenc, int32_t *d_lvdotr, int64_t *nfound)
+{
+    if (nfound) *nfound = 0;
+    if (nenc <= 0) return SWCU_OK;
+    auto &E = ctx->enc;
+    SWCU_CUDA(ctx, E.counters.ensure(64));
+    unsigned long long *d_count = E.counters.as<unsigned long long>() + 3;
+    SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
+    {
+        FamTimer ft(ctx, FAM_SWEEP);
+        symba_check_list_kernel<<<cdiv(nenc, 256), 256, 0, ctx->stream>>>(nenc, d_i1, d_i2, d_mask, to_dev(l1), d_radius1,
+                                                                        to_dev(l2), d_radius2, dt, std::sqrt(DBL_MIN),
+                                                                        d_lenc, d_lvdotr, d_count);
+        SWCU_KERNEL_CHECK(ctx);
+    }
+    unsigned long long h = 0;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(&h, d_count, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (nfound) *nfound = (int64_t)h;
     return SWCU_OK;
 }
 

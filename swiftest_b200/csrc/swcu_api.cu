@@ -853,6 +853,137 @@ extern "C" int swcu_util_get_energy_and_momentum(swcu_context *ctx, int32_t npl,
 }
 
 // ======================================================================================================
+// tier 1: triangular encounter checks, pl-tp discard, SyMBA list check
+// ======================================================================================================
+extern "C" int swcu_encounter_check_all_triangular_plpl(swcu_context *ctx, int32_t npl, const double *r, const double *v,
+                                                        const double *renc, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || npl < 0) return fail(ctx, SWCU_ERR_ARG, "tri_plpl: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (npl == 0) return SWCU_OK;
+    if (!r || !v || !renc) return fail(ctx, SWCU_ERR_ARG, "tri_plpl: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, npl, r, v, renc));
+    return encounter_triangular(ctx, sweep_list(ctx->s_pl, 0, npl, true), nullptr, dt, nenc);
+}
+
+extern "C" int swcu_encounter_check_all_triangular_pltp(swcu_context *ctx, int32_t npl, int32_t ntp, const double *rpl,
+                                                        const double *vpl, const double *rtp, const double *vtp,
+                                                        const double *rencpl, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || npl < 0 || ntp < 0) return fail(ctx, SWCU_ERR_ARG, "tri_pltp: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (npl == 0 || ntp == 0) return SWCU_OK;
+    if (!rpl || !vpl || !rtp || !vtp || !rencpl) return fail(ctx, SWCU_ERR_ARG, "tri_pltp: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, npl, rpl, vpl, rencpl));
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, ntp, rtp, vtp, nullptr));
+    SweepList l2 = sweep_list(ctx->s_tp, 0, ntp, false);
+    return encounter_triangular(ctx, sweep_list(ctx->s_pl, 0, npl, true), &l2, dt, nenc);
+}
+
+extern "C" int swcu_encounter_check_all_triangular_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt, const double *rplm,
+                                                         const double *vplm, const double *rplt, const double *vplt,
+                                                         const double *rencm, const double *renct, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!nenc || nplm < 0 || nplt < 0) return fail(ctx, SWCU_ERR_ARG, "tri_plplm: bad argument");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (nplm == 0 || nplt == 0) return SWCU_OK;
+    if (!rplm || !vplm || !rplt || !vplt || !rencm || !renct) return fail(ctx, SWCU_ERR_ARG, "tri_plplm: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, nplm, rplm, vplm, rencm));
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, nplt, rplt, vplt, renct));
+    SweepList l2 = sweep_list(ctx->s_tp, 0, nplt, true);
+    return encounter_triangular(ctx, sweep_list(ctx->s_pl, 0, nplm, true), &l2, dt, nenc);
+}
+
+extern "C" int swcu_discard_pl_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double *rtp, const double *vtp,
+                                  const int32_t *lactive, const double *rpl, const double *vpl, const double *radius,
+                                  double dt, int32_t *iplanet, int32_t *ndiscard)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (ntp < 0 || npl < 0 || !iplanet) return fail(ctx, SWCU_ERR_ARG, "discard_pl_tp: bad argument");
+    if (ndiscard) *ndiscard = 0;
+    if (ntp == 0) return SWCU_OK;
+    if (npl == 0) {
+        for (int32_t i = 0; i < ntp; ++i) iplanet[i] = 0;
+        return SWCU_OK;
+    }
+    if (!rtp || !vtp || !rpl || !vpl || !radius) return fail(ctx, SWCU_ERR_ARG, "discard_pl_tp: null array");
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, npl, rpl, vpl, nullptr));
+    SWCU_TRY(put_or_fill(ctx, radius, npl, ctx->s_pl.radius, 0.0));
+    SWCU_TRY(stage_population(ctx, ctx->s_tp, ntp, rtp, vtp, nullptr));
+    if (lactive)
+        SWCU_TRY(upload_arr(ctx, lactive, sizeof(int32_t) * (size_t)ntp, ctx->s_tp.lmask));
+    else
+        SWCU_TRY(fill_i32(ctx, ctx->s_tp.lmask.as<int32_t>(), 1, ntp));
+    int32_t nd = 0;
+    SWCU_TRY(discard_pl_tp(ctx, ctx->s_tp, ctx->s_pl, ctx->s_tp.lmask.as<int32_t>(), dt, ctx->s_tp.iflag.as<int32_t>(), &nd));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(iplanet, ctx->s_tp.iflag.p, sizeof(int32_t) * (size_t)ntp, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ndiscard) *ndiscard = nd;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_symba_encounter_check_list(swcu_context *ctx, int64_t nenc, const int32_t *index1,
+                                               const int32_t *index2, const int32_t *lencmask, int32_t n1, const double *r1,
+                                               const double *v1, const double *renc1, const double *radius1, int32_t n2,
+                                               const double *r2, const double *v2, const double *renc2,
+                                               const double *radius2, double dt, int32_t *lencounter, int32_t *lvdotr,
+                                               int64_t *nfound)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (nenc < 0 || n1 < 0 || n2 < 0) return fail(ctx, SWCU_ERR_ARG, "symba_encounter_check_list: bad argument");
+    if (nfound) *nfound = 0;
+    if (nenc == 0) return SWCU_OK;  // symba_encounter_check.f90:105
+    if (!index1 || !index2 || !r1 || !v1 || !renc1 || !radius1 || !lencounter || !lvdotr || n1 == 0)
+        return fail(ctx, SWCU_ERR_ARG, "symba_encounter_check_list: null array");
+    const bool two = (n2 > 0);
+    if (two && (!r2 || !v2)) return fail(ctx, SWCU_ERR_ARG, "symba_encounter_check_list: null second list");
+    const int32_t nmax2 = two ? n2 : n1;
+    for (int64_t k = 0; k < nenc; ++k) {  // the reference trusts its own lists; a foreign caller gets a checked error
+        if (lencmask && !lencmask[k]) continue;
+        if (index1[k] < 1 || index1[k] > n1 || index2[k] < 1 || index2[k] > nmax2)
+            return fail(ctx, SWCU_ERR_ARG, "symba_encounter_check_list: pair %lld = (%d,%d) out of range", (long long)k,
+                        index1[k], index2[k]);
+    }
+    SWCU_TRY(stage_population(ctx, ctx->s_pl, n1, r1, v1, renc1));
+    SWCU_TRY(put_or_fill(ctx, radius1, n1, ctx->s_pl.radius, 0.0));
+    SweepList l1 = sweep_list(ctx->s_pl, 0, n1, true), l2 = l1;
+    const double *d_rad2 = ctx->s_pl.radius.as<double>();
+    if (two) {
+        SWCU_TRY(stage_population(ctx, ctx->s_tp, n2, r2, v2, renc2));
+        l2 = sweep_list(ctx->s_tp, 0, n2, renc2 != nullptr);
+        d_rad2 = nullptr;
+        if (radius2) {
+            SWCU_TRY(put_or_fill(ctx, radius2, n2, ctx->s_tp.radius, 0.0));
+            d_rad2 = ctx->s_tp.radius.as<double>();
+        }
+    }
+    const size_t ib = sizeof(int32_t) * (size_t)nenc;
+    SWCU_CUDA(ctx, ctx->istage[0].ensure(2 * ib));
+    SWCU_CUDA(ctx, ctx->istage[1].ensure(3 * ib));
+    int32_t *d_i1 = ctx->istage[0].as<int32_t>(), *d_i2 = d_i1 + nenc;
+    int32_t *d_mask = ctx->istage[1].as<int32_t>(), *d_lenc = d_mask + nenc, *d_lvd = d_lenc + nenc;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_i1, index1, ib, cudaMemcpyHostToDevice, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_i2, index2, ib, cudaMemcpyHostToDevice, ctx->stream));
+    if (lencmask) SWCU_CUDA(ctx, cudaMemcpyAsync(d_mask, lencmask, ib, cudaMemcpyHostToDevice, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_lvd, lvdotr, ib, cudaMemcpyHostToDevice, ctx->stream));  // kept outside the mask
+    SWCU_TRY(symba_check_list(ctx, nenc, d_i1, d_i2, lencmask ? d_mask : nullptr, l1, ctx->s_pl.radius.as<double>(), l2,
+                              d_rad2, dt, d_lenc, d_lvd, nfound));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(lencounter, d_lenc, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(lvdotr, d_lvd, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+// ======================================================================================================
 // measurement helpers
 // ======================================================================================================
 extern "C" int swcu_timer_start(swcu_context *ctx)

@@ -270,6 +270,12 @@ struct SweepList {
 int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc);
 int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc);
 int set_renc(swcu_context *ctx, Body &pl, int irec);
+int encounter_triangular(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc);
+int discard_pl_tp(swcu_context *ctx, const Body &tp, const Body &pl, const int32_t *d_lactive, double dt,
+                  int32_t *d_iplanet, int32_t *ndiscard);
+int symba_check_list(swcu_context *ctx, int64_t nenc, const int32_t *d_i1, const int32_t *d_i2, const int32_t *d_mask,
+                     const SweepList &l1, const double *d_radius1, const SweepList &l2, const double *d_radius2, double dt,
+                     int32_t *d_lenc, int32_t *d_lvdotr, int64_t *nfound);
 
 // ---- comm : comm.cu ----
 int comm_allgather_pl(swcu_context *ctx, int with_v);

@@ -1,0 +1,124 @@
+"""GPU parity tests for SURVEY.md 8(f) ranks 3-4: triangular encounter checks, pl-tp discard, SyMBA list check.
+All integer / index results: BIT-EXACT against the CPU restatement (the kernels are compiled without FMA contraction).
+"""
+import numpy as np
+import pytest
+
+from swiftest_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _same(got, ref):
+    n, g1, g2, glv = got
+    r1, r2, rlv = ref
+    assert n == len(r1)
+    assert np.array_equal(g1, r1) and np.array_equal(g2, r2)
+    assert glv.all()
+
+
+@pytest.mark.parametrize("n,boost", [(1, 1.0), (2, 50.0), (129, 6.0), (1000, 4.0), (5000, 2.0)])
+def test_triangular_plpl_matches_oracle(ctx, oracle, n, boost):
+    d = W.disk(n, seed=500 + n)
+    renc = oracle.set_renc(d["rhill"], 0) * boost
+    ref = oracle.encounter_plpl(d["rh"], d["vh"], renc, d["dt"], triangular=True)
+    got = ctx.encounter_check_all_triangular_plpl(n, d["rh"], d["vh"], renc, d["dt"])
+    _same(got, ref)
+    if n >= 1000:
+        assert got[0] > 0
+        # the sweep finds a subset of it
+        sw = ctx.encounter_check_all_sort_and_sweep_plpl(n, d["rh"], d["vh"], renc, d["dt"])
+        assert set(zip(sw[1].tolist(), sw[2].tolist())) <= set(zip(got[1].tolist(), got[2].tolist()))
+
+
+def test_triangular_plpl_candidate_buffer_growth(ctx, oracle):
+    """More hits than the initial candidate buffer: the call grows it and repeats."""
+    n = 700
+    rng = np.random.default_rng(3)
+    r = rng.normal(size=(n, 3))
+    v = np.zeros((n, 3))
+    renc = np.full(n, 10.0)  # everybody is inside everybody's encounter radius: n(n-1)/2 = 244650 pairs
+    got = ctx.encounter_check_all_triangular_plpl(n, r, v, renc, 0.1)
+    assert got[0] == n * (n - 1) // 2
+    iu = np.triu_indices(n, 1)
+    assert np.array_equal(got[1], iu[0] + 1) and np.array_equal(got[2], iu[1] + 1)
+
+
+def test_triangular_pltp_and_plplm_match_oracle(ctx, oracle):
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(6000, seed=31)
+    renc = p["rhill"] * 6.5 * 3
+    ref = oracle.encounter_pltp(p["rh"], p["vh"], tp["rh"], tp["vh"], renc, 0.05, triangular=True)
+    got = ctx.encounter_check_all_triangular_pltp(8, 6000, p["rh"], p["vh"], tp["rh"], tp["vh"], renc, 0.05)
+    _same(got, ref)
+    assert got[0] > 0
+    f = W.fixture("108pl_50tp")
+    order = np.argsort(-f["pl_Gmass"], kind="stable")
+    nplm = int((f["pl_Gmass"] >= float(f["GMTINY"])).sum())
+    r, v = f["pl_rh"][order], f["pl_vh"][order]
+    rc = oracle.set_renc(f["pl_rhill"][order], 0) * 20
+    ref = oracle.encounter_plplm(r[:nplm], v[:nplm], r[nplm:], v[nplm:], rc[:nplm], rc[nplm:], 0.05, triangular=True)
+    got = ctx.encounter_check_all_triangular_plplm(nplm, 108 - nplm, r[:nplm], v[:nplm], r[nplm:], v[nplm:], rc[:nplm],
+                                                   rc[nplm:], 0.05)
+    _same(got, ref)
+    assert got[0] > 0
+    assert ctx.encounter_check_all_triangular_pltp(8, 0, p["rh"], p["vh"], np.zeros((0, 3)), np.zeros((0, 3)), renc, 0.05)[0] == 0
+
+
+@pytest.mark.parametrize("npl,ntp", [(8, 20000), (300, 5000), (1, 1)])
+def test_discard_pl_tp_matches_oracle(ctx, oracle, npl, ntp):
+    rng = np.random.default_rng(npl + ntp)
+    if npl == 8:
+        p = W.planets8_year_units()
+        rpl, vpl = p["rh"], p["vh"]
+    else:
+        d = W.disk(npl, seed=npl)
+        rpl, vpl = d["rh"], d["vh"]
+    # particles scattered around the planets so that a good fraction is, or will be, inside the (inflated) radii
+    host = rng.integers(0, npl, ntp)
+    rtp = rpl[host] + rng.normal(scale=0.02, size=(ntp, 3))
+    vtp = vpl[host] + rng.normal(scale=1.0, size=(ntp, 3))
+    radius = np.full(npl, 0.01)
+    act = (rng.uniform(size=ntp) > 0.1).astype(np.int32)
+    ref, nref = oracle.discard_pl_tp(rtp, vtp, act, rpl, vpl, radius, 0.01)
+    got, ngot = ctx.discard_pl_tp(rtp, vtp, act, rpl, vpl, radius, 0.01)
+    assert np.array_equal(got, ref) and ngot == nref
+    if ntp > 1:
+        assert 0 < nref < ntp
+        assert not got[act == 0].any()
+    got2, _ = ctx.discard_pl_tp(rtp, vtp, None, rpl, vpl, radius, 0.01)
+    ref2, _ = oracle.discard_pl_tp(rtp, vtp, None, rpl, vpl, radius, 0.01)
+    assert np.array_equal(got2, ref2)
+
+
+def test_symba_encounter_check_list_matches_oracle(ctx, oracle):
+    n = 4000
+    d = W.disk(n, seed=77)
+    renc0 = oracle.set_renc(d["rhill"], 0) * 3
+    _, i1, i2, _ = ctx.encounter_check_all_triangular_plpl(n, d["rh"], d["vh"], renc0, d["dt"])
+    assert len(i1) > 50
+    rng = np.random.default_rng(1)
+    mask = (rng.uniform(size=len(i1)) > 0.3).astype(np.int32)
+    renc1 = oracle.set_renc(d["rhill"], 1) * 3  # next recursion level: smaller shells
+    radius = d["radius"] * 200                   # inflated so that some pairs count as overlapping
+    lv0 = np.full(len(i1), 5, np.int32)
+    ref = oracle.symba_encounter_check_list(i1, i2, mask, d["rh"], d["vh"], renc1, radius, d["dt"] / 3, lvdotr=lv0)
+    got = ctx.symba_encounter_check_list(i1, i2, mask, d["rh"], d["vh"], renc1, radius, d["dt"] / 3, lvdotr=lv0)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert 0 < ref[2] < mask.sum()
+    assert (got[1][mask == 0] == 5).all()
+    # pl-tp form: second list without renc / radius
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(3000, seed=2)
+    rc = p["rhill"] * 6.5 * 4
+    _, j1, j2, _ = ctx.encounter_check_all_triangular_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], rc, 0.05)
+    assert len(j1) > 5
+    ref = oracle.symba_encounter_check_list(j1, j2, None, p["rh"], p["vh"], rc * 0.48075, p["radius"], 0.02,
+                                            r2=tp["rh"], v2=tp["vh"])
+    got = ctx.symba_encounter_check_list(j1, j2, None, p["rh"], p["vh"], rc * 0.48075, p["radius"], 0.02,
+                                         r2=tp["rh"], v2=tp["vh"])
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    import swiftest_b200 as S
+    with pytest.raises(S.SwcuError):  # an index outside the population is a checked error, not a wild read
+        ctx.symba_encounter_check_list([1], [9999], None, p["rh"], p["vh"], rc, p["radius"], 0.02)
+    assert ctx.symba_encounter_check_list([], [], None, p["rh"], p["vh"], rc, p["radius"], 0.02)[2] == 0

@@ -407,3 +407,53 @@ def test_energy_and_momentum_on_planets(oracle):
     assert abs(e1["te"] - e0["te"]) < 1e-6 * abs(e0["te"])
     assert e0["ke_orbit"] > 0 and e0["pe"] < 0 and e0["be"] == 0.0
     assert abs(e0["GMtot"] - (GMcb + p["Gmass"].sum())) < 1e-12
+
+
+# ---------------------------------------------------------------- discard, triangular plplm, SyMBA list check (8f 3-4)
+def test_discard_pl_tp_first_planet_and_cases(oracle):
+    rpl = np.array([[1.0, 0, 0], [2.0, 0, 0], [1.0, 0.0005, 0]])
+    vpl = np.zeros((3, 3))
+    radius = np.array([1e-3, 1e-3, 1e-3])
+    rtp = np.array([[1.0005, 0, 0],      # inside planet 1 now (and planet 3): first one wins
+                    [2.1, 0, 0],         # approaching planet 2, arrives within dt
+                    [2.1, 0, 0],         # same place, receding
+                    [5.0, 5.0, 0],       # far away
+                    [1.0005, 0, 0]])     # inactive
+    vtp = np.array([[0, 0, 0], [-1.0, 0, 0], [1.0, 0, 0], [0, 0, 0], [0, 0, 0.0]])
+    act = np.array([1, 1, 1, 1, 0], np.int32)
+    ipl, nd = oracle.discard_pl_tp(rtp, vtp, act, rpl, vpl, radius, 0.2)
+    assert ipl.tolist() == [1, 2, 0, 0, 0] and nd == 2
+    ipl, nd = oracle.discard_pl_tp(rtp, vtp, act, rpl, vpl, radius, 0.05)  # too short a step to reach planet 2
+    assert ipl.tolist() == [1, 0, 0, 0, 0] and nd == 1
+
+
+def test_triangular_plplm_matches_brute_force(oracle):
+    f, nplm = _fixture108()
+    order = np.argsort(-f["pl_Gmass"], kind="stable")
+    r, v, rh = f["pl_rh"][order], f["pl_vh"][order], f["pl_rhill"][order]
+    renc = oracle.set_renc(rh, 0) * 20
+    i1, i2, _ = oracle.encounter_plplm(r[:nplm], v[:nplm], r[nplm:], v[nplm:], renc[:nplm], renc[nplm:], 0.05,
+                                        triangular=True)
+    n = len(i1)
+    want = []
+    for i in range(nplm):
+        for j in range(108 - nplm):
+            d, w = r[nplm + j] - r[i], v[nplm + j] - v[i]
+            if oracle.encounter_check_one(d[0], d[1], d[2], w[0], w[1], w[2], renc[i] + renc[nplm + j], 0.05)[0]:
+                want.append((i + 1, j + 1))
+    assert n == len(want) > 0 and list(zip(i1.tolist(), i2.tolist())) == want
+
+
+def test_symba_encounter_check_list_filters_overlap_and_mask(oracle):
+    r = np.array([[0.0, 0, 0], [1.0, 0, 0], [1.0005, 0, 0], [3.0, 0, 0]])
+    v = np.array([[0.0, 0, 0], [0, 0, 0], [0, 0, 0], [-10.0, 0, 0]])
+    renc = np.array([0.1, 0.1, 0.1, 0.1])
+    radius = np.array([1e-3, 1e-3, 1e-3, 1e-3])
+    i1 = np.array([1, 2, 2, 1], np.int32)
+    i2 = np.array([2, 3, 4, 4], np.int32)
+    mask = np.array([1, 1, 1, 0], np.int32)
+    lenc, lvd, n = oracle.symba_encounter_check_list(i1, i2, mask, r, v, renc, radius, 0.5, lvdotr=[7, 7, 7, 7])
+    # (1,2): far apart and at rest -> no; (2,3): inside renc but physically overlapping -> dropped;
+    # (2,4): approaching fast, reaches within dt -> yes; (1,4): masked out, lvdotr untouched
+    assert lenc.tolist() == [0, 0, 1, 0] and n == 1
+    assert lvd.tolist() == [0, 1, 1, 7]
