@@ -367,6 +367,43 @@ module swiftest_cuda
          integer(c_int), intent(inout) :: lvdotr(*)
          integer(c_int64_t), intent(out) :: nfound
       end function
+      integer(c_int) function swcu_symba_kick_list_plpl(ctx, nenc, index1, index2, lactive, npl, levelg, rh, rhill, Gmass, &
+            dt, irec, sgn, vb, lgood) bind(C, name="swcu_symba_kick_list_plpl")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lactive(*), levelg(*)
+         integer(c_int), value :: npl, irec, sgn
+         real(c_double), intent(in) :: rh(3,*), rhill(*), Gmass(*)
+         real(c_double), value :: dt
+         real(c_double), intent(inout) :: vb(3,*)
+         integer(c_int), intent(out) :: lgood(*)
+      end function
+      integer(c_int) function swcu_symba_kick_list_pltp(ctx, nenc, index1, index2, lactive, npl, ntp, levelg_pl, levelg_tp, &
+            rh_pl, rhill, Gmass, rh_tp, dt, irec, sgn, vb_tp, lgood) bind(C, name="swcu_symba_kick_list_pltp")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lactive(*), levelg_pl(*), levelg_tp(*)
+         integer(c_int), value :: npl, ntp, irec, sgn
+         real(c_double), intent(in) :: rh_pl(3,*), rhill(*), Gmass(*), rh_tp(3,*)
+         real(c_double), value :: dt
+         real(c_double), intent(inout) :: vb_tp(3,*)
+         integer(c_int), intent(out) :: lgood(*)
+      end function
+      integer(c_int) function swcu_collision_check_list(ctx, nenc, index1, index2, lmask, lvdotr, n1, r1, v1, Gmass1, &
+            radius1, n2, r2, v2, dt, lcollision, lclosest, ncollision) bind(C, name="swcu_collision_check_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lmask(*), lvdotr(*)
+         integer(c_int), value :: n1, n2
+         real(c_double), intent(in) :: r1(3,*), v1(3,*), Gmass1(*), radius1(*)
+         type(c_ptr), value :: r2, v2            !! c_null_ptr (and n2 = 0) for the pl-pl form
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: lcollision(*), lclosest(*)
+         integer(c_int64_t), intent(out) :: ncollision
+      end function
    end interface
 
 contains

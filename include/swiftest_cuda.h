@@ -222,6 +222,28 @@ int swcu_symba_encounter_check_list(swcu_context *ctx, int64_t nenc, const int32
                                     const double *v2, const double *renc2, const double *radius2, double dt,
                                     int32_t *lencounter, int32_t *lvdotr, int64_t *nfound);
 
+/* symba_kick_list_plpl / _pltp (symba/symba_kick.f90:126-337): kick the barycentric velocities of the bodies whose
+ * pairs are at recursion level irec (lactive(k) = status(k) == ACTIVE, may be NULL; levelg = pl%levelg / tp%levelg).
+ * vb(3,n) is updated in place with the reference's serial summation order per body (bit-identical outside the shell
+ * where the reference calls r2**(-1.5)); lgood (optional) returns the final lgoodlevel mask.  The caller zeroes
+ * ah(:,i) of the bodies of the initially good pairs, as the reference leaves them. */
+int swcu_symba_kick_list_plpl(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                              const int32_t *lactive, int32_t npl, const int32_t *levelg, const double *rh,
+                              const double *rhill, const double *Gmass, double dt, int32_t irec, int32_t sgn, double *vb,
+                              int32_t *lgood);
+int swcu_symba_kick_list_pltp(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                              const int32_t *lactive, int32_t npl, int32_t ntp, const int32_t *levelg_pl,
+                              const int32_t *levelg_tp, const double *rh_pl, const double *rhill, const double *Gmass,
+                              const double *rh_tp, double dt, int32_t irec, int32_t sgn, double *vb_tp, int32_t *lgood);
+/* the pair loop of collision_check_plpl / _pltp (collision/collision_check.f90:96-110, 213-223) with
+ * collision_check_one (:15-58) and swiftest_orbel_xv2aeq (swiftest_orbel.f90:700-764): lcollision(k), lclosest(k) for
+ * the pairs of lmask (both 0 elsewhere).  n2 == 0: pl-pl (rlim = radius(i)+radius(j), Gmtot = Gm(i)+Gm(j));
+ * n2 > 0: index2 addresses the test particles (rlim = radius(i), Gmtot = Gm(i)). */
+int swcu_collision_check_list(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                              const int32_t *lmask, const int32_t *lvdotr, int32_t n1, const double *r1, const double *v1,
+                              const double *Gmass1, const double *radius1, int32_t n2, const double *r2, const double *v2,
+                              double dt, int32_t *lcollision, int32_t *lclosest, int64_t *ncollision);
+
 /* ---- tier 1: energy and angular momentum of the massive bodies -------------------------------
  * swiftest_util_get_potential_energy_flat / _triangular (swiftest_util.f90:1291-1394): both add the same terms, one
  * kernel serves both.  rb(3,npl) barycentric positions, mass = Gmass/GU; lmask may be NULL (all bodies). */

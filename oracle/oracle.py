@@ -69,6 +69,11 @@ class Oracle:
         L.swo_helio_step_pl.argtypes = [i32, d, p, p, C.c_int, p, p, d, p, p, p, p, p, p, p, p, p, p]
         L.swo_helio_step_tp.argtypes = [i32, i32, d, p, p, p, p, p, p, p, d, p, p, p, p, p]
         L.swo_whm_kick_getacch_ah0.argtypes = [i32, p, p, p]
+        L.swo_symba_kick_list_plpl.argtypes = [i64, p, p, p, i32, p, p, p, p, d, i32, i32, p, p, p]
+        L.swo_symba_kick_list_pltp.argtypes = [i64, p, p, p, i32, i32, p, p, p, p, p, p, d, i32, i32, p, p, p]
+        L.swo_collision_check_list.restype = i64
+        L.swo_collision_check_list.argtypes = [i64, p, p, p, p, p, p, p, p, p, p, p, p, d, p, p]
+        L.swo_orbel_xv2aeq.argtypes = [d, d, d, d, d, d, d, p, p, p]
         L.swo_discard_pl_tp.restype = i32
         L.swo_discard_pl_tp.argtypes = [i32, i32, p, p, p, p, p, p, d, p]
         L.swo_symba_encounter_check_list.restype = i64
@@ -359,6 +364,53 @@ class Oracle:
                                                     self._a(v1), self._a(renc1), self._a(radius1), self._a(r2), self._a(v2),
                                                     self._a(renc2), self._a(radius2), float(dt), self._a(lenc), self._a(lvd))
         return lenc, lvd, int(n)
+
+    def symba_kick_list_plpl(self, index1, index2, lactive, levelg, rh, rhill, Gmass, dt, irec, sgn, vb, ah=None):
+        index1, index2 = _c(index1, _i32), _c(index2, _i32)
+        la = None if lactive is None else _c(lactive, _i32)
+        levelg, rh, rhill, Gmass = _c(levelg, _i32), _c(rh), _c(rhill), _c(Gmass)
+        vb = _c(vb).copy()
+        ah = np.full_like(vb, 123.0) if ah is None else _c(ah).copy()
+        lgood = np.zeros(len(index1), _i32)
+        self.lib.swo_symba_kick_list_plpl(len(index1), self._a(index1), self._a(index2), self._a(la), len(rhill),
+                                          self._a(levelg), self._a(rh), self._a(rhill), self._a(Gmass), float(dt), int(irec),
+                                          int(sgn), self._a(vb), self._a(ah), self._a(lgood))
+        return vb, lgood, ah
+
+    def symba_kick_list_pltp(self, index1, index2, lactive, levelg_pl, levelg_tp, rh_pl, rhill, Gmass, rh_tp, dt, irec,
+                             sgn, vb_tp):
+        index1, index2 = _c(index1, _i32), _c(index2, _i32)
+        la = None if lactive is None else _c(lactive, _i32)
+        levelg_pl, levelg_tp = _c(levelg_pl, _i32), _c(levelg_tp, _i32)
+        rh_pl, rhill, Gmass, rh_tp = _c(rh_pl), _c(rhill), _c(Gmass), _c(rh_tp)
+        vb = _c(vb_tp).copy()
+        ah = np.full_like(vb, 123.0)
+        lgood = np.zeros(len(index1), _i32)
+        self.lib.swo_symba_kick_list_pltp(len(index1), self._a(index1), self._a(index2), self._a(la), len(rhill), len(rh_tp),
+                                          self._a(levelg_pl), self._a(levelg_tp), self._a(rh_pl), self._a(rhill),
+                                          self._a(Gmass), self._a(rh_tp), float(dt), int(irec), int(sgn), self._a(vb),
+                                          self._a(ah), self._a(lgood))
+        return vb, lgood, ah
+
+    def collision_check_list(self, index1, index2, lmask, lvdotr, r1, v1, Gmass1, radius1, dt, r2=None, v2=None):
+        index1, index2 = _c(index1, _i32), _c(index2, _i32)
+        lm = None if lmask is None else _c(lmask, _i32)
+        lvdotr = _c(lvdotr, _i32)
+        r1, v1, Gmass1, radius1 = _c(r1), _c(v1), _c(Gmass1), _c(radius1)
+        if r2 is None:
+            r2, v2, g2, rad2 = r1, v1, Gmass1, radius1
+        else:
+            r2, v2, g2, rad2 = _c(r2), _c(v2), None, None
+        lcol, lclo = np.zeros(len(index1), _i32), np.zeros(len(index1), _i32)
+        n = self.lib.swo_collision_check_list(len(index1), self._a(index1), self._a(index2), self._a(lm), self._a(lvdotr),
+                                              self._a(r1), self._a(v1), self._a(Gmass1), self._a(radius1), self._a(r2),
+                                              self._a(v2), self._a(g2), self._a(rad2), float(dt), self._a(lcol), self._a(lclo))
+        return lcol, lclo, int(n)
+
+    def orbel_xv2aeq(self, mu, r, v):
+        a, e, q = C.c_double(), C.c_double(), C.c_double()
+        self.lib.swo_orbel_xv2aeq(mu, r[0], r[1], r[2], v[0], v[1], v[2], C.byref(a), C.byref(e), C.byref(q))
+        return a.value, e.value, q.value
 
 
 _cache = {}

@@ -130,6 +130,23 @@ int64_t swo_symba_encounter_check_list(int64_t nenc, const int32_t *index1, cons
                                        const int32_t *lencmask, const double *r1, const double *v1, const double *renc1,
                                        const double *radius1, const double *r2, const double *v2, const double *renc2,
                                        const double *radius2, double dt, int32_t *lencounter, int32_t *lvdotr);
+double swo_pow_r8_i4(double a, int32_t b);
+void swo_symba_kick_list_plpl(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lactive,
+                              int32_t npl, const int32_t *levelg, const double *rh, const double *rhill,
+                              const double *Gmass, double dt, int32_t irec, int32_t sgn, double *vb, double *ah,
+                              int32_t *lgood_out);
+void swo_symba_kick_list_pltp(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lactive,
+                              int32_t npl, int32_t ntp, const int32_t *levelg_pl, const int32_t *levelg_tp,
+                              const double *rh_pl, const double *rhill, const double *Gmass, const double *rh_tp,
+                              double dt, int32_t irec, int32_t sgn, double *vb_tp, double *ah_tp, int32_t *lgood_out);
+void swo_orbel_xv2aeq(double mu, double rx, double ry, double rz, double vx, double vy, double vz, double *a, double *e,
+                      double *q);
+void swo_collision_check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr, double Gmtot,
+                             double rlim, double dt, int32_t lvdotr, int32_t *lcollision, int32_t *lclosest);
+int64_t swo_collision_check_list(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lmask,
+                                 const int32_t *lvdotr, const double *r1, const double *v1, const double *Gmass1,
+                                 const double *radius1, const double *r2, const double *v2, const double *Gmass2,
+                                 const double *radius2, double dt, int32_t *lcollision, int32_t *lclosest);
 void swo_whm_kick_getacch_ah0(int32_t n, const double *mu, const double *rhp, double *ah0);
 void swo_get_potential_energy_tri(int32_t npl, const int32_t *lmask, double GMcb, const double *Gmass,
                                   const double *mass, const double *rb, double *pe);

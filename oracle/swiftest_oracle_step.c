@@ -408,3 +408,242 @@ int64_t swo_symba_encounter_check_list(int64_t nenc, const int32_t *index1, cons
     }
     return n;
 }
+
+/* x**n with an integer variable exponent as libgfortran evaluates it (_gfortran_pow_r8_i4: binary exponentiation) */
+double swo_pow_r8_i4(double a, int32_t b)
+{
+    double pw = 1.0, x = a;
+    int32_t n = b;
+    if (n != 0) {
+        uint32_t u;
+        if (n < 0) {
+            u = (uint32_t)(-n);
+            x = pw / x;
+        } else {
+            u = (uint32_t)n;
+        }
+        for (;;) {
+            if (u & 1u) pw *= x;
+            u >>= 1;
+            if (u) x *= x;
+            else break;
+        }
+    }
+    return pw;
+}
+
+#define SWO_RHSCALE 6.5     /* symba_module.f90:22 */
+#define SWO_RSHELL 0.48075  /* symba_module.f90:23 */
+
+/* the force factor of symba_kick_list_plpl / _pltp for one pair (symba/symba_kick.f90:180-201, 284-304):
+ * returns 0 and *fac when the pair is kicked at this level, 1 when it lies inside the inner shell (r2 < rim1) */
+static int symba_list_fac(double rhsum, double r2, int32_t irecl, double *fac)
+{
+    const double ri = (rhsum * rhsum) * (SWO_RHSCALE * SWO_RHSCALE) * swo_pow_r8_i4(SWO_RSHELL, 2 * irecl);
+    const double rim1 = ri * (SWO_RSHELL * SWO_RSHELL);
+    if (r2 < rim1) {
+        *fac = 0.0;
+        return 1;
+    }
+    if (r2 < ri) {
+        const double ris = sqrt(ri);
+        const double r = sqrt(r2);
+        const double rr = (ris - r) / (ris * (1.0 - SWO_RSHELL));
+        *fac = pow(r2, -1.5) * (1.0 - 3 * (rr * rr) + 2 * (rr * rr * rr));
+    } else {
+        *fac = 1.0 / (r2 * sqrt(r2));
+    }
+    return 0;
+}
+
+/* symba_kick_list_plpl, symba/symba_kick.f90:126-231.  lactive(k) = (status(k) == ACTIVE).  vb and ah are updated in
+ * place exactly as the serial reference does; lgood (optional) returns the final lgoodlevel mask. */
+void swo_symba_kick_list_plpl(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lactive,
+                              int32_t npl, const int32_t *levelg, const double *rh, const double *rhill,
+                              const double *Gmass, double dt, int32_t irec, int32_t sgn, double *vb, double *ah,
+                              int32_t *lgood_out)
+{
+    if (nenc == 0 || npl == 0) return;
+    int32_t *lgood = (int32_t *)malloc(sizeof(int32_t) * (size_t)nenc);
+    const int32_t irm1 = irec - 1;
+    const int32_t irecl = (sgn < 0) ? irec - 1 : irec;
+    int64_t ngood = 0;
+    for (int64_t k = 0; k < nenc; ++k) {
+        const int32_t i = index1[k] - 1, j = index2[k] - 1;
+        lgood[k] = (levelg[i] >= irm1) && (levelg[j] >= irm1) && (!lactive || lactive[k]);
+        ngood += lgood[k];
+    }
+    if (ngood > 0) {
+        for (int64_t k = 0; k < nenc; ++k) {
+            if (!lgood[k]) continue;
+            const int32_t i = index1[k] - 1, j = index2[k] - 1;
+            for (int c = 0; c < 3; ++c) ah[3 * i + c] = ah[3 * j + c] = 0.0;
+        }
+        for (int64_t k = 0; k < nenc; ++k) {
+            if (!lgood[k]) continue;
+            const int32_t i = index1[k] - 1, j = index2[k] - 1;
+            double dx[3], fac;
+            for (int c = 0; c < 3; ++c) dx[c] = rh[3 * j + c] - rh[3 * i + c];
+            const double r2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+            if (symba_list_fac(rhill[i] + rhill[j], r2, irecl, &fac)) {
+                lgood[k] = 0;
+                continue;
+            }
+            const double faci = fac * Gmass[i], facj = fac * Gmass[j];
+            for (int c = 0; c < 3; ++c) {
+                ah[3 * i + c] = ah[3 * i + c] + facj * dx[c];
+                ah[3 * j + c] = ah[3 * j + c] - faci * dx[c];
+            }
+        }
+        const double sdt = sgn * dt;
+        for (int64_t k = 0; k < nenc; ++k) {
+            if (!lgood[k]) continue;
+            const int32_t i = index1[k] - 1, j = index2[k] - 1;
+            for (int c = 0; c < 3; ++c) {
+                vb[3 * i + c] = vb[3 * i + c] + sdt * ah[3 * i + c];
+                vb[3 * j + c] = vb[3 * j + c] + sdt * ah[3 * j + c];
+                ah[3 * i + c] = 0.0;
+                ah[3 * j + c] = 0.0;
+            }
+        }
+    }
+    if (lgood_out) memcpy(lgood_out, lgood, sizeof(int32_t) * (size_t)nenc);
+    free(lgood);
+}
+
+/* symba_kick_list_pltp, symba_kick.f90:234-337: only the test particle (index2) is kicked */
+void swo_symba_kick_list_pltp(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lactive,
+                              int32_t npl, int32_t ntp, const int32_t *levelg_pl, const int32_t *levelg_tp,
+                              const double *rh_pl, const double *rhill, const double *Gmass, const double *rh_tp,
+                              double dt, int32_t irec, int32_t sgn, double *vb_tp, double *ah_tp, int32_t *lgood_out)
+{
+    if (nenc == 0 || npl == 0 || ntp == 0) return;
+    int32_t *lgood = (int32_t *)malloc(sizeof(int32_t) * (size_t)nenc);
+    const int32_t irm1 = irec - 1;
+    const int32_t irecl = (sgn < 0) ? irec - 1 : irec;
+    int64_t ngood = 0;
+    for (int64_t k = 0; k < nenc; ++k) {
+        const int32_t i = index1[k] - 1, j = index2[k] - 1;
+        lgood[k] = (levelg_pl[i] >= irm1) && (levelg_tp[j] >= irm1) && (!lactive || lactive[k]);
+        ngood += lgood[k];
+    }
+    if (ngood > 0) {
+        for (int64_t k = 0; k < nenc; ++k)
+            if (lgood[k])
+                for (int c = 0; c < 3; ++c) ah_tp[3 * (index2[k] - 1) + c] = 0.0;
+        for (int64_t k = 0; k < nenc; ++k) {
+            if (!lgood[k]) continue;
+            const int32_t i = index1[k] - 1, j = index2[k] - 1;
+            double dx[3], fac;
+            for (int c = 0; c < 3; ++c) dx[c] = rh_tp[3 * j + c] - rh_pl[3 * i + c];
+            const double r2 = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+            if (symba_list_fac(rhill[i], r2, irecl, &fac)) {
+                lgood[k] = 0;
+                continue;
+            }
+            const double faci = fac * Gmass[i];
+            for (int c = 0; c < 3; ++c) ah_tp[3 * j + c] = ah_tp[3 * j + c] - faci * dx[c];
+        }
+        const double sdt = sgn * dt;
+        for (int64_t k = 0; k < nenc; ++k) {
+            if (!lgood[k]) continue;
+            const int32_t j = index2[k] - 1;
+            for (int c = 0; c < 3; ++c) {
+                vb_tp[3 * j + c] = vb_tp[3 * j + c] + sdt * ah_tp[3 * j + c];
+                ah_tp[3 * j + c] = 0.0;
+            }
+        }
+    }
+    if (lgood_out) memcpy(lgood_out, lgood, sizeof(int32_t) * (size_t)nenc);
+    free(lgood);
+}
+
+/* swiftest_orbel_xv2aeq, swiftest/swiftest_orbel.f90:700-764 */
+#define SWO_TINYVALUE 4.0e-15 /* swiftest_orbel.f90:11 */
+void swo_orbel_xv2aeq(double mu, double rx, double ry, double rz, double vx, double vy, double vz, double *a, double *e,
+                      double *q)
+{
+    *a = 0.0;
+    *e = 0.0;
+    *q = 0.0;
+    const double r = sqrt(rx * rx + ry * ry + rz * rz);
+    const double v2 = vx * vx + vy * vy + vz * vz;
+    const double hx = ry * vz - rz * vy, hy = rz * vx - rx * vz, hz = rx * vy - ry * vx;
+    const double h2 = hx * hx + hy * hy + hz * hz;
+    if (h2 < 2.2250738585072014e-308) return; /* tiny(h2) */
+    const double energy = 0.5 * v2 - mu / r;
+    int type; /* -1 ellipse, 0 parabola, 1 hyperbola */
+    double fac = 0.0;
+    if (fabs(energy * r / mu) < sqrt(SWO_TINYVALUE)) {
+        type = 0;
+    } else {
+        *a = -0.5 * mu / energy;
+        if (*a < 0.0) {
+            fac = -h2 / (mu * *a);
+            type = (fac > SWO_TINYVALUE) ? 1 : 0;
+        } else {
+            type = -1;
+        }
+    }
+    if (type == -1) {
+        fac = 1.0 - h2 / (mu * *a);
+        if (fac > SWO_TINYVALUE) *e = sqrt(fac);
+        *q = *a * (1.0 - *e);
+    } else if (type == 0) {
+        *a = 0.5 * h2 / mu;
+        *e = 1.0;
+        *q = *a;
+    } else {
+        *e = sqrt(1.0 + fac);
+        *q = *a * (1.0 - *e);
+    }
+}
+
+/* collision_check_one, collision/collision_check.f90:15-58 */
+void swo_collision_check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr, double Gmtot,
+                             double rlim, double dt, int32_t lvdotr, int32_t *lcollision, int32_t *lclosest)
+{
+    const double r2 = xr * xr + yr * yr + zr * zr;
+    const double rlim2 = rlim * rlim;
+    *lclosest = 0;
+    if (r2 <= rlim2) {
+        *lcollision = 1;
+    } else {
+        *lcollision = 0;
+        const double vdotr = xr * vxr + yr * vyr + zr * vzr;
+        if (lvdotr && (vdotr > 0.0)) {
+            const double tcr2 = r2 / (vxr * vxr + vyr * vyr + vzr * vzr);
+            const double dt2 = dt * dt;
+            if (tcr2 <= dt2) {
+                double a, e, q;
+                swo_orbel_xv2aeq(Gmtot, xr, yr, zr, vxr, vyr, vzr, &a, &e, &q);
+                *lcollision = (q < rlim);
+            }
+            *lclosest = !*lcollision;
+        }
+    }
+}
+
+/* the pair loop of collision_check_plpl (:96-110) / _pltp (:213-223): xr = r1(i) - r2(j), vr = v1(i) - v2(j);
+ * plpl (Gmass2/radius2 given): rlim = radius1(i) + radius2(j), Gmtot = Gmass1(i) + Gmass2(j);
+ * pltp (Gmass2 == NULL): rlim = radius1(i), Gmtot = Gmass1(i).  lclosest is cleared for every k first (:93). */
+int64_t swo_collision_check_list(int64_t nenc, const int32_t *index1, const int32_t *index2, const int32_t *lmask,
+                                 const int32_t *lvdotr, const double *r1, const double *v1, const double *Gmass1,
+                                 const double *radius1, const double *r2, const double *v2, const double *Gmass2,
+                                 const double *radius2, double dt, int32_t *lcollision, int32_t *lclosest)
+{
+    int64_t n = 0;
+    for (int64_t k = 0; k < nenc; ++k) {
+        lcollision[k] = 0;
+        lclosest[k] = 0;
+        if (lmask && !lmask[k]) continue;
+        const int32_t i = index1[k] - 1, j = index2[k] - 1;
+        const double xr = r1[3 * i] - r2[3 * j], yr = r1[3 * i + 1] - r2[3 * j + 1], zr = r1[3 * i + 2] - r2[3 * j + 2];
+        const double vxr = v1[3 * i] - v2[3 * j], vyr = v1[3 * i + 1] - v2[3 * j + 1], vzr = v1[3 * i + 2] - v2[3 * j + 2];
+        const double rlim = Gmass2 ? radius1[i] + radius2[j] : radius1[i];
+        const double Gmtot = Gmass2 ? Gmass1[i] + Gmass2[j] : Gmass1[i];
+        swo_collision_check_one(xr, yr, zr, vxr, vyr, vzr, Gmtot, rlim, dt, lvdotr[k], &lcollision[k], &lclosest[k]);
+        n += lcollision[k] ? 1 : 0;
+    }
+    return n;
+}

@@ -82,6 +82,9 @@ def load():
         "swcu_encounter_check_all_triangular_plplm": [p, i32, i32, p, p, p, p, p, p, d, p],
         "swcu_discard_pl_tp": [p, i32, i32, p, p, p, p, p, p, d, p, p],
         "swcu_symba_encounter_check_list": [p, i64, p, p, p, i32, p, p, p, p, i32, p, p, p, p, d, p, p, p],
+        "swcu_symba_kick_list_plpl": [p, i64, p, p, p, i32, p, p, p, p, d, i32, i32, p, p],
+        "swcu_symba_kick_list_pltp": [p, i64, p, p, p, i32, i32, p, p, p, p, p, p, d, i32, i32, p, p],
+        "swcu_collision_check_list": [p, i64, p, p, p, p, i32, p, p, p, p, i32, p, p, d, p, p, p],
         "swcu_util_get_potential_energy": [p, i32, p, d, p, p, p, p],
         "swcu_util_get_energy_and_momentum": [p, i32, p, d, d, p, p, p, p, p, p, p, i32, p],
         "swcu_pl_encounter_check": [p, d, p],

@@ -392,6 +392,57 @@ class Context:
             n2, _ptr(r2), _ptr(v2), _ptr(renc2), _ptr(radius2), float(dt), _ptr(lenc), _ptr(lvd), C.byref(nf)))
         return lenc, lvd, nf.value
 
+    def symba_kick_list_plpl(self, index1, index2, lactive, levelg, rh, rhill, Gmass, dt, irec, sgn, vb):
+        """symba_kick_list_plpl: returns (vb after the kick, final lgoodlevel mask)."""
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        rh = _vec3(rh)
+        npl = rh.shape[0]
+        lactive = None if lactive is None else _vec(lactive, nenc, _i32)
+        levelg, rhill, Gmass = _vec(levelg, npl, _i32), _vec(rhill, npl), _vec(Gmass, npl)
+        vb = _vec3(vb, npl).copy()
+        lgood = np.zeros(nenc, _i32)
+        self._ck(self._L.swcu_symba_kick_list_plpl(self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lactive), npl,
+                                                   _ptr(levelg), _ptr(rh), _ptr(rhill), _ptr(Gmass), float(dt), int(irec),
+                                                   int(sgn), _ptr(vb), _ptr(lgood)))
+        return vb, lgood
+
+    def symba_kick_list_pltp(self, index1, index2, lactive, levelg_pl, levelg_tp, rh_pl, rhill, Gmass, rh_tp, dt, irec,
+                             sgn, vb_tp):
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        rh_pl, rh_tp = _vec3(rh_pl), _vec3(rh_tp)
+        npl, ntp = rh_pl.shape[0], rh_tp.shape[0]
+        lactive = None if lactive is None else _vec(lactive, nenc, _i32)
+        levelg_pl, levelg_tp = _vec(levelg_pl, npl, _i32), _vec(levelg_tp, ntp, _i32)
+        rhill, Gmass = _vec(rhill, npl), _vec(Gmass, npl)
+        vb = _vec3(vb_tp, ntp).copy()
+        lgood = np.zeros(nenc, _i32)
+        self._ck(self._L.swcu_symba_kick_list_pltp(self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lactive), npl, ntp,
+                                                   _ptr(levelg_pl), _ptr(levelg_tp), _ptr(rh_pl), _ptr(rhill), _ptr(Gmass),
+                                                   _ptr(rh_tp), float(dt), int(irec), int(sgn), _ptr(vb), _ptr(lgood)))
+        return vb, lgood
+
+    def collision_check_list(self, index1, index2, lmask, lvdotr, r1, v1, Gmass1, radius1, dt, r2=None, v2=None):
+        """Pair loop of collision_check_plpl (r2 None) / _pltp.  Returns (lcollision, lclosest, ncollision)."""
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lmask = None if lmask is None else _vec(lmask, nenc, _i32)
+        lvdotr = _vec(lvdotr, nenc, _i32)
+        r1, v1 = _vec3(r1), _vec3(v1)
+        n1 = r1.shape[0]
+        Gmass1, radius1 = _vec(Gmass1, n1), _vec(radius1, n1)
+        n2 = 0
+        if r2 is not None:
+            r2, v2 = _vec3(r2), _vec3(v2)
+            n2 = r2.shape[0]
+        lcol, lclo = np.zeros(nenc, _i32), np.zeros(nenc, _i32)
+        nc = C.c_int64()
+        self._ck(self._L.swcu_collision_check_list(self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lmask), _ptr(lvdotr), n1,
+                                                   _ptr(r1), _ptr(v1), _ptr(Gmass1), _ptr(radius1), n2, _ptr(r2), _ptr(v2),
+                                                   float(dt), _ptr(lcol), _ptr(lclo), C.byref(nc)))
+        return lcol, lclo, nc.value
+
     # ---- energy and momentum (swiftest_util.f90:1172-1394) ----
     def util_get_potential_energy(self, npl, lmask, GMcb, Gmass, mass, rb):
         lmask = None if lmask is None else _vec(lmask, npl, _i32)

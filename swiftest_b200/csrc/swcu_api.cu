@@ -171,6 +171,7 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     ctx->flush.release();
     ctx->cbs.release();
     ctx->sumbuf.release();
+    for (auto &b : ctx->lists) b.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
     auto &E = ctx->enc;

@@ -125,6 +125,7 @@ struct swcu_context {
     // [0..3] raw sums of the last reduction, [4..6] vbcb, [8..10] ptbeg, [12..14] ptend, [16] GMtot, [20..27] energy sums
     swcu::DevBuf cbs;
     swcu::DevBuf sumbuf;  // per-CTA partials of the tree reductions + ticket counter (zeroed when allocated)
+    swcu::DevBuf lists[16];  // staging of the encounter-list kernels (list_kernels.cu)
 
     // multi-GPU
     swcu::NcclApi *nccl = nullptr;

@@ -122,3 +122,91 @@ def test_symba_encounter_check_list_matches_oracle(ctx, oracle):
     with pytest.raises(S.SwcuError):  # an index outside the population is a checked error, not a wild read
         ctx.symba_encounter_check_list([1], [9999], None, p["rh"], p["vh"], rc, p["radius"], 0.02)
     assert ctx.symba_encounter_check_list([], [], None, p["rh"], p["vh"], rc, p["radius"], 0.02)[2] == 0
+
+
+def _disk_list(ctx, oracle, n, seed, boost):
+    d = W.disk(n, seed=seed)
+    renc = oracle.set_renc(d["rhill"], 0) * boost
+    _, i1, i2, _ = ctx.encounter_check_all_triangular_plpl(n, d["rh"], d["vh"], renc, d["dt"])
+    return d, i1, i2
+
+
+@pytest.mark.parametrize("irec,sgn", [(0, 1), (1, 1), (1, -1), (2, -1)])
+def test_symba_kick_list_plpl_matches_serial_oracle(ctx, oracle, irec, sgn):
+    """Bodies appear in many pairs; the device must add each body's contributions in list order.  Pairs outside every
+    shell use IEEE arithmetic only -> bit-exact; pairs inside the shell call pow(r2,-1.5) -> 4 ulp on the factor."""
+    n = 3000
+    d, i1, i2 = _disk_list(ctx, oracle, n, 21, 6.0)
+    assert len(i1) > 500
+    rng = np.random.default_rng(irec * 7 + sgn)
+    levelg = rng.integers(max(irec - 1, 0), irec + 2, n).astype(np.int32)
+    active = (rng.uniform(size=len(i1)) > 0.1).astype(np.int32)
+    rhill = d["rhill"] * (3.0 if irec == 0 else 6.0)   # inflate so that all three branches (inner, shell, outside) occur
+    vb0 = d["vh"].copy()
+    ref_vb, ref_good, _ = oracle.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], rhill, d["Gmass"], d["dt"], irec, sgn, vb0)
+    got_vb, got_good = ctx.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], rhill, d["Gmass"], d["dt"], irec, sgn, vb0)
+    assert np.array_equal(got_good, ref_good)
+    assert 0 < ref_good.sum() < len(i1)
+    dv_ref, dv_got = ref_vb - vb0, got_vb - vb0
+    touched = np.abs(dv_ref).sum(1) > 0
+    assert touched.sum() > 10
+    assert np.array_equal(got_vb[~touched], vb0[~touched])
+    scale = np.abs(dv_ref).max(1, keepdims=True)[touched]
+    assert np.max(np.abs(dv_got[touched] - dv_ref[touched]) / scale) < 1e-14
+    # with the shell pushed inside every pair (tiny Hill radii) nothing calls pow: identical bits
+    ref_vb, ref_good, _ = oracle.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], rhill * 1e-6, d["Gmass"], d["dt"], irec,
+                                                      sgn, vb0)
+    got_vb, got_good = ctx.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], rhill * 1e-6, d["Gmass"], d["dt"], irec, sgn,
+                                                vb0)
+    assert np.array_equal(got_good, ref_good) and np.array_equal(got_vb, ref_vb)
+
+
+def test_symba_kick_list_pltp_matches_serial_oracle(ctx, oracle):
+    p = W.planets8_year_units()
+    ntp = 4000
+    tp = W.tp_cloud(ntp, seed=8)
+    rc = p["rhill"] * 6.5 * 6
+    _, i1, i2, _ = ctx.encounter_check_all_triangular_pltp(8, ntp, p["rh"], p["vh"], tp["rh"], tp["vh"], rc, 0.05)
+    assert len(i1) > 20
+    rng = np.random.default_rng(4)
+    lev_pl = np.ones(8, np.int32)
+    lev_tp = rng.integers(0, 2, ntp).astype(np.int32)
+    vb0 = tp["vh"].copy()
+    for rh_scale in (6.0, 1e-6):
+        ref_vb, ref_good, _ = oracle.symba_kick_list_pltp(i1, i2, None, lev_pl, lev_tp, p["rh"], p["rhill"] * rh_scale,
+                                                          p["Gmass"], tp["rh"], 0.01, 1, 1, vb0)
+        got_vb, got_good = ctx.symba_kick_list_pltp(i1, i2, None, lev_pl, lev_tp, p["rh"], p["rhill"] * rh_scale,
+                                                    p["Gmass"], tp["rh"], 0.01, 1, 1, vb0)
+        assert np.array_equal(got_good, ref_good) and ref_good.sum() > 0
+        if rh_scale < 1:
+            assert np.array_equal(got_vb, ref_vb)
+        else:
+            dv = np.abs(ref_vb - vb0).max()
+            assert np.max(np.abs(got_vb - ref_vb)) < 1e-14 * dv
+
+
+def test_collision_check_list_matches_oracle(ctx, oracle):
+    n = 3000
+    d, i1, i2 = _disk_list(ctx, oracle, n, 33, 6.0)
+    rng = np.random.default_rng(6)
+    mask = (rng.uniform(size=len(i1)) > 0.2).astype(np.int32)
+    lvdotr = (rng.uniform(size=len(i1)) > 0.3).astype(np.int32)
+    radius = d["radius"] * 300   # inflated: some pairs overlap now, some have q < rlim
+    for dt in (d["dt"], 50 * d["dt"]):
+        ref = oracle.collision_check_list(i1, i2, mask, lvdotr, d["rh"], d["vh"], d["Gmass"], radius, dt)
+        got = ctx.collision_check_list(i1, i2, mask, lvdotr, d["rh"], d["vh"], d["Gmass"], radius, dt)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert ref[0].sum() > 0 and ref[1].sum() > 0
+    assert not got[0][mask == 0].any() and not got[1][mask == 0].any()
+    # pl-tp form
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(3000, seed=12)
+    rc = p["rhill"] * 6.5 * 6
+    _, j1, j2, _ = ctx.encounter_check_all_triangular_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], rc, 0.05)
+    lv = np.ones(len(j1), np.int32)
+    ref = oracle.collision_check_list(j1, j2, None, lv, p["rh"], p["vh"], p["Gmass"], p["rhill"] * 2, 5.0, r2=tp["rh"],
+                                      v2=tp["vh"])
+    got = ctx.collision_check_list(j1, j2, None, lv, p["rh"], p["vh"], p["Gmass"], p["rhill"] * 2, 5.0, r2=tp["rh"],
+                                   v2=tp["vh"])
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert ctx.collision_check_list([], [], None, [], p["rh"], p["vh"], p["Gmass"], p["radius"], 1.0)[2] == 0

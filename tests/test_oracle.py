@@ -457,3 +457,57 @@ def test_symba_encounter_check_list_filters_overlap_and_mask(oracle):
     # (2,4): approaching fast, reaches within dt -> yes; (1,4): masked out, lvdotr untouched
     assert lenc.tolist() == [0, 0, 1, 0] and n == 1
     assert lvd.tolist() == [0, 1, 1, 7]
+
+
+def test_pow_r8_i4_and_xv2aeq(oracle):
+    L = oracle.lib
+    L.swo_pow_r8_i4.restype = __import__("ctypes").c_double
+    L.swo_pow_r8_i4.argtypes = [__import__("ctypes").c_double, __import__("ctypes").c_int32]
+    for n in (-4, -2, 0, 1, 2, 6, 10):
+        assert abs(L.swo_pow_r8_i4(0.48075, n) - 0.48075 ** n) <= 4e-16 * 0.48075 ** n
+    assert L.swo_pow_r8_i4(0.48075, 2) == 0.48075 * 0.48075
+    # circular orbit: a = q = r, e = 0; radial infall: h = 0 -> zeros
+    a, e, q = oracle.orbel_xv2aeq(1.0, [2.0, 0, 0], [0, np.sqrt(0.5), 0])
+    assert abs(a - 2) < 1e-14 and e < 1e-7 and abs(q - 2) < 1e-6
+    assert oracle.orbel_xv2aeq(1.0, [2.0, 0, 0], [-1.0, 0, 0]) == (0.0, 0.0, 0.0)
+    # hyperbolic flyby: q from energy and angular momentum
+    a, e, q = oracle.orbel_xv2aeq(1.0, [10.0, 1.0, 0], [-2.0, 0, 0])
+    assert a < 0 and e > 1 and abs(q - a * (1 - e)) < 1e-15 and q > 0
+
+
+def test_symba_kick_list_plpl_serial_semantics(oracle):
+    """Three bodies, pairs (1,2), (1,3), (2,3): momentum is conserved pairwise, a pair inside the inner shell is
+    dropped, bodies below the recursion level are skipped, vb changes only for bodies of surviving pairs."""
+    rh = np.array([[0.0, 0, 0], [0.08, 0, 0], [0.0, 0.5, 0]])   # pair (1,2) inside the level-0 shell (0.0625 < r < 0.13)
+    rhill = np.array([0.01, 0.01, 0.01])
+    Gm = np.array([1e-3, 2e-3, 3e-3])
+    vb0 = np.zeros((3, 3))
+    i1, i2 = [1, 1, 2], [2, 3, 3]
+    lev = np.array([0, 0, 0], np.int32)
+    vb, lgood, ah = oracle.symba_kick_list_plpl(i1, i2, None, lev, rh, rhill, Gm, 0.1, 0, 1, vb0)
+    assert lgood.tolist() == [1, 1, 1]
+    assert np.allclose((Gm[:, None] * vb).sum(0), 0.0, atol=1e-18)   # third law
+    assert (ah == 0).all()
+    # closer than RSHELL * shell radius -> dropped at level 0, body 1/2 still kicked by body 3
+    rh2 = rh.copy()
+    rh2[1] = [0.01, 0, 0]
+    vb2, lgood2, _ = oracle.symba_kick_list_plpl(i1, i2, None, lev, rh2, rhill, Gm, 0.1, 0, 1, vb0)
+    assert lgood2.tolist() == [0, 1, 1]
+    # inactive pair and a body below the level
+    vb3, lgood3, ah3 = oracle.symba_kick_list_plpl(i1, i2, [1, 0, 1], np.array([1, 1, 0], np.int32), rh, rhill, Gm, 0.1, 2,
+                                                   -1, vb0)
+    assert lgood3.tolist() == [1, 0, 0]
+    assert np.array_equal(vb3[2], vb0[2]) and (ah3[2] == 123.0).all()   # body 3 untouched, its ah not even zeroed
+    assert not np.array_equal(vb3[0], vb0[0])
+
+
+def test_collision_check_list_cases(oracle):
+    r = np.array([[0.0, 0, 0], [1e-4, 0, 0], [1.0, 0, 0], [1.0, 0.01, 0]])
+    v = np.array([[0.0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0.2, 0.0]])
+    Gm = np.full(4, 1e-6)
+    radius = np.full(4, 1e-3)
+    # (1,2) overlapping now; (3,4) receding (xr.vr > 0 for xr = r3 - r4? xr = (0,-0.01,0), vr = (0,-0.2,0) -> vdotr > 0)
+    lcol, lclo, n = oracle.collision_check_list([1, 3, 3], [2, 4, 4], [1, 1, 0], [1, 1, 1], r, v, Gm, radius, 1.0)
+    assert lcol.tolist()[0] == 1 and lcol.tolist()[2] == 0 and lclo.tolist()[2] == 0
+    assert lcol[1] + lclo[1] == 1   # either it collides on the way out or this was the closest approach
+    assert n == lcol.sum()
