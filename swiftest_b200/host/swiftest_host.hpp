@@ -13,7 +13,9 @@
 // Arrays use the Fortran memory layout: r(3,n) == std::vector<double> of size 3n {x1,y1,z1,x2,...}; indices are 1-based.
 #pragma once
 #include <cstdint>
+#include <algorithm>
 #include <stdexcept>
+#include <utility>
 #include <string>
 #include <vector>
 
@@ -131,44 +133,84 @@ inline void fetch(cuda_context &c, I8B nenc, encounter_list &out)
         c.check(swcu_encounter_fetch(c.handle(), nenc, out.index1.data(), out.index2.data(), out.lvdotr.data()),
                 "encounter_fetch");
 }
-inline void require_sas(bool sas, const char *what)
-{
-    if (!sas)
-        throw fatal_error(std::string(what) + ": ENCOUNTER_CHECK TRIANGULAR is outside the device path "
-                                              "(SURVEY.md section 8f rank 4); use SORTSWEEP");
-}
 }  // namespace detail
 
-// encounter_check_all_plpl (encounter_check.f90:14-39)
+// encounter_check_all_plpl (encounter_check.f90:14-39): SORTSWEEP or TRIANGULAR by param%lencounter_sas_plpl
 inline void encounter_check_all_plpl(cuda_context &c, const swiftest_parameters &param, I4B npl, const DP *r, const DP *v,
                                      const DP *renc, DP dt, encounter_list &out)
 {
-    detail::require_sas(param.lencounter_sas_plpl, "encounter_check_all_plpl");
     I8B nenc = 0;
-    c.check(swcu_encounter_check_all_sort_and_sweep_plpl(c.handle(), npl, r, v, renc, dt, &nenc), "sas_plpl");
+    if (param.lencounter_sas_plpl)
+        c.check(swcu_encounter_check_all_sort_and_sweep_plpl(c.handle(), npl, r, v, renc, dt, &nenc), "sas_plpl");
+    else
+        c.check(swcu_encounter_check_all_triangular_plpl(c.handle(), npl, r, v, renc, dt, &nenc), "tri_plpl");
     detail::fetch(c, nenc, out);
 }
-// encounter_check_all_plplm (encounter_check.f90:42-109)
+// encounter_check_all_plplm (encounter_check.f90:42-109): plpl on the fully interacting block + plm x plt, index2
+// shifted by nplm, merged.  The sort-and-sweep form merges on the device; the triangular form merges here like :77-103
+// (the reference orders by index1 only; lexicographic order is one of the orders it allows).
 inline void encounter_check_all_plplm(cuda_context &c, const swiftest_parameters &param, I4B nplm, I4B nplt, const DP *rplm,
                                       const DP *vplm, const DP *rplt, const DP *vplt, const DP *rencm, const DP *renct,
                                       DP dt, encounter_list &out)
 {
-    detail::require_sas(param.lencounter_sas_plpl, "encounter_check_all_plplm");
     I8B nenc = 0;
-    c.check(swcu_encounter_check_all_plplm(c.handle(), nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt, &nenc),
-            "all_plplm");
-    detail::fetch(c, nenc, out);
+    if (param.lencounter_sas_plpl) {
+        c.check(swcu_encounter_check_all_plplm(c.handle(), nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt, &nenc),
+                "all_plplm");
+        detail::fetch(c, nenc, out);
+        return;
+    }
+    encounter_list a, b;
+    c.check(swcu_encounter_check_all_triangular_plpl(c.handle(), nplm, rplm, vplm, rencm, dt, &nenc), "tri_plpl");
+    detail::fetch(c, nenc, a);
+    c.check(swcu_encounter_check_all_triangular_plplm(c.handle(), nplm, nplt, rplm, vplm, rplt, vplt, rencm, renct, dt, &nenc),
+            "tri_plplm");
+    detail::fetch(c, nenc, b);
+    std::vector<std::pair<I4B, I4B>> all;
+    all.reserve((size_t)(a.nenc + b.nenc));
+    for (I8B k = 0; k < a.nenc; ++k) all.emplace_back(a.index1[k], a.index2[k]);
+    for (I8B k = 0; k < b.nenc; ++k) all.emplace_back(b.index1[k], b.index2[k] + nplm);
+    std::sort(all.begin(), all.end());
+    out.resize((I8B)all.size());
+    for (size_t k = 0; k < all.size(); ++k) {
+        out.index1[k] = all[k].first;
+        out.index2[k] = all[k].second;
+        out.lvdotr[k] = 1;
+    }
 }
 // encounter_check_all_pltp (encounter_check.f90:112-140)
 inline void encounter_check_all_pltp(cuda_context &c, const swiftest_parameters &param, I4B npl, I4B ntp, const DP *rpl,
                                      const DP *vpl, const DP *rtp, const DP *vtp, const DP *renc, DP dt,
                                      encounter_list &out)
 {
-    detail::require_sas(param.lencounter_sas_pltp, "encounter_check_all_pltp");
     I8B nenc = 0;
-    c.check(swcu_encounter_check_all_sort_and_sweep_pltp(c.handle(), npl, ntp, rpl, vpl, rtp, vtp, renc, dt, &nenc),
-            "sas_pltp");
+    if (param.lencounter_sas_pltp)
+        c.check(swcu_encounter_check_all_sort_and_sweep_pltp(c.handle(), npl, ntp, rpl, vpl, rtp, vtp, renc, dt, &nenc),
+                "sas_pltp");
+    else
+        c.check(swcu_encounter_check_all_triangular_pltp(c.handle(), npl, ntp, rpl, vpl, rtp, vtp, renc, dt, &nenc),
+                "tri_pltp");
     detail::fetch(c, nenc, out);
+}
+
+// swiftest_util_get_potential_energy (generic of _flat / _triangular, swiftest_util.f90:1291-1394)
+inline DP swiftest_util_get_potential_energy(cuda_context &c, I4B npl, const I4B *lmask, DP GMcb, const DP *Gmass,
+                                             const DP *mass, const DP *rb)
+{
+    DP pe = 0.0;
+    c.check(swcu_util_get_potential_energy(c.handle(), npl, lmask, GMcb, Gmass, mass, rb, &pe), "get_potential_energy");
+    return pe;
+}
+
+// the double loop of swiftest_discard_pl_tp (swiftest_discard.f90:261-288): iplanet(i) = discarding planet or 0
+inline I4B swiftest_discard_pl_tp(cuda_context &c, I4B ntp, I4B npl, const DP *rtp, const DP *vtp, const I4B *lactive,
+                                  const DP *rpl, const DP *vpl, const DP *radius, DP dt, std::vector<I4B> &iplanet)
+{
+    iplanet.assign((size_t)ntp, 0);
+    I4B nd = 0;
+    c.check(swcu_discard_pl_tp(c.handle(), ntp, npl, rtp, vtp, lactive, rpl, vpl, radius, dt, iplanet.data(), &nd),
+            "discard_pl_tp");
+    return nd;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
