@@ -395,8 +395,11 @@ def run_ours(args):
 
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
-        extra = side_legs(ctx, args, d, hbm_peak, peak_src)
-        extra["next_rows"] = next_row_legs(ctx, args, d, hbm_peak, fp64_peak)
+        try:
+            extra = side_legs(ctx, args, d, hbm_peak, peak_src)
+            extra["next_rows"] = next_row_legs(ctx, args, d, hbm_peak, fp64_peak)
+        except Exception as e:  # side legs are reported figures, never a dependency of the headline number
+            extra["error"] = str(e)
     cpu = None
     if not args.no_extra and rank == 0 and world == 1:
         try:
@@ -407,7 +410,10 @@ def run_ours(args):
         extra["conservation"] = conservation_run(ctx, args.conservation)
 
     if world > 1 and not args.no_extra:
-        extra["whm_tp_sharded"] = tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak)
+        try:  # a side leg must never cost the headline line
+            extra["whm_tp_sharded"] = tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak)
+        except Exception as e:
+            extra["whm_tp_sharded"] = {"error": str(e)}
 
     if rank == 0:
         line = {
