@@ -538,7 +538,7 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     SWCU_CUDA(ctx, E.counters.ensure(64));
     unsigned long long *d_count = E.counters.as<unsigned long long>();       // [0] candidates emitted
     unsigned long long *d_nbox = d_count + 1;                                 // [1] sum nbox
-    int *d_nuniq = reinterpret_cast<int *>(d_count + 2);                      // [2] unique count
+    // [2] unique count (canonical_order), [3] hits of the list check
     SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, 32, ctx->stream));
 
     ListDev a = to_dev(l1), b;

@@ -43,12 +43,6 @@ __global__ void flush_kernel(double2 *buf, size_t n)
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) buf[i] = z;
 }
 
-__global__ void mask_merge_iflag_kernel(int n, const int32_t *lmask, const int32_t *computed, int32_t *inout)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n && lmask[i] != 0) inout[i] = computed[i];
-}
-
 int check_ctx(swcu_context *ctx)
 {
     if (!ctx) return SWCU_ERR_ARG;
