@@ -12,7 +12,7 @@
 // Pair kernel: blocks of PE_T = 256 bodies, cyclic block pairing (row block bi against column blocks bi, bi+1, ...,
 // bi + nb/2 mod nb: every unordered block pair exactly once, equal work per row block).  A thread keeps one row body in
 // registers and walks the column block staged in shared memory as (x, y, z, m); 1/r comes from the FP32 MUFU.RSQ seed
-// and one third-order Newton step of kick_math.cuh (12 FP64 + ~6 other instructions per pair against 21 + 10 for the
+// and one third-order Newton step of kick_math.cuh (12 FP64 + ~10 other instructions per pair against 20 + 9 for the
 // force: the FP64 issue model of profiles/r01_fp64_pipe.md applies unchanged).  Pairs the seed cannot take (coincident
 // bodies, coordinates outside the FP32 exponent range) make the thread redo its tile row with IEEE sqrt and divide.
 // Per-CTA partial sums are folded by a fixed tree: same bits run to run, independent of the SM count.

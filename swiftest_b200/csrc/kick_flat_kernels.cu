@@ -5,7 +5,7 @@
 // (nplplm, symba/symba_util.f90:202), and the lmtiny branch of the triangular variants (kick.f90:189-217).
 // The 8-byte-per-pair k_plpl table (40 GB at npl = 1e5) is never built: (i,j) come from tile coordinates.
 //
-// Design: each unordered pair is evaluated ONCE (21 FP64 instructions instead of 2 x 17 for the full-row kernel).
+// Design: each unordered pair is evaluated ONCE (20 FP64 instructions instead of 2 x 16 for the full-row kernel).
 // Bodies are cut into blocks of 128.  A warp keeps one block resident -- every lane owns 4 "i" bodies (position, Gm,
 // accumulators) in registers -- and meets another block 32 "j" bodies at a time.  The chunk is staged in the warp's
 // private shared-memory tile; at step s lane l works on column body (l+s) mod 32, so all 32 lanes read different

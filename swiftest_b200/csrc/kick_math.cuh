@@ -3,7 +3,8 @@
 // Measured on B200 (scripts/fp64_microbench.cu, profiles/r01_fp64_pipe.md): an FP64 instruction holds the SMSP issue
 // port for 2 cycles and nothing co-issues in its shadow, every other instruction costs 1 cycle.  The cost of a pair
 // evaluation is therefore 2*N_fp64 + N_other issue cycles and BOTH counts are minimised here:
-//   * 1/r^3 from an FP32 MUFU.RSQ seed + one third-order Newton step (5 FP64) instead of IEEE sqrt + divide (~60);
+//   * 1/r^3 from an FP32 MUFU.RSQ seed refined directly in six FP64 instructions (rcube_seeded) instead of IEEE
+//     sqrt + divide (~60); the potential-energy kernel needs 1/r and uses the five-instruction rsqrt_seeded;
 //   * the double<->float conversions are integer moves on the high word (no F2F, which issues at quarter rate);
 //   * ONE unsigned compare on the high word of r^2 decides "usable by the fast path": r^2 is a normal float, nonzero,
 //     finite AND safely outside the sum of radii.  Pairs that fail contribute exactly zero and are redone by the
@@ -28,7 +29,7 @@ __device__ __forceinline__ void seed_threshold(double rlim2, unsigned &thr, unsi
     span = SEED_HI_MAX - t;
 }
 
-// y ~ r2^(-1/2) to ~2e-17 relative when ok; when not, y is a denormal whose cube (all callers use y^3) is exactly 0.
+// y ~ r2^(-1/2) to ~2e-17 relative when ok; when not, y is a denormal (callers treat the pair as rejected and redo it).
 // Seed: the top 20 mantissa bits of r2 re-biased into a float, MUFU.RSQ, top 20 bits widened back (relative error
 // < 2^-19), then y = y0*(1 + e/2 + 3e^2/8) with e = 1 - r2*y0^2 (error ~ 5/16 e^3 < 2^-55).
 // `hy` returns the selected high word of the seed (0 when the pair was rejected): callers that only need to know whether
