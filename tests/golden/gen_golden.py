@@ -11,6 +11,9 @@
      (swiftest/tool.py el2xv_one + danby, imported from /root/reference with a stub for the uninstalled xarray)
      evaluates the same elliptic orbit at mean anomaly M0 and M0 + n*dt.  The drift oracle must carry the first
      state into the second (tests/test_oracle.py, tolerance 1e-11 relative: the Python solver stops at 1e-14).
+3. xv2aeq_ref.npz
+     REFERENCE-GENERATED vectors for swiftest_orbel_xv2aeq (the orbital elements inside collision_check_one): a and e
+     from the reference's Python xv2el_one on 200 random elliptic relative orbits.
 """
 import importlib.util
 import os
@@ -106,8 +109,28 @@ def write_drift_golden():
     print("drift golden", rows.shape)
 
 
+def write_xv2aeq_golden():
+    """REFERENCE-GENERATED vectors for swiftest_orbel_xv2aeq (used by collision_check_one): the reference's Python
+    xv2el_one (swiftest/tool.py:377-455) gives a and e of the relative orbit; q = a(1-e)."""
+    tool = load_reference_tool()
+    rng = np.random.default_rng(7002)
+    rows = []
+    for _ in range(200):
+        mu = 10.0 ** rng.uniform(-8, 2)
+        a = 10.0 ** rng.uniform(-3, 2)
+        e = rng.uniform(0.0, 0.98)
+        inc, Om, om, M = rng.uniform(0, 180), rng.uniform(0, 360), rng.uniform(0, 360), rng.uniform(0, 360)
+        r, v = tool.el2xv_one(mu, a, e, inc, Om, om, M)
+        el = tool.xv2el_one(mu, np.asarray(r), np.asarray(v))
+        rows.append(np.concatenate([[mu], r, v, [float(el[0]), float(el[1])]]))
+    rows = np.array(rows)
+    np.savez(os.path.join(OUT, "xv2aeq_ref.npz"), mu=rows[:, 0], r=rows[:, 1:4], v=rows[:, 4:7], a=rows[:, 7], e=rows[:, 8])
+    print("xv2aeq golden", rows.shape)
+
+
 if __name__ == "__main__":
     write_fixture("108pl_50tp", "cb.in", "pl.swiftest.in", "tp.swiftest.in",
                   dict(dt=0.005, GMTINY=2.1554293571575797e-06))
     write_fixture("8pl_0tp", "cb.swiftest.in", "pl.swiftest.in", "tp.swiftest.in", dict(dt=1.0))
     write_drift_golden()
+    write_xv2aeq_golden()

@@ -511,3 +511,16 @@ def test_collision_check_list_cases(oracle):
     assert lcol.tolist()[0] == 1 and lcol.tolist()[2] == 0 and lclo.tolist()[2] == 0
     assert lcol[1] + lclo[1] == 1   # either it collides on the way out or this was the closest approach
     assert n == lcol.sum()
+
+
+def test_xv2aeq_matches_reference_python_golden(oracle):
+    """swo_orbel_xv2aeq (inside collision_check_one) against a, e computed by the REFERENCE's own Python xv2el_one
+    (tests/golden/gen_golden.py imports swiftest/tool.py from the reference tree): pins the elliptic branch."""
+    z = np.load(os.path.join(GOLD, "xv2aeq_ref.npz"))
+    worst = 0.0
+    for k in range(len(z["mu"])):
+        a, e, q = oracle.orbel_xv2aeq(float(z["mu"][k]), z["r"][k], z["v"][k])
+        worst = max(worst, abs(a - z["a"][k]) / z["a"][k], abs(e - z["e"][k]))
+        assert abs(q - z["a"][k] * (1 - z["e"][k])) <= 1e-11 * z["a"][k]
+    # e comes from sqrt(1 - h^2/(mu a)): relative 1e-16 on the argument is 1e-16/e on e; the vectors go down to e ~ 1e-3
+    assert worst < 1e-11
