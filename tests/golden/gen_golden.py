@@ -14,6 +14,8 @@
 3. xv2aeq_ref.npz
      REFERENCE-GENERATED vectors for swiftest_orbel_xv2aeq (the orbital elements inside collision_check_one): a and e
      from the reference's Python xv2el_one on 200 random elliptic relative orbits.
+4. el2xv_ref.npz
+     REFERENCE-GENERATED states from el2xv_one for the element ranges of the synthetic workloads.
 """
 import importlib.util
 import os
@@ -109,6 +111,23 @@ def write_drift_golden():
     print("drift golden", rows.shape)
 
 
+def write_el2xv_golden():
+    """REFERENCE-GENERATED states for the synthetic-workload generator: el2xv_one (swiftest/tool.py:221-343) on the
+    element ranges of the disk / test-particle workloads (swiftest_b200/workloads.py restates it, vectorised)."""
+    tool = load_reference_tool()
+    rng = np.random.default_rng(4711)
+    mu = 39.476926408897626
+    rows = []
+    for _ in range(150):
+        a, e = rng.uniform(0.3, 40.0), rng.uniform(0.0, 0.3)
+        inc, Om, om, M = rng.uniform(0, 30), rng.uniform(0, 360), rng.uniform(0, 360), rng.uniform(0, 360)
+        r, v = tool.el2xv_one(mu, a, e, inc, Om, om, M)
+        rows.append(np.concatenate([[a, e, inc, Om, om, M], r, v]))
+    rows = np.array(rows)
+    np.savez(os.path.join(OUT, "el2xv_ref.npz"), mu=mu, elements_deg=rows[:, :6], r=rows[:, 6:9], v=rows[:, 9:12])
+    print("el2xv golden", rows.shape)
+
+
 def write_xv2aeq_golden():
     """REFERENCE-GENERATED vectors for swiftest_orbel_xv2aeq (used by collision_check_one): the reference's Python
     xv2el_one (swiftest/tool.py:377-455) gives a and e of the relative orbit; q = a(1-e)."""
@@ -134,3 +153,4 @@ if __name__ == "__main__":
     write_fixture("8pl_0tp", "cb.swiftest.in", "pl.swiftest.in", "tp.swiftest.in", dict(dt=1.0))
     write_drift_golden()
     write_xv2aeq_golden()
+    write_el2xv_golden()

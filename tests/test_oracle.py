@@ -524,3 +524,14 @@ def test_xv2aeq_matches_reference_python_golden(oracle):
         assert abs(q - z["a"][k] * (1 - z["e"][k])) <= 1e-11 * z["a"][k]
     # e comes from sqrt(1 - h^2/(mu a)): relative 1e-16 on the argument is 1e-16/e on e; the vectors go down to e ~ 1e-3
     assert worst < 1e-11
+
+
+def test_workload_el2xv_matches_reference_python_golden():
+    """The synthetic workloads (disk, tp cloud) are built with a vectorised restatement of the reference's el2xv_one;
+    it must reproduce reference-generated states (tests/golden/el2xv_ref.npz) to rounding."""
+    z = np.load(os.path.join(GOLD, "el2xv_ref.npz"))
+    el = z["elements_deg"]
+    d = np.deg2rad
+    r, v = W.el2xv(float(z["mu"]), el[:, 0], el[:, 1], d(el[:, 2]), d(el[:, 3]), d(el[:, 4]), d(el[:, 5]))
+    assert np.max(np.abs(r - z["r"]) / np.linalg.norm(z["r"], axis=1, keepdims=True)) < 1e-12
+    assert np.max(np.abs(v - z["v"]) / np.linalg.norm(z["v"], axis=1, keepdims=True)) < 1e-12
