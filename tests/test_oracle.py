@@ -535,3 +535,86 @@ def test_workload_el2xv_matches_reference_python_golden():
     r, v = W.el2xv(float(z["mu"]), el[:, 0], el[:, 1], d(el[:, 2]), d(el[:, 3]), d(el[:, 4]), d(el[:, 5]))
     assert np.max(np.abs(r - z["r"]) / np.linalg.norm(z["r"], axis=1, keepdims=True)) < 1e-12
     assert np.max(np.abs(v - z["v"]) / np.linalg.norm(z["v"], axis=1, keepdims=True)) < 1e-12
+
+
+# ---------------------------------------------------------------- symmetry properties (the kick and the sweep are unpinned)
+def _rot(rng):
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    return q * np.sign(np.linalg.det(q))
+
+
+def test_kick_symmetries(oracle):
+    """Translation invariance, rotation covariance, the 1/lambda^2 scaling law and linearity in the masses."""
+    rng = np.random.default_rng(17)
+    n = 200
+    d = W.disk(n, seed=17)
+    r, Gm = d["rh"], d["Gmass"]
+    a0 = oracle.kick_tri_pl(r, Gm, None, np.zeros((n, 3)))
+    scale = oracle.kick_tri_abs_scale(r, Gm, None)
+    a1 = oracle.kick_tri_pl(r + np.array([3.0, -2.0, 0.5]), Gm, None, np.zeros((n, 3)))
+    assert np.max(np.abs(a1 - a0) / scale) < 1e-11            # differences of shifted coordinates lose ~4 digits
+    R = _rot(rng)
+    a2 = oracle.kick_tri_pl(r @ R.T, Gm, None, np.zeros((n, 3)))
+    assert np.max(np.abs(a2 - a0 @ R.T) / np.linalg.norm(scale, axis=1, keepdims=True)) < 1e-13
+    a3 = oracle.kick_tri_pl(2.0 * r, Gm, None, np.zeros((n, 3)))
+    assert np.array_equal(a3, a0 / 4.0)                        # powers of two: exact
+    a4 = oracle.kick_tri_pl(r, 4.0 * Gm, None, np.zeros((n, 3)))
+    assert np.array_equal(a4, 4.0 * a0)                        # linear in the masses (power of two: exact)
+    a5 = oracle.kick_tri_pl(r, 3.0 * Gm, None, np.zeros((n, 3)))
+    assert np.max(np.abs(a5 - 3.0 * a0) / scale) < 1e-13
+    # the flat variant obeys the same laws
+    f3 = oracle.kick_flat_pl(2.0 * r, Gm, None, np.zeros((n, 3)))
+    assert np.array_equal(f3, oracle.kick_flat_pl(r, Gm, None, np.zeros((n, 3))) / 4.0)
+
+
+def test_sweep_is_equivariant_under_relabeling_and_rotation(oracle):
+    """Permuting the bodies permutes the pair list; rotating the system (|r| and all relative quantities unchanged up
+    to rounding) keeps it.  Guards the sort / index bookkeeping of the sweep, which no reference vector pins."""
+    rng = np.random.default_rng(23)
+    n = 800
+    d = W.disk(n, seed=23)
+    renc = oracle.set_renc(d["rhill"], 0) * 4
+    i1, i2, _ = oracle.encounter_plpl(d["rh"], d["vh"], renc, d["dt"])
+    base = set(zip(i1.tolist(), i2.tolist()))
+    assert len(base) > 20
+    perm = rng.permutation(n)
+    inv = np.empty(n, int)
+    inv[perm] = np.arange(n)
+    j1, j2, _ = oracle.encounter_plpl(d["rh"][perm], d["vh"][perm], renc[perm], d["dt"])
+    mapped = set()
+    for a, b in zip(j1.tolist(), j2.tolist()):
+        x, y = perm[a - 1] + 1, perm[b - 1] + 1
+        mapped.add((min(x, y), max(x, y)))
+    assert mapped == base
+    R = _rot(rng)
+    k1, k2, _ = oracle.encounter_plpl(d["rh"] @ R.T, d["vh"] @ R.T, renc, d["dt"])
+    rot = set(zip(k1.tolist(), k2.tolist()))
+    # a rotation changes every coordinate in the last bits: only pairs sitting exactly on a threshold may flip
+    assert len(rot ^ base) <= 2
+
+
+def test_encounter_check_one_scale_invariance(oracle):
+    rng = np.random.default_rng(5)
+    for _ in range(300):
+        x, v = rng.normal(size=3), rng.normal(size=3)
+        renc, dt = abs(rng.normal()) * 0.7, abs(rng.normal())
+        a = oracle.encounter_check_one(*x, *v, renc, dt)
+        b = oracle.encounter_check_one(*(4.0 * x), *(4.0 * v), 4.0 * renc, dt)      # lengths scaled by a power of two
+        c = oracle.encounter_check_one(*x, *(0.5 * v), renc, 2.0 * dt)              # time scaled by a power of two
+        assert a == b == c
+
+
+def test_drift_group_property_and_invariants(oracle):
+    """drift(dt1) then drift(dt2) = drift(dt1 + dt2) on the same Kepler orbit; energy and angular momentum stay."""
+    tp = W.tp_cloud(500, seed=3)
+    mu = np.full(500, W.GMSUN)
+    x1, v1, f1 = oracle.drift_all(mu, tp["rh"], tp["vh"], 0.013)
+    x2, v2, f2 = oracle.drift_all(mu, x1, v1, 0.021)
+    x3, v3, f3 = oracle.drift_all(mu, tp["rh"], tp["vh"], 0.034)
+    assert not (f1.any() or f2.any() or f3.any())
+    assert np.max(np.abs(x2 - x3) / np.linalg.norm(x3, axis=1, keepdims=True)) < 1e-12
+    E0 = 0.5 * (tp["vh"] ** 2).sum(1) - W.GMSUN / np.linalg.norm(tp["rh"], axis=1)
+    E3 = 0.5 * (v3 ** 2).sum(1) - W.GMSUN / np.linalg.norm(x3, axis=1)
+    assert np.max(np.abs(E3 - E0) / np.abs(E0)) < 1e-12
+    L0, L3 = np.cross(tp["rh"], tp["vh"]), np.cross(x3, v3)
+    assert np.max(np.abs(L3 - L0)) / np.abs(L0).max() < 1e-13
