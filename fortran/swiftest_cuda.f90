@@ -404,6 +404,123 @@ module swiftest_cuda
          integer(c_int), intent(out) :: lcollision(*), lclosest(*)
          integer(c_int64_t), intent(out) :: ncollision
       end function
+
+      ! ---- the rest of the ABI: context services, multi-GPU plumbing, statistics and measurement helpers ----
+      integer(c_int) function swcu_version() bind(C, name="swcu_version")
+         import :: c_int
+      end function
+      integer(c_int) function swcu_set_stream(ctx, cuda_stream) bind(C, name="swcu_set_stream")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx, cuda_stream
+      end function
+      integer(c_int) function swcu_synchronize(ctx) bind(C, name="swcu_synchronize")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_device_info(ctx, sm_count, cc, mem_bytes) bind(C, name="swcu_device_info")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), intent(out) :: sm_count, cc
+         integer(c_int64_t), intent(out) :: mem_bytes
+      end function
+      integer(c_int) function swcu_encounter_check_all_sort_and_sweep_plplm(ctx, nplm, nplt, rplm, vplm, rplt, vplt, rencm, &
+            renct, dt, nenc) bind(C, name="swcu_encounter_check_all_sort_and_sweep_plplm")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nplm, nplt
+         real(c_double), intent(in) :: rplm(3,*), vplm(3,*), rplt(3,*), vplt(3,*), rencm(*), renct(*)
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_encounter_stats(ctx, nbox_total, ncandidates_emitted) bind(C, name="swcu_encounter_stats")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), intent(out) :: nbox_total, ncandidates_emitted
+      end function
+      integer(c_int) function swcu_body_count(ctx, kind, n, nplm, generation) bind(C, name="swcu_body_count")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         integer(c_int), intent(out) :: n, nplm
+         integer(c_int64_t), intent(out) :: generation
+      end function
+      integer(c_int) function swcu_comm_unique_id(ctx, id128) bind(C, name="swcu_comm_unique_id")
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: ctx
+         character(kind=c_char), intent(out) :: id128(128)
+      end function
+      integer(c_int) function swcu_comm_init(ctx, nranks, rank, id128) bind(C, name="swcu_comm_init")
+         import :: c_int, c_ptr, c_char
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: nranks, rank
+         character(kind=c_char), intent(in) :: id128(128)
+      end function
+      integer(c_int) function swcu_comm_finalize(ctx) bind(C, name="swcu_comm_finalize")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_pl_set_slice(ctx, i0, i1) bind(C, name="swcu_pl_set_slice")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: i0, i1
+      end function
+      integer(c_int) function swcu_pl_allgather(ctx, with_v) bind(C, name="swcu_pl_allgather")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: with_v
+      end function
+      integer(c_int) function swcu_partition(n, nranks, rank, i0, i1) bind(C, name="swcu_partition")
+         import :: c_int
+         integer(c_int), value :: n, nranks, rank
+         integer(c_int), intent(out) :: i0, i1
+      end function
+      integer(c_int) function swcu_p2p_close(ctx) bind(C, name="swcu_p2p_close")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_timer_start(ctx) bind(C, name="swcu_timer_start")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_timer_stop(ctx, elapsed_ms) bind(C, name="swcu_timer_stop")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), intent(out) :: elapsed_ms
+      end function
+      integer(c_int) function swcu_probe_fp64_peak(ctx, tflops) bind(C, name="swcu_probe_fp64_peak")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), intent(out) :: tflops
+      end function
+      integer(c_int) function swcu_probe_hbm_copy(ctx, bytes, gbs) bind(C, name="swcu_probe_hbm_copy")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: bytes
+         real(c_double), intent(out) :: gbs
+      end function
+      integer(c_int) function swcu_flush_l2(ctx) bind(C, name="swcu_flush_l2")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_last_kernel_ms(ctx, family, ms) bind(C, name="swcu_last_kernel_ms")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: family
+         real(c_double), intent(out) :: ms
+      end function
+      integer(c_int) function swcu_enable_kernel_timing(ctx, on) bind(C, name="swcu_enable_kernel_timing")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: on
+      end function
+      integer(c_int) function swcu_kernel_ms_accumulated(ctx, family, total_ms, count) &
+            bind(C, name="swcu_kernel_ms_accumulated")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: family
+         real(c_double), intent(out) :: total_ms
+         integer(c_int), intent(out) :: count
+      end function
    end interface
 
 contains

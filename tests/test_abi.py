@@ -100,3 +100,57 @@ def test_python_harness_validates_shapes_before_calling_the_library():
         Context._inplace3(np.zeros((4, 3), dtype=np.float32), 4)
     with pytest.raises(ValueError):
         Context._inplace3(np.zeros((3, 4)).T, 4)  # not C-contiguous
+
+
+def _c_prototypes():
+    """name -> list of (is_pointer, text) for every function include/swiftest_cuda.h declares."""
+    import re
+    text = open(_lib.HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char \*)\s*(swcu_[a-z0-9_]+)\s*\((.*?)\)\s*;", text, flags=re.S):
+        args = " ".join(m.group(2).split())
+        params = [] if args == "void" else [a.strip() for a in args.split(",")]
+        protos[m.group(1)] = [("*" in a, a) for a in params]
+    return protos
+
+
+def _fortran_interfaces():
+    """bind(C) name -> (dummy argument list, set of dummies declared with the `value` attribute)."""
+    import re
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fortran", "swiftest_cuda.f90")
+    src = open(path).read()
+    src = re.sub(r"&\s*\n\s*", " ", src)                      # join continuation lines
+    out = {}
+    for m in re.finditer(r"function\s+(\w+)\s*\(([^)]*)\)\s*bind\(C,\s*name=\"(\w+)\"\)(.*?)end function", src,
+                         flags=re.S | re.I):
+        dummies = [a.strip() for a in m.group(2).split(",") if a.strip()]
+        body = re.sub(r"!.*", "", m.group(4))
+        by_value = set()
+        for line in body.splitlines():
+            if "::" in line and re.search(r"\bvalue\b", line.split("::")[0]):
+                by_value.update(v.strip().split("(")[0] for v in line.split("::")[1].split(","))
+        assert m.group(1) == m.group(3), (m.group(1), m.group(3))
+        out[m.group(3)] = (dummies, by_value)
+    return out
+
+
+def test_fortran_interfaces_match_the_c_prototypes():
+    """The Fortran binding module cannot be compiled here (no Fortran compiler), so guard it structurally: every
+    bind(C) interface names a function the header declares, with the same number of arguments, and passes exactly the
+    C scalars by value (type(c_ptr), value counts as a pointer-sized scalar for a C pointer parameter)."""
+    protos = _c_prototypes()
+    ifaces = _fortran_interfaces()
+    assert sorted(ifaces) == sorted(protos), sorted(set(protos) ^ set(ifaces))   # the module binds the WHOLE header
+    for name, (dummies, by_value) in ifaces.items():
+        assert name in protos, f"{name}: not declared in swiftest_cuda.h"
+        cparams = protos[name]
+        assert len(dummies) == len(cparams), f"{name}: {len(dummies)} Fortran dummies vs {len(cparams)} C parameters"
+        for dummy, (is_ptr, ctext) in zip(dummies, cparams):
+            if not is_ptr:
+                assert dummy in by_value, f"{name}: C scalar `{ctext}` must be passed by value (dummy {dummy})"
+    # and the names the hot path itself needs are all bound
+    for need in ("swcu_create", "swcu_kick_getacch_int_all_flat_pl", "swcu_kick_getacch_int_all_tri_pl",
+                 "swcu_kick_getacch_int_all_tp", "swcu_drift_all", "swcu_encounter_check_all_sort_and_sweep_plpl",
+                 "swcu_encounter_fetch", "swcu_body_sync", "swcu_helio_step_pl"):
+        assert need in ifaces, need
