@@ -154,3 +154,24 @@ def test_fortran_interfaces_match_the_c_prototypes():
                  "swcu_kick_getacch_int_all_tp", "swcu_drift_all", "swcu_encounter_check_all_sort_and_sweep_plpl",
                  "swcu_encounter_fetch", "swcu_body_sync", "swcu_helio_step_pl"):
         assert need in ifaces, need
+
+
+def test_ctypes_signatures_match_the_c_prototypes():
+    """Every function of the header has ctypes argtypes in swiftest_b200/_lib.py with the right arity, pointers where C
+    has pointers, and the right scalar width (int32_t / int64_t / uint64_t / double / int)."""
+    L = _lib.load()
+    protos = _c_prototypes()
+    scalar = {"int32_t": C.c_int32, "int64_t": C.c_int64, "uint64_t": C.c_uint64, "double": C.c_double, "int": C.c_int}
+    for name, params in protos.items():
+        fn = getattr(L, name)
+        at = fn.argtypes
+        if name in ("swcu_version", "swcu_last_error", "swcu_launch_count") and at is None:
+            continue
+        assert at is not None, f"{name}: no argtypes"
+        assert len(at) == len(params), f"{name}: {len(at)} ctypes args vs {len(params)} C parameters"
+        for t, (is_ptr, text) in zip(at, params):
+            if is_ptr:
+                assert t in (C.c_void_p, C.c_char_p) or hasattr(t, "contents") or issubclass(t, C._Pointer), (name, text)
+            else:
+                ctype = text.replace("const ", "").split()[0]
+                assert C.sizeof(t) == C.sizeof(scalar[ctype]), f"{name}: `{text}` bound as {t}"
