@@ -561,7 +561,7 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     const int grid = cdiv(units, FWARPS);
     a.trace = nullptr;
     static const char *trace_path = getenv("SWCU_FLAT_TRACE");
-    static DevBuf trace_buf;
+    DevBuf &trace_buf = ctx->flat_trace;
     if (trace_path) {
         SWCU_CUDA(ctx, trace_buf.ensure(sizeof(unsigned long long) * 4 * (size_t)grid * FWARPS));
         SWCU_CUDA(ctx, cudaMemsetAsync(trace_buf.p, 0, sizeof(unsigned long long) * 4 * (size_t)grid * FWARPS, ctx->stream));

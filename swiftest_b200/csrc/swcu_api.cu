@@ -166,6 +166,7 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     ctx->cbs.release();
     ctx->sumbuf.release();
     for (auto &b : ctx->lists) b.release();
+    ctx->flat_trace.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
     auto &E = ctx->enc;

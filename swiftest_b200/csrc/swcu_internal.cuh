@@ -126,6 +126,7 @@ struct swcu_context {
     swcu::DevBuf cbs;
     swcu::DevBuf sumbuf;  // per-CTA partials of the tree reductions + ticket counter (zeroed when allocated)
     swcu::DevBuf lists[16];  // staging of the encounter-list kernels (list_kernels.cu)
+    swcu::DevBuf flat_trace; // per-warp timeline of the third-law kernel (development aid, SWCU_FLAT_TRACE)
 
     // multi-GPU
     swcu::NcclApi *nccl = nullptr;
