@@ -152,3 +152,59 @@ def test_rebalance_plan_properties():
                 got[dst][dlo + t] = (src, lo + t)
         flat = [x for blk in got for x in blk]
         assert None not in flat and flat == sorted(flat) and len(flat) == ntot
+
+
+def _pair_slice_worker(rank, world, port, n, out):
+    """The decomposition of the fused peer-memory step (swcu_pl_kick_drift_p2p): every rank evaluates a run of the
+    flattened pair list into its own partial-acceleration buffer, then for ITS slice of bodies sums the partials of all
+    ranks in rank order (reduce-scatter), kicks, drifts, and delivers the slice to everybody (allgather)."""
+    sys.path.insert(0, ROOT)
+    from oracle import load
+    from swiftest_b200 import shard, workloads as W
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = load()
+    d = W.disk(n, seed=77)
+    rh, vb = d["rh"].copy(), d["vh"].copy()
+    iu = np.triu_indices(n, 1)
+    k_all = np.stack([iu[0] + 1, iu[1] + 1], axis=1).astype(np.int32)       # canonical flattened order, 1-based
+    p0, p1 = shard.partition(len(k_all), world, rank)
+    i0, i1 = shard.partition(n, world, rank)
+    for _ in range(2):
+        F = o.kick_flat_pl(rh, d["Gmass"], d["radius"], np.zeros((n, 3)), k_plpl=k_all[p0:p1])
+        parts = [torch.zeros(n, 3, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(F))
+        ah = np.zeros((i1 - i0, 3))
+        for r in range(world):                                                 # fixed rank order, own slice only
+            ah = ah + parts[r][i0:i1].numpy()
+        v = vb[i0:i1] + ah * d["dt"]
+        x, v, fl = o.drift_all(d["mu"][i0:i1], rh[i0:i1], v, d["dt"])
+        assert not fl.any()
+        got = [None] * world
+        dist.all_gather_object(got, (i0, i1, x, v))
+        for (a, b, xs, vs) in got:
+            rh[a:b], vb[a:b] = xs, vs
+    if rank == 0:
+        np.savez(out, rh=rh, vb=vb)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_pair_slices_reduce_scatter_matches_single_process(tmp_path, oracle):
+    from swiftest_b200 import workloads as W
+    n, world = 257, 2
+    out = str(tmp_path / "p2p.npz")
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_pair_slice_worker, args=(world, port, n, out), nprocs=world, join=True)
+    res = np.load(out)
+    d = W.disk(n, seed=77)
+    rh, vb = d["rh"].copy(), d["vh"].copy()
+    for _ in range(2):
+        ah = oracle.kick_flat_pl(rh, d["Gmass"], d["radius"], np.zeros((n, 3)))
+        vb = vb + ah * d["dt"]
+        rh, vb, fl = oracle.drift_all(d["mu"], rh, vb, d["dt"])
+    # the partial sums are regrouped by rank: same terms, different association
+    assert np.max(np.abs(res["rh"] - rh) / np.linalg.norm(rh, axis=1, keepdims=True)) < 1e-14
+    assert np.max(np.abs(res["vb"] - vb) / np.linalg.norm(vb, axis=1, keepdims=True)) < 1e-13
