@@ -69,6 +69,13 @@ class Oracle:
         L.swo_helio_step_pl.argtypes = [i32, d, p, p, C.c_int, p, p, d, p, p, p, p, p, p, p, p, p, p]
         L.swo_helio_step_tp.argtypes = [i32, i32, d, p, p, p, p, p, p, p, d, p, p, p, p, p]
         L.swo_whm_kick_getacch_ah0.argtypes = [i32, p, p, p]
+        L.swo_whm_set_mu_eta.argtypes = [i32, d, p, p, p, p]
+        L.swo_whm_coord_h2j.argtypes = [i32, p, p, p, p, p, p]
+        L.swo_whm_coord_j2h.argtypes = [i32, p, p, p, p, p, p]
+        L.swo_whm_coord_vh2vj.argtypes = [i32, p, p, p, p]
+        L.swo_whm_kick_getacch_pl.argtypes = [i32, d, p, p, C.c_int, p, p, p, p]
+        L.swo_whm_step_pl.argtypes = [i32, d, p, p, C.c_int, p, p, p, p, d, p, p, p, p, p, p, p, p]
+        L.swo_whm_step_tp.argtypes = [i32, i32, d, p, p, p, p, p, d, p, p, p, p]
         L.swo_symba_kick_list_plpl.argtypes = [i64, p, p, p, i32, p, p, p, p, d, i32, i32, p, p, p]
         L.swo_symba_kick_list_pltp.argtypes = [i64, p, p, p, i32, i32, p, p, p, p, p, p, d, i32, i32, p, p, p]
         L.swo_collision_check_list.restype = i64
@@ -411,6 +418,64 @@ class Oracle:
         a, e, q = C.c_double(), C.c_double(), C.c_double()
         self.lib.swo_orbel_xv2aeq(mu, r[0], r[1], r[2], v[0], v[1], v[2], C.byref(a), C.byref(e), C.byref(q))
         return a.value, e.value, q.value
+
+    # ---- swiftest_oracle_whm.c: Wisdom-Holman step ----
+    def whm_set_mu_eta(self, GMcb, Gmass):
+        Gmass = _c(Gmass)
+        n = len(Gmass)
+        mu, eta, muj = np.zeros(n), np.zeros(n), np.zeros(n)
+        self.lib.swo_whm_set_mu_eta(n, GMcb, self._a(Gmass), self._a(mu), self._a(eta), self._a(muj))
+        return mu, eta, muj
+
+    def whm_coord_h2j(self, Gmass, eta, rh, vh):
+        Gmass, eta, rh, vh = _c(Gmass), _c(eta), _c(rh), _c(vh)
+        xj, vj = np.zeros_like(rh), np.zeros_like(vh)
+        self.lib.swo_whm_coord_h2j(len(Gmass), self._a(Gmass), self._a(eta), self._a(rh), self._a(vh), self._a(xj), self._a(vj))
+        return xj, vj
+
+    def whm_coord_j2h(self, Gmass, eta, xj, vj):
+        Gmass, eta, xj, vj = _c(Gmass), _c(eta), _c(xj), _c(vj)
+        rh, vh = np.zeros_like(xj), np.zeros_like(vj)
+        self.lib.swo_whm_coord_j2h(len(Gmass), self._a(Gmass), self._a(eta), self._a(xj), self._a(vj), self._a(rh), self._a(vh))
+        return rh, vh
+
+    def whm_step_pl(self, st, GMcb, Gmass, radius, dt, lflat=False, lmask=None):
+        """st: dict with rh, vh (+ xj, vj, ah, eta, muj, lfirst created on the first call); updated in place."""
+        Gmass = _c(Gmass)
+        n = len(Gmass)
+        radius = None if radius is None else _c(radius)
+        lm = None if lmask is None else _c(lmask, _i32)
+        if "eta" not in st:
+            _, st["eta"], st["muj"] = self.whm_set_mu_eta(GMcb, Gmass)
+            st["xj"], st["vj"], st["ah"] = np.zeros((n, 3)), np.zeros((n, 3)), np.zeros((n, 3))
+            st.setdefault("lfirst", True)
+        for k in ("rh", "vh", "xj", "vj", "ah"):
+            st[k] = _c(st[k])
+        st["rbeg"], st["rend"] = np.zeros((n, 3)), np.zeros((n, 3))
+        lf = C.c_int32(int(st["lfirst"]))
+        iflag = np.zeros(n, _i32)
+        self.lib.swo_whm_step_pl(n, GMcb, self._a(Gmass), self._a(radius), int(lflat), self._a(lm), self._a(st["eta"]),
+                                 self._a(st["muj"]), C.byref(lf), dt, self._a(st["rh"]), self._a(st["vh"]), self._a(st["xj"]),
+                                 self._a(st["vj"]), self._a(st["ah"]), self._a(st["rbeg"]), self._a(st["rend"]),
+                                 self._a(iflag))
+        st["lfirst"] = bool(lf.value)
+        return iflag
+
+    def whm_step_tp(self, st, pl, GMcb, GMpl, dt, lmask=None):
+        """st: tp dict (rh, vh, ah, lfirst); pl: planets' dict after whm_step_pl of the same step (rbeg, rend)."""
+        n = len(st["rh"])
+        GMpl = _c(GMpl)
+        lm = None if lmask is None else _c(lmask, _i32)
+        st.setdefault("ah", np.zeros((n, 3)))
+        st.setdefault("lfirst", True)
+        for k in ("rh", "vh", "ah"):
+            st[k] = _c(st[k])
+        lf = C.c_int32(int(st["lfirst"]))
+        iflag = np.zeros(n, _i32)
+        self.lib.swo_whm_step_tp(n, len(GMpl), GMcb, self._a(GMpl), self._a(pl["rbeg"]), self._a(pl["rend"]), self._a(lm),
+                                 C.byref(lf), dt, self._a(st["rh"]), self._a(st["vh"]), self._a(st["ah"]), self._a(iflag))
+        st["lfirst"] = bool(lf.value)
+        return iflag
 
 
 _cache = {}

@@ -157,6 +157,21 @@ void swo_get_energy_and_momentum(int32_t npl, const int32_t *lmask, double GMcb,
                                  const double *vbcb, const double *Gmass, const double *mass, const double *radius,
                                  const double *rb, const double *vb, int lclose, int lflat, double *out);
 
+/* ---- Wisdom-Holman step around the hot path (swiftest_oracle_whm.c) ---- */
+void swo_whm_set_mu_eta(int32_t npl, double GMcb, const double *Gmass, double *mu, double *eta, double *muj);
+void swo_whm_coord_h2j(int32_t npl, const double *Gmass, const double *eta, const double *rh, const double *vh,
+                       double *xj, double *vj);
+void swo_whm_coord_j2h(int32_t npl, const double *Gmass, const double *eta, const double *xj, const double *vj,
+                       double *rh, double *vh);
+void swo_whm_coord_vh2vj(int32_t npl, const double *Gmass, const double *eta, const double *vh, double *vj);
+void swo_whm_kick_getacch_pl(int32_t npl, double GMcb, const double *Gmass, const double *radius, int lflat,
+                             const int32_t *lmask, const double *rh, const double *xj, double *ah);
+void swo_whm_step_pl(int32_t npl, double GMcb, const double *Gmass, const double *radius, int lflat,
+                     const int32_t *lmask, const double *eta, const double *muj, int32_t *lfirst, double dt, double *rh,
+                     double *vh, double *xj, double *vj, double *ah, double *rbeg, double *rend, int32_t *iflag);
+void swo_whm_step_tp(int32_t ntp, int32_t npl, double GMcb, const double *GMpl, const double *rbeg, const double *rend,
+                     const int32_t *lmask, int32_t *lfirst, double dt, double *rh, double *vh, double *ah, int32_t *iflag);
+
 #ifdef __cplusplus
 }
 #endif

@@ -618,3 +618,68 @@ def test_drift_group_property_and_invariants(oracle):
     assert np.max(np.abs(E3 - E0) / np.abs(E0)) < 1e-12
     L0, L3 = np.cross(tp["rh"], tp["vh"]), np.cross(x3, v3)
     assert np.max(np.abs(L3 - L0)) / np.abs(L0).max() < 1e-13
+
+
+# ---------------------------------------------------------------- Wisdom-Holman step (BASELINE configs[1])
+def test_whm_jacobi_round_trip_and_single_planet_is_exact_kepler(oracle):
+    p = W.planets8_year_units()
+    GMcb = float(p["cb_Gmass"])
+    _, eta, muj = oracle.whm_set_mu_eta(GMcb, p["Gmass"])
+    assert eta[0] == GMcb + p["Gmass"][0] and abs(eta[-1] - (GMcb + p["Gmass"].sum())) < 1e-13
+    xj, vj = oracle.whm_coord_h2j(p["Gmass"], eta, p["rh"], p["vh"])
+    assert np.array_equal(xj[0], p["rh"][0])
+    rh, vh = oracle.whm_coord_j2h(p["Gmass"], eta, xj, vj)
+    assert np.max(np.abs(rh - p["rh"])) < 1e-14 and np.max(np.abs(vh - p["vh"])) < 1e-14
+    # one planet: no indirect terms, no interactions -> the WHM step is the Kepler drift with mu = GMcb + Gm
+    st = dict(rh=p["rh"][2:3].copy(), vh=p["vh"][2:3].copy())
+    fl = oracle.whm_step_pl(st, GMcb, p["Gmass"][2:3], p["radius"][2:3], 0.01)
+    x, v, f2 = oracle.drift_all(GMcb + p["Gmass"][2:3], p["rh"][2:3], p["vh"][2:3], 0.01)
+    assert not fl.any() and np.array_equal(st["rh"], x) and np.array_equal(st["vh"], v)
+
+
+def test_whm_integration_conserves_energy_and_agrees_with_helio(oracle):
+    """Same bounds as the reference's system test (tests/test_swiftest.py:112-169) for the restated WHM step, and the
+    two second-order integrators (WHM, democratic heliocentric) stay within O(dt^2) of each other."""
+    from tests.helio import HelioSystem, OracleBackend
+    p = W.planets8_year_units()
+    GMcb, dt, nsteps = float(p["cb_Gmass"]), 0.01, 3000
+    ref = HelioSystem(GMcb, p["Gmass"], p["rh"], p["vh"], p["radius"], OracleBackend(oracle))
+    E0, L0 = ref.energy_and_momentum()
+    st = dict(rh=p["rh"].copy(), vh=p["vh"].copy())
+    dE = []
+    for k in range(nsteps):
+        assert not oracle.whm_step_pl(st, GMcb, p["Gmass"], p["radius"], dt).any()
+        ref.step(dt)
+        if (k + 1) % 300 == 0:
+            probe = HelioSystem(GMcb, p["Gmass"], st["rh"], st["vh"], p["radius"], OracleBackend(oracle))
+            E, L = probe.energy_and_momentum()
+            dE.append((E - E0) / abs(E0))
+            assert np.linalg.norm(L - L0) / np.linalg.norm(L0) < 1e-11
+    assert np.max(np.abs(dE)) < 1e-6
+    assert abs(np.polyfit(np.arange(len(dE)) * 300 * dt, dE, 1)[0]) < 1e-8
+    # 30 years: Mercury has made ~125 orbits; the two splittings differ by a phase error of order dt^2
+    assert np.max(np.linalg.norm(st["rh"] - ref.rh, axis=1) / np.linalg.norm(ref.rh, axis=1)) < 5e-3
+
+
+def test_whm_step_tp_cases(oracle):
+    p = W.planets8_year_units()
+    GMcb, dt = float(p["cb_Gmass"]), 0.01
+    tp = W.tp_cloud(200, seed=4)
+    # massless planets: the tp step is the pure Kepler drift (two half kicks with zero acceleration)
+    pl = dict(rbeg=p["rh"].copy(), rend=p["rh"].copy())
+    st = dict(rh=tp["rh"].copy(), vh=tp["vh"].copy())
+    fl = oracle.whm_step_tp(st, pl, GMcb, np.zeros(8), dt)
+    x, v, _ = oracle.drift_all(GMcb, tp["rh"], tp["vh"], dt)
+    assert not fl.any() and np.array_equal(st["rh"], x) and np.array_equal(st["vh"], v)
+    # with the real planets: the kept accelerations equal ah0 + direct terms at rend, masked particles do not move
+    mask = np.ones(200, np.int32)
+    mask[::7] = 0
+    pls = dict(rh=p["rh"].copy(), vh=p["vh"].copy())
+    oracle.whm_step_pl(pls, GMcb, p["Gmass"], p["radius"], dt)
+    st = dict(rh=tp["rh"].copy(), vh=tp["vh"].copy())
+    oracle.whm_step_tp(st, pls, GMcb, p["Gmass"], dt, lmask=mask)
+    want = oracle.kick_all_tp(st["rh"], pls["rend"], p["Gmass"], mask, np.zeros((200, 3)))
+    want[mask == 1] += oracle.whm_kick_getacch_ah0(p["Gmass"], pls["rend"])
+    on = mask == 1
+    assert np.max(np.abs(st["ah"][on] - want[on])) <= 1e-15 * np.abs(want).max()
+    assert np.array_equal(st["rh"][~on], tp["rh"][~on]) and np.array_equal(st["vh"][~on], tp["vh"][~on])
