@@ -175,3 +175,13 @@ def test_ctypes_signatures_match_the_c_prototypes():
             else:
                 ctype = text.replace("const ", "").split()[0]
                 assert C.sizeof(t) == C.sizeof(scalar[ctype]), f"{name}: `{text}` bound as {t}"
+
+
+def test_cpp_host_mirror_cpu_checks():
+    """The GPU-free parts of the compiled C++ host mirror: pair counts of pl%flatten, symba_pl%set_renc, and the
+    no-fallback rule (cuda_context throws without an sm_100 GPU)."""
+    exe = os.path.join(os.path.dirname(_lib.LIB_PATH), "host_cpu_check")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(_lib.LIB_PATH)), "csrc")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "HOST-CPU-CHECK-OK" in out.stdout, out.stdout + out.stderr
