@@ -409,6 +409,10 @@ module swiftest_cuda
       integer(c_int) function swcu_version() bind(C, name="swcu_version")
          import :: c_int
       end function
+      integer(c_int64_t) function swcu_launch_count(ctx) bind(C, name="swcu_launch_count")
+         import :: c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+      end function
       integer(c_int) function swcu_set_stream(ctx, cuda_stream) bind(C, name="swcu_set_stream")
          import :: c_int, c_ptr
          type(c_ptr), value :: ctx, cuda_stream

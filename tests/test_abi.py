@@ -108,7 +108,7 @@ def _c_prototypes():
     text = open(_lib.HEADER_PATH).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(?:int|const char \*)\s*(swcu_[a-z0-9_]+)\s*\((.*?)\)\s*;", text, flags=re.S):
+    for m in re.finditer(r"\b(?:int|int64_t|const char \*)\s*(swcu_[a-z0-9_]+)\s*\((.*?)\)\s*;", text, flags=re.S):
         args = " ".join(m.group(2).split())
         params = [] if args == "void" else [a.strip() for a in args.split(",")]
         protos[m.group(1)] = [("*" in a, a) for a in params]
