@@ -514,6 +514,9 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         fine_read = true;
         if (const char *e = getenv("SWCU_FLAT_FINE")) sscanf(e, "%d,%d,%d,%d", &fine[0], &fine[1], &fine[2], &fine[3]);
     }
+    // Eight GPUs on one counter: the single-chunk phase would ask for ~28k claims within ~25 us (> 1 G claims/s to one
+    // address over NVLink; 0.6 G/s was measured harmless at four GPUs), so it is left out there unless overridden.
+    const bool skip_single = (sharers >= 8) && !getenv("SWCU_FLAT_FINE");
     auto split_quanta = [&](long long items, long long warps_all) -> long long {
         const long long U = items * FIB, G = (long long)a.quantum * FIB;
         long long left = U;
@@ -521,6 +524,7 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         const int sz[5] = {(int)G, 8, 4, 2, 1};
         for (int k = 4; k >= 1; --k) {  // carve the fine phases off the end of the run
             if (sz[k] >= G) continue;
+            if (k == 4 && skip_single) continue;
             long long want = std::min<long long>(left, warps_all * fine[4 - k]);
             want -= want % sz[k];
             nq[k] = want / sz[k];

@@ -90,7 +90,7 @@ def claim_range(q, ph_q, ph_u, sz, unit0, unit1):
 
 def test_graded_schedule_tiles_the_run_exactly():
     shapes = itertools.product((1, 2, 3, 7, 50, 391, 5000, 38269), (1, 4, 12, 1776, 14208), (1, 2, 4, 6),
-                               ((2, 4, 8, 16), (0, 0, 0, 0), (4, 4, 8, 0), (1, 1, 1, 1)))
+                               ((2, 4, 8, 16), (0, 4, 8, 16), (0, 0, 0, 0), (4, 4, 8, 0), (1, 1, 1, 1)))
     for items, warps, quantum, fine in shapes:
         for unit0 in (0, 4 * 123):
             ph_q, ph_u, sz, nquanta = split_quanta(items, warps, quantum, fine)
