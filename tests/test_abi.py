@@ -185,3 +185,44 @@ def test_cpp_host_mirror_cpu_checks():
         subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(os.path.dirname(_lib.LIB_PATH)), "csrc")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "HOST-CPU-CHECK-OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_partition_and_rebalance_properties_hypothesis():
+    """Property tests of the host sharding logic: slices tile [0,n) in rank order with sizes differing by at most one;
+    a rebalance plan moves every particle exactly once and keeps the global order."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 10 ** 6), st.integers(1, 16))
+    def slices(n, nranks):
+        cuts = [shard.partition(n, nranks, r) for r in range(nranks)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
+        sizes = [b - a for a, b in cuts]
+        assert max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
+        blocks = [shard.tp_block_partition(n, nranks, r) for r in range(nranks)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n and all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.lists(st.integers(0, 500), min_size=1, max_size=8))
+    def plan(counts):
+        moves = shard.rebalance_plan(counts)
+        ntot, nimg = sum(counts), len(counts)
+        taken = [[False] * c for c in counts]
+        dest = {}
+        for src, lo, hi, dst, dlo in moves:
+            for t in range(hi - lo):
+                assert not taken[src][lo + t]
+                taken[src][lo + t] = True
+                dest[(dst, dlo + t)] = (src, lo + t)
+        assert all(all(row) for row in taken) and len(dest) == ntot
+        order = [dest[k] for k in sorted(dest)]
+        assert order == sorted(order)
+        for k in range(nimg):
+            a, b = shard.tp_block_partition(ntot, nimg, k)
+            assert sum(1 for (d, _) in dest if d == k) == b - a
+        if max(counts) - min(counts) < nimg:
+            assert not shard.needs_rebalance(counts)
+
+    slices()
+    plan()
