@@ -683,3 +683,36 @@ def test_whm_step_tp_cases(oracle):
     on = mask == 1
     assert np.max(np.abs(st["ah"][on] - want[on])) <= 1e-15 * np.abs(want).max()
     assert np.array_equal(st["rh"][~on], tp["rh"][~on]) and np.array_equal(st["vh"][~on], tp["vh"][~on])
+
+
+def test_encounter_check_one_is_monotone_in_radius_and_time(oracle):
+    """A larger encounter radius or a longer step can only add encounters (the minimum separation over [0, dt] is
+    monotone in dt and the test is r2min <= renc^2)."""
+    rng = np.random.default_rng(31)
+    for _ in range(2000):
+        x, v = rng.normal(size=3), rng.normal(size=3)
+        renc, dt = abs(rng.normal()) * 0.8, abs(rng.normal())
+        a = oracle.encounter_check_one(*x, *v, renc, dt)[0]
+        if a:
+            assert oracle.encounter_check_one(*x, *v, renc * 1.5, dt)[0]
+            assert oracle.encounter_check_one(*x, *v, renc, dt * 2.0)[0]
+        else:
+            assert not oracle.encounter_check_one(*x, *v, renc * 0.5, dt)[0]
+            assert not oracle.encounter_check_one(*x, *v, renc, dt * 0.5)[0]
+
+
+def test_discard_is_consistent_with_the_encounter_predicate(oracle):
+    """swiftest_discard_pl_close and encounter_check_one implement the same closest-approach test (one with a radius
+    squared, one with a radius): with approaching bodies they must agree."""
+    rng = np.random.default_rng(32)
+    agree = 0
+    for _ in range(3000):
+        x, v = rng.normal(size=3), rng.normal(size=3)
+        if x @ v >= 0:
+            continue
+        rad, dt = abs(rng.normal()) * 0.6, abs(rng.normal())
+        ipl, _ = oracle.discard_pl_tp(x[None, :], v[None, :], None, np.zeros((1, 3)), np.zeros((1, 3)), np.array([rad]), dt)
+        enc = oracle.encounter_check_one(*x, *v, rad, dt)[0]
+        assert bool(ipl[0]) == bool(enc)
+        agree += 1
+    assert agree > 1000
