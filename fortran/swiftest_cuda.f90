@@ -525,6 +525,11 @@ module swiftest_cuda
          real(c_double), intent(out) :: total_ms
          integer(c_int), intent(out) :: count
       end function
+      integer(c_int) function swcu_flat_redo_count(ctx, chunks) bind(C, name="swcu_flat_redo_count")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), intent(out) :: chunks
+      end function
    end interface
 
 contains

@@ -307,6 +307,9 @@ int swcu_last_kernel_ms(swcu_context *ctx, int32_t family, double *ms);
  * since this call, read later with swcu_kernel_ms_accumulated (no stream synchronisation inside the timed region) */
 int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on);
 int swcu_kernel_ms_accumulated(swcu_context *ctx, int32_t family, double *total_ms, int32_t *count);
+/* third-law gravity kernel: 32-column chunks that were rolled back and recomputed with the reference's IEEE expression
+ * (overlapping bodies, coincident bodies, coordinates outside the seeded range) since the context was created */
+int swcu_flat_redo_count(swcu_context *ctx, uint64_t *chunks);
 
 #ifdef __cplusplus
 }

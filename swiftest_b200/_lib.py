@@ -107,6 +107,7 @@ def load():
         "swcu_last_kernel_ms": [p, i32, p],
         "swcu_enable_kernel_timing": [p, i32],
         "swcu_kernel_ms_accumulated": [p, i32, p, p],
+        "swcu_flat_redo_count": [p, p],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -531,6 +531,12 @@ class Context:
         self._ck(self._L.swcu_last_kernel_ms(self._h, family, C.byref(ms)))
         return ms.value
 
+    def flat_redo_count(self):
+        """Chunks the third-law gravity kernel rolled back and redid with the IEEE expression since create."""
+        n = C.c_uint64()
+        self._ck(self._L.swcu_flat_redo_count(self._h, C.byref(n)))
+        return int(n.value)
+
     def probe_fp64_peak(self):
         t = C.c_double()
         self._ck(self._L.swcu_probe_fp64_peak(self._h, C.byref(t)))

@@ -8,14 +8,24 @@
 // Design: each unordered pair is evaluated ONCE (20 FP64 instructions instead of 2 x 16 for the full-row kernel).
 // Bodies are cut into blocks of 128.  A warp keeps one block resident -- every lane owns 4 "i" bodies (position, Gm,
 // accumulators) in registers -- and meets another block 32 "j" bodies at a time.  The chunk is staged in the warp's
-// private shared-memory tile; at step s lane l works on column body (l+s) mod 32, so all 32 lanes read different
-// words (conflict free) and no two lanes ever update the same j in the same step.  The reaction on j is kept in a
-// travelling accumulator that moves to the neighbouring lane after every step (3 SHFL.64), or in the shared tile
-// (template switch, chosen by measurement); after 32 steps every j has met all 128 i and the chunk ends with one
-// coalesced RED.ADD.F64 per component.  Block pairs are assigned cyclically (block I meets I+1 .. I+(nb-1)/2 mod nb)
-// so every block owns the same amount of work; a persistent grid of warps claims runs of 2 consecutive (I,k) items
-// from a global counter (dynamic scheduling; a static one-wave split proved fragile, see kick_flat_kernel).  Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is not fixed (FP64 atomics);
-// the full-row kernel (kick_kernels.cu) is the bitwise-reproducible variant.
+// private shared-memory tile; at step s lane l works on the column body in slot l+s (the 32 bodies are stored twice, so
+// there is no wrap-around and every tile address is "lane base + immediate"): all 32 lanes read different words
+// (conflict free) and no two lanes ever update the same j in the same step.  The reaction on j is accumulated in the
+// tile; after 32 steps every j has met all 128 i and the chunk ends with one coalesced RED.ADD.F64 per component.
+//
+// Pair arithmetic: r^-3 from a MUFU.RSQ64H seed (one instruction from the high word of r^2 to the high word of an FP64
+// seed) refined in six FP64 instructions (kick_math.cuh).  The fast path carries NO per-pair test: the step loop only
+// keeps the running minimum of the high words of r^2 (one 3-input integer min per two pairs); when a chunk ends with
+// that minimum below the block pair's threshold (first high word safely outside (max radius of I + max radius of J)^2
+// and inside the range the refinement handles), the chunk is ROLLED BACK -- the row accumulators are restored from a
+// snapshot taken at its start, the column accumulators are dropped -- and recomputed with the reference's IEEE
+// expression and exact radius test (redo_chunk).  Hot loop: 20 FP64 + 3.3 other instructions per pair.
+//
+// Block pairs are assigned cyclically (block I meets I+1 .. I+(nb-1)/2 mod nb) so every block owns the same amount of
+// work; a persistent grid of warps claims runs of consecutive (I,k) items from a global counter (dynamic scheduling; a
+// static one-wave split proved fragile, see kick_flat_kernel).  Column bodies travel global -> staging area (cp.async,
+// one chunk ahead, across block pairs) -> tile.  Like the reference's OpenMP reduction(+:ahi,ahj) the summation order is
+// not fixed (FP64 atomics); the full-row kernel (kick_kernels.cu) is the bitwise-reproducible variant.
 #include "swcu_internal.cuh"
 #include "kick_math.cuh"
 
@@ -28,17 +38,13 @@ namespace {
 constexpr int FIB = 4;          // i bodies per lane
 constexpr int FT = 32 * FIB;    // bodies per block
 constexpr int FWARPS = 4;       // warps (independent work units) per CTA
-#ifndef FLAT_MIN_CTAS
-#define FLAT_MIN_CTAS 3
-#endif
-
-// ordering of a lane's accumulator store before its neighbour's load of the same slot in the next step
-// (a compiler-only fence was tried and is NOT sufficient: it produced wrong sums in blocks that take the masked path)
-#define FLAT_STEP_FENCE() __syncwarp()
+// steps per iteration of the step loop (all tile offsets become immediates) and CTAs per SM are template parameters of
+// the kernel: the combination in use was chosen by measurement (profiles/r02_kick_flat.md)
 
 struct FlatArgs {
     const double *x, *y, *z, *gm, *rad;
-    const double *radmax;  // device scalars: [0] max radius over all bodies, [1] max |coordinate|
+    const double *radmax;    // device scalars: [0] max radius over all bodies, [1] max |coordinate|
+    const double *blockrad;  // max radius of every block of FT bodies (radius-checked variant)
     int n, nplm;
     int nb, nbm;          // blocks in total / blocks that own rows (cover [0,nplm))
     int Km, evenm;        // cyclic half-range among the owner blocks, and whether nbm is even
@@ -54,16 +60,23 @@ struct FlatArgs {
     int system_scope;             // 1: the counter lives in (possibly remote) peer memory -> system-scope atomics
     long long first_warp, total_warps;  // this launch's first global warp id and the warps of all sharers together
     double *fx, *fy, *fz; // zero-initialised accumulation target
+    unsigned long long *redo_count;  // chunks that went through the exact path (diagnostic, may be null)
     unsigned long long *trace;  // development aid (SWCU_FLAT_TRACE): per warp {start, end} %globaltimer, items done
 };
 
-// every array has the same 16-byte stride so one byte offset addresses all four
+// A warp's private tile.  The 32 column bodies of a chunk are stored TWICE (slots k and k+32) and the reaction
+// accumulators have 64 slots as well: at step s lane l works on slot l+s (no wrap-around), so every tile address of the
+// unrolled step loop is "lane base + immediate" and the loop carries one pointer.  Slots k and k+32 of the accumulators
+// are two partial sums of column body k, added when the chunk ends.  Every array has a 16-byte stride.
 struct __align__(16) WarpTile {
-    double2 xy[32];
-    double2 zg[32];   // z, Gm
-    double2 axy[32];  // reaction accumulators (ACC_SMEM variant)
-    double2 az[32];   // .x used
+    double2 xy[64];
+    double2 zg[64];       // z, Gm
+    double2 axy[64];      // reaction accumulators
+    double2 az[64];       // .x used
+    double2 save[6][32];  // the lane's 12 row accumulators at the start of the chunk (restored if the chunk is redone)
+    double stage[4][32];  // x, y, z, Gm of the NEXT chunk's column bodies, filled by cp.async while this chunk is computed
 };
+constexpr unsigned T_ZG = 1024, T_AXY = 2048, T_AZ = 3072;
 
 // number of items owned by block I: diagonal + cyclic partners among owner blocks + all non-owner blocks
 __device__ __host__ __forceinline__ int items_of(int I, int nb, int nbm, int Km, int evenm)
@@ -71,215 +84,315 @@ __device__ __host__ __forceinline__ int items_of(int I, int nb, int nbm, int Km,
     return 1 + Km + ((evenm && I < nbm / 2) ? 1 : 0) + (nb - nbm);
 }
 
-__device__ __forceinline__ void item_decode(long long t, const FlatArgs &a, int &I, int &J, bool &diag)
+// (32-bit arithmetic: the launcher refuses populations whose item count does not fit an int)
+__device__ __forceinline__ void item_decode(int t, const FlatArgs &a, int &I, int &J, bool &diag)
 {
     const int base = 1 + a.Km + (a.nb - a.nbm);
     int k;
     if (a.evenm) {
-        const long long big = (long long)(base + 1) * (a.nbm / 2);
+        const int big = (base + 1) * (a.nbm / 2);
         if (t < big) {
-            I = (int)(t / (base + 1));
-            k = (int)(t % (base + 1));
+            I = t / (base + 1);
+            k = t - I * (base + 1);
         } else {
             t -= big;
-            I = a.nbm / 2 + (int)(t / base);
-            k = (int)(t % base);
+            const int d = t / base;
+            I = a.nbm / 2 + d;
+            k = t - d * base;
         }
     } else {
-        I = (int)(t / base);
-        k = (int)(t % base);
+        I = t / base;
+        k = t - I * base;
     }
     const int kmI = a.Km + ((a.evenm && I < a.nbm / 2) ? 1 : 0);
     diag = (k == 0);
     if (k == 0)
         J = I;
-    else if (k <= kmI)
-        J = (I + k) % a.nbm;
-    else
+    else if (k <= kmI) {
+        J = I + k;
+        J -= (J >= a.nbm) ? a.nbm : 0;
+    } else
         J = a.nbm + (k - 1 - kmI);
 }
 
-// Rare path: the pairs of one 32-body chunk that the seeded evaluation skipped (r^2 == 0, denormal, > FLT_MAX or not
-// safely outside the radii), with the reference's IEEE expression irij3 = 1/(r2*sqrt(r2)) (kick.f90:435), the exact
-// radius test (kick.f90:106-107) and all index masks.
+// Rare path: one whole 32-column chunk of a block pair with the reference's IEEE expression
+// irij3 = 1/(r2*sqrt(r2)) (kick.f90:435), the exact radius test (kick.f90:106-107) and all index masks.  Taken when the
+// seeded evaluation of the chunk met a pair it may not handle (r^2 not safely outside the radii, zero, tiny or not
+// finite); the seeded results of that chunk are discarded.  Reads everything from global memory by index and adds
+// straight into the accumulation target, so it shares no registers with the caller (no stack frame in the hot kernel).
+// (Scalar arguments only: a reference to the kernel's parameter block would force a copy of it into local memory.)
 template <bool RAD>
-__device__ __noinline__ void redo_chunk(const FlatArgs &a, int jbase, bool diag, int lane, const double (&xi)[FIB],
-                                        const double (&yi)[FIB], const double (&zi)[FIB], const double (&gmi)[FIB],
-                                        const unsigned (&thr)[FIB], const unsigned (&span)[FIB], const int (&idx_i)[FIB],
-                                        double (&axi)[FIB], double (&ayi)[FIB], double (&azi)[FIB])
+__device__ __noinline__ void redo_chunk(const double *__restrict__ x, const double *__restrict__ y,
+                                        const double *__restrict__ z, const double *__restrict__ gm,
+                                        const double *__restrict__ rad, double *fx, double *fy, double *fz, int n,
+                                        int nplm, int I, int jbase, bool diag, int lane)
 {
-    for (int s = 0; s < 32; ++s) {
-        const int jcur = jbase + ((lane + s) & 31);
-        if (jcur >= a.n) continue;
-        const double xj = a.x[jcur], yj = a.y[jcur], zj = a.z[jcur], gmj = a.gm[jcur];
-#pragma unroll
-        for (int b = 0; b < FIB; ++b) {
-            const double dx = xj - xi[b], dy = yj - yi[b], dz = zj - zi[b];
+#pragma unroll 1
+    for (int b = 0; b < FIB; ++b) {
+        const int i = I * FT + b * 32 + lane;
+        if (i >= n) continue;
+        const double xi = x[i], yi = y[i], zi = z[i], gmi = gm[i];
+        const double ri = RAD ? rad[i] : 0.0;
+        double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll 1
+        for (int s = 0; s < 32; ++s) {
+            const int j = jbase + ((lane + s) & 31);
+            if (j >= n || j == i) continue;
+            if (!((i < nplm) || (j < nplm))) continue;
+            const double dx = x[j] - xi, dy = y[j] - yi, dz = z[j] - zi;
             const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-            if (seed_ok(r2, thr[b], span[b])) continue;  // already done by the fast path
-            if (idx_i[b] == jcur || idx_i[b] >= a.n) continue;
-            if (!((idx_i[b] < a.nplm) || (jcur < a.nplm))) continue;
             if (RAD) {
-                const double rl = a.rad[idx_i[b]] + a.rad[jcur];
+                const double rl = ri + rad[j];
                 if (!(r2 > rl * rl)) continue;
             }
             const double irij3 = 1.0 / (r2 * sqrt(r2));
-            const double fj = gmj * irij3, fi = gmi[b] * irij3;
-            axi[b] = fma(fj, dx, axi[b]);
-            ayi[b] = fma(fj, dy, ayi[b]);
-            azi[b] = fma(fj, dz, azi[b]);
-            if (!diag) {
-                atomicAdd(a.fx + jcur, -(fi * dx));
-                atomicAdd(a.fy + jcur, -(fi * dy));
-                atomicAdd(a.fz + jcur, -(fi * dz));
+            const double fj = gm[j] * irij3, fi = gmi * irij3;
+            ax = fma(fj, dx, ax);
+            ay = fma(fj, dy, ay);
+            az = fma(fj, dz, az);
+            if (!diag) {  // a diagonal block visits (i,j) and (j,i)
+                atomicAdd(fx + j, -(fi * dx));
+                atomicAdd(fy + j, -(fi * dy));
+                atomicAdd(fz + j, -(fi * dz));
             }
         }
+        atomicAdd(fx + i, ax);
+        atomicAdd(fy + i, ay);
+        atomicAdd(fz + i, az);
     }
 }
 
-// One step of block_pair: lane l meets column body `slot`; everything in the warp tile is addressed with the single byte
-// offset off = 16*slot.  The column body of the NEXT step is fetched first so its LDS latency hides behind the math.
-template <bool RAD, bool CHECKED, bool ACC_SMEM>
-__device__ __forceinline__ void flat_step(const FlatArgs &a, char *wb, unsigned off, unsigned off_next, const double2 xy,
-                                          const double2 zg, double2 &nxy, double2 &nzg, int jbase, bool diag, int src,
-                                          const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
-                                          const double (&gmi)[FIB], const unsigned (&thr)[FIB],
-                                          const unsigned (&span)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
-                                          double (&ayi)[FIB], double (&azi)[FIB], double &ajx, double &ajy, double &ajz,
-                                          unsigned &hymin)
+// The reaction accumulators are read by one lane and were written by its neighbour one step earlier.  The warp is
+// converged in the step loop and a warp's shared-memory accesses are performed in issue order, so what has to be kept is
+// the PROGRAM order store(step s) -> load(step s+1): volatile accesses are never reordered among themselves by nvvm or
+// ptxas (tests/test_sass.py checks the order in the SASS), and cost no issue slot, unlike a per-step __syncwarp().
+template <int OFF>
+__device__ __forceinline__ double2 lds_acc2(unsigned addr)
 {
-    nxy = *reinterpret_cast<const double2 *>(wb + off_next);
-    nzg = *reinterpret_cast<const double2 *>(wb + 512 + off_next);
-    if (ACC_SMEM) {
-        const double2 t2 = *reinterpret_cast<const double2 *>(wb + 1024 + off);
-        ajx = t2.x;
-        ajy = t2.y;
-        ajz = *reinterpret_cast<const double *>(wb + 1536 + off);
+    double2 v;
+    asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(v.x), "=d"(v.y) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ double lds_acc1(unsigned addr)
+{
+    double v;
+    asm volatile("ld.volatile.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+template <int OFF>
+__device__ __forceinline__ void sts_acc2(unsigned addr, double x, double y)
+{
+    asm volatile("st.volatile.shared.v2.f64 [%0+%1], {%2, %3};" ::"r"(addr), "n"(OFF), "d"(x), "d"(y));
+}
+template <int OFF>
+__device__ __forceinline__ void sts_acc1(unsigned addr, double x)
+{
+    asm volatile("st.volatile.shared.f64 [%0+%1], %2;" ::"r"(addr), "n"(OFF), "d"(x));
+}
+
+// One step of a chunk: lane l meets the column body in slot l+s.  `pc` / `pa` address slot l + s0 (generic pointer for
+// the column data, shared-window address for the volatile accumulator accesses), K = s - s0 is a compile-time constant.
+// The column body of the NEXT step is fetched first so that its LDS latency hides behind the arithmetic.
+template <bool CHECKED, bool PRE, int K>
+__device__ __forceinline__ void flat_step(const FlatArgs &a, const char *pc, unsigned pa, double2 &cxy, double2 &czg,
+                                          int jslot0, int jbase, bool diag, int ibase, const double (&xi)[FIB],
+                                          const double (&yi)[FIB], const double (&zi)[FIB], const double (&gmi)[FIB],
+                                          double (&axi)[FIB], double (&ayi)[FIB], double (&azi)[FIB], unsigned &himin)
+{
+    double2 xy, zg;
+    if (PRE) {  // the column body of the NEXT step is fetched first: its LDS latency hides behind this step's arithmetic
+        xy = cxy, zg = czg;
+        cxy = *reinterpret_cast<const double2 *>(pc + 16 * (K + 1));
+        czg = *reinterpret_cast<const double2 *>(pc + T_ZG + 16 * (K + 1));
+    } else {
+        xy = *reinterpret_cast<const double2 *>(pc + 16 * K);
+        zg = *reinterpret_cast<const double2 *>(pc + T_ZG + 16 * K);
     }
-    const int jcur = jbase + (int)(off >> 4);
-    unsigned hy[FIB];
+    const double2 t2 = lds_acc2<T_AXY + 16 * K>(pa);
+    double ajx = t2.x, ajy = t2.y;
+    double ajz = lds_acc1<T_AZ + 16 * K>(pa);
+    const int jcur = jbase + ((jslot0 + K) & 31);  // CHECKED only
+    // The four pairs of the step are written stage by stage (all differences, all seeds, all refinements ...): four
+    // independent dependency chains side by side, which is the order the issue port wants (an FP64 result is usable
+    // ~8 cycles after issue, an FP64 instruction issues every 2).
+    unsigned hi[FIB];
+    double dx[FIB], dy[FIB], dz[FIB], r2[FIB], s[FIB];
 #pragma unroll
     for (int b = 0; b < FIB; ++b) {
-        const double dx = xy.x - xi[b];
-        const double dy = xy.y - yi[b];
-        const double dz = zg.x - zi[b];
-        const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        double y3;
+        dx[b] = xy.x - xi[b];
+        dy[b] = xy.y - yi[b];
+        dz[b] = zg.x - zi[b];
+    }
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) {
+        const double r2xy = fma(dy[b], dy[b], dx[b] * dx[b]);
+        r2[b] = fma(dz[b], dz[b], r2xy);
+        bool m = true;
         if (CHECKED) {
-            const bool m = (idx_i[b] != jcur) && (jcur < a.n) && (idx_i[b] < a.n) &&
-                           ((idx_i[b] < a.nplm) || (jcur < a.nplm));
-            // a masked pair never contributes (always-failing test: the result is exactly zero) and must not send
-            // the chunk to redo_chunk either: every chunk of a diagonal block holds a self pair per lane
-            y3 = rcube_seeded<true>(r2, thr[b], m ? span[b] : 0u, hy[b]);
-            hy[b] = m ? hy[b] : 0xffffffffu;
-        } else {
-            y3 = rcube_seeded<false>(r2, thr[b], span[b], hy[b]);  // the caller guarantees |coordinates| < 2^62
+            // a masked pair contributes exactly zero (seed 0) and is left out of the running minimum: every chunk of a
+            // diagonal block holds one self pair per lane
+            const int i = ibase + 32 * b;
+            m = (i != jcur) && (jcur < a.n) && (i < a.n) && ((i < a.nplm) || (jcur < a.nplm));
         }
-        const double fj = zg.y * y3;  // acts on i
-        double fi = gmi[b] * y3;      // acts on j
+        s[b] = rsq64h_seed<CHECKED>(r2[b], r2xy, m, hi[b]);
+    }
+    double s2[FIB], e[FIB], s3[FIB], y3[FIB];
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) s2[b] = s[b] * s[b];
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) {
+        e[b] = fma(-r2[b], s2[b], 1.0);
+        s3[b] = s2[b] * s[b];
+    }
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) {
+        const double q = fma(1.875, e[b], 1.5);
+        const double se = s3[b] * e[b];
+        y3[b] = fma(se, q, s3[b]);
+    }
+#pragma unroll
+    for (int b = 0; b < FIB; ++b) {
+        const double fj = zg.y * y3[b];  // acts on i
+        double fi = gmi[b] * y3[b];      // acts on j
         if (CHECKED) fi = diag ? 0.0 : fi;  // a diagonal block visits (i,j) and (j,i)
-        axi[b] = fma(fj, dx, axi[b]);
-        ayi[b] = fma(fj, dy, ayi[b]);
-        azi[b] = fma(fj, dz, azi[b]);
-        ajx = fma(-fi, dx, ajx);
-        ajy = fma(-fi, dy, ajy);
-        ajz = fma(-fi, dz, ajz);
+        axi[b] = fma(fj, dx[b], axi[b]);
+        ayi[b] = fma(fj, dy[b], ayi[b]);
+        azi[b] = fma(fj, dz[b], azi[b]);
+        ajx = fma(-fi, dx[b], ajx);
+        ajy = fma(-fi, dy[b], ajy);
+        ajz = fma(-fi, dz[b], ajz);
     }
-    static_assert(FIB == 4, "the seed-word minimum below is written for 4 row bodies per lane");
-    hymin = __vimin3_u32(__vimin3_u32(hymin, hy[0], hy[1]), hy[2], hy[3]);  // 2 x VIMNMX3 for 4 pairs
-    if (ACC_SMEM) {
-        *reinterpret_cast<double2 *>(wb + 1024 + off) = make_double2(ajx, ajy);
-        *reinterpret_cast<double *>(wb + 1536 + off) = ajz;
-        // The neighbour lane reads this slot in the next step.  The warp is converged here (no divergent branch inside
-        // the chunk loop) and a warp's shared-memory accesses are performed in program order, so a compiler-level fence
-        // is sufficient; the full __syncwarp() stays at the chunk boundaries.
-        FLAT_STEP_FENCE();
-    } else {
-        ajx = __shfl_sync(0xffffffffu, ajx, src);
-        ajy = __shfl_sync(0xffffffffu, ajy, src);
-        ajz = __shfl_sync(0xffffffffu, ajz, src);
-    }
+    static_assert(FIB == 4, "the high-word minimum below is written for 4 row bodies per lane");
+    himin = __vimin3_u32(__vimin3_u32(himin, hi[0], hi[1]), hi[2], hi[3]);  // 2 x VIMNMX3 for 4 pairs
+    sts_acc2<T_AXY + 16 * K>(pa, ajx, ajy);
+    sts_acc1<T_AZ + 16 * K>(pa, ajz);
 }
+
+template <bool CHECKED, bool PRE, int K>
+struct StepSeq {
+    template <class... A>
+    static __device__ __forceinline__ void run(A &&...args)
+    {
+        StepSeq<CHECKED, PRE, K - 1>::run(args...);
+        flat_step<CHECKED, PRE, K - 1>(args...);
+    }
+};
+template <bool CHECKED, bool PRE>
+struct StepSeq<CHECKED, PRE, 0> {
+    template <class... A>
+    static __device__ __forceinline__ void run(A &&...) {}
+};
 
 // One block pair: block I resident in registers, block J streamed through the warp's shared tile 32 bodies at a time.
 // CHECKED adds the index masks needed by diagonal blocks, the ragged last block and blocks that straddle nplm.
-template <bool RAD, bool CHECKED, bool ACC_SMEM>
-__device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int J, bool diag, int lane,
-                                           const double (&xi)[FIB], const double (&yi)[FIB], const double (&zi)[FIB],
-                                           const double (&gmi)[FIB], const unsigned (&thr)[FIB],
-                                           const unsigned (&span)[FIB], const int (&idx_i)[FIB], double (&axi)[FIB],
-                                           double (&ayi)[FIB], double (&azi)[FIB], int c0 = 0, int c1 = FIB)
+// `thr` = first high word of r^2 that is safely outside (max radius of I + max radius of J)^2 and inside the range the
+// seeded refinement handles; a chunk in which any unmasked pair falls below it is rolled back and redone exactly.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const double *gsrc)
 {
-    const int src = (lane + 1) & 31;
-    // prefetch the first chunk
-    int jc = min(J * FT + c0 * 32 + lane, a.n - 1);
-    double nx = a.x[jc], ny = a.y[jc], nz = a.z[jc], ng = a.gm[jc];
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+                 : "memory");
+}
+
+template <bool RAD, bool CHECKED, int FUNROLL, bool PRE>
+__device__ __forceinline__ void block_pair(const FlatArgs &a, WarpTile &w, int I, int J, bool diag, int lane, unsigned thr,
+                                           bool force_exact, const double (&xi)[FIB], const double (&yi)[FIB],
+                                           const double (&zi)[FIB], const double (&gmi)[FIB], double (&axi)[FIB],
+                                           double (&ayi)[FIB], double (&azi)[FIB], int c0, int c1, int &fetched_j,
+                                           int next_jfirst)
+{
+    const int ibase = I * FT + lane;
+    // the column bodies of a chunk travel global -> w.stage (cp.async, issued one chunk ahead) -> tile; nothing of the
+    // next chunk is held in registers while this one is computed
+    auto fetch = [&](int jfirst) {
+        const int jc = min(jfirst + lane, a.n - 1);
+        cp_async8(&w.stage[0][lane], a.x + jc);
+        cp_async8(&w.stage[1][lane], a.y + jc);
+        cp_async8(&w.stage[2][lane], a.z + jc);
+        cp_async8(&w.stage[3][lane], a.gm + jc);
+    };
+    // `fetched_j`: first column of the chunk that is in flight into w.stage (the previous block pair fetches the first
+    // chunk of this one: `next_jfirst`), so the global-memory latency is exposed only at the start of the launch
+    if (fetched_j != J * FT + c0 * 32) fetch(J * FT + c0 * 32);
+    char *wb = reinterpret_cast<char *>(&w);
+    const unsigned wa = (unsigned)__cvta_generic_to_shared(wb);
 #pragma unroll 1
     for (int c = c0; c < c1; ++c) {
         const int jbase = J * FT + c * 32;
         const int jidx = jbase + lane;
-        __syncwarp();  // every lane is done reading the previous chunk
-        w.xy[lane] = make_double2(nx, ny);
-        w.zg[lane] = make_double2(nz, ng);
-        if (ACC_SMEM) {
-            w.axy[lane] = make_double2(0.0, 0.0);
-            w.az[lane] = make_double2(0.0, 0.0);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        {
+            const double nx = w.stage[0][lane], ny = w.stage[1][lane], nz = w.stage[2][lane], ng = w.stage[3][lane];
+            __syncwarp();  // every lane is done with the previous chunk
+            w.xy[lane] = w.xy[lane + 32] = make_double2(nx, ny);
+            w.zg[lane] = w.zg[lane + 32] = make_double2(nz, ng);
+        }
+        w.axy[lane] = w.axy[lane + 32] = make_double2(0.0, 0.0);
+        w.az[lane] = w.az[lane + 32] = make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            w.save[k][lane] = make_double2(axi[2 * k], axi[2 * k + 1]);
+            w.save[2 + k][lane] = make_double2(ayi[2 * k], ayi[2 * k + 1]);
+            w.save[4 + k][lane] = make_double2(azi[2 * k], azi[2 * k + 1]);
+        }
+        // the next chunk's loads (of this block pair, or the first chunk of the next one) fly while this one is computed
+        if (c + 1 < c1) {
+            fetch(jbase + 32);
+        } else {
+            fetched_j = next_jfirst;
+            if (next_jfirst >= 0) fetch(next_jfirst);
         }
         __syncwarp();
-        if (c + 1 < c1) {  // next chunk's loads fly while this one is computed
-            jc = min(jbase + 32 + lane, a.n - 1);
-            nx = a.x[jc];
-            ny = a.y[jc];
-            nz = a.z[jc];
-            ng = a.gm[jc];
+        unsigned himin = 0xffffffffu;  // running minimum of the high words of r^2 over the chunk's unmasked pairs
+        const char *pc = wb + 16 * lane;
+        unsigned pa = wa + 16 * lane;
+        double2 cxy = make_double2(0.0, 0.0), czg = cxy;
+        if (PRE) {
+            cxy = *reinterpret_cast<const double2 *>(pc);
+            czg = *reinterpret_cast<const double2 *>(pc + T_ZG);
         }
-        double ajx = 0.0, ajy = 0.0, ajz = 0.0;
-        unsigned hymin = 0xffffffffu;  // running minimum of the seed words: 0 <=> some pair was rejected
-        char *wb = reinterpret_cast<char *>(&w);
-        // two steps per iteration with two named register sets (A, B): no register copies for the prefetch
-        unsigned off = (unsigned)lane << 4;
-        double2 axy_ = *reinterpret_cast<const double2 *>(wb + off);
-        double2 azg_ = *reinterpret_cast<const double2 *>(wb + 512 + off);
-        double2 bxy_, bzg_;
 #pragma unroll 1
-        for (int s = 0; s < 32; s += 2) {
-            const unsigned off1 = (off + 16u) & 0x1f0u, off2 = (off + 32u) & 0x1f0u;
-            flat_step<RAD, CHECKED, ACC_SMEM>(a, wb, off, off1, axy_, azg_, bxy_, bzg_, jbase, diag, src, xi, yi, zi, gmi,
-                                              thr, span, idx_i, axi, ayi, azi, ajx, ajy, ajz, hymin);
-            flat_step<RAD, CHECKED, ACC_SMEM>(a, wb, off1, off2, bxy_, bzg_, axy_, azg_, jbase, diag, src, xi, yi, zi, gmi,
-                                              thr, span, idx_i, axi, ayi, azi, ajx, ajy, ajz, hymin);
-            off = off2;
+        for (int s0 = 0; s0 < 32; s0 += FUNROLL) {
+            StepSeq<CHECKED, PRE, FUNROLL>::run(a, pc, pa, cxy, czg, lane + s0, jbase, diag, ibase, xi, yi, zi, gmi, axi, ayi,
+                                           azi, himin);
+            pc += 16 * FUNROLL;
+            pa += 16 * FUNROLL;
         }
-        const bool bad = (hymin == 0u);
-        if (ACC_SMEM) {
-            const double2 t2 = w.axy[lane];
-            ajx = t2.x;
-            ajy = t2.y;
-            ajz = w.az[lane].x;
+        __syncwarp();  // all accumulator stores of the chunk are done (and ordered before the plain loads below)
+        const bool bad = __any_sync(0xffffffffu, himin < thr) || force_exact;
+        if (__builtin_expect(bad, 0)) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const double2 sx = w.save[k][lane], sy = w.save[2 + k][lane], sz = w.save[4 + k][lane];
+                axi[2 * k] = sx.x, axi[2 * k + 1] = sx.y;
+                ayi[2 * k] = sy.x, ayi[2 * k + 1] = sy.y;
+                azi[2 * k] = sz.x, azi[2 * k + 1] = sz.y;
+            }
+            redo_chunk<RAD>(a.x, a.y, a.z, a.gm, a.rad, a.fx, a.fy, a.fz, a.n, a.nplm, I, jbase, diag, lane);
+            if (a.redo_count && lane == 0) atomicAdd(a.redo_count, 1ull);
+        } else if (!diag && jidx < a.n) {
+            // the two partial sums of column body jbase+lane
+            const double2 p0 = w.axy[lane], p1 = w.axy[lane + 32];
+            const double z0 = w.az[lane].x, z1 = w.az[lane + 32].x;
+            atomicAdd(a.fx + jidx, p0.x + p1.x);
+            atomicAdd(a.fy + jidx, p0.y + p1.y);
+            atomicAdd(a.fz + jidx, z0 + z1);
         }
-        // the accumulator of column body jbase+lane is now in this lane
-        if (!diag && jidx < a.n) {
-            atomicAdd(a.fx + jidx, ajx);
-            atomicAdd(a.fy + jidx, ajy);
-            atomicAdd(a.fz + jidx, ajz);
-        }
-        if (__builtin_expect(bad, 0))
-            redo_chunk<RAD>(a, jbase, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi);
     }
 }
 
-template <bool RAD, bool ACC_SMEM>
-__global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(const FlatArgs a)
+template <bool RAD, int CTAS, int FUNROLL, bool PRE>
+__global__ void __launch_bounds__(32 * FWARPS, CTAS) kick_flat_kernel(const FlatArgs a)
 {
     __shared__ WarpTile tiles[FWARPS];
     const int lane = threadIdx.x & 31;
     WarpTile &w = tiles[threadIdx.x >> 5];
     double xi[FIB], yi[FIB], zi[FIB], gmi[FIB], axi[FIB], ayi[FIB], azi[FIB];
-    unsigned thr[FIB], span[FIB];
-    int idx_i[FIB];
     int Icur = -1;
-    const double radmax = RAD ? a.radmax[0] : 0.0;
-    const bool coords_safe = a.radmax[1] < COORD_SAFE_MAX;  // else every block pair takes the fully checked path
+    int fetched_j = -1;  // first column of the chunk whose cp.async copies are in flight into the warp's staging area
+    double radI = 0.0;
+    // coordinates beyond COORD_SAFE_MAX could overflow r^2: every chunk then takes the exact path
+    const bool force_exact = !(a.radmax[1] < COORD_SAFE_MAX);
     unsigned long long *tr = a.trace ? a.trace + 4 * ((size_t)blockIdx.x * FWARPS + (threadIdx.x >> 5)) : nullptr;
     unsigned long long ndone = 0;
     if (tr && lane == 0) {
@@ -292,10 +405,11 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
         if (Icur < 0) return;
 #pragma unroll
         for (int b = 0; b < FIB; ++b) {
-            if (idx_i[b] < a.n) {
-                atomicAdd(a.fx + idx_i[b], axi[b]);
-                atomicAdd(a.fy + idx_i[b], ayi[b]);
-                atomicAdd(a.fz + idx_i[b], azi[b]);
+            const int i = Icur * FT + b * 32 + lane;
+            if (i < a.n) {
+                atomicAdd(a.fx + i, axi[b]);
+                atomicAdd(a.fy + i, ayi[b]);
+                atomicAdd(a.fz + i, azi[b]);
             }
         }
     };
@@ -342,40 +456,57 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
             qnext = claim();
         }
         while (u < u_end) {
-            const long long t = u / FIB;
-            const int c0 = (int)(u - t * FIB);
+            const int t = (int)(u / FIB);
+            const int c0 = (int)(u - (long long)t * FIB);
             const int c1 = (int)min((long long)FIB, c0 + (u_end - u));
             u += c1 - c0;
             ndone += c1 - c0;
             int I, J;
             bool diag;
             item_decode(t, a, I, J, diag);
+            // first column of the work that follows (next item of this claim, or the start of the prefetched claim)
+            int next_jfirst = -1;
+            {
+                long long un = u, un_end = u_end;
+                if (un >= un_end) {
+                    const unsigned long long qn = __shfl_sync(0xffffffffu, qnext, 0);
+                    if (!range(qn, un, un_end)) un = -1;
+                }
+                if (un >= 0) {
+                    const int tn = (int)(un / FIB);
+                    int In, Jn;
+                    bool dn;
+                    item_decode(tn, a, In, Jn, dn);
+                    next_jfirst = Jn * FT + (int)(un - (long long)tn * FIB) * 32;
+                }
+            }
             if (I != Icur) {
                 flush();
                 Icur = I;
 #pragma unroll
                 for (int b = 0; b < FIB; ++b) {
-                    idx_i[b] = I * FT + b * 32 + lane;
-                    const int ic = min(idx_i[b], a.n - 1);
+                    const int ic = min(I * FT + b * 32 + lane, a.n - 1);
                     xi[b] = a.x[ic];
                     yi[b] = a.y[ic];
                     zi[b] = a.z[ic];
                     gmi[b] = a.gm[ic];
-                    double rl2 = 0.0;
-                    if (RAD) {
-                        const double rl = a.rad[ic] + radmax;
-                        rl2 = rl * rl;
-                    }
-                    seed_threshold(rl2, thr[b], span[b]);
                     axi[b] = ayi[b] = azi[b] = 0.0;
                 }
+                radI = RAD ? a.blockrad[I] : 0.0;
             }
-            const bool checked = !coords_safe || diag || I == a.nb - 1 || J == a.nb - 1 ||
+            unsigned thr = RSQ64H_HI_MIN;
+            if (RAD) {
+                const double rl = radI + a.blockrad[J];
+                thr = rsq64h_threshold(rl * rl);
+            }
+            const bool checked = diag || I == a.nb - 1 || J == a.nb - 1 ||
                                  (a.nplm < a.n && (I == a.nbm - 1 || J == a.nbm - 1));
             if (checked)
-                block_pair<RAD, true, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi, c0, c1);
+                block_pair<RAD, true, FUNROLL, PRE>(a, w, I, J, diag, lane, thr, force_exact, xi, yi, zi, gmi, axi, ayi, azi,
+                                                    c0, c1, fetched_j, next_jfirst);
             else
-                block_pair<RAD, false, ACC_SMEM>(a, w, J, diag, lane, xi, yi, zi, gmi, thr, span, idx_i, axi, ayi, azi, c0, c1);
+                block_pair<RAD, false, FUNROLL, PRE>(a, w, I, J, diag, lane, thr, force_exact, xi, yi, zi, gmi, axi, ayi, azi,
+                                                     c0, c1, fetched_j, next_jfirst);
         }
         q = __shfl_sync(0xffffffffu, qnext, 0);
         long long dummy0, dummy1;
@@ -394,6 +525,21 @@ __global__ void __launch_bounds__(32 * FWARPS, FLAT_MIN_CTAS) kick_flat_kernel(c
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
         tr[3] = t2;
     }
+}
+
+// blockrad[B] = max radius over bodies [B*FT, min((B+1)*FT, n)): one warp per block
+__global__ void block_max_radius_kernel(const double *radius, int n, int nb, double *blockrad)
+{
+    const int B = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (B >= nb) return;
+    const int lane = threadIdx.x & 31;
+    double m = 0.0;
+    for (int k = lane; k < FT; k += 32) {
+        const int i = B * FT + k;
+        if (i < n) m = fmax(m, fabs(radius[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) blockrad[B] = m;
 }
 
 // out[0] = max |radius[i]| (0 when radius == nullptr), out[1] = max over bodies of max(|x|,|y|,|z|); the bit patterns of
@@ -452,12 +598,20 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     a.n = n;
     a.nplm = std::min(nplm_rows, n);
     a.nb = cdiv(n, FT);
+    a.blockrad = nullptr;
+    if (lrad) {  // per-block radius bound: the fast-path threshold of a block pair follows the bodies that are in it
+        SWCU_CUDA(ctx, ctx->flat_blockrad.ensure(sizeof(double) * a.nb));
+        block_max_radius_kernel<<<cdiv(a.nb, 4), 128, 0, ctx->stream>>>(a.rad, n, a.nb, ctx->flat_blockrad.as<double>());
+        SWCU_KERNEL_CHECK(ctx);
+        a.blockrad = ctx->flat_blockrad.as<double>();
+    }
     a.nbm = cdiv(a.nplm, FT);
     a.Km = (a.nbm - 1) / 2;
     a.evenm = (a.nbm % 2 == 0) ? 1 : 0;
     long long total = 0;
     for (int I = 0; I < a.nbm; ++I) total += items_of(I, a.nb, a.nbm, a.Km, a.evenm);
     a.total_items = total;
+    if (total * FIB >= (1ll << 31)) return fail(ctx, SWCU_ERR_ARG, "kick_pl_flat: npl=%d exceeds the third-law kernel's 32-bit work index", n);
 
     // zeroed accumulation target, then acc += F
     const size_t stride = ((size_t)n + 31) & ~size_t(31);
@@ -472,10 +626,19 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     a.fz = a.fy + stride;
     SWCU_CUDA(ctx, cudaMemsetAsync(a.fx, 0, sizeof(double) * 3 * stride, ctx->stream));
 
-    // measured on B200 at npl = 1e5 (profiles/r01_fp64_pipe.md): shared-memory accumulators beat the SHFL-travelling ones
-    static const bool acc_smem = getenv("SWCU_FLAT_ACC_SMEM") ? atoi(getenv("SWCU_FLAT_ACC_SMEM")) != 0 : true;
-    void (*kern)(const FlatArgs) = lrad ? (acc_smem ? kick_flat_kernel<true, true> : kick_flat_kernel<true, false>)
-                                        : (acc_smem ? kick_flat_kernel<false, true> : kick_flat_kernel<false, false>);
+    // (CTAs per SM, steps per loop iteration, column prefetch) = (3, 2, 1) by measurement at npl = 1e5
+    // (profiles/r02_kick_flat.md: 2, 3 and 4 CTAs/SM and 2/4/8 steps all land within 2 % of each other -- the hot loop
+    // sits at the rate the FP64 pipe sustains for three-register operands).  SWCU_FLAT_CFG selects the alternates that
+    // are kept compiled for re-measurement: 381 (8 steps per iteration), 480 (4 CTAs/SM at 128 registers).
+    static const int cfg = getenv("SWCU_FLAT_CFG") ? atoi(getenv("SWCU_FLAT_CFG")) : 321;
+    void (*kern)(const FlatArgs);
+    switch (cfg) {
+#define FLAT_CFG(C, U, P) \
+    case C * 100 + U * 10 + P: kern = lrad ? kick_flat_kernel<true, C, U, P> : kick_flat_kernel<false, C, U, P>; break;
+        FLAT_CFG(3, 8, 1) FLAT_CFG(4, 8, 0)
+        default: kern = lrad ? kick_flat_kernel<true, 3, 2, 1> : kick_flat_kernel<false, 3, 2, 1>;
+#undef FLAT_CFG
+    }
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * FWARPS, 0);
     occ = std::max(1, occ);
@@ -501,6 +664,11 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     if (ctx->tune_nsplit > 0) a.quantum = ctx->tune_nsplit;
     SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
     a.counter = ctx->scratch64.as<unsigned long long>() + 3;
+    if (!ctx->flat_redo.p) {
+        SWCU_CUDA(ctx, ctx->flat_redo.ensure(sizeof(unsigned long long)));
+        SWCU_CUDA(ctx, cudaMemsetAsync(ctx->flat_redo.p, 0, sizeof(unsigned long long), ctx->stream));
+    }
+    a.redo_count = ctx->flat_redo.as<unsigned long long>();  // cumulative over launches (swcu_flat_redo_count)
     a.counter_base = 0;
     a.system_scope = 0;
     // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work).  The last

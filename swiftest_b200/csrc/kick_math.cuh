@@ -86,6 +86,58 @@ __device__ __forceinline__ double rcube_seeded(double r2, unsigned thr, unsigned
     return fma(se, q, s3);
 }
 
+// ---- FP64 seed straight from the special-function unit (MUFU.RSQ64H, PTX rsqrt.approx.ftz.f64) ----
+// One instruction maps the high word of r2 to the high word of a double s ~ r2^(-1/2) (low word zero): no re-biasing
+// into a float and back (3 integer instructions per pair with the FP32 seed above) and no FP32 exponent range to guard.
+// Measured on B200 over 4.2e6 samples (scripts/rsq64h_microbench.cu, profiles/r02_rsq64h.md): e = 1 - r2*s^2 within
+// +-2^-19.05, so the same second-order refinement s^3 (1 + e (3/2 + 15/8 e)) leaves 35/16 e^3 < 2^-56; max relative
+// error of r2^(-3/2) against long double 2.3e-16.  r2 = 0 / denormal give s = inf, r2 < 2^-680 overflows s^3 and
+// r2 = inf gives NaN: callers keep r2 inside [2^-600, inf) with the running-minimum test below and a coordinate guard.
+constexpr unsigned RSQ64H_HI_MIN = 0x1A700000u;        // high word of 2^-600
+constexpr double COORD_SAFE_MAX_F64 = 0x1p500;         // |coordinate| below this: r2 <= 3*(2^501)^2 stays finite
+
+// first high word of r2 that guarantees r2 > rlim2 (and r2 >= 2^-600)
+__device__ __forceinline__ unsigned rsq64h_threshold(double rlim2)
+{
+    unsigned t = (unsigned)__double2hiint(rlim2) + 1u;
+    t = max(t, RSQ64H_HI_MIN);
+    return min(t, 0x7FE00000u);
+}
+
+// r2^(-3/2); `hi` returns the high word of r2 for the caller's running minimum (0xffffffff for a masked pair).  With
+// MASKED a pair whose mask is false contributes exactly zero (seed high word 0: s is a denormal, s2 underflows to 0,
+// e = 1, s3 = 0, result 0) whatever r2 is.  An unmasked pair below the caller's threshold returns garbage (possibly
+// inf/NaN): the caller must discard the results of the whole tile and redo it with the reference's IEEE expression.
+// `lo_donor` is any double that is dead after this call (the callers pass the partial sum dx^2+dy^2): MUFU.RSQ64H only
+// produces a high word, and taking the low word from a dying register pair lets the seed be written in place -- no
+// instruction to build the pair.  The donated low word perturbs the seed by < 2^-20: |e| < 2^-18.3, truncation error
+// 35/16 e^3 < 6e-17.
+template <bool MASKED>
+__device__ __forceinline__ double rsq64h_seed(double r2, double lo_donor, bool m, unsigned &hi)
+{
+    double t;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(t) : "d"(r2));
+    hi = (unsigned)__double2hiint(r2);
+    int sh = __double2hiint(t);
+    if (MASKED) {
+        sh = m ? sh : 0;
+        hi = m ? hi : 0xffffffffu;
+    }
+    return __hiloint2double(sh, __double2loint(lo_donor));
+}
+
+template <bool MASKED>
+__device__ __forceinline__ double rcube_rsq64h(double r2, double lo_donor, bool m, unsigned &hi)
+{
+    const double s = rsq64h_seed<MASKED>(r2, lo_donor, m, hi);
+    const double s2 = s * s;
+    const double e = fma(-r2, s2, 1.0);
+    const double s3 = s2 * s;
+    const double q = fma(1.875, e, 1.5);
+    const double se = s3 * e;
+    return fma(se, q, s3);
+}
+
 // Same test as rsqrt_seeded without the arithmetic (used by the redo paths to find the skipped pairs).
 __device__ __forceinline__ bool seed_ok(double r2, unsigned thr, unsigned span)
 {

@@ -167,6 +167,8 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     ctx->sumbuf.release();
     for (auto &b : ctx->lists) b.release();
     ctx->flat_trace.release();
+    ctx->flat_blockrad.release();
+    ctx->flat_redo.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
     auto &E = ctx->enc;
@@ -1060,6 +1062,17 @@ extern "C" int swcu_probe_fp64_peak(swcu_context *ctx, double *tflops)
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_flat_redo_count(swcu_context *ctx, uint64_t *chunks)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!chunks) return SWCU_ERR_ARG;
+    *chunks = 0;
+    if (!ctx->flat_redo.p) return SWCU_OK;  // the third-law kernel has not run yet
+    SWCU_CUDA(ctx, cudaMemcpyAsync(chunks, ctx->flat_redo.p, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SWCU_OK;
 }
 

@@ -126,6 +126,8 @@ struct swcu_context {
     swcu::DevBuf cbs;
     swcu::DevBuf sumbuf;  // per-CTA partials of the tree reductions + ticket counter (zeroed when allocated)
     swcu::DevBuf lists[16];  // staging of the encounter-list kernels (list_kernels.cu)
+    swcu::DevBuf flat_blockrad; // max radius per block of 128 bodies (third-law kernel)
+    swcu::DevBuf flat_redo;  // u64 count of chunks the third-law kernel redid exactly (zeroed when allocated)
     swcu::DevBuf flat_trace; // per-warp timeline of the third-law kernel (development aid, SWCU_FLAT_TRACE)
 
     // multi-GPU

@@ -166,6 +166,78 @@ def test_kick_coordinate_guard_for_both_kernels(ctx, oracle, far):
         assert _scaled(got, ref, scale) < ACC_TOL
 
 
+def test_kick_flat_rollback_of_chunks_with_close_pairs(ctx, oracle):
+    """The third-law fast path carries no per-pair test: a chunk that met a pair inside the block pair's radius bound,
+    a coincident pair or a self pair outside a diagonal block is rolled back and redone with the IEEE expression.  Close
+    pairs are planted inside one block, across two blocks and against the ragged last block."""
+    n = 2100
+    d = W.disk(n, seed=21)
+    r, rad = d["rh"].copy(), d["radius"].copy()
+    rmax = rad.max()
+    plant = [(5, 40, 0.5), (10, 700, 1.5), (130, 2090, 0.0), (1500, 1501, 1.99), (64, 2050, 2.5)]  # (i, j, distance / rmax)
+    for i, j, f in plant:
+        r[j] = r[i] + np.array([f * rmax, 0.0, 0.0])
+    n0 = ctx.flat_redo_count()
+    ref = oracle.kick_tri_pl(r, d["Gmass"], rad, np.zeros((n, 3)))
+    got = np.zeros((n, 3))
+    ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, r, d["Gmass"], rad, got)
+    assert np.all(np.isfinite(got))
+    scale = oracle.kick_tri_abs_scale(r, d["Gmass"], rad)
+    assert _scaled(got, ref, scale) < ACC_TOL
+    redone = ctx.flat_redo_count() - n0
+    assert 4 <= redone <= 64, redone    # the planted pairs (the 2.5 rmax one is outside every bound), not the whole run
+    # without the radius test only the coincident pair is special (r^2 = 0: the reference yields inf/NaN there, so
+    # move it apart first)
+    r[2090] = r[130] + np.array([1e-9, 0.0, 0.0])
+    n0 = ctx.flat_redo_count()
+    ref = oracle.kick_tri_pl(r, d["Gmass"], None, np.zeros((n, 3)))
+    got = np.zeros((n, 3))
+    ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, r, d["Gmass"], None, got)
+    scale = oracle.kick_tri_abs_scale(r, d["Gmass"], None)
+    assert _scaled(got, ref, scale) < ACC_TOL
+    assert ctx.flat_redo_count() == n0
+
+
+def test_kick_flat_radius_bound_is_per_block(ctx, oracle):
+    """One giant body must not push the whole population onto the exact path: the fast-path threshold of a block pair
+    comes from the largest radii INSIDE the two blocks."""
+    n = 3000
+    d = W.disk(n, seed=22)
+    rad = d["radius"].copy()
+    rad[3] = 2e-2                      # a "planet" as large as the spacing of the disk bodies, in block 0
+    n0 = ctx.flat_redo_count()
+    ref = oracle.kick_tri_pl(d["rh"], d["Gmass"], rad, np.zeros((n, 3)))
+    got = np.zeros((n, 3))
+    ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, d["rh"], d["Gmass"], rad, got)
+    scale = oracle.kick_tri_abs_scale(d["rh"], d["Gmass"], rad)
+    assert _scaled(got, ref, scale) < ACC_TOL
+    redone = ctx.flat_redo_count() - n0
+    nb = -(-n // 128)
+    assert 0 < redone <= 4 * nb, (redone, nb)    # only chunks of block pairs that contain block 0
+
+
+def test_kick_flat_plain_disk_never_leaves_the_fast_path(ctx):
+    n = 4000
+    d = W.disk(n, seed=23)
+    n0 = ctx.flat_redo_count()
+    ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, d["rh"], d["Gmass"], d["radius"], np.zeros((n, 3)))
+    assert ctx.flat_redo_count() == n0
+
+
+def test_kick_flat_overflowing_r2_takes_exact_path(ctx, oracle):
+    """|coordinate| beyond 2^500: r^2 overflows to inf, the reference's 1/(r2*sqrt(r2)) gives 0 for those pairs."""
+    n = 300
+    d = W.disk(n, seed=24)
+    r = d["rh"].copy()
+    r[7] = [1e160, 0.0, -1e158]
+    ref = oracle.kick_tri_pl(r, d["Gmass"], d["radius"], np.zeros((n, 3)))
+    got = np.zeros((n, 3))
+    ctx.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, r, d["Gmass"], d["radius"], got)
+    assert np.all(np.isfinite(got))
+    scale = oracle.kick_tri_abs_scale(r, d["Gmass"], d["radius"])
+    assert _scaled(got, ref, scale) < ACC_TOL
+
+
 @pytest.mark.parametrize("ntp,npl", [(50, 108), (1000, 8), (100000, 8), (3000, 700)])
 def test_kick_tp(ctx, oracle, ntp, npl):
     rng = np.random.default_rng(ntp + npl)

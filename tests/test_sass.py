@@ -48,25 +48,56 @@ def _op(t):
     return re.sub(r"^@!?U?P\d+\s+", "", t).split()[0].split(".")[0]
 
 
-def test_third_law_hot_loop_instruction_mix():
+FLAT_KERNEL = "kick_flat_kernelILb1ELi3ELi2ELb1"   # radius-checked, 3 CTAs/SM, 2 steps per iteration, column prefetch
+
+
+def _flat_hot_loop():
     funcs = _sass("kick_flat_kernels.o")
-    name = next(n for n in funcs if "kick_flat_kernelILb1ELb1" in n)   # radius-checked, shared-memory accumulators
+    name = next(n for n in funcs if FLAT_KERNEL in n)
     best = None
     for body in _loops(funcs[name]):
-        if sum("MUFU.RSQ" in t for _, t in body) != 8:                  # 2 steps x 4 row bodies per iteration
+        if sum("MUFU.RSQ64H" in t for _, t in body) != 8:               # 2 steps x 4 row bodies per iteration
             continue
-        ops = collections.Counter(_op(t) for _, t in body)
-        fp64 = ops["DFMA"] + ops["DMUL"] + ops["DADD"]
-        other = len(body) - fp64
-        if best is None or len(body) < best[0]:
-            best = (len(body), fp64, other, ops)
+        if best is None or len(body) < len(best):
+            best = body                                                 # the unchecked variant is the shortest
     assert best is not None, "hot loop not found"
-    n, fp64, other, ops = best
+    return best
+
+
+def test_third_law_hot_loop_instruction_mix():
+    body = _flat_hot_loop()
+    ops = collections.Counter(_op(t) for _, t in body)
+    fp64 = ops["DFMA"] + ops["DMUL"] + ops["DADD"]
+    other = len(body) - fp64
     # 20 FP64 per pair: 3 differences, 3 for r^2, 6 for r^-3, 2 mass factors, 6 accumulations
     assert fp64 == 160, (fp64, dict(ops))
-    # everything else (seed conversion, compare/select, min, LDS/STS, loop): at most 9.5 per pair
-    assert other <= 76, (other, dict(ops))
-    assert not any(o in ops for o in ("F2F", "LDL", "STL", "DSETP")), dict(ops)   # no conversions, spills or FP64 compares
+    # everything else: one MUFU.RSQ64H per pair, half a 3-input min, LDS/STS of the column and its accumulators, the
+    # loop -- at most 4 per pair (profiles/r02_kick_flat.md); no seed conversion, compare or select on the fast path
+    assert other <= 32, (other, dict(ops))
+    assert ops["MUFU"] == 8 and ops["VIMNMX3"] == 4, dict(ops)
+    assert not any(o in ops for o in ("F2F", "LDL", "STL", "DSETP", "SEL", "FSEL", "ISETP2", "LEA", "SHFL", "BAR", "WARPSYNC")), dict(ops)
+    assert ops["ISETP"] <= 1, dict(ops)                                 # the loop test only
+
+
+def test_third_law_accumulator_accesses_stay_in_program_order():
+    """The j-side accumulators are read by one lane one step after the neighbouring lane wrote them; the kernel relies
+    on the volatile shared-memory accesses keeping their program order (no __syncwarp per step): in every step the
+    accumulator loads come before its stores, and the next step's loads after them."""
+    body = _flat_hot_loop()
+    seq = []
+    for _, t in body:
+        m = re.match(r"(?:@!?P\d+\s+)?(LDS|STS)\.(128|64)\s+(.*)", t)
+        if not m:
+            continue
+        kind, width, rest = m.groups()
+        off = re.search(r"\[R\d+(?:\+(-?0x[0-9a-f]+))?\]", rest)
+        o = int(off.group(1), 16) if off and off.group(1) else 0
+        if kind == "STS" or width == "64" or (o & 0xf00) == 0x800:     # column bodies are LDS.128 below +0x800
+            seq.append((kind, width, o))
+    # per step: LDS.128 axy, LDS.64 az (either order), then STS.128 axy, STS.64 az; steps in ascending slot order
+    assert [k for k, _, _ in seq] == ["LDS", "LDS", "STS", "STS"] * 2, seq
+    slots = [o & 0xff for _, _, o in seq]
+    assert slots[:4] == [slots[0]] * 4 and slots[4:] == [slots[0] + 0x10] * 4, seq
 
 
 def test_full_row_kernel_uses_tma_bulk_copies_and_16_fp64_per_evaluation():
@@ -85,10 +116,21 @@ def test_full_row_kernel_uses_tma_bulk_copies_and_16_fp64_per_evaluation():
     assert counts and min(counts) == 16.0, counts
 
 
+def test_third_law_kernel_keeps_its_bookkeeping_spills_small():
+    """The third-law kernel runs at the 168-register cap of 3 CTAs/SM; a few words of claim bookkeeping may spill
+    OUTSIDE the step loop (the hot-loop test above forbids LDL/STL inside it), the parameter block must not be copied
+    to local memory (that was a 576-byte frame in round 1)."""
+    log = open(os.path.join(BUILD, "kick_flat_kernels.ptxas.log")).read()
+    for k in ("kick_flat_kernelILb1ELi3ELi2ELb1", "kick_flat_kernelILb0ELi3ELi2ELb1"):
+        m = re.search(r"Compiling entry function '[^']*" + re.escape(k) + r"[^']*' for 'sm_100a'.*?\n\s*(\d+) bytes stack frame, "
+                      r"(\d+) bytes spill stores, (\d+) bytes spill loads", log, flags=re.S)
+        assert m, k
+        assert int(m.group(1)) <= 64 and int(m.group(2)) <= 64, (k, m.groups())
+
+
 def test_hot_kernels_do_not_spill():
     logs = {f: open(os.path.join(BUILD, f)).read() for f in os.listdir(BUILD) if f.endswith(".ptxas.log")}
-    want = {"kick_flat_kernels.ptxas.log": ["kick_flat_kernelILb1ELb1", "kick_flat_kernelILb0ELb1"],
-            "kick_kernels.ptxas.log": ["kick_rows_kernelILi4", "kick_tp_small_kernel"],
+    want = {"kick_kernels.ptxas.log": ["kick_rows_kernelILi4", "kick_tp_small_kernel"],
             "energy_kernels.ptxas.log": ["pe_pairs_kernel"],
             "encounter_kernels.ptxas.log": ["sweep_kernel", "tri_check_kernel"]}
     for log, kernels in want.items():
