@@ -3,19 +3,23 @@
 
   python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA through the C ABI)
   python bench.py --impl reference --steps K --warmup W    reference arm: the CPU path on the host cores
-  torchrun ... bench.py --gpus N ...                        N>1: one rank per GPU, NCCL inside the library
+  torchrun ... bench.py --gpus N ...                        N>1: one rank per GPU
 
 Metric: FP64 pair-interactions/s of the SyMBA planetesimal disk, npl = 1e5 fully interacting massive bodies
 (BASELINE.json configs[3]; fits one GPU).  One STEP = one pass of the hot path over the resident system:
    ah = 0 ; pl%accel_int (pl-pl gravity, radius-checked, all N(N-1)/2 pairs) ; vb += ah*dt ; pl%drift (Kepler drift)
-   ; [N>1: third-law kernel: allreduce of the partial ah inside accel_int; full-row kernel: allgather of the drifted
-   slices] .
-`value` = N(N-1)/2 pairs per step / step time with everything resident in HBM (strong scaling: the system is fixed,
-block pairs -- or rows -- are split over the ranks).  `e2e` = the same step with that step's positions and velocities copied from pinned
-host memory and the accelerations/positions/velocities read back, every step.
-The sort-and-sweep encounter check and the WHM test-particle configuration (8 planets + 1e6 tp: pl->tp gravity and tp
-drift) are HBM-bound side legs of the same path; they are timed outside the K steps and reported under "extra" with
-their own roofline figures.
+   ; [N>1: third-law kernel on this rank's run of block pairs, then ONE kernel that reduce-scatters the partial
+   accelerations out of every rank's memory, kicks and drifts this rank's slice and allgathers it into every rank's
+   arrays over NVLink peer memory (--collective nccl: ncclAllReduce instead; --variant tri: row slices + allgather)].
+`value` = N(N-1)/2 pairs per step / step time with everything resident in HBM (strong scaling: the system is fixed).
+Timing: K laps, one CUDA-event pair per step on the library's stream, L2 flushed (160 MiB write) BETWEEN the laps,
+barrier + synchronize on both sides, max over ranks.  `e2e` = the same step with that step's positions and velocities
+copied from pinned host memory and accelerations / positions / velocities read back, every step (N>1: every rank moves
+its own slice of the bodies and the slices are allgathered on the device), host wall clock, max over ranks.
+After the timed region `parity_check` compares the result of the timed code path with the CPU oracle (N=1) or with a
+one-GPU run of the same steps (N>1; all ranks must hold identical bits).
+The sort-and-sweep encounter check, the WHM test-particle configuration (8 planets + 1e6..1e8 tp), the 1e4-body SyMBA
+disk (flat vs full-row) and the 1e4-step conservation runs are side legs reported under "extra".
 """
 import argparse
 import json
@@ -54,9 +58,22 @@ def parse_args():
                     help="N>1, third-law kernel: fused reduce+update+allgather over NVLink peer memory (p2p) or "
                          "ncclAllReduce of the partial accelerations (nccl)")
     ap.add_argument("--no-extra", action="store_true", help="skip the sweep / tp side legs and the CPU baseline")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the cpu_baseline sample")
-    ap.add_argument("--conservation", type=int, default=0, help="run an n-step energy/L tracking run (extra)")
+    ap.add_argument("--cpu-evals", type=int, default=3, help="full CPU force evaluations timed for cpu_baseline")
+    ap.add_argument("--conservation", type=int, default=10000,
+                    help="steps of the Sun + 8 planets energy/L tracking run (extra.conservation; 0 = skip)")
+    ap.add_argument("--disk-steps", type=int, default=1000,
+                    help="steps of the 1e4-body disk energy/L tracking run (extra.conservation_disk; 0 = skip)")
+    ap.add_argument("--tp-sizes", default="1e6,1e7,1e8", help="total test particles of the sharded WHM tp legs")
     return ap.parse_args()
+
+
+def common_config(n):
+    """The workload both arms run; identical in the two JSON lines."""
+    return {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n, "nplm": n, "lclose": True,
+            "step": "zero_accel + pl-pl accel_int (all N(N-1)/2 pairs, radius-checked) + kick_velocity + Kepler drift",
+            "generator": "Chambers-style disk, swiftest_b200/workloads.py::disk", "seed": 3031179,
+            "l2": "GPU arm: L2 flushed between timed steps (160 MiB write = 1.33 x L2, outside the per-step event pairs); "
+                  "CPU arm: not applicable"}
 
 
 def peaks():
@@ -167,72 +184,65 @@ class ClockSampler:
 # =====================================================================================================================
 # reference arm / CPU baseline: the oracle's reference-shaped OpenMP loops on the host cores
 # =====================================================================================================================
-def cpu_kick_sample(o, d, rows, reps=1):
-    """Time `rows` rows of the full-row pl-pl loop (swiftest_kick.f90:219-240 shape, schedule(static), all threads).
-    Returns seconds per call."""
+def cpu_full_evaluation(o, d):
+    """One full pl-pl force evaluation: ALL rows of the full-row loop (swiftest_kick.f90:219-240 shape, OpenMP
+    schedule(static), every thread this process may use).  Returns seconds."""
     n = d["n"]
     acc = np.zeros((n, 3))
-    best = 1e300
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        o.omp_kick_tri_rad_pl_rows(d["rh"], d["Gmass"], d["radius"], acc, n, 0, rows)
-        best = min(best, time.perf_counter() - t0)
-    return best
+    t0 = time.perf_counter()
+    o.omp_kick_tri_rad_pl_rows(d["rh"], d["Gmass"], d["radius"], acc, n, 0, n)
+    return time.perf_counter() - t0
 
 
-def cpu_baseline(d, seconds):
+def cpu_baseline(d, evals):
     from oracle import load
     o = load(native=True)
+    threads = o.omp_set_threads()
     n = d["n"]
-    threads = o.omp_threads()
-    probe_rows = min(n, 8 * threads)
-    t = cpu_kick_sample(o, d, probe_rows)
-    rows = int(min(n, max(probe_rows, probe_rows * seconds / max(t, 1e-6))))
-    rows = max(threads, rows - rows % threads)
-    t = cpu_kick_sample(o, d, rows)
-    t_full = t * n / rows
+    cpu_full_evaluation(o, d)  # warm-up
+    ts = [cpu_full_evaluation(o, d) for _ in range(max(1, evals))]
+    t = float(np.mean(ts))
     pairs = n * (n - 1) / 2.0
-    return {"value": pairs / t_full, "unit": "pair-interactions/s", "cores": threads, "kind": "port",
-            "sample": f"{rows} of {n} rows of the full-row pl-pl loop (kick.f90:219-240 shape, OpenMP schedule(static), "
-                      f"{threads} threads, gcc -O3 -march=x86-64-v3 strict IEEE), {t:.2f} s measured, scaled to all rows",
-            "seconds_full_evaluation_est": t_full}
+    return {"value": pairs / t, "unit": "pair-interactions/s", "cores": threads, "kind": "port",
+            "sample": f"{len(ts)} full force evaluations (all {n} rows of the full-row pl-pl loop, kick.f90:219-240 shape, "
+                      f"OpenMP schedule(static), {threads} threads, gcc -O3 -march=x86-64-v3 strict IEEE), "
+                      f"{t:.2f} s each; nothing extrapolated",
+            "seconds_full_evaluation": t}
 
 
 def run_reference(args):
-    """--impl reference: the CPU path (oracle port; the Fortran reference cannot be built in this image) on the host
-    cores.  A step = a bounded row sample of the pl-pl kick scaled to the whole system + the full serial drift."""
+    """--impl reference: the CPU path (oracle port; the Fortran reference cannot be built in this image or on the GPU
+    box: profiles/r02_fortran_probe.txt) on the host cores.  A step = the full pl-pl kick (all rows, all threads this
+    process may use -- set explicitly, torchrun exports OMP_NUM_THREADS=1) + the serial Kepler drift of all bodies."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from oracle import load
     from swiftest_b200 import workloads as W
     o = load(native=True)
+    threads = o.omp_set_threads()
     d = W.disk(args.npl, seed=3031179)
     n = d["n"]
-    threads = o.omp_threads()
-    rows = min(n, 8 * threads)
-    t = cpu_kick_sample(o, d, rows)
-    rows = int(min(n, max(rows, rows * 2.0 / max(t, 1e-6))))  # ~2 s of CPU work per step
-    rows = max(threads, rows - rows % threads)
     pairs = n * (n - 1) / 2.0
     times = []
     for it in range(args.warmup + args.steps):
-        tk = cpu_kick_sample(o, d, rows)
         t0 = time.perf_counter()
-        x, v, fl = o.drift_all(d["mu"], d["rh"], d["vh"], d["dt"])  # serial, as in the reference (drift.f90:99-103)
-        td = time.perf_counter() - t0
+        acc = np.zeros((n, 3))
+        o.omp_kick_tri_rad_pl_rows(d["rh"], d["Gmass"], d["radius"], acc, n, 0, n)
+        v = d["vh"] + acc * d["dt"]
+        x, v, fl = o.drift_all(d["mu"], d["rh"], v, d["dt"])  # serial, as in the reference (drift.f90:99-103)
         if it >= args.warmup:
-            times.append(tk * n / rows + td)
+            times.append(time.perf_counter() - t0)
     step = float(np.mean(times))
     val = pairs / step
-    sample = (f"per step: {rows} of {n} rows of the full-row pl-pl loop on {threads} OpenMP threads scaled to all rows "
-              f"+ serial Kepler drift of all {n} bodies")
+    sample = (f"per step: all {n} rows of the full-row pl-pl loop on {threads} OpenMP threads + velocity kick + serial "
+              f"Kepler drift of all {n} bodies; nothing extrapolated")
     print(json.dumps({
         "impl": "reference", "metric": "FP64 pair-interactions/s (pl-pl N=1e5)", "value": val,
         "unit": "pair-interactions/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n,
-                                        "loop": "triangular full-row, radius-checked", "host": "cpu"},
+        "data": "synthetic", "config": common_config(n),
+        "impl_detail": {"loop": "triangular full-row, radius-checked", "host": "cpu", "threads": threads},
         "cpu_baseline": {"value": val, "unit": "pair-interactions/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pair-interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -310,8 +320,7 @@ def run_ours(args):
             use_p2p = False
         dist.barrier()
 
-    def step():
-        ctx.flush_l2()
+    def step():  # one pass of the hot path over the resident system (no flush in here)
         if use_p2p:
             ctx.pl_kick_drift_p2p(dt, True, want_nfail=False)
             return
@@ -322,11 +331,9 @@ def run_ours(args):
         if world > 1 and variant == LOOP_TRIANGULAR:
             ctx.pl_allgather(with_v=True)
 
-    def reset_state():
-        ctx.body_put(PL, r=d["rh"], v=d["vh"])
-
     # ---------------- device-resident timing ----------------
     for _ in range(args.warmup):
+        ctx.flush_l2()
         step()
     barrier()
     sampler = ClockSampler(local)
@@ -335,31 +342,60 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     barrier()
     ctx.enable_kernel_timing(2)  # an event pair per launch group, read after the loop: nothing stalls the stream
-    ctx.timer_start()
     for _ in range(args.steps):
+        # the flush goes first and is NOT inside the lap: while it runs (~26 us) the host queues the step's first
+        # launches, so the lap starts on a busy stream exactly when the flush ends
+        ctx.flush_l2()
+        ctx.timer_lap_begin()
         step()
-    ms_total = ctx.timer_stop()
+        ctx.timer_lap_end()
+    ms_total, nlaps, laps = ctx.timer_laps(each=args.steps)
+    assert nlaps == args.steps
     barrier()
     fam_ms = {name: ctx.kernel_ms_accumulated(f) for name, f in
               (("gravity", FAM_PLPL), ("drift", FAM_DRIFT), ("collective", FAM_ALLGATHER))}
     ctx.enable_kernel_timing(0)
-    launches = ctx.launch_count() - launches0
+    launches = ctx.launch_count() - launches0 - args.steps  # the flush kernels are not part of the step
     clocks = sampler.stop() if rank == 0 else None
     ms_step = max_over_ranks(ms_total / args.steps)
     value = pairs / (ms_step * 1e-3)
     kick_ms_avg = max_over_ranks(fam_ms["gravity"][0] / max(1, fam_ms["gravity"][1]))
     breakdown = {k: (max_over_ranks(v[0] / args.steps) if v[1] else 0.0) for k, v in fam_ms.items()}
+    breakdown["step_min"], breakdown["step_max"] = float(min(laps)), float(max(laps))
     fp64_peak = ctx.probe_fp64_peak()
 
     # ---------------- end-to-end: host buffers in, results out, every step ----------------
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
-    h_r, h_v = pin(d["rh"]), pin(d["vh"])
-    out = {"r": pin(np.zeros((n, 3))), "v": pin(np.zeros((n, 3))), "a": pin(np.zeros((n, 3)))}
+    if world == 1:
+        h_r, h_v = pin(d["rh"]), pin(d["vh"])
+        out = {"r": pin(np.zeros((n, 3))), "v": pin(np.zeros((n, 3))), "a": pin(np.zeros((n, 3)))}
 
-    def step_e2e():
-        ctx.body_put(PL, r=h_r, v=h_v)
-        step()
-        ctx.body_get(PL, out=out)
+        def step_e2e():
+            ctx.body_put(PL, r=h_r, v=h_v)
+            step()
+            ctx.body_get(PL, out=out)
+
+        h2d, d2h = 2 * 3 * n * 8, 3 * 3 * n * 8
+        e2e_path = "swcu_body_put(r,v) -> zero/accel_int/kick/drift -> swcu_body_get(r,v,a), pinned host arrays"
+    else:
+        # every rank owns a slice of the bodies on the host side too (the shape of swiftest_coarray_distribute_system):
+        # it uploads its slice, the slices are allgathered on the device, and it reads its slice of the results back
+        m = i1 - i0
+        h_r, h_v = pin(d["rh"][i0:i1]), pin(d["vh"][i0:i1])
+        out = {"r": pin(np.zeros((m, 3))), "v": pin(np.zeros((m, 3))), "a": pin(np.zeros((m, 3)))}
+
+        def step_e2e():
+            ctx.body_put_range(PL, i0, i1, r=h_r, v=h_v)
+            ctx.pl_set_slice(i0, i1)
+            ctx.pl_allgather(with_v=True)
+            if variant != LOOP_TRIANGULAR:
+                ctx.pl_set_slice(0, n)   # the third-law step kicks/drifts through its own partition
+            step()
+            ctx.body_get_range(PL, i0, i1, out=out)
+
+        h2d, d2h = 2 * 3 * n * 8, 3 * 3 * n * 8   # summed over the ranks: every body crosses PCIe once each way
+        e2e_path = ("per rank: swcu_body_put_range(slice r,v) -> swcu_pl_allgather (device) -> step -> "
+                    "swcu_body_get_range(slice r,v,a), pinned host arrays")
 
     for _ in range(max(1, args.warmup)):
         step_e2e()
@@ -369,10 +405,19 @@ def run_ours(args):
         step_e2e()
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    e2e = {"value": pairs / e2e_s, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(2 * 3 * n * 8 * world),
-           "d2h_bytes_per_step": int(3 * 3 * n * 8 * world), "ms_per_step": e2e_s * 1e3,
-           "path": "swcu_body_put(r,v) -> zero/accel_int/kick/drift[/allgather] -> swcu_body_get(r,v,a), pinned host arrays"}
+    e2e = {"value": pairs / e2e_s, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(h2d),
+           "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3, "path": e2e_path}
 
+    # ---------------- parity of the timed code path (outside the timed regions) ----------------
+    try:
+        parity = parity_check(ctx, args, d, variant, use_p2p, rank, world, local, dist, step, i0, i1)
+    except Exception as e:
+        parity = {"ok": False, "error": str(e)}
+
+    if use_p2p:  # the side legs re-sync other populations: the peer mappings of the 1e5-body arrays go first
+        barrier()
+        ctx.p2p_close()
+        barrier()
     hbm_peak, peak_src = peaks()
     flops_kernel = FLOP_PER_PAIR_RAD * pairs / world  # algorithmic flop of one rank's launch (balanced shares)
     achieved = flops_kernel / (kick_ms_avg * 1e-3) / 1e12
@@ -389,9 +434,10 @@ def run_ours(args):
                 "peak_source": "DFMA microbenchmark run in this process (swcu_probe_fp64_peak); MEASURED_PEAKS.json holds "
                                "no FP64 figure",
                 "algorithmic_flop_per_pair": FLOP_PER_PAIR_RAD, "kernel_ms": kick_ms_avg,
-                "note": "kernel_ms brackets the gravity launch group (memset/max-radius, kernel, +allreduce at N>1, +ah update); "
-                        "FP64 instructions hold the B200 issue port 2 cycles and nothing co-issues, so the bound is "
-                        "2*N_fp64 + N_other issue cycles per pair, not the DFMA peak (profiles/r01_fp64_pipe.md)"}
+                "note": "kernel_ms brackets the gravity launch group (memset, radius bounds, kernel, +ah update); an FP64 "
+                        "instruction holds the B200 issue port 2 cycles and nothing co-issues, and three-register FP64 "
+                        "streams sustain ~0.455 of the 0.5 inst/cycle/SMSP the peak probe reaches "
+                        "(profiles/r02_kick_flat.md)"}
 
     extra = {}
     if not args.no_extra and rank == 0 and world == 1:
@@ -400,81 +446,253 @@ def run_ours(args):
             extra["next_rows"] = next_row_legs(ctx, args, d, hbm_peak, fp64_peak)
         except Exception as e:  # side legs are reported figures, never a dependency of the headline number
             extra["error"] = str(e)
+        try:
+            extra["symba_1e4"] = symba_1e4_leg(ctx, hbm_peak, fp64_peak)
+        except Exception as e:
+            extra["symba_1e4"] = {"error": str(e)}
     cpu = None
     if not args.no_extra and rank == 0 and world == 1:
         try:
-            cpu = cpu_baseline(d, args.cpu_seconds)
+            cpu = cpu_baseline(d, args.cpu_evals)
         except Exception as e:  # the CPU baseline is a reported figure, never a dependency of the GPU number
             cpu = {"value": None, "unit": "pair-interactions/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
-    if args.conservation and rank == 0 and world == 1:
-        extra["conservation"] = conservation_run(ctx, args.conservation)
+    if not args.no_extra and rank == 0 and world == 1:
+        if args.conservation:
+            try:
+                extra["conservation"] = conservation_run(ctx, args.conservation)
+            except Exception as e:
+                extra["conservation"] = {"error": str(e)}
+        if args.disk_steps:
+            try:
+                extra["conservation_disk"] = conservation_disk_run(ctx, args.disk_steps)
+            except Exception as e:
+                extra["conservation_disk"] = {"error": str(e)}
 
-    if world > 1 and not args.no_extra:
-        try:  # a side leg must never cost the headline line
-            extra["whm_tp_sharded"] = tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak)
-        except Exception as e:
-            extra["whm_tp_sharded"] = {"error": str(e)}
+    if not args.no_extra:
+        legs = {}
+        for tok in args.tp_sizes.split(","):
+            ntp_total = int(float(tok))
+            try:  # a side leg must never cost the headline line
+                legs[f"ntp_{tok.strip()}"] = tp_sharded_leg(ctx, ntp_total, rank, world, barrier, max_over_ranks, hbm_peak, dist)
+            except Exception as e:
+                legs[f"ntp_{tok.strip()}"] = {"error": str(e)}
+        extra["whm_tp_sharded"] = legs
 
     if rank == 0:
         line = {
             "metric": "FP64 pair-interactions/s (pl-pl N=1e5)", "value": value, "unit": "pair-interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n, "nplm": n,
-                       "loop": "triangular full-row" if variant == LOOP_TRIANGULAR else "flat third-law",
-                       "lclose": True,
-                       "step": "zero_accel+accel_int+kick_velocity+drift" +
-                               ((("[reduce-scatter+kick+drift+allgather fused over NVLink peer memory]" if use_p2p
-                                  else "+ncclAllReduce(ah)") if variant == LOOP_FLAT else "+allgather(r,v)") if world > 1 else ""),
-                       "sharding": (f"block-pair runs over {world} rank(s)" if variant == LOOP_FLAT
-                                    else f"i-slices over {world} rank(s), allgather of drifted r,v"),
-                       "collective": ("p2p-fused" if use_p2p else ("nccl" if world > 1 else "none")),
-                       "l2": "flushed between steps (160 MiB write = 1.33 x L2, inside the timed region)",
-                       "seed": 3031179},
+            "config": common_config(n),
+            "impl_detail": {"loop": "triangular full-row" if variant == LOOP_TRIANGULAR else "flat third-law",
+                            "multi_gpu_step": ((("reduce-scatter + kick + drift + allgather fused in one kernel over NVLink "
+                                                 "peer memory" if use_p2p else "ncclAllReduce(ah)") if variant == LOOP_FLAT
+                                                else "allgather(r,v)") if world > 1 else "none"),
+                            "sharding": (f"balanced runs of block pairs over {world} rank(s), per-rank work counters"
+                                         if variant == LOOP_FLAT else f"i-slices over {world} rank(s)"),
+                            "collective": ("p2p-fused" if use_p2p else ("nccl" if world > 1 else "none")),
+                            "timing": "one CUDA-event pair per step on the library's stream (laps), L2 flush between laps, "
+                                      "max over ranks of the mean lap"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "breakdown_ms_per_step": breakdown,
+            "parity_check": parity, "breakdown_ms_per_step": breakdown,
             "peaks": {"fp64_tflops_measured": fp64_peak, "hbm_gbs": hbm_peak, "hbm_source": peak_src},
             "extra": extra}
         print(json.dumps(line))
     if dist:
         dist.barrier()
-        if use_p2p:
-            ctx.p2p_close()
         ctx.comm_finalize()
         dist.destroy_process_group()
     ctx.close()
 
 
-def tp_sharded_leg(ctx, args, rank, world, barrier, max_over_ranks, hbm_peak):
-    """WHM test particles over several GPUs: block partition like swiftest_coarray_distribute_system
-    (swiftest_coarray.f90:705-711), planets replicated, no per-step communication.  Fused tp step, all ranks."""
+def parity_check(ctx, args, d, variant, use_p2p, rank, world, local, dist, step, i0, i1):
+    """Result of the timed code path against an independent computation, outside the timed regions.
+    N = 1: the accelerations of one pass against the CPU oracle's full-row loop on 1e4 sampled rows (1e-12 of the
+    per-component sum of |terms|), and r, v after the pass against oracle kick + drift on those rows.
+    N > 1: M passes of the multi-GPU step from the initial state; every rank must end with bit-identical r, v, and
+    they must agree with the same M passes of the ONE-GPU path (a second context on rank 0's GPU) to 1e-12."""
+    import torch
+    from swiftest_b200 import Context, PL, LOOP_FLAT
+    n, dt = d["n"], d["dt"]
+    tol = 1e-12
+    if world == 1:
+        from oracle import load
+        o = load(native=True)
+        o.omp_set_threads()
+        ctx.body_put(PL, r=d["rh"], v=d["vh"])
+        step()
+        got = ctx.body_get(PL)
+        blocks = [(b0, min(n, b0 + 2500)) for b0 in np.linspace(0, max(0, n - 2500), 4).astype(int)] if n > 10000 else [(0, n)]
+        rows = np.unique(np.concatenate([np.arange(a, b) for a, b in blocks]))
+        ref = np.zeros((n, 3))
+        for a, b in blocks:
+            ref[a:b] = 0.0
+            o.omp_kick_tri_rad_pl_rows(d["rh"], d["Gmass"], d["radius"], ref, n, int(a), int(b))
+        scale = o.kick_tri_abs_scale(d["rh"], d["Gmass"], d["radius"])
+        acc_err = float(np.max(np.abs(got["a"][rows] - ref[rows]) / np.where(scale[rows] > 0, scale[rows], 1.0)))
+        v1 = d["vh"][rows] + ref[rows] * dt
+        xr, vr, fr = o.drift_all(d["mu"][rows], d["rh"][rows], v1, dt)
+        r_err = float(np.max(np.abs(got["r"][rows] - xr) / np.linalg.norm(xr, axis=1, keepdims=True)))
+        v_err = float(np.max(np.abs(got["v"][rows] - vr) / np.linalg.norm(vr, axis=1, keepdims=True)))
+        return {"against": "CPU oracle (full-row OpenMP loop + Kepler drift)", "rows_compared": int(len(rows)),
+                "acc_max_err_over_sum_abs_terms": acc_err, "r_max_rel_err": r_err, "v_max_rel_err": v_err, "tol": tol,
+                "redo_chunks": ctx.flat_redo_count(), "ok": bool(acc_err < tol and r_err < tol and v_err < tol)}
+    M = 3
+    ctx.body_put(PL, r=d["rh"], v=d["vh"])
+    ctx.synchronize()
+    dist.barrier()
+    for _ in range(M):
+        step()
+    got = ctx.body_get(PL, a=False)
+    # identical bits on every rank: compare 64-bit digests of r and v
+    words = np.concatenate([got["r"].ravel(), got["v"].ravel()]).view(np.uint64)
+    digest = np.array([np.bitwise_xor.reduce(words), np.add.reduce(words, dtype=np.uint64)], dtype=np.uint64)
+    t = torch.from_numpy(digest.view(np.int64)).cuda()
+    allt = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allt, t)
+    identical = all(bool(torch.equal(allt[0], x)) for x in allt)
+    res = {"against": f"one-GPU run of the same {M} steps (second context on rank 0)", "steps": M, "ranks": world,
+           "ranks_bit_identical": identical, "rows_compared": n, "tol": tol}
+    if rank == 0:
+        with Context(local) as c1:
+            c1.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                         mu=d["mu"], generation=1)
+            for _ in range(M):
+                c1.body_zero_accel(PL)
+                c1.pl_accel_int(variant, True)
+                c1.body_kick_velocity(PL, dt)
+                c1.body_drift(PL, dt, want_nfail=False)
+            one = c1.body_get(PL, a=False)
+        res["r_max_rel_err"] = float(np.max(np.abs(got["r"] - one["r"]) / np.linalg.norm(one["r"], axis=1, keepdims=True)))
+        res["v_max_rel_err"] = float(np.max(np.abs(got["v"] - one["v"]) / np.linalg.norm(one["v"], axis=1, keepdims=True)))
+        res["ok"] = bool(identical and res["r_max_rel_err"] < tol and res["v_max_rel_err"] < tol)
+    dist.barrier()
+    return res
+
+
+def tp_shard(ntp_total, t0, t1):
+    """Bodies [t0, t1) of a synthetic cloud of ntp_total test particles: the 1e6-particle cloud of the WHM configuration
+    (workloads.tp_cloud, seed 123) tiled, replica k scaled by (1 + 1e-3 k / replicas) in r and by the matching
+    Keplerian factor in v, so every particle stays on a bound, distinct orbit.  Generated shard by shard: a rank never
+    materialises the whole cloud."""
+    from swiftest_b200 import workloads as W
+    base_n = min(ntp_total, 1_000_000)
+    base = _TP_BASE.get(base_n)
+    if base is None:
+        base = _TP_BASE[base_n] = W.tp_cloud(base_n, seed=123)
+    reps = max(1, -(-ntp_total // base_n))
+    idx = np.arange(t0, t1, dtype=np.int64)
+    k = (idx // base_n).astype(np.float64) / reps
+    src = idx % base_n
+    f = (1.0 + 1e-3 * k)[:, None]
+    return base["rh"][src] * f, base["vh"][src] / np.sqrt(f)
+
+
+_TP_BASE = {}
+
+
+def tp_sharded_leg(ctx, ntp_total, rank, world, barrier, max_over_ranks, hbm_peak, dist):
+    """WHM test particles over the GPUs of the run: block partition like swiftest_coarray_distribute_system
+    (swiftest_coarray.f90:705-711), planets replicated, NO per-step communication.  The fused tp step (152 B per tp) is
+    timed lap by lap (one event pair per launch); the L2 flush between laps is outside them and is skipped when the
+    shard is larger than L2 anyway."""
+    import psutil
+    import torch
     from swiftest_b200 import PL, TP, shard, workloads as W
     p = W.planets8_year_units()
-    ntp = args.ntp
-    tp = W.tp_cloud(ntp, seed=123)
-    t0, t1 = shard.tp_block_partition(ntp, world, rank)
+    t0, t1 = shard.tp_block_partition(ntp_total, world, rank)
+    m = t1 - t0
+    need_host = m * 8 * (3 + 3 + 1) * 2.5   # r, v, mu + temporaries of the generator
+    need_dev = m * 130 + 2 * m * 24         # resident arrays + staging of the upload
+    ok = psutil.virtual_memory().available > need_host + (8 << 30) and torch.cuda.mem_get_info()[0] > need_dev + (4 << 30)
+    if dist is not None:
+        t = torch.tensor([1.0 if ok else 0.0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        ok = bool(t.item() > 0)
+    if not ok:
+        return {"skipped": f"not enough free host or device memory for {m} particles per rank"}
+    r, v = tp_shard(ntp_total, t0, t1)
     ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
-                  mu=p["cb_Gmass"] + p["Gmass"], generation=902)
-    ctx.body_sync(TP, t1 - t0, r=tp["rh"][t0:t1], v=tp["vh"][t0:t1], mu=np.full(t1 - t0, p["cb_Gmass"]), generation=903)
+                  mu=p["cb_Gmass"] + p["Gmass"], generation=902 + ntp_total % 1000)
+    ctx.body_sync(TP, m, r=r, v=v, mu=np.full(m, p["cb_Gmass"]), generation=903 + ntp_total)
+    del r, v
     ah0 = np.zeros(3)
     for i in range(8):
         r2 = float(p["rh"][i] @ p["rh"][i])
         ah0 -= p["Gmass"][i] / (r2 * np.sqrt(r2)) * p["rh"][i]
     ctx.body_zero_accel(TP)
     ctx.tp_accel_int()
+    flush = m * 152 < 2 * 126e6
     for _ in range(3):
         ctx.whm_tp_step(0.01, ah0, want_nfail=False)
-    nsteps = 20
+    nsteps = 20 if ntp_total <= 10_000_000 else 8
     barrier()
-    ctx.timer_start()
     for _ in range(nsteps):
-        ctx.flush_l2()
+        if flush:
+            ctx.flush_l2()
+        ctx.timer_lap_begin()
         ctx.whm_tp_step(0.01, ah0, want_nfail=False)
-    ms = max_over_ranks(ctx.timer_stop() / nsteps)
+        ctx.timer_lap_end()
+    tot, cnt = ctx.timer_laps()
+    ms = max_over_ranks(tot / cnt)
+    nfail = ctx.body_get(TP, r=False, v=False, a=False, iflag=True)["iflag"]
+    bad = max_over_ranks(float(np.count_nonzero(nfail)))
     barrier()
-    return {"ntp_total": ntp, "ranks": world, "ms_per_step": ms, "tp_steps_per_s": ntp / (ms * 1e-3),
+    gbs = 152.0 * ntp_total / (ms * 1e-3) / 1e9
+    return {"ntp_total": ntp_total, "ranks": world, "ntp_per_rank": m, "ms_per_step": ms,
+            "tp_steps_per_s": ntp_total / (ms * 1e-3), "drift_failures": int(bad),
             "partition": "block (coarray_distribute shape), planets replicated, no per-step communication",
-            "note": "includes the 160 MiB L2 flush between steps"}
+            "timing": "mean of per-launch event pairs, max over ranks; L2 flush between launches"
+                      + ("" if flush else " skipped (shard > 2 x L2)"),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak * world, "unit": "GB/s",
+                         "frac": gbs / (hbm_peak * world), "bytes_per_tp": 152,
+                         "note": "aggregate over the ranks against ranks x measured HBM copy bandwidth"}}
+
+
+def symba_1e4_leg(ctx, hbm_peak, fp64_peak):
+    """BASELINE.json configs[2]: SyMBA planetesimal disk, 1e4 fully interacting bodies -- flat (third-law) vs
+    triangular (full-row) pl-pl kernel, and the pl-pl sort-and-sweep."""
+    from swiftest_b200 import PL, LOOP_FLAT, LOOP_TRIANGULAR, workloads as W
+    from swiftest_b200.context import FAM_PLPL, FAM_SWEEP
+    n = 10000
+    d = W.disk(n, seed=3031179)
+    pairs = n * (n - 1) / 2.0
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                  mu=d["mu"], generation=41)
+    ctx.enable_kernel_timing(True)
+    res = {"npl": n, "pairs": pairs}
+    acc = {}
+    for name, var in (("flat", LOOP_FLAT), ("tri", LOOP_TRIANGULAR)):
+        ms = []
+        for it in range(8):
+            ctx.flush_l2()
+            ctx.body_zero_accel(PL)
+            ctx.pl_accel_int(var, True)
+            if it >= 3:
+                ms.append(ctx.last_kernel_ms(FAM_PLPL))
+        acc[name] = ctx.body_get(PL, r=False, v=False)["a"]
+        t = float(np.mean(ms)) * 1e-3
+        tf = FLOP_PER_PAIR_RAD * pairs / t / 1e12
+        res[name] = {"ms": t * 1e3, "pairs_per_s": pairs / t,
+                     "roofline": {"bound": "fp64", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak}}
+    res["flat_vs_tri_max_rel_diff"] = float(np.max(np.abs(acc["flat"] - acc["tri"])) / np.max(np.abs(acc["tri"])))
+    res["auto_picks"] = "flat" if res["flat"]["ms"] < res["tri"]["ms"] else "tri"
+    ctx.pl_set_renc(0)
+    ms = []
+    for it in range(6):
+        ctx.flush_l2()
+        nenc = ctx.pl_encounter_check(d["dt"], fetch=False)
+        if it >= 2:
+            ms.append(ctx.last_kernel_ms(FAM_SWEEP))
+    st = ctx.encounter_stats()
+    b = SWEEP_BYTES
+    bytes_alg = n * b["body"] + 2 * n * b["sort"] / 2 + 2 * n * 56.0 + st["nbox_total"] * b["cand"] + nenc * b["out"]
+    t = float(np.mean(ms)) * 1e-3
+    res["sweep_plpl"] = {"nenc": int(nenc), "nbox_total": int(st["nbox_total"]), "ms": t * 1e3, "algorithmic_bytes": bytes_alg,
+                         "roofline": {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": bytes_alg / t / 1e9 / hbm_peak}}
+    ctx.enable_kernel_timing(False)
+    return res
 
 
 def side_legs(ctx, args, d, hbm_peak, peak_src):
@@ -636,15 +854,99 @@ def conservation_run(ctx, nsteps):
     a = HelioSystem(p["cb_Gmass"], p["Gmass"], p["rh"], p["vh"], p["radius"], OracleBackend(load()))
     b = HelioSystem(p["cb_Gmass"], p["Gmass"], p["rh"], p["vh"], p["radius"], GpuBackend(ctx))
     E0, L0 = a.energy_and_momentum()
-    for _ in range(nsteps):
+    every = max(1, nsteps // 20)
+    ts, dEa, dEb, dLa, dLb = [], [], [], [], []
+    for k in range(1, nsteps + 1):
         a.step(0.01)
         b.step(0.01)
-    Ea, La = a.energy_and_momentum()
-    Eb, Lb = b.energy_and_momentum()
-    return {"steps": nsteps, "dt": 0.01, "dE_cpu": (Ea - E0) / abs(E0), "dE_gpu": (Eb - E0) / abs(E0),
-            "dL_cpu": float(np.linalg.norm(La - L0) / np.linalg.norm(L0)),
-            "dL_gpu": float(np.linalg.norm(Lb - L0) / np.linalg.norm(L0)),
+        if k % every == 0 or k == nsteps:
+            Ea, La = a.energy_and_momentum()
+            Eb, Lb = b.energy_and_momentum()
+            ts.append(k * 0.01)
+            dEa.append((Ea - E0) / abs(E0))
+            dEb.append((Eb - E0) / abs(E0))
+            dLa.append(float(np.linalg.norm(La - L0) / np.linalg.norm(L0)))
+            dLb.append(float(np.linalg.norm(Lb - L0) / np.linalg.norm(L0)))
+    return {"system": "Sun + 8 planets (reference fixture 8pl_0tp)", "steps": nsteps, "dt": 0.01, "years": nsteps * 0.01,
+            "dE_cpu": dEa[-1], "dE_gpu": dEb[-1], "dL_cpu": dLa[-1], "dL_gpu": dLb[-1],
+            "max_abs_dE_gpu": float(np.max(np.abs(dEb))), "max_abs_dE_cpu": float(np.max(np.abs(dEa))),
+            "gpu_minus_cpu_dE": float(np.max(np.abs(np.array(dEa) - np.array(dEb)))),
+            "gpu_minus_cpu_dL": float(np.max(np.abs(np.array(dLa) - np.array(dLb)))),
+            "dE_slope_per_year_gpu": _slope_per_year(ts, np.abs(dEb)), "dL_slope_per_year_gpu": _slope_per_year(ts, dLb),
+            "dE_slope_per_year_cpu": _slope_per_year(ts, np.abs(dEa)), "dL_slope_per_year_cpu": _slope_per_year(ts, dLa),
+            "reference_limits": "tests/test_swiftest.py:119-121: |dE/E0| slope < 1e-8 /y, |dL/L0| slope < 1e-10 /y",
             "max_position_difference": float(np.max(np.abs(a.rh - b.rh)))}
+
+
+def _slope_per_year(t, y):
+    """least-squares slope of y(t)"""
+    t, y = np.asarray(t, float), np.asarray(y, float)
+    return float(np.polyfit(t, y, 1)[0]) if len(t) > 1 else 0.0
+
+
+def conservation_disk_run(ctx, nsteps, n=10000):
+    """SyMBA-style disk of 1e4 fully interacting bodies, democratic-heliocentric steps (helio_step.f90:37-78):
+    the device-resident swcu_helio_step_pl against the CPU oracle's swo_helio_step_pl (full-row kick through its OpenMP
+    row loop), energy / angular momentum sampled every nsteps/10 steps -- the GPU state through
+    swcu_util_get_energy_and_momentum, the CPU state through the oracle's restatement of
+    swiftest_util_get_energy_and_momentum_system (swiftest_util.f90:1222-1394)."""
+    from oracle import load
+    from swiftest_b200 import PL, LOOP_AUTO, workloads as W
+    o = load(native=True)
+    o.omp_set_threads()
+    o.use_omp_kick(True)
+    d = W.disk(n, seed=3031179)
+    GMcb, dt = W.GMSUN, d["dt"]
+    Gm, rad = d["Gmass"], d["radius"]
+    mass = Gm / GMcb
+
+    def energy_gpu(rh, vh):
+        rb, vb, rbcb, vbcb = o.coord_h2b_pl(GMcb, Gm, rh, vh)
+        e = ctx.util_get_energy_and_momentum(n, None, GMcb, 1.0, rbcb, vbcb, Gm, mass, rad, rb, vb, True)
+        return e["te"], e["L_orbit"] + np.cross(rbcb, vbcb)
+
+    def energy_cpu(rh, vh):
+        rb, vb, rbcb, vbcb = o.coord_h2b_pl(GMcb, Gm, rh, vh)
+        e = o.get_energy_and_momentum(GMcb, 1.0, rbcb, vbcb, Gm, mass, rad, rb, vb, None, True)
+        return e["te"], e["L_orbit"] + np.cross(rbcb, vbcb)
+
+    st = {"rh": d["rh"].copy(), "vh": d["vh"].copy(), "vb": np.zeros((n, 3)), "lfirst": True}
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=Gm, radius=rad, rhill=d["rhill"], mu=np.full(n, GMcb),
+                  generation=51)
+    E0g, L0g = energy_gpu(d["rh"], d["vh"])
+    E0c, L0c = energy_cpu(d["rh"], d["vh"])
+    every = max(1, nsteps // 10)
+    ts, dEg, dEc, dLg, dLc, dpos = [], [], [], [], [], []
+    t_gpu = t_cpu = 0.0
+    nfail_gpu = nfail_cpu = 0
+    for k in range(1, nsteps + 1):
+        t0 = time.perf_counter()
+        nfail_gpu += ctx.helio_step_pl(GMcb, dt, LOOP_AUTO, True, lfirst=(k == 1), want_nfail=(k % every == 0))
+        t1 = time.perf_counter()
+        nfail_cpu += int(np.count_nonzero(o.helio_step_pl(st, GMcb, Gm, rad, dt)))
+        t_cpu += time.perf_counter() - t1
+        t_gpu += t1 - t0
+        if k % every == 0 or k == nsteps:
+            g = ctx.body_get(PL, a=False)
+            Eg, Lg = energy_gpu(g["r"], g["v"])
+            Ec, Lc = energy_cpu(st["rh"], st["vh"])
+            ts.append(k * dt)
+            dEg.append((Eg - E0g) / abs(E0g))
+            dEc.append((Ec - E0c) / abs(E0c))
+            dLg.append(float(np.linalg.norm(Lg - L0g) / np.linalg.norm(L0g)))
+            dLc.append(float(np.linalg.norm(Lc - L0c) / np.linalg.norm(L0c)))
+            dpos.append(float(np.max(np.linalg.norm(g["r"] - st["rh"], axis=1) / np.linalg.norm(st["rh"], axis=1))))
+    o.use_omp_kick(False)
+    return {"npl": n, "steps": nsteps, "dt": dt, "years": nsteps * dt, "samples_at_years": ts,
+            "dE_over_E0_gpu": dEg, "dE_over_E0_cpu": dEc, "dL_over_L0_gpu": dLg, "dL_over_L0_cpu": dLc,
+            "gpu_minus_cpu_dE": float(np.max(np.abs(np.array(dEg) - np.array(dEc)))),
+            "gpu_minus_cpu_dL": float(np.max(np.abs(np.array(dLg) - np.array(dLc)))),
+            "max_rel_position_difference": dpos, "E0_gpu_vs_cpu_rel": abs(E0g - E0c) / abs(E0c),
+            "dE_slope_per_year_gpu": _slope_per_year(ts, dEg), "dL_slope_per_year_gpu": _slope_per_year(ts, dLg),
+            "reference_limits": "tests/test_swiftest.py:119-121: |dE/E0| slope < 1e-8 /y, |dL/L0| slope < 1e-10 /y "
+                                "(set for Sun + 8 planets; the disk run has no close-encounter handling, like HELIO)",
+            "drift_failures": {"gpu": int(nfail_gpu), "cpu": int(nfail_cpu)},
+            "seconds": {"gpu_steps": t_gpu, "cpu_steps": t_cpu}}
 
 
 if __name__ == "__main__":

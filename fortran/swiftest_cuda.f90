@@ -176,6 +176,19 @@ module swiftest_cuda
          integer(c_int), value :: kind
          type(c_ptr), value :: r, v, a, iflag
       end function
+      !! slice forms: bodies i0+1 .. i1 (0-based half-open [i0,i1) on the C side), arrays of that length
+      integer(c_int) function swcu_body_put_range(ctx, kind, i0, i1, r, v) bind(C, name="swcu_body_put_range")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, i0, i1
+         type(c_ptr), value :: r, v
+      end function
+      integer(c_int) function swcu_body_get_range(ctx, kind, i0, i1, r, v, a) bind(C, name="swcu_body_get_range")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, i0, i1
+         type(c_ptr), value :: r, v, a
+      end function
       !! whm_step_tp in one kernel (whm/whm_step.f90:72-100); ah0 = whm_kick_getacch_ah0 at the end-of-step planets
       integer(c_int) function swcu_whm_tp_step(ctx, dt, ah0, nfail) bind(C, name="swcu_whm_tp_step")
          import :: c_int, c_ptr, c_double
@@ -524,6 +537,22 @@ module swiftest_cuda
          integer(c_int), value :: family
          real(c_double), intent(out) :: total_ms
          integer(c_int), intent(out) :: count
+      end function
+      integer(c_int) function swcu_timer_lap_begin(ctx) bind(C, name="swcu_timer_lap_begin")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_timer_lap_end(ctx) bind(C, name="swcu_timer_lap_end")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_timer_laps(ctx, total_ms, count, each_ms, each_cap) bind(C, name="swcu_timer_laps")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), intent(out) :: total_ms
+         integer(c_int), intent(out) :: count
+         type(c_ptr), value :: each_ms      !! c_null_ptr, or c_loc of a real(c_double) array of each_cap elements
+         integer(c_int), value :: each_cap
       end function
       integer(c_int) function swcu_flat_redo_count(ctx, chunks) bind(C, name="swcu_flat_redo_count")
          import :: c_int, c_int64_t, c_ptr

@@ -135,6 +135,10 @@ int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_t nplm, con
 int swcu_body_put(swcu_context *ctx, int32_t kind, const double *r, const double *v, const double *a,
                   const int32_t *lmask);
 int swcu_body_get(swcu_context *ctx, int32_t kind, double *r, double *v, double *a, int32_t *iflag);
+/* slice forms: the host arrays hold bodies [i0, i1) (0-based, half open) only, 3*(i1-i0) doubles each -- what a rank
+ * of a multi-GPU run exchanges with its host (the coarray images of swiftest_coarray.f90:705-711 own slices too) */
+int swcu_body_put_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, const double *r, const double *v);
+int swcu_body_get_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, double *r, double *v, double *a);
 int swcu_body_count(swcu_context *ctx, int32_t kind, int32_t *n, int32_t *nplm, uint64_t *generation);
 
 /* ah = 0 (helio_kick_vb_pl zeroes ah before accel, helio_kick.f90:113) */
@@ -294,6 +298,11 @@ int swcu_pl_kick_drift_p2p(swcu_context *ctx, int32_t lclose, double dt, int32_t
  * ---------------------------------------------------------------------------------------------------- */
 int swcu_timer_start(swcu_context *ctx);
 int swcu_timer_stop(swcu_context *ctx, double *elapsed_ms); /* synchronises on the stop event */
+/* laps: one event pair per bracketed region, logged without synchronising; swcu_timer_laps returns their sum (and each
+ * lap, up to each_cap, when each_ms is not NULL), synchronises the stream and clears the log */
+int swcu_timer_lap_begin(swcu_context *ctx);
+int swcu_timer_lap_end(swcu_context *ctx);
+int swcu_timer_laps(swcu_context *ctx, double *total_ms, int32_t *count, double *each_ms, int32_t each_cap);
 /* register-resident DFMA loop: achieved FP64 TFLOP/s (2 flop per DFMA) on this device at current clocks */
 int swcu_probe_fp64_peak(swcu_context *ctx, double *tflops);
 /* device-to-device copy of `bytes`: achieved read+write GB/s */

@@ -176,6 +176,18 @@ class Oracle:
     def omp_threads(self):
         return int(self.lib.swo_omp_max_threads())
 
+    def omp_set_threads(self, n=None):
+        """Thread count of the OpenMP loops; default = the CPUs this process may run on (ignores OMP_NUM_THREADS, which
+        torchrun sets to 1 for its workers)."""
+        import os
+        n = len(os.sched_getaffinity(0)) if n is None else int(n)
+        self.lib.swo_omp_set_num_threads(n)
+        return self.omp_threads()
+
+    def use_omp_kick(self, on=True):
+        """Steppers: full-row pl-pl kick through the OpenMP row loop (bit-identical to the serial loop)."""
+        self.lib.swo_use_omp_kick(int(bool(on)))
+
     # ---------------- drift ----------------
     def drift_all(self, mu, x, v, dt, lmask=None, lgr=False, inv_c2=0.0, omp=False):
         """swiftest_drift_all. Returns (x, v, iflag) new arrays."""

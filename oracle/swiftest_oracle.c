@@ -300,6 +300,24 @@ void swo_symba_kick_subtract_enc(int32_t npl, int64_t nenc, const int32_t *index
 
 /* ---------------- reference-shaped OpenMP loops (timed CPU baseline only) ---------------- */
 
+/* thread count of the OpenMP loops, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which is not the
+ * configuration the reference's OpenMP build runs in (bench.py passes the size of the process's CPU affinity set) */
+void swo_omp_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* steppers (swiftest_oracle_step.c): run the full-row pl-pl kick through the OpenMP row loop below.  The reference's
+ * loop IS an OpenMP do over i with every row summed by one thread in ascending j (swiftest_kick.f90:219-240), so the
+ * result is bit-identical to the serial restatement for any thread count. */
+static int swo_parallel_kick = 0;
+void swo_use_omp_kick(int on) { swo_parallel_kick = on; }
+int swo_omp_kick_enabled(void) { return swo_parallel_kick; }
+
 int swo_omp_max_threads(void)
 {
 #ifdef _OPENMP

@@ -61,6 +61,9 @@ void swo_omp_kick_all_tp(int32_t ntp, int32_t npl, const double *rtp, const doub
 void swo_omp_drift_all(const double *mu, double *x, double *v, int32_t n, int lgr, double inv_c2, double dt,
                        const int32_t *lmask, int32_t *iflag);
 int swo_omp_max_threads(void);
+void swo_omp_set_num_threads(int n);
+void swo_use_omp_kick(int on);
+int swo_omp_kick_enabled(void);
 
 /* ---- drift: swiftest/swiftest_drift.f90, swiftest/swiftest_orbel.f90:147-172 ---- */
 void swo_drift_all(const double *mu, double *x, double *v, int32_t n, int lgr, double inv_c2, double dt,

@@ -55,6 +55,8 @@ def load():
         "swcu_body_sync": [p, i32, i32, i32, p, p, p, p, p, p, p, u64],
         "swcu_body_put": [p, i32, p, p, p, p],
         "swcu_body_get": [p, i32, p, p, p, p],
+        "swcu_body_put_range": [p, i32, i32, i32, p, p],
+        "swcu_body_get_range": [p, i32, i32, i32, p, p, p],
         "swcu_body_count": [p, i32, p, p, p],
         "swcu_body_zero_accel": [p, i32],
         "swcu_pl_accel_int": [p, i32, i32],
@@ -101,6 +103,9 @@ def load():
         "swcu_pl_kick_drift_p2p": [p, i32, d, p],
         "swcu_timer_start": [p],
         "swcu_timer_stop": [p, p],
+        "swcu_timer_lap_begin": [p],
+        "swcu_timer_lap_end": [p],
+        "swcu_timer_laps": [p, p, p, p, i32],
         "swcu_probe_fp64_peak": [p, p],
         "swcu_probe_hbm_copy": [p, i64, p],
         "swcu_flush_l2": [p],

@@ -203,6 +203,21 @@ class Context:
         lmask = None if lmask is None else _vec(lmask, dt=_i32)
         self._ck(self._L.swcu_body_put(self._h, kind, _ptr(r), _ptr(v), _ptr(a), _ptr(lmask)))
 
+    def body_put_range(self, kind, i0, i1, r=None, v=None):
+        """Refresh bodies [i0, i1) from host arrays of that length (a rank's slice)."""
+        r, v = [None if q is None else _vec3(q, i1 - i0) for q in (r, v)]
+        self._ck(self._L.swcu_body_put_range(self._h, kind, int(i0), int(i1), _ptr(r), _ptr(v)))
+
+    def body_get_range(self, kind, i0, i1, r=True, v=True, a=True, out=None):
+        """Read bodies [i0, i1) back; `out` may supply preallocated (pinned) arrays keyed 'r','v','a'."""
+        out, res = dict(out or {}), {}
+        for key, want in (("r", r), ("v", v), ("a", a)):
+            if want:
+                res[key] = out.get(key) if out.get(key) is not None else np.empty((i1 - i0, 3), _f64)
+        self._ck(self._L.swcu_body_get_range(self._h, kind, int(i0), int(i1), _ptr(res.get("r")), _ptr(res.get("v")),
+                                             _ptr(res.get("a"))))
+        return res
+
     def body_count(self, kind):
         n, nplm, gen = C.c_int32(), C.c_int32(), C.c_uint64()
         self._ck(self._L.swcu_body_count(self._h, kind, C.byref(n), C.byref(nplm), C.byref(gen)))
@@ -516,6 +531,21 @@ class Context:
         ms = C.c_double()
         self._ck(self._L.swcu_timer_stop(self._h, C.byref(ms)))
         return ms.value
+
+    def timer_lap_begin(self):
+        self._ck(self._L.swcu_timer_lap_begin(self._h))
+
+    def timer_lap_end(self):
+        self._ck(self._L.swcu_timer_lap_end(self._h))
+
+    def timer_laps(self, each=0):
+        """(total ms, count[, per-lap ms]) of the laps since the last call; synchronises."""
+        ms, n = C.c_double(), C.c_int32()
+        buf = (C.c_double * each)() if each else None
+        self._ck(self._L.swcu_timer_laps(self._h, C.byref(ms), C.byref(n), buf, int(each)))
+        if each:
+            return ms.value, n.value, [buf[k] for k in range(min(each, n.value))]
+        return ms.value, n.value
 
     def enable_kernel_timing(self, on=True):
         """False/0 off, True/1 last launch group per family, 2 accumulate every launch group (kernel_ms_accumulated)."""

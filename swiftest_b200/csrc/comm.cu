@@ -267,9 +267,25 @@ extern "C" int swcu_p2p_import(swcu_context *ctx, int32_t nranks, int32_t rank, 
     P.nranks = nranks;
     P.rank = rank;
     P.epoch = 0;
+    if (!P.h_err) SWCU_CUDA(ctx, cudaHostAlloc((void **)&P.h_err, sizeof(unsigned long long), cudaHostAllocDefault));
+    *P.h_err = 0ull;
     P.ready = true;
     return SWCU_OK;
 }
+
+namespace swcu {
+// A bounded spin of the peer-memory exchange ran out on some rank (a peer died, hung or was never launched): the
+// kernels raised the error word on every rank instead of hanging; turn it into a status and clear it.
+int p2p_check_error(swcu_context *ctx)
+{
+    auto &P = ctx->p2p;
+    if (!P.ready || !P.h_err || *P.h_err == 0ull) return SWCU_OK;
+    *P.h_err = 0ull;
+    cudaMemsetAsync((unsigned long long *)P.peer[P.rank][7] + 32, 0, sizeof(unsigned long long), ctx->stream);
+    return fail(ctx, SWCU_ERR_STATE, "peer-memory exchange timed out (rank %d of %d, epoch %llu): a peer never signalled; "
+                                     "the resident pl state is not valid", P.rank, P.nranks, P.epoch);
+}
+}  // namespace swcu
 
 extern "C" int swcu_p2p_close(swcu_context *ctx)
 {
@@ -283,10 +299,13 @@ extern "C" int swcu_p2p_close(swcu_context *ctx)
                 for (int b = 0; b < SWCU_P2P_NBUF; ++b)
                     if (P.peer[r][b]) cudaIpcCloseMemHandle(P.peer[r][b]);
     }
+    const int rc = P.ready ? p2p_check_error(ctx) : SWCU_OK;
     P.ready = false;
     P.nranks = 1;
     P.rank = 0;
-    return SWCU_OK;
+    if (P.h_err) cudaFreeHost(P.h_err);
+    P.h_err = nullptr;
+    return rc;
 }
 
 extern "C" int swcu_pl_kick_drift_p2p(swcu_context *ctx, int32_t lclose, double dt, int32_t *nfail)
@@ -296,6 +315,7 @@ extern "C" int swcu_pl_kick_drift_p2p(swcu_context *ctx, int32_t lclose, double 
     if (!ctx->p2p.ready) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_kick_drift_p2p: peer buffers not imported");
     Body &pl = ctx->pl;
     if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "swcu_pl_kick_drift_p2p: pl population not resident");
+    SWCU_TRY(p2p_check_error(ctx));  // a timeout reported by an earlier step
     SWCU_TRY(kick_pl_flat(ctx, pl, lclose != 0, pl.nplm, /*reduce=*/false));
     return p2p_step_after_kick(ctx, dt, nfail);
 }

@@ -55,10 +55,8 @@ struct FlatArgs {
     // ph_u[k] of this launch's run; sizes shrink towards the end of the run (whole items ... one chunk)
     long long ph_q[6], ph_u[6];
     int ph_sz[5];
-    unsigned long long *counter;  // work counter (dynamic scheduling); in peer-memory mode ONE counter shared by all GPUs
-    unsigned long long counter_base;  // value of the counter at which this launch's first quantum sits
-    int system_scope;             // 1: the counter lives in (possibly remote) peer memory -> system-scope atomics
-    long long first_warp, total_warps;  // this launch's first global warp id and the warps of all sharers together
+    unsigned long long *counter;  // work counter of this GPU (dynamic scheduling), zeroed before every launch
+    long long total_warps;        // warps of this launch: claims 0..total_warps-1 are static (the warp's own id)
     double *fx, *fy, *fz; // zero-initialised accumulation target
     unsigned long long *redo_count;  // chunks that went through the exact path (diagnostic, may be null)
     unsigned long long *trace;  // development aid (SWCU_FLAT_TRACE): per warp {start, end} %globaltimer, items done
@@ -417,15 +415,12 @@ __global__ void __launch_bounds__(32 * FWARPS, CTAS) kick_flat_kernel(const Flat
     // Dynamic scheduling: a warp claims `quantum` consecutive items at a time from a global counter.  (A static split
     // sized to exactly one resident wave was measured to be fragile: when the tail of the previous kernel still
     // occupies an SM at launch, one CTA is left over, runs alone after the others and doubles the kernel time.)
-    // The first quantum of every warp is static (its global warp id): no claim storm on the counter at launch, which
-    // with eight GPUs sharing one counter cost ~0.1 ms.  Claimed values then map to quanta total_warps, total_warps+1, ...
-    // The claim for the NEXT quantum is issued before the current one is processed, so the round trip of the atomic
-    // (a couple of microseconds over NVLink when the counter lives on another GPU) hides behind ~15 us of arithmetic.
+    // The first quantum of every warp is static (its warp id): no claim storm on the counter at launch.  Claimed values
+    // then map to quanta total_warps, total_warps+1, ...  The claim for the NEXT quantum is issued before the current
+    // one is processed, so the round trip of the atomic hides behind the arithmetic.
     auto claim = [&]() -> unsigned long long {
         unsigned long long c = 0;
-        if (lane == 0)
-            c = (a.system_scope ? atomicAdd_system(a.counter, 1ull) : atomicAdd(a.counter, 1ull)) - a.counter_base +
-                (unsigned long long)a.total_warps;
+        if (lane == 0) c = atomicAdd(a.counter, 1ull) + (unsigned long long)a.total_warps;
         return c;  // valid in lane 0 only; broadcast when it is consumed
     };
     // Claim q covers chunk units [u0, u1) of this launch's run (4 units = the 32-column chunks of one block pair).  The
@@ -444,7 +439,7 @@ __global__ void __launch_bounds__(32 * FWARPS, CTAS) kick_flat_kernel(const Flat
         u1 = min(u0 + a.ph_sz[k], unit0 + a.ph_u[k + 1]);  // the last claim of a phase may be short
         return u0 < unit1;
     };
-    unsigned long long q = (unsigned long long)(a.first_warp + (long long)blockIdx.x * FWARPS + (threadIdx.x >> 5));
+    unsigned long long q = (unsigned long long)((long long)blockIdx.x * FWARPS + (threadIdx.x >> 5));
     unsigned long long qnext = claim();
     for (;;) {
         long long u, u_end;
@@ -644,9 +639,12 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     occ = std::max(1, occ);
     a.item0 = 0;
     a.item1 = total;
-    // NCCL mode: balanced consecutive runs of items per rank.  Peer-memory mode: all ranks claim quanta from ONE counter
-    // in rank 0's memory (system-scope atomics over NVLink), so the GPUs finish together whatever their speed.
-    const int nr = reduce ? ctx->nranks : 1, rk = reduce ? ctx->rank : 0;
+    // Several GPUs (peer-memory or NCCL mode alike): every rank owns a balanced consecutive run of items and schedules it
+    // with its OWN counter, exactly like a single GPU schedules the whole triangle.  (Round 1 let all GPUs claim from one
+    // counter in rank 0's memory over NVLink; at eight GPUs the claim traffic to one address and the ragged end cost 9 %
+    // of the gravity time, and the shared counter's epoch arithmetic was fragile -- ADVICE r1.  Identical GPUs at
+    // identical clocks finish equal shares within the same ~2 % as the warps of one GPU do.)
+    const int nr = reduce ? ctx->nranks : ctx->p2p.nranks, rk = reduce ? ctx->rank : ctx->p2p.rank;
     if (nr > 1) {  // balanced consecutive runs, like swcu_partition
         const long long q = total / nr, r = total % nr;
         a.item0 = rk * q + std::min<long long>(rk, r);
@@ -654,13 +652,12 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     }
     const long long mine = a.item1 - a.item0;
     const long long warps_max = (long long)ctx->prop.multiProcessorCount * occ * FWARPS;
-    // Items per coarse claim.  Every claim switches the resident row block (12 REDs + 20 loads + thresholds, with only
-    // three warps per SMSP to hide it): measured at npl = 1e5 with the graded end of the schedule, 1 item 7.90 ms,
-    // 2 items 7.73, 4 items 7.67, 6 items 7.65 (but slower at 7e4 bodies).  Fewer items per warp -> smaller claims.
-    const int sharers = reduce ? 1 : ctx->p2p.nranks;
+    // Items per coarse claim.  Every claim switches the resident row block (12 REDs + 16 loads, with only three warps
+    // per SMSP to hide it): measured at npl = 1e5 with the graded end of the schedule, 1 item 7.90 ms, 2 items 7.73,
+    // 4 items 7.67, 6 items 7.65 (but slower at 7e4 bodies).  Fewer items per warp -> smaller claims.
     a.quantum = 4;
-    if (mine < 32 * warps_max * sharers) a.quantum = 2;
-    if (mine < 16 * warps_max * sharers) a.quantum = 1;
+    if (mine < 32 * warps_max) a.quantum = 2;
+    if (mine < 16 * warps_max) a.quantum = 1;
     if (ctx->tune_nsplit > 0) a.quantum = ctx->tune_nsplit;
     SWCU_CUDA(ctx, ctx->scratch64.ensure(128));
     a.counter = ctx->scratch64.as<unsigned long long>() + 3;
@@ -669,22 +666,16 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         SWCU_CUDA(ctx, cudaMemsetAsync(ctx->flat_redo.p, 0, sizeof(unsigned long long), ctx->stream));
     }
     a.redo_count = ctx->flat_redo.as<unsigned long long>();  // cumulative over launches (swcu_flat_redo_count)
-    a.counter_base = 0;
-    a.system_scope = 0;
-    // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work).  The last
-    // `fine` chunks per warp (of all sharers) are handed out one 32-column chunk at a time (see the kernel's `range`).
-    // chunks per warp (of all sharers) handed out in 1-, 2-, 4- and 8-chunk claims at the end of the run.  A claim of s
-    // chunks can take ~2 s chunk-times on a warp the scheduler disfavours, so everything finer than s has to last that
-    // long: 2 s chunks per warp for size s.
+    // persistent grid: every SM filled to its occupancy (or fewer CTAs when there is little work).  The last chunks per
+    // warp are handed out in 8-, 4-, 2- and 1-chunk claims at the end of the run.  A claim of s chunks can take ~2 s
+    // chunk-times on a warp the scheduler disfavours, so everything finer than s has to last that long: 2 s chunks per
+    // warp for size s.
     static int fine[4] = {2, 4, 8, 16};
     static bool fine_read = false;
     if (!fine_read) {
         fine_read = true;
         if (const char *e = getenv("SWCU_FLAT_FINE")) sscanf(e, "%d,%d,%d,%d", &fine[0], &fine[1], &fine[2], &fine[3]);
     }
-    // Eight GPUs on one counter: the single-chunk phase would ask for ~28k claims within ~25 us (> 1 G claims/s to one
-    // address over NVLink; 0.6 G/s was measured harmless at four GPUs), so it is left out there unless overridden.
-    const bool skip_single = (sharers >= 8) && !getenv("SWCU_FLAT_FINE");
     auto split_quanta = [&](long long items, long long warps_all) -> long long {
         const long long U = items * FIB, G = (long long)a.quantum * FIB;
         long long left = U;
@@ -692,7 +683,6 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         const int sz[5] = {(int)G, 8, 4, 2, 1};
         for (int k = 4; k >= 1; --k) {  // carve the fine phases off the end of the run
             if (sz[k] >= G) continue;
-            if (k == 4 && skip_single) continue;
             long long want = std::min<long long>(left, warps_all * fine[4 - k]);
             want -= want % sz[k];
             nq[k] = want / sz[k];
@@ -712,24 +702,10 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         a.ph_u[5] = uacc;
         return qacc;
     };
-    const long long nquanta = split_quanta(mine, warps_max * sharers);
-    long long units = std::max<long long>(1, std::min<long long>(warps_max, nquanta));
-    if (!reduce && ctx->p2p.nranks > 1) {
-        // shared counter: never reset (a fast rank must not see a stale zero); every launch consumes exactly
-        // max(nquanta - total_warps, 0) successful claims + one failed claim per warp of every rank, so all ranks agree
-        // on the base of each epoch
-        units = warps_max;  // identical grids on all ranks keep that sum predictable
-        const unsigned long long per_epoch = (unsigned long long)std::max<long long>(nquanta, units * ctx->p2p.nranks);
-        a.counter = reinterpret_cast<unsigned long long *>(ctx->p2p.peer[0][7]) + 40;
-        a.counter_base = ctx->p2p.epoch * per_epoch;  // epoch counts completed steps (incremented after the kick)
-        a.system_scope = 1;
-        a.first_warp = units * ctx->p2p.rank;
-        a.total_warps = units * ctx->p2p.nranks;
-    } else {
-        a.first_warp = 0;
-        a.total_warps = units;
-        SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
-    }
+    const long long nquanta = split_quanta(mine, warps_max);
+    const long long units = std::max<long long>(1, std::min<long long>(warps_max, nquanta));
+    a.total_warps = units;
+    SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
     const int grid = cdiv(units, FWARPS);
     a.trace = nullptr;
     static const char *trace_path = getenv("SWCU_FLAT_TRACE");
@@ -745,7 +721,9 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
         std::vector<unsigned long long> h((size_t)4 * grid * FWARPS);
         SWCU_CUDA(ctx, cudaMemcpyAsync(h.data(), trace_buf.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
         SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (FILE *f = fopen(trace_path, "wb")) {
+        std::string path = trace_path;
+        if (nr > 1) path += ".rank" + std::to_string(rk);
+        if (FILE *f = fopen(path.c_str(), "wb")) {
             fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
             fclose(f);
         }

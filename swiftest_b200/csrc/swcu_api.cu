@@ -205,7 +205,7 @@ extern "C" int swcu_synchronize(swcu_context *ctx)
 {
     SWCU_TRY(check_ctx(ctx));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SWCU_OK;
+    return p2p_check_error(ctx);  // reports a peer-memory exchange that timed out since the last check
 }
 
 extern "C" int swcu_device_info(swcu_context *ctx, int32_t *sm_count, int32_t *cc, int64_t *mem_bytes)
@@ -281,6 +281,10 @@ extern "C" int swcu_kick_getacch_int_all_flat_pl(swcu_context *ctx, int32_t npl,
         SWCU_TRY(download_vec3(ctx, acc, npl, 1, b.ax, b.ay, b.az));
     } else {
         // explicit pair table: ahi/ahj accumulate from zero, then acc = acc + (ahi + ahj) (kick.f90:92-112)
+        for (int64_t k = 0; k < nplpl; ++k)  // the reference trusts its own table; a foreign caller gets a checked error
+            if (k_plpl[2 * k] < 1 || k_plpl[2 * k] > npl || k_plpl[2 * k + 1] < 1 || k_plpl[2 * k + 1] > npl)
+                return fail(ctx, SWCU_ERR_ARG, "flat_pl: k_plpl(:,%lld) = (%d,%d) out of range 1..%d", (long long)k + 1,
+                            k_plpl[2 * k], k_plpl[2 * k + 1], npl);
         SWCU_CUDA(ctx, ctx->istage[0].ensure(sizeof(int32_t) * 2 * (size_t)nplpl));
         SWCU_CUDA(ctx, ctx->istage[1].ensure(sizeof(int32_t) * 2 * (size_t)nplpl));
         // de-interleave k_plpl(2,nplpl) on the host side of the copy: two strided copies
@@ -309,6 +313,10 @@ extern "C" int swcu_symba_kick_subtract_encounters(swcu_context *ctx, int32_t np
     SWCU_TRY(check_ctx(ctx));
     if (npl <= 0 || nenc <= 0) return SWCU_OK;  // symba_kick.f90:54,59
     if (!index1 || !index2 || !rh || !Gmass || !radius || !ah) return fail(ctx, SWCU_ERR_ARG, "symba subtract: null array");
+    for (int64_t k = 0; k < nenc; ++k)
+        if (index1[k] < 1 || index1[k] > npl || index2[k] < 1 || index2[k] > npl)
+            return fail(ctx, SWCU_ERR_ARG, "symba subtract: pair %lld = (%d,%d) out of range 1..%d", (long long)k + 1,
+                        index1[k], index2[k], npl);
     Body &b = ctx->s_pl;
     SWCU_TRY(ensure_body(ctx, b, npl));
     b.n = npl;
@@ -464,6 +472,11 @@ extern "C" int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_
     Body &b = body_of(ctx, kind);
     if (kind == SWCU_PL && (nplm < 0 || nplm > n)) return fail(ctx, SWCU_ERR_ARG, "body_sync: bad nplm=%d (npl=%d)", nplm, n);
     if (b.valid && b.generation == generation && b.n == n) return SWCU_OK;  // nothing changed on the host side
+    // Peers hold CUDA-IPC mappings of the pl arrays and of F (sized by n): a population of another size would leave them
+    // pointing at freed or too-short allocations.  The caller closes the mapping, re-syncs and exports/imports again.
+    if (kind == SWCU_PL && ctx->p2p.ready && n != b.n)
+        return fail(ctx, SWCU_ERR_STATE, "body_sync: npl changes %d -> %d while peer buffers are mapped; call swcu_p2p_close, "
+                                         "sync, then swcu_p2p_export/import again", b.n, n);
     SWCU_TRY(ensure_body(ctx, b, n));
     b.helio_ready = false;  // vb, rbeg, rend are re-derived after a re-upload
     b.n = n;
@@ -514,7 +527,53 @@ extern "C" int swcu_body_get(swcu_context *ctx, int32_t kind, double *r, double 
     if (iflag && b.n > 0)
         SWCU_CUDA(ctx, cudaMemcpyAsync(iflag, b.iflag.p, sizeof(int32_t) * (size_t)b.n, cudaMemcpyDeviceToHost, ctx->stream));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return p2p_check_error(ctx);
+}
+
+// slice forms: the host arrays hold bodies [i0, i1) only (3*(i1-i0) doubles each)
+extern "C" int swcu_body_put_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, const double *r, const double *v)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_put_range: population not resident");
+    if (i0 < 0 || i1 < i0 || i1 > b.n) return fail(ctx, SWCU_ERR_ARG, "body_put_range: bad range [%d,%d) of %d", i0, i1, b.n);
+    const int m = i1 - i0;
+    if (m == 0) return SWCU_OK;
+    const size_t bytes = sizeof(double) * 3 * (size_t)m;
+    const double *src[2] = {r, v};
+    double *dst[2][3] = {{b.rx.as<double>(), b.ry.as<double>(), b.rz.as<double>()},
+                         {b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>()}};
+    for (int k = 0; k < 2; ++k) {
+        if (!src[k]) continue;
+        SWCU_CUDA(ctx, ctx->stage[k].ensure(bytes));
+        SWCU_CUDA(ctx, cudaMemcpyAsync(ctx->stage[k].p, src[k], bytes, cudaMemcpyHostToDevice, ctx->stream));
+        SWCU_TRY(aos_to_soa3(ctx, ctx->stage[k].as<double>(), dst[k][0] + i0, dst[k][1] + i0, dst[k][2] + i0, m));
+    }
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return SWCU_OK;
+}
+
+extern "C" int swcu_body_get_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, double *r, double *v, double *a)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_get_range: population not resident");
+    if (i0 < 0 || i1 < i0 || i1 > b.n) return fail(ctx, SWCU_ERR_ARG, "body_get_range: bad range [%d,%d) of %d", i0, i1, b.n);
+    const int m = i1 - i0;
+    if (m == 0) return SWCU_OK;
+    const size_t bytes = sizeof(double) * 3 * (size_t)m;
+    double *dsth[3] = {r, v, a};
+    const double *srcd[3][3] = {{b.rx.as<double>(), b.ry.as<double>(), b.rz.as<double>()},
+                                {b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>()},
+                                {b.ax.as<double>(), b.ay.as<double>(), b.az.as<double>()}};
+    for (int k = 0; k < 3; ++k) {
+        if (!dsth[k]) continue;
+        SWCU_CUDA(ctx, ctx->stage[k].ensure(bytes));
+        SWCU_TRY(soa_to_aos3(ctx, srcd[k][0] + i0, srcd[k][1] + i0, srcd[k][2] + i0, ctx->stage[k].as<double>(), m));
+        SWCU_CUDA(ctx, cudaMemcpyAsync(dsth[k], ctx->stage[k].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return p2p_check_error(ctx);
 }
 
 extern "C" int swcu_body_count(swcu_context *ctx, int32_t kind, int32_t *n, int32_t *nplm, uint64_t *generation)
@@ -1000,6 +1059,50 @@ extern "C" int swcu_timer_stop(swcu_context *ctx, double *elapsed_ms)
     SWCU_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (elapsed_ms) *elapsed_ms = ms;
     return SWCU_OK;
+}
+
+// Laps: an event pair per bracketed region, logged without synchronising; swcu_timer_laps sums them.  bench.py times
+// the K steps of a run this way with the L2 flush BETWEEN the laps.
+extern "C" int swcu_timer_lap_begin(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (ctx->lap_used >= ctx->lap0.size()) {
+        cudaEvent_t a, b;
+        SWCU_CUDA(ctx, cudaEventCreate(&a));
+        SWCU_CUDA(ctx, cudaEventCreate(&b));
+        ctx->lap0.push_back(a);
+        ctx->lap1.push_back(b);
+    }
+    SWCU_CUDA(ctx, cudaEventRecord(ctx->lap0[ctx->lap_used], ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_timer_lap_end(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (ctx->lap_used >= ctx->lap0.size()) return fail(ctx, SWCU_ERR_STATE, "timer_lap_end without timer_lap_begin");
+    SWCU_CUDA(ctx, cudaEventRecord(ctx->lap1[ctx->lap_used], ctx->stream));
+    ctx->lap_used++;
+    return SWCU_OK;
+}
+
+// total (and optionally every lap) in ms since the last call; synchronises the stream and clears the log
+extern "C" int swcu_timer_laps(swcu_context *ctx, double *total_ms, int32_t *count, double *each_ms, int32_t each_cap)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!total_ms) return SWCU_ERR_ARG;
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    double sum = 0.0;
+    for (size_t k = 0; k < ctx->lap_used; ++k) {
+        float t = 0.f;
+        SWCU_CUDA(ctx, cudaEventElapsedTime(&t, ctx->lap0[k], ctx->lap1[k]));
+        sum += t;
+        if (each_ms && (int32_t)k < each_cap) each_ms[k] = t;
+    }
+    *total_ms = sum;
+    if (count) *count = (int32_t)ctx->lap_used;
+    ctx->lap_used = 0;
+    return p2p_check_error(ctx);
 }
 
 extern "C" int swcu_enable_kernel_timing(swcu_context *ctx, int32_t on)

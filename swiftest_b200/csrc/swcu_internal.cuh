@@ -120,6 +120,8 @@ struct swcu_context {
     size_t fam_log_used[swcu::FAM_COUNT] = {};
 
     swcu::DevBuf flush;
+    std::vector<cudaEvent_t> lap0, lap1;  // swcu_timer_lap_begin/_end
+    size_t lap_used = 0;
 
     // central-body scalars of the integrator glue, on the device (step_kernels.cu): doubles
     // [0..3] raw sums of the last reduction, [4..6] vbcb, [8..10] ptbeg, [12..14] ptend, [16] GMtot, [20..27] energy sums
@@ -144,6 +146,7 @@ struct swcu_context {
         swcu::DevBuf F, flags;          // local: partial accelerations [3][stride]; flags [2][16] u64 + error word
         void *peer[8][SWCU_P2P_NBUF];   // mapped pointers of every rank's exported buffers (own rank: local pointers)
         unsigned long long epoch = 0;
+        unsigned long long *h_err = nullptr;  // pinned host copy of the error word flags[32], refreshed after every step
     } p2p;
 
     // tuning overrides (environment: SWCU_KICK_IB, SWCU_KICK_NSPLIT, SWCU_KICK_VARIANT)
@@ -285,6 +288,7 @@ int symba_check_list(swcu_context *ctx, int64_t nenc, const int32_t *d_i1, const
 int comm_allgather_pl(swcu_context *ctx, int with_v);
 int comm_allreduce_sum(swcu_context *ctx, double *buf, size_t count);
 int p2p_step_after_kick(swcu_context *ctx, double dt, int32_t *nfail);  // drift_kernels.cu
+int p2p_check_error(swcu_context *ctx);  // comm.cu: SWCU_ERR_STATE if a peer-memory exchange timed out (clears the word)
 void comm_release(swcu_context *ctx);
 
 }  // namespace swcu

@@ -23,6 +23,26 @@ def test_reference_arm_prints_one_json_line():
     assert "workload" in d["config"] and "model" not in d["config"]
 
 
+def test_reference_arm_ignores_torchrun_thread_limit_and_times_whole_steps():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers (the reference arm ran single-threaded at N > 1):
+    the arm sets its thread count from the CPU affinity set, and nothing in its line is extrapolated."""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2")
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--npl", "2000",
+                                   "--steps", "1", "--warmup", "0", "--gpus", "2"], text=True, cwd=ROOT, env=env)
+    d = json.loads([l for l in out.strip().splitlines() if l.startswith("{")][0])
+    assert d["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert "all 2000 rows" in d["cpu_baseline"]["sample"] and "nothing extrapolated" in d["cpu_baseline"]["sample"]
+    assert d["n_gpus"] == 2
+
+
+def test_both_arms_print_the_same_config():
+    import bench
+    ours = bench.common_config(100000)
+    assert ours["workload"] == "symba_disk_npl100000_fully_interacting" and "model" not in ours
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": common_config(n)') == 2      # the reference line and our line
+
+
 def test_reference_arm_other_ranks_print_nothing():
     env = dict(os.environ, RANK="1", WORLD_SIZE="2")
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--npl", "2000",

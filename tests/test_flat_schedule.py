@@ -113,11 +113,32 @@ def test_graded_schedule_tiles_the_run_exactly():
             assert all((unit0 + i * G) % FIB == 0 for i in range(n_coarse))
 
 
-def test_shared_counter_accounting():
-    """Peer-memory mode: the counter is never reset; an epoch consumes max(nquanta - W, 0) successful dynamic claims
-    plus one failed claim per warp, W = warps of all ranks (the first claim of every warp is static)."""
-    for items, warps in ((38269 * 8, 14208), (100, 14208), (306153, 3552)):
-        _, _, _, nquanta = split_quanta(items, warps, 2)
-        successful = max(nquanta - warps, 0)
-        per_epoch = max(nquanta, warps)
-        assert successful + warps == per_epoch
+def rank_runs(total, nranks):
+    """kick_pl_flat: balanced consecutive runs of items per rank (the shape of swcu_partition)."""
+    q, r = divmod(total, nranks)
+    out = []
+    for rk in range(nranks):
+        i0 = rk * q + min(rk, r)
+        out.append((i0, i0 + q + (1 if rk < r else 0)))
+    return out
+
+
+def test_rank_runs_tile_the_items_and_every_rank_schedules_its_own_run():
+    """Several GPUs: every rank owns a consecutive run of items and hands it out with its OWN counter (no shared
+    counter over NVLink any more); the runs tile [0, total) with sizes within one item, and the graded schedule of every
+    run covers exactly that run."""
+    for total, nranks in ((306153, 8), (306153, 4), (306153, 2), (7, 8), (8, 8), (100, 3), (1, 2)):
+        runs = rank_runs(total, nranks)
+        assert runs[0][0] == 0 and runs[-1][1] == total
+        assert all(a[1] == b[0] for a, b in zip(runs, runs[1:]))
+        sizes = [b - a for a, b in runs]
+        assert max(sizes) - min(sizes) <= 1
+        for i0, i1 in runs:
+            items = i1 - i0
+            ph_q, ph_u, sz, nquanta = split_quanta(items, 1776, 4 if items >= 32 * 1776 else (2 if items >= 16 * 1776 else 1))
+            cursor = i0 * FIB
+            for q in range(nquanta):
+                r = claim_range(q, ph_q, ph_u, sz, i0 * FIB, i1 * FIB)
+                assert r is not None and r[0] == cursor
+                cursor = r[1]
+            assert cursor == i1 * FIB

@@ -53,6 +53,21 @@ def _worker(rank, world, port, n, out):
         assert c.pl_kick_drift_p2p(dt, True) == 0
     g = c.body_get(PL)
     res["p2p_r"], res["p2p_v"] = g["r"], g["v"]
+    # slice forms: a rank refreshes / reads only its own bodies
+    i0, i1 = shard.partition(n, world, rank)
+    sl = c.body_get_range(PL, i0, i1)
+    assert np.array_equal(sl["r"], g["r"][i0:i1]) and np.array_equal(sl["v"], g["v"][i0:i1])
+    c.body_put_range(PL, i0, i1, r=d["rh"][i0:i1], v=d["vh"][i0:i1])
+    back = c.body_get(PL, a=False)
+    assert np.array_equal(back["r"][i0:i1], d["rh"][i0:i1]) and np.array_equal(back["v"][i0:i1], d["vh"][i0:i1])
+    if i0 > 0:
+        assert np.array_equal(back["r"][:i0], g["r"][:i0])
+    # a population of another size must not slip under live peer mappings (they would dangle)
+    try:
+        c.body_sync(PL, n - 1, nplm=n - 1, r=d["rh"][:-1], v=d["vh"][:-1], Gmass=d["Gmass"][:-1], generation=778)
+        raise AssertionError("body_sync with another npl was accepted while peer buffers are mapped")
+    except Exception as e:
+        assert "peer buffers are mapped" in str(e), e
     dist.barrier()
     c.p2p_close()
     gathered = [None] * world
@@ -68,12 +83,13 @@ def _worker(rank, world, port, n, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.timeout(600)
-def test_two_gpu_slices_and_pair_slices_match_oracle(tmp_path, oracle):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_slices_and_pair_slices_match_oracle(tmp_path, oracle, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     from swiftest_b200 import workloads as W
-    n, world = 5003, 2
+    n = 5003
     out = str(tmp_path / "res.npz")
     port = 29600 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, n, out), nprocs=world, join=True)
