@@ -189,6 +189,24 @@ module swiftest_cuda
          integer(c_int), value :: kind, i0, i1
          type(c_ptr), value :: r, v, a
       end function
+      !! asynchronous slice forms (page-locked arrays, e.g. allocated with cudaHostAlloc through iso_c_binding or
+      !! registered with cudaHostRegister); complete after swcu_io_wait
+      integer(c_int) function swcu_body_put_range_async(ctx, kind, i0, i1, r, v) bind(C, name="swcu_body_put_range_async")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, i0, i1
+         type(c_ptr), value :: r, v
+      end function
+      integer(c_int) function swcu_body_get_range_async(ctx, kind, i0, i1, r, v, a) bind(C, name="swcu_body_get_range_async")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind, i0, i1
+         type(c_ptr), value :: r, v, a
+      end function
+      integer(c_int) function swcu_io_wait(ctx) bind(C, name="swcu_io_wait")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
       !! whm_step_tp in one kernel (whm/whm_step.f90:72-100); ah0 = whm_kick_getacch_ah0 at the end-of-step planets
       integer(c_int) function swcu_whm_tp_step(ctx, dt, ah0, nfail) bind(C, name="swcu_whm_tp_step")
          import :: c_int, c_ptr, c_double
@@ -562,6 +580,27 @@ module swiftest_cuda
    end interface
 
 contains
+
+   subroutine swcu_ensure_ctx()
+      !! One context per process (per coarray image: device = this_image() - 1), created at the first call of any
+      !! replacement body and kept for the run.  Without an sm_100 GPU swcu_create fails and the run stops: there is no
+      !! CPU fallback behind USE_CUDA.
+      integer(c_int) :: device
+      if (c_associated(swcu_ctx)) return
+      device = 0_c_int
+#ifdef COARRAY
+      device = int(this_image() - 1, c_int)
+#endif
+      call swcu_check(swcu_create(device, swcu_ctx), "swcu_create")
+   end subroutine swcu_ensure_ctx
+
+   subroutine swcu_finalize()
+      !! Called once from the driver's shutdown path (optional: the process exit releases the device as well)
+      integer(c_int) :: status
+      if (.not. c_associated(swcu_ctx)) return
+      status = swcu_destroy(swcu_ctx)
+      swcu_ctx = c_null_ptr
+   end subroutine swcu_finalize
 
    subroutine swcu_check(status, where)
       !! Maps a nonzero status to the reference's fatal-error convention (base_util_exit(FAILURE), base_module.f90:589)

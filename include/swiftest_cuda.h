@@ -139,6 +139,13 @@ int swcu_body_get(swcu_context *ctx, int32_t kind, double *r, double *v, double 
  * of a multi-GPU run exchanges with its host (the coarray images of swiftest_coarray.f90:705-711 own slices too) */
 int swcu_body_put_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, const double *r, const double *v);
 int swcu_body_get_range(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, double *r, double *v, double *a);
+/* asynchronous forms for page-locked host arrays: the calls only enqueue -- PCIe copies on the library's copy streams
+ * (they overlap the kernels of the compute stream), the AoS<->SoA kernels on the compute stream in call order, staging
+ * double-buffered.  A put issued after step k is enqueued overlaps step k; a get issued after step k copies out while
+ * step k+1 runs.  Host arrays must stay valid (puts: unchanged) until swcu_io_wait or swcu_synchronize returns. */
+int swcu_body_put_range_async(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, const double *r, const double *v);
+int swcu_body_get_range_async(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, double *r, double *v, double *a);
+int swcu_io_wait(swcu_context *ctx);
 int swcu_body_count(swcu_context *ctx, int32_t kind, int32_t *n, int32_t *nplm, uint64_t *generation);
 
 /* ah = 0 (helio_kick_vb_pl zeroes ah before accel, helio_kick.f90:113) */

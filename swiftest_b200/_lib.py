@@ -57,6 +57,9 @@ def load():
         "swcu_body_get": [p, i32, p, p, p, p],
         "swcu_body_put_range": [p, i32, i32, i32, p, p],
         "swcu_body_get_range": [p, i32, i32, i32, p, p, p],
+        "swcu_body_put_range_async": [p, i32, i32, i32, p, p],
+        "swcu_body_get_range_async": [p, i32, i32, i32, p, p, p],
+        "swcu_io_wait": [p],
         "swcu_body_count": [p, i32, p, p, p],
         "swcu_body_zero_accel": [p, i32],
         "swcu_pl_accel_int": [p, i32, i32],

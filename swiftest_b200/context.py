@@ -218,6 +218,24 @@ class Context:
                                              _ptr(res.get("a"))))
         return res
 
+    def body_put_range_async(self, kind, i0, i1, r=None, v=None):
+        """Enqueue the refresh of bodies [i0, i1) from PINNED host arrays (kept alive by the caller until io_wait)."""
+        for q in (r, v):
+            if q is not None and not (q.dtype == _f64 and q.flags.c_contiguous and q.shape == (i1 - i0, 3)):
+                raise ValueError("async arrays must be C-contiguous float64 of shape (i1-i0, 3)")
+        self._ck(self._L.swcu_body_put_range_async(self._h, kind, int(i0), int(i1), _ptr(r), _ptr(v)))
+
+    def body_get_range_async(self, kind, i0, i1, out):
+        """Enqueue the read-back of bodies [i0, i1) into the PINNED arrays out['r'|'v'|'a'] (defined after io_wait)."""
+        for q in out.values():
+            if not (q.dtype == _f64 and q.flags.c_contiguous and q.shape == (i1 - i0, 3)):
+                raise ValueError("async arrays must be C-contiguous float64 of shape (i1-i0, 3)")
+        self._ck(self._L.swcu_body_get_range_async(self._h, kind, int(i0), int(i1), _ptr(out.get("r")), _ptr(out.get("v")),
+                                                   _ptr(out.get("a"))))
+
+    def io_wait(self):
+        self._ck(self._L.swcu_io_wait(self._h))
+
     def body_count(self, kind):
         n, nplm, gen = C.c_int32(), C.c_int32(), C.c_uint64()
         self._ck(self._L.swcu_body_count(self._h, kind, C.byref(n), C.byref(nplm), C.byref(gen)))

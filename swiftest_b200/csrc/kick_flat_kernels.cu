@@ -644,7 +644,14 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     // counter in rank 0's memory over NVLink; at eight GPUs the claim traffic to one address and the ragged end cost 9 %
     // of the gravity time, and the shared counter's epoch arithmetic was fragile -- ADVICE r1.  Identical GPUs at
     // identical clocks finish equal shares within the same ~2 % as the warps of one GPU do.)
-    const int nr = reduce ? ctx->nranks : ctx->p2p.nranks, rk = reduce ? ctx->rank : ctx->p2p.rank;
+    int nr = reduce ? ctx->nranks : ctx->p2p.nranks, rk = reduce ? ctx->rank : ctx->p2p.rank;
+    // development aid: time the share one of SWCU_FLAT_EMULATE_RANKS ranks would get on a single GPU (the result is
+    // then incomplete, only the launch time means something; the kernel has no cross-GPU interaction any more)
+    static const int emulate = getenv("SWCU_FLAT_EMULATE_RANKS") ? atoi(getenv("SWCU_FLAT_EMULATE_RANKS")) : 0;
+    if (nr == 1 && emulate > 1) {
+        nr = emulate;
+        rk = emulate / 2;
+    }
     if (nr > 1) {  // balanced consecutive runs, like swcu_partition
         const long long q = total / nr, r = total % nr;
         a.item0 = rk * q + std::min<long long>(rk, r);

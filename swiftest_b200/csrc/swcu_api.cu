@@ -167,6 +167,19 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     ctx->sumbuf.release();
     for (auto &b : ctx->lists) b.release();
     ctx->flat_trace.release();
+    if (ctx->aio.ready) {
+        cudaStreamDestroy(ctx->aio.h2d);
+        cudaStreamDestroy(ctx->aio.d2h);
+        for (int b = 0; b < 2; ++b) {
+            cudaEventDestroy(ctx->aio.h2d_done[b]);
+            cudaEventDestroy(ctx->aio.unpacked[b]);
+            cudaEventDestroy(ctx->aio.packed[b]);
+            cudaEventDestroy(ctx->aio.d2h_done[b]);
+            ctx->aio.in[b].release();
+            ctx->aio.out[b].release();
+        }
+        ctx->aio.ready = false;
+    }
     ctx->flat_blockrad.release();
     ctx->flat_redo.release();
     ctx->sendbuf.release();
@@ -573,6 +586,107 @@ extern "C" int swcu_body_get_range(swcu_context *ctx, int32_t kind, int32_t i0, 
         SWCU_CUDA(ctx, cudaMemcpyAsync(dsth[k], ctx->stage[k].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     }
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return p2p_check_error(ctx);
+}
+
+// ---- asynchronous slice I/O: the PCIe copies run on their own streams and overlap the compute stream's kernels ----
+static int aio_setup(swcu_context *ctx)
+{
+    auto &A = ctx->aio;
+    if (A.ready) return SWCU_OK;
+    SWCU_CUDA(ctx, cudaStreamCreateWithFlags(&A.h2d, cudaStreamNonBlocking));
+    SWCU_CUDA(ctx, cudaStreamCreateWithFlags(&A.d2h, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        SWCU_CUDA(ctx, cudaEventCreateWithFlags(&A.h2d_done[b], cudaEventDisableTiming));
+        SWCU_CUDA(ctx, cudaEventCreateWithFlags(&A.unpacked[b], cudaEventDisableTiming));
+        SWCU_CUDA(ctx, cudaEventCreateWithFlags(&A.packed[b], cudaEventDisableTiming));
+        SWCU_CUDA(ctx, cudaEventCreateWithFlags(&A.d2h_done[b], cudaEventDisableTiming));
+    }
+    A.ready = true;
+    return SWCU_OK;
+}
+
+// Enqueue only: the H2D copies go to the copy stream (they overlap whatever the compute stream is running), the
+// transposing kernels to the compute stream behind everything queued so far.  r, v must be page-locked and stay
+// unchanged until swcu_io_wait / swcu_synchronize.
+extern "C" int swcu_body_put_range_async(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, const double *r,
+                                         const double *v)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_put_range_async: population not resident");
+    if (i0 < 0 || i1 < i0 || i1 > b.n) return fail(ctx, SWCU_ERR_ARG, "body_put_range_async: bad range [%d,%d) of %d", i0, i1, b.n);
+    const int m = i1 - i0;
+    if (m == 0 || (!r && !v)) return SWCU_OK;
+    SWCU_TRY(aio_setup(ctx));
+    auto &A = ctx->aio;
+    const int k = (int)(A.put_seq++ & 1);
+    const size_t bytes = sizeof(double) * 3 * (size_t)m;
+    if (A.in[k].cap < 2 * bytes + 256) {  // (re)allocation: nothing may still be using the old buffer
+        SWCU_CUDA(ctx, cudaStreamSynchronize(A.h2d));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SWCU_CUDA(ctx, A.in[k].ensure(2 * bytes));
+    }
+    SWCU_CUDA(ctx, cudaStreamWaitEvent(A.h2d, A.unpacked[k], 0));  // the previous contents of this buffer were consumed
+    double *st = A.in[k].as<double>();
+    if (r) SWCU_CUDA(ctx, cudaMemcpyAsync(st, r, bytes, cudaMemcpyHostToDevice, A.h2d));
+    if (v) SWCU_CUDA(ctx, cudaMemcpyAsync(st + 3 * (size_t)m, v, bytes, cudaMemcpyHostToDevice, A.h2d));
+    SWCU_CUDA(ctx, cudaEventRecord(A.h2d_done[k], A.h2d));
+    SWCU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, A.h2d_done[k], 0));
+    if (r) SWCU_TRY(aos_to_soa3(ctx, st, b.rx.as<double>() + i0, b.ry.as<double>() + i0, b.rz.as<double>() + i0, m));
+    if (v) SWCU_TRY(aos_to_soa3(ctx, st + 3 * (size_t)m, b.vx.as<double>() + i0, b.vy.as<double>() + i0, b.vz.as<double>() + i0, m));
+    SWCU_CUDA(ctx, cudaEventRecord(A.unpacked[k], ctx->stream));
+    return SWCU_OK;
+}
+
+// Enqueue only: the transposing kernels run on the compute stream where the call is made (after the step that produced
+// the values), the D2H copies on the copy stream behind them.  r, v, a must be page-locked; their contents are defined
+// after swcu_io_wait / swcu_synchronize.
+extern "C" int swcu_body_get_range_async(swcu_context *ctx, int32_t kind, int32_t i0, int32_t i1, double *r, double *v,
+                                         double *a)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_get_range_async: population not resident");
+    if (i0 < 0 || i1 < i0 || i1 > b.n) return fail(ctx, SWCU_ERR_ARG, "body_get_range_async: bad range [%d,%d) of %d", i0, i1, b.n);
+    const int m = i1 - i0;
+    if (m == 0 || (!r && !v && !a)) return SWCU_OK;
+    SWCU_TRY(aio_setup(ctx));
+    auto &A = ctx->aio;
+    const int k = (int)(A.get_seq++ & 1);
+    const size_t bytes = sizeof(double) * 3 * (size_t)m;
+    if (A.out[k].cap < 3 * bytes + 256) {
+        SWCU_CUDA(ctx, cudaStreamSynchronize(A.d2h));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SWCU_CUDA(ctx, A.out[k].ensure(3 * bytes));
+    }
+    SWCU_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, A.d2h_done[k], 0));  // the previous copy out of this buffer is done
+    double *st = A.out[k].as<double>();
+    double *dsth[3] = {r, v, a};
+    const double *srcd[3][3] = {{b.rx.as<double>(), b.ry.as<double>(), b.rz.as<double>()},
+                                {b.vx.as<double>(), b.vy.as<double>(), b.vz.as<double>()},
+                                {b.ax.as<double>(), b.ay.as<double>(), b.az.as<double>()}};
+    for (int q = 0; q < 3; ++q)
+        if (dsth[q]) SWCU_TRY(soa_to_aos3(ctx, srcd[q][0] + i0, srcd[q][1] + i0, srcd[q][2] + i0, st + 3 * (size_t)m * q, m));
+    SWCU_CUDA(ctx, cudaEventRecord(A.packed[k], ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamWaitEvent(A.d2h, A.packed[k], 0));
+    for (int q = 0; q < 3; ++q)
+        if (dsth[q]) SWCU_CUDA(ctx, cudaMemcpyAsync(dsth[q], st + 3 * (size_t)m * q, bytes, cudaMemcpyDeviceToHost, A.d2h));
+    SWCU_CUDA(ctx, cudaEventRecord(A.d2h_done[k], A.d2h));
+    return SWCU_OK;
+}
+
+// all asynchronous transfers issued so far are complete (host buffers of the gets are filled, of the puts reusable)
+extern "C" int swcu_io_wait(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (ctx->aio.ready) {
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->aio.h2d));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->aio.d2h));
+    } else {
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return p2p_check_error(ctx);
 }
 

@@ -120,6 +120,15 @@ struct swcu_context {
     size_t fam_log_used[swcu::FAM_COUNT] = {};
 
     swcu::DevBuf flush;
+    // asynchronous slice I/O (swcu_body_put_range_async / _get_range_async): dedicated copy streams, double-buffered
+    // AoS staging, events that order copy stream <-> compute stream
+    struct AsyncIO {
+        cudaStream_t h2d = nullptr, d2h = nullptr;
+        swcu::DevBuf in[2], out[2];
+        cudaEvent_t h2d_done[2] = {}, unpacked[2] = {}, packed[2] = {}, d2h_done[2] = {};
+        unsigned long long put_seq = 0, get_seq = 0;
+        bool ready = false;
+    } aio;
     std::vector<cudaEvent_t> lap0, lap1;  // swcu_timer_lap_begin/_end
     size_t lap_used = 0;
 

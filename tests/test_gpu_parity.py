@@ -607,6 +607,39 @@ def test_helio_integration_tracks_oracle_run(ctx, oracle):
 
 
 # ---------------------------------------------------------------------------------------------- error behaviour
+def test_slice_put_get_blocking_and_async(ctx):
+    """swcu_body_put_range / _get_range and their asynchronous forms (copy streams, double-buffered staging): a slice
+    round-trips bit for bit, bodies outside it are untouched, and back-to-back async calls keep their order."""
+    import torch
+    n = 5000
+    d = W.disk(n, seed=71)
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"], mu=d["mu"],
+                  generation=7101)
+    i0, i1 = 1234, 4321
+    rng = np.random.default_rng(1)
+    r1, v1 = rng.normal(size=(i1 - i0, 3)), rng.normal(size=(i1 - i0, 3))
+    ctx.body_put_range(PL, i0, i1, r=r1, v=v1)
+    g = ctx.body_get(PL, a=False)
+    assert np.array_equal(g["r"][i0:i1], r1) and np.array_equal(g["v"][i0:i1], v1)
+    assert np.array_equal(g["r"][:i0], d["rh"][:i0]) and np.array_equal(g["v"][i1:], d["vh"][i1:])
+    sl = ctx.body_get_range(PL, i0, i1)
+    assert np.array_equal(sl["r"], r1) and np.array_equal(sl["v"], v1) and sl["a"].shape == (i1 - i0, 3)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    ins = [(pin(rng.normal(size=(i1 - i0, 3))), pin(rng.normal(size=(i1 - i0, 3)))) for _ in range(5)]
+    outs = [{k: pin(np.zeros((i1 - i0, 3))) for k in ("r", "v", "a")} for _ in range(5)]
+    for (r, v), o in zip(ins, outs):      # five put/get pairs in flight, no host synchronisation in between
+        ctx.body_put_range_async(PL, i0, i1, r=r, v=v)
+        ctx.body_get_range_async(PL, i0, i1, o)
+    ctx.io_wait()
+    for (r, v), o in zip(ins, outs):
+        assert np.array_equal(o["r"], r) and np.array_equal(o["v"], v)
+    g = ctx.body_get(PL, a=False)
+    assert np.array_equal(g["r"][i0:i1], ins[-1][0]) and np.array_equal(g["r"][:i0], d["rh"][:i0])
+    from swiftest_b200 import SwcuError
+    with pytest.raises(SwcuError):
+        ctx.body_put_range(PL, 10, n + 1, r=np.zeros((n - 9, 3)))
+
+
 def test_error_paths_return_status_and_message(ctx):
     """The reference's conventions: early returns for empty populations, fatal status for inconsistent calls."""
     from swiftest_b200 import Context, SwcuError
