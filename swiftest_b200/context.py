@@ -276,10 +276,27 @@ class Context:
     def whm_tp_step(self, dt, ah0, want_nfail=True):
         """Fused whm_step_tp on the resident test particles (kick dt/2 with the kept ah, drift dt, new ah at the resident
         planets' positions + ah0, kick dt/2).  Returns the number of particles whose drift failed."""
-        ah0 = _vec(ah0, 3, name="ah0")
+        ah0 = None if ah0 is None else _vec(ah0, 3, name="ah0")   # None: the value whm_step_pl left on the device
         nf = C.c_int32()
         self._ck(self._L.swcu_whm_tp_step(self._h, float(dt), _ptr(ah0), C.byref(nf) if want_nfail else None))
         return nf.value
+
+    def whm_step_pl(self, GMcb, dt, loop_variant=LOOP_AUTO, lclose=True, lfirst=False, want_nfail=True):
+        """whm_step_pl on the resident planets (Jacobi chains, ah0+ah1+ah2+accel_int, kick, drift, kick)."""
+        nf = C.c_int32()
+        self._ck(self._L.swcu_whm_step_pl(self._h, float(GMcb), float(dt), loop_variant, int(bool(lclose)), int(bool(lfirst)),
+                                          C.byref(nf) if want_nfail else None))
+        return nf.value
+
+    def whm_tp_first_accel(self):
+        """ah of the resident test particles for their first WHM step (planets at their current = begin positions)."""
+        self._ck(self._L.swcu_whm_tp_first_accel(self._h))
+
+    def whm_get_jacobi(self):
+        n = self.body_count(PL)[0]
+        xj, vj = np.empty((n, 3), _f64), np.empty((n, 3), _f64)
+        self._ck(self._L.swcu_whm_get_jacobi(self._h, _ptr(xj), _ptr(vj)))
+        return xj, vj
 
     def body_kick_velocity(self, kind, dt):
         self._ck(self._L.swcu_body_kick_velocity(self._h, kind, float(dt)))

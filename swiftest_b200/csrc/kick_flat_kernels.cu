@@ -43,7 +43,7 @@ constexpr int FWARPS = 4;       // warps (independent work units) per CTA
 
 struct FlatArgs {
     const double *x, *y, *z, *gm, *rad;
-    const double *radmax;    // device scalars: [0] max radius over all bodies, [1] max |coordinate|
+    const double *coordmax;  // device scalar: max |coordinate| of this launch's positions (set by flat_prologue_kernel)
     const double *blockrad;  // max radius of every block of FT bodies (radius-checked variant)
     int n, nplm;
     int nb, nbm;          // blocks in total / blocks that own rows (cover [0,nplm))
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(32 * FWARPS, CTAS) kick_flat_kernel(const Flat
     int fetched_j = -1;  // first column of the chunk whose cp.async copies are in flight into the warp's staging area
     double radI = 0.0;
     // coordinates beyond COORD_SAFE_MAX could overflow r^2: every chunk then takes the exact path
-    const bool force_exact = !(a.radmax[1] < COORD_SAFE_MAX);
+    const bool force_exact = !(a.coordmax[0] < COORD_SAFE_MAX_F64);
     unsigned long long *tr = a.trace ? a.trace + 4 * ((size_t)blockIdx.x * FWARPS + (threadIdx.x >> 5)) : nullptr;
     unsigned long long ndone = 0;
     if (tr && lane == 0) {
@@ -522,19 +522,43 @@ __global__ void __launch_bounds__(32 * FWARPS, CTAS) kick_flat_kernel(const Flat
     }
 }
 
-// blockrad[B] = max radius over bodies [B*FT, min((B+1)*FT, n)): one warp per block
-__global__ void block_max_radius_kernel(const double *radius, int n, int nb, double *blockrad)
+// Everything the third-law kernel needs prepared, in ONE launch (it used to be two memsets and two kernels, each a
+// launch gap on a stream that otherwise holds a 0.9 ms kernel when eight GPUs share the work):
+//   * the accumulation target F (3*stride doubles) zeroed,
+//   * guard[parity] = max |coordinate| (integer max of the bit patterns) -- guard[1-parity] is zeroed for the NEXT
+//     launch, so no separate reset is needed (the launcher alternates `parity`),
+//   * blockrad[B] = max radius of block B (radius-checked variant),
+//   * the work counter reset.
+__global__ void __launch_bounds__(256) flat_prologue_kernel(double2 *F, size_t nF2, const double *radius, const double *x,
+                                                            const double *y, const double *z, int n, int nb, double *blockrad,
+                                                            unsigned long long *guard, int parity,
+                                                            unsigned long long *counter)
 {
-    const int B = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (B >= nb) return;
-    const int lane = threadIdx.x & 31;
-    double m = 0.0;
-    for (int k = lane; k < FT; k += 32) {
-        const int i = B * FT + k;
-        if (i < n) m = fmax(m, fabs(radius[i]));
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = tid; k < nF2; k += nth) F[k] = make_double2(0.0, 0.0);
+    unsigned long long mc = 0ull;
+    for (size_t i = tid; i < (size_t)n; i += nth) {
+        const double c = fmax(fabs(x[i]), fmax(fabs(y[i]), fabs(z[i])));
+        mc = max(mc, (unsigned long long)__double_as_longlong(c));  // NaN orders above every finite value: unsafe
     }
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) blockrad[B] = m;
+    for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+    if ((threadIdx.x & 31) == 0 && mc != 0ull) atomicMax(guard + parity, mc);
+    if (tid == 0) {
+        guard[1 - parity] = 0ull;
+        *counter = 0ull;
+    }
+    if (radius != nullptr) {  // one warp per block of FT bodies
+        const int lane = threadIdx.x & 31;
+        for (int B = (int)(tid >> 5); B < nb; B += (int)(nth >> 5)) {
+            double m = 0.0;
+            for (int k = lane; k < FT; k += 32) {
+                const int i = B * FT + k;
+                if (i < n) m = fmax(m, fabs(radius[i]));
+            }
+            for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) blockrad[B] = m;
+        }
+    }
 }
 
 // out[0] = max |radius[i]| (0 when radius == nullptr), out[1] = max over bodies of max(|x|,|y|,|z|); the bit patterns of
@@ -589,15 +613,12 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     a.z = pl.rz.as<double>();
     a.gm = pl.Gm.as<double>();
     a.rad = lrad ? pl.radius.as<double>() : nullptr;
-    SWCU_TRY(max_radius(ctx, a.rad, a.x, a.y, a.z, n, 1, &a.radmax));
     a.n = n;
     a.nplm = std::min(nplm_rows, n);
     a.nb = cdiv(n, FT);
     a.blockrad = nullptr;
     if (lrad) {  // per-block radius bound: the fast-path threshold of a block pair follows the bodies that are in it
         SWCU_CUDA(ctx, ctx->flat_blockrad.ensure(sizeof(double) * a.nb));
-        block_max_radius_kernel<<<cdiv(a.nb, 4), 128, 0, ctx->stream>>>(a.rad, n, a.nb, ctx->flat_blockrad.as<double>());
-        SWCU_KERNEL_CHECK(ctx);
         a.blockrad = ctx->flat_blockrad.as<double>();
     }
     a.nbm = cdiv(a.nplm, FT);
@@ -619,7 +640,6 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     }
     a.fy = a.fx + stride;
     a.fz = a.fy + stride;
-    SWCU_CUDA(ctx, cudaMemsetAsync(a.fx, 0, sizeof(double) * 3 * stride, ctx->stream));
 
     // (CTAs per SM, steps per loop iteration, column prefetch) = (3, 2, 1) by measurement at npl = 1e5
     // (profiles/r02_kick_flat.md: 2, 3 and 4 CTAs/SM and 2/4/8 steps all land within 2 % of each other -- the hot loop
@@ -712,7 +732,19 @@ int kick_pl_flat(swcu_context *ctx, Body &pl, bool lrad, int nplm_rows, bool red
     const long long nquanta = split_quanta(mine, warps_max);
     const long long units = std::max<long long>(1, std::min<long long>(warps_max, nquanta));
     a.total_warps = units;
-    SWCU_CUDA(ctx, cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), ctx->stream));
+    // one prologue launch: F = 0, max |coordinate| guard, block radius bounds, work counter = 0
+    if (!ctx->flat_guard.p) {
+        SWCU_CUDA(ctx, ctx->flat_guard.ensure(2 * sizeof(unsigned long long)));
+        SWCU_CUDA(ctx, cudaMemsetAsync(ctx->flat_guard.p, 0, 2 * sizeof(unsigned long long), ctx->stream));
+        ctx->flat_parity = 0;
+    }
+    const int parity = ctx->flat_parity;
+    ctx->flat_parity ^= 1;
+    a.coordmax = reinterpret_cast<const double *>(ctx->flat_guard.as<unsigned long long>() + parity);
+    flat_prologue_kernel<<<2 * ctx->prop.multiProcessorCount, 256, 0, ctx->stream>>>(
+        reinterpret_cast<double2 *>(a.fx), 3 * stride / 2, a.rad, a.x, a.y, a.z, n, a.nb, ctx->flat_blockrad.as<double>(),
+        ctx->flat_guard.as<unsigned long long>(), parity, a.counter);
+    SWCU_KERNEL_CHECK(ctx);
     const int grid = cdiv(units, FWARPS);
     a.trace = nullptr;
     static const char *trace_path = getenv("SWCU_FLAT_TRACE");

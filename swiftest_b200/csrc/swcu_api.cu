@@ -181,6 +181,12 @@ extern "C" int swcu_destroy(swcu_context *ctx)
         ctx->aio.ready = false;
     }
     ctx->flat_blockrad.release();
+    ctx->flat_guard.release();
+    {
+        auto &W = ctx->whm;
+        DevBuf *wb[] = {&W.xjx, &W.xjy, &W.xjz, &W.vjx, &W.vjy, &W.vjz, &W.eta, &W.muj, &W.ir3j};
+        for (DevBuf *b : wb) b->release();
+    }
     ctx->flat_redo.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
@@ -769,9 +775,30 @@ extern "C" int swcu_whm_tp_step(swcu_context *ctx, double dt, const double *ah0,
 {
     SWCU_TRY(check_ctx(ctx));
     if (!ctx->tp.valid || !ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "whm_tp_step: tp and pl populations must be resident");
-    if (!ah0) return fail(ctx, SWCU_ERR_ARG, "whm_tp_step: null ah0");
     if (ctx->tp.n == 0 || ctx->pl.n == 0) return SWCU_OK;  // whm_kick.f90:91
     return whm_tp_step(ctx, ctx->tp, ctx->pl, dt, ah0, nfail);
+}
+
+extern "C" int swcu_whm_step_pl(swcu_context *ctx, double GMcb, double dt, int32_t loop_variant, int32_t lclose, int32_t lfirst,
+                                int32_t *nfail)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "whm_step_pl: pl population not resident");
+    return whm_step_pl(ctx, GMcb, dt, loop_variant, lclose, lfirst, nfail);
+}
+
+extern "C" int swcu_whm_tp_first_accel(swcu_context *ctx)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->tp.valid || !ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "whm_tp_first_accel: tp and pl populations must be resident");
+    return whm_tp_first_accel(ctx);
+}
+
+extern "C" int swcu_whm_get_jacobi(swcu_context *ctx, double *xj, double *vj)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (!ctx->pl.valid) return fail(ctx, SWCU_ERR_STATE, "whm_get_jacobi: pl population not resident");
+    return whm_get_jacobi(ctx, xj, vj);
 }
 
 extern "C" int swcu_body_kick_velocity(swcu_context *ctx, int32_t kind, double dt)

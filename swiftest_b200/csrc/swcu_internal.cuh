@@ -136,8 +136,18 @@ struct swcu_context {
     // [0..3] raw sums of the last reduction, [4..6] vbcb, [8..10] ptbeg, [12..14] ptend, [16] GMtot, [20..27] energy sums
     swcu::DevBuf cbs;
     swcu::DevBuf sumbuf;  // per-CTA partials of the tree reductions + ticket counter (zeroed when allocated)
+    // Wisdom-Holman planet step (whm_kernels.cu): Jacobi coordinates, running masses, per-body 1/|xj|^3
+    struct Whm {
+        swcu::DevBuf xjx, xjy, xjz, vjx, vjy, vjz, eta, muj, ir3j;
+        uint64_t generation = ~uint64_t(0);
+        int n = -1;
+        double gmcb = 0.0;
+        bool ah0tp_valid = false;  // cbs[CBS_AH0TP] holds whm_kick_getacch_ah0 of the planets for the tp step
+    } whm;
     swcu::DevBuf lists[16];  // staging of the encounter-list kernels (list_kernels.cu)
     swcu::DevBuf flat_blockrad; // max radius per block of 128 bodies (third-law kernel)
+    swcu::DevBuf flat_guard; // 2 x u64: max |coordinate| bit pattern of the current / next launch (flat_prologue_kernel)
+    int flat_parity = 0;
     swcu::DevBuf flat_redo;  // u64 count of chunks the third-law kernel redid exactly (zeroed when allocated)
     swcu::DevBuf flat_trace; // per-warp timeline of the third-law kernel (development aid, SWCU_FLAT_TRACE)
 
@@ -258,9 +268,13 @@ int axpy3(swcu_context *ctx, double alpha, const double *x0, const double *x1, c
 int drift_bodies(swcu_context *ctx, Body &b, int i0, int i1, double dt, int lgr, double inv_c2, int32_t *nfail,
                  int vsel = 0, double mu_scalar = 0.0);
 int helio_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double gmcb, double dt, int lfirst, int32_t *nfail);
+// Danby drift of arbitrary SoA arrays with a per-body mu (WHM: Jacobi coordinates with muj); failures counted in scratch64[0]
+int drift_arrays(swcu_context *ctx, int n, const double *mu, double *x, double *y, double *z, double *vx, double *vy,
+                 double *vz, const int32_t *lmask, int32_t *iflag, double dt);
 
 // ---- integrator glue : step_kernels.cu ----
-constexpr int CBS_SUM = 0, CBS_VBCB = 4, CBS_PTBEG = 8, CBS_PTEND = 12, CBS_GMTOT = 16, CBS_ENERGY = 20, CBS_DOUBLES = 32;
+constexpr int CBS_SUM = 0, CBS_VBCB = 4, CBS_PTBEG = 8, CBS_PTEND = 12, CBS_GMTOT = 16, CBS_ENERGY = 20, CBS_AH0PL = 28,
+              CBS_AH0TP = 32, CBS_DOUBLES = 40;
 int ensure_step_state(swcu_context *ctx);
 int ensure_helio(swcu_context *ctx, Body &b);
 int pl_vh2vb(swcu_context *ctx, double gmcb);
@@ -271,12 +285,17 @@ int tp_vh2vb(swcu_context *ctx, int lbeg);  // vbcb = -ptbeg / -ptend (helio_ste
 int tp_vb2vh(swcu_context *ctx, int lbeg);
 int kick_vb_save(swcu_context *ctx, Body &b, double dt, int save /*0 none, 1 rbeg, 2 rend*/);
 int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclose, int lfirst, int32_t *nfail);
+// ---- Wisdom-Holman planet step : whm_kernels.cu ----
+int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclose, int lfirst, int32_t *nfail);
+int whm_tp_first_accel(swcu_context *ctx);
+int whm_get_jacobi(swcu_context *ctx, double *xj, double *vj);
 int pl_accel_int(swcu_context *ctx, int loop_variant, int lclose);  // swcu_api.cu
 
 // ---- energy and momentum : energy_kernels.cu ----
 // positions / velocities in the s_pl scratch population (rb in r*, vb in v*), mass in s_pl.mu, Gmass in s_pl.Gm
 int energy_and_momentum(swcu_context *ctx, Body &b, double gmcb, int lclose, bool pe_only, double *out8);
-int whm_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double dt, const double ah0[3], int32_t *nfail);
+// ah0 == nullptr: use whm_kick_getacch_ah0 left in cbs[CBS_AH0TP] by whm_step_pl of the same step
+int whm_tp_step(swcu_context *ctx, Body &tp, const Body &pl, double dt, const double *ah0, int32_t *nfail);
 
 // ---- encounters : encounter_kernels.cu ----
 struct SweepList {

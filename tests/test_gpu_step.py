@@ -278,3 +278,85 @@ def test_potential_energy_large_disk_against_blocked_numpy(ctx):
     got = ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, rb)
     assert abs(got - ref) <= 1e-12 * abs(ref)
     assert got == ctx.util_get_potential_energy(n, None, GMcb, d["Gmass"], mass, rb)  # reproducible bits
+
+
+# ---------------------------------------------------------------------------------------------- WHM planet step
+def test_whm_step_pl_resident_matches_oracle(ctx, oracle):
+    """whm_step_pl on the device-resident planets (Jacobi chains, ah0 + ah1 + ah2 + accel_int, kick, drift, kick) against
+    the C restatement of whm/whm_step.f90:37-69, step after step: the serial chains keep the reference's order, so the
+    Jacobi coordinates and the state agree to rounding of the O(N^2) term only."""
+    from swiftest_b200 import LOOP_TRIANGULAR, LOOP_FLAT
+    for name, n_steps in (("8pl", 40), ("108pl", 10)):
+        if name == "8pl":
+            p = W.planets8_year_units()
+            GMcb, Gm, rh, vh, rad, rhill, dt = p["cb_Gmass"], p["Gmass"], p["rh"], p["vh"], p["radius"], p["rhill"], 0.01
+        else:
+            f = W.fixture("108pl_50tp")
+            order = np.argsort(-f["pl_Gmass"], kind="stable")
+            GMcb, dt = float(f["cb_Gmass"]), float(f["dt"])
+            Gm, rh, vh, rad, rhill = (f["pl_" + k][order] for k in ("Gmass", "rh", "vh", "radius", "rhill"))
+        n = len(Gm)
+        mask = np.ones(n, np.int32)
+        if name == "108pl":
+            mask[[5, 77]] = 0
+        for variant, lflat in ((LOOP_TRIANGULAR, False), (LOOP_FLAT, True)):
+            st = {"rh": rh.copy(), "vh": vh.copy(), "lfirst": True}
+            ctx.body_sync(PL, n, nplm=n, r=rh, v=vh, Gmass=Gm, radius=rad, rhill=rhill, mu=GMcb + Gm, lmask=mask,
+                          generation=8800 + 10 * n + int(lflat))
+            for k in range(n_steps):
+                fl = oracle.whm_step_pl(st, GMcb, Gm, rad, dt, lflat=lflat, lmask=mask)
+                assert not fl.any()
+                assert ctx.whm_step_pl(GMcb, dt, variant, True, lfirst=(k == 0)) == 0
+            got = ctx.body_get(PL)
+            xj, vj = ctx.whm_get_jacobi()
+            scale_r, scale_v = np.linalg.norm(st["rh"], axis=1, keepdims=True), np.linalg.norm(st["vh"], axis=1, keepdims=True)
+            assert np.max(np.abs(got["r"] - st["rh"]) / scale_r) < 1e-11, (name, lflat)
+            assert np.max(np.abs(got["v"] - st["vh"]) / scale_v) < 1e-11
+            assert np.max(np.abs(xj - st["xj"]) / scale_r) < 1e-11 and np.max(np.abs(vj - st["vj"]) / scale_v) < 1e-11
+            on = mask.astype(bool)
+            assert np.max(np.abs(got["a"][on] - st["ah"][on])) <= 1e-11 * np.abs(st["ah"]).max()
+            vb = ctx.body_get_vb(PL, vb=False, rbeg=True, rend=True)
+            assert np.max(np.abs(vb["rbeg"] - st["rbeg"])) <= 1e-11 * np.abs(st["rbeg"]).max()
+            assert np.max(np.abs(vb["rend"] - st["rend"])) <= 1e-11 * np.abs(st["rend"]).max()
+
+
+def test_whm_first_step_is_bit_identical_where_the_chains_decide(ctx, oracle):
+    """One first step of the Sun + 8 planets system: eta/muj, h2j and the ah0/ah1/ah2 chains run in the reference's serial
+    order with no FMA contraction; only pl%accel_int (28 pairs) and libm-free drift arithmetic follow, so positions agree
+    to a few ulp."""
+    from swiftest_b200 import LOOP_TRIANGULAR
+    p = W.planets8_year_units()
+    st = {"rh": p["rh"].copy(), "vh": p["vh"].copy(), "lfirst": True}
+    oracle.whm_step_pl(st, p["cb_Gmass"], p["Gmass"], p["radius"], 0.01)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=p["cb_Gmass"] + p["Gmass"], generation=8899)
+    assert ctx.whm_step_pl(p["cb_Gmass"], 0.01, LOOP_TRIANGULAR, True, lfirst=True) == 0
+    got = ctx.body_get(PL)
+    assert np.max(np.abs(got["r"] - st["rh"]) / np.linalg.norm(st["rh"], axis=1, keepdims=True)) < 2e-15
+    assert np.max(np.abs(got["v"] - st["vh"]) / np.linalg.norm(st["vh"], axis=1, keepdims=True)) < 2e-15
+
+
+def test_whm_resident_planets_and_test_particles_never_leave_the_device(ctx, oracle):
+    """BASELINE configs[1] flow: swcu_whm_tp_first_accel, then per step swcu_whm_step_pl + swcu_whm_tp_step(ah0 = NULL: the
+    value the planet step left on the device) against swo_whm_step_pl + swo_whm_step_tp."""
+    from swiftest_b200 import LOOP_TRIANGULAR
+    p = W.planets8_year_units()
+    ntp, dt, nsteps = 20000, 0.01, 5
+    tp = W.tp_cloud(ntp, seed=17)
+    GMcb = p["cb_Gmass"]
+    spl = {"rh": p["rh"].copy(), "vh": p["vh"].copy(), "lfirst": True}
+    stp = {"rh": tp["rh"].copy(), "vh": tp["vh"].copy(), "lfirst": True}
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=GMcb + p["Gmass"], generation=8901)
+    ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], mu=np.full(ntp, GMcb), generation=8902)
+    ctx.whm_tp_first_accel()
+    for k in range(nsteps):
+        oracle.whm_step_pl(spl, GMcb, p["Gmass"], p["radius"], dt)
+        fl = oracle.whm_step_tp(stp, spl, GMcb, p["Gmass"], dt)
+        assert not fl.any()
+        assert ctx.whm_step_pl(GMcb, dt, LOOP_TRIANGULAR, True, lfirst=(k == 0)) == 0
+        assert ctx.whm_tp_step(dt, None) == 0
+    got = ctx.body_get(TP)
+    assert np.max(np.abs(got["r"] - stp["rh"]) / np.linalg.norm(stp["rh"], axis=1, keepdims=True)) < 1e-11
+    assert np.max(np.abs(got["v"] - stp["vh"]) / np.linalg.norm(stp["vh"], axis=1, keepdims=True)) < 1e-11
+    assert np.max(np.abs(got["a"] - stp["ah"])) <= 1e-11 * np.abs(stp["ah"]).max()
