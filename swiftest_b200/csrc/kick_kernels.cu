@@ -447,16 +447,9 @@ int kick_rows(swcu_context *ctx, const KickProblem &p, int family)
     }
     int ib = ctx->tune_ib;
     if (ib != 1 && ib != 2 && ib != 4) {
-        const double work = (double)nrows * (double)ncols;
-        const int nsm = ctx->prop.multiProcessorCount;
-        if (ncols <= 64)
-            ib = 1;  // pl -> tp with a handful of planets: HBM bound, one tp per thread
-        else if (work >= 1e8 && nrows >= KNT * 4 * 8)
-            ib = 4;
-        else if (nrows >= nsm * KNT * 2)
-            ib = 2;
-        else
-            ib = 1;
+        // rows per thread, by measurement (scripts/tri_ib_scan.sh, profiles/r02_crossover.md): one row per thread is the
+        // fastest up to ~4e4 rows (more CTAs, better tail), two rows per thread win by 1 % from ~6e4 rows; four never do
+        ib = (ncols > 64 && nrows >= 60000) ? 2 : 1;
     }
     switch (ib) {
         case 4: return launch_rows<4>(ctx, p, ctx->tune_nsplit);

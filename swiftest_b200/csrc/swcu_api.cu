@@ -722,9 +722,10 @@ int pl_accel_int(swcu_context *ctx, int loop_variant, int lclose)
     Body &pl = ctx->pl;
     if (pl.n == 0) return SWCU_OK;
     int variant = ctx->tune_variant >= 0 ? ctx->tune_variant : loop_variant;
-    // AUTO: the third-law kernel measured 1.43x faster than the full-row kernel at npl = 1e5 and is never slower from
-    // a few hundred bodies up; tiny systems are launch bound either way and take the deterministic full-row kernel
-    if (variant == SWCU_LOOP_AUTO) variant = (pl.n >= 1024) ? SWCU_LOOP_FLAT : SWCU_LOOP_TRIANGULAR;
+    // AUTO by measurement (scripts/crossover_scan.py, profiles/r02_crossover.md): the third-law kernel is faster from
+    // npl = 128 up (0.88x the full-row time at 128, 0.52x at 512, 0.29x at 1e4, 0.61x at 1e5); below that both are launch
+    // bound within 5 % of each other and the bitwise-reproducible full-row kernel is taken
+    if (variant == SWCU_LOOP_AUTO) variant = (pl.n >= 128) ? SWCU_LOOP_FLAT : SWCU_LOOP_TRIANGULAR;
     if (variant == SWCU_LOOP_FLAT) return kick_pl_flat(ctx, pl, lclose != 0, pl.nplm);
     return kick_pl_tri(ctx, pl, lclose != 0, pl.slice0, pl.slice1);
 }
