@@ -34,4 +34,44 @@ with Context(0) as c:
     c.body_zero_accel(TP)
     c.tp_accel_int()
     print("fused nfail", c.whm_tp_step(0.01, np.zeros(3)))
+    # round 2: third-law rollback path (planted overlapping / coincident pairs), WHM planet step with the device ah0,
+    # helio steps, slice I/O (blocking and asynchronous), energy sums
+    from swiftest_b200 import LOOP_AUTO
+    n = 900
+    d = W.disk(n, seed=5)
+    r = d["rh"].copy()
+    r[700] = r[3] + np.array([0.5 * d["radius"].max(), 0.0, 0.0])
+    r[650] = r[140]
+    acc = np.zeros((n, 3))
+    c.kick_getacch_int_all_flat_pl(n, n * (n - 1) // 2, None, r, d["Gmass"], d["radius"], acc)
+    print("flat redo chunks", c.flat_redo_count())
+    c.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                mu=p["cb_Gmass"] + p["Gmass"], generation=3)
+    c.body_put(TP, r=tp["rh"], v=tp["vh"])
+    c.whm_tp_first_accel()
+    for k in range(2):
+        c.whm_step_pl(p["cb_Gmass"], 0.01, LOOP_TRIANGULAR, True, lfirst=(k == 0))
+        c.whm_tp_step(0.01, None)
+    c.whm_get_jacobi()
+    for k in range(2):
+        c.helio_step_pl(p["cb_Gmass"], 0.01, LOOP_AUTO, True, lfirst=(k == 0))
+        c.helio_step_tp(p["cb_Gmass"], 0.01, lfirst=(k == 0))
+    c.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"], mu=d["mu"],
+                generation=4)
+    import torch
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()  # noqa: E731
+    hr, hv = pin(d["rh"][100:400]), pin(d["vh"][100:400])
+    out = {k: pin(np.zeros((300, 3))) for k in ("r", "v", "a")}
+    for _ in range(3):
+        c.body_put_range_async(PL, 100, 400, r=hr, v=hv)
+        c.body_zero_accel(PL)
+        c.pl_accel_int(LOOP_FLAT, True)
+        c.body_kick_velocity(PL, d["dt"])
+        c.body_drift(PL, d["dt"])
+        c.body_get_range_async(PL, 100, 400, out)
+    c.io_wait()
+    c.body_put_range(PL, 0, 10, r=d["rh"][:10])
+    c.body_get_range(PL, 5, 50)
+    mass = d["Gmass"] / W.GMSUN
+    print("pe", c.util_get_potential_energy(n, None, W.GMSUN, d["Gmass"], mass, d["rh"]))
 print("sanitize pass done")

@@ -72,16 +72,17 @@ def test_third_law_hot_loop_instruction_mix():
     # 20 FP64 per pair: 3 differences, 3 for r^2, 6 for r^-3, 2 mass factors, 6 accumulations
     assert fp64 == 160, (fp64, dict(ops))
     # everything else: one MUFU.RSQ64H per pair, half a 3-input min, LDS/STS of the column and its accumulators, the
-    # loop -- at most 4 per pair (profiles/r02_kick_flat.md); no seed conversion, compare or select on the fast path
-    assert other <= 32, (other, dict(ops))
+    # per-step __syncwarp (BRA.DIV + NOP) and the loop -- at most 4.5 per pair (profiles/r02_kick_flat.md); no seed
+    # conversion, compare or select on the fast path
+    assert other <= 36, (other, dict(ops))
     assert ops["MUFU"] == 8 and ops["VIMNMX3"] == 4, dict(ops)
-    assert not any(o in ops for o in ("F2F", "LDL", "STL", "DSETP", "SEL", "FSEL", "ISETP2", "LEA", "SHFL", "BAR", "WARPSYNC")), dict(ops)
+    assert not any(o in ops for o in ("F2F", "LDL", "STL", "DSETP", "SEL", "FSEL", "LEA", "SHFL", "BAR")), dict(ops)
     assert ops["ISETP"] <= 1, dict(ops)                                 # the loop test only
 
 
 def test_third_law_accumulator_accesses_stay_in_program_order():
-    """The j-side accumulators are read by one lane one step after the neighbouring lane wrote them; the kernel relies
-    on the volatile shared-memory accesses keeping their program order (no __syncwarp per step): in every step the
+    """The j-side accumulators are read by one lane one step after the neighbouring lane wrote them (a __syncwarp ends
+    every step); the volatile shared-memory accesses must also keep their program order in the SASS: in every step the
     accumulator loads come before its stores, and the next step's loads after them."""
     body = _flat_hot_loop()
     seq = []
