@@ -315,7 +315,7 @@ def main():
                     "    TARGET_LINK_LIBRARIES(${SWIFTEST_LIBRARY} PUBLIC ${SWIFTEST_CUDA_LIB})\n"
                     "ENDIF ()\n")
         out += difflib.unified_diff(old.split("\n"), new.split("\n"), "a/" + path, "b/" + path, n=1, lineterm="")
-    dst = os.path.join(HERE, "swiftest_use_cuda.diff")
+    dst = os.environ.get("SWCU_PATCH_OUT") or os.path.join(HERE, "swiftest_use_cuda.diff")
     with open(dst, "w") as f:
         f.write("\n".join(out) + "\n")
     print(f"wrote {dst}: {sum(1 for l in out if l.startswith('+') and not l.startswith('+++'))} added lines, "

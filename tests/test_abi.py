@@ -226,3 +226,37 @@ def test_partition_and_rebalance_properties_hypothesis():
 
     slices()
     plan()
+
+
+def test_use_cuda_patch_is_current_and_names_real_entry_points(tmp_path):
+    """patches/swiftest_use_cuda.diff: every swcu_* function the Fortran blocks call is declared in the C header and has
+    an interface in fortran/swiftest_cuda.f90; when the reference tree is present (this container only) the committed
+    diff equals what patches/make_patch.py generates and applies to it."""
+    import re
+    import shutil
+    import subprocess
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    diff = open(os.path.join(ROOT, "patches", "swiftest_use_cuda.diff")).read()
+    added = "\n".join(l[1:] for l in diff.splitlines() if l.startswith("+") and not l.startswith("+++"))
+    called = set(re.findall(r"\b(swcu_[a-z0-9_]+)\s*\(", added)) - {"swcu_check", "swcu_ensure_ctx", "swcu_iplanet"}
+    assert len(called) >= 10
+    declared = set(_lib.declared_symbols())
+    fortran = open(os.path.join(ROOT, "fortran", "swiftest_cuda.f90")).read()
+    for name in called:
+        assert name in declared, name
+        assert f'name="{name}"' in fortran, name
+    assert "subroutine swcu_ensure_ctx" in fortran and "subroutine swcu_check" in fortran
+    assert added.count("#ifdef USE_CUDA") == added.count("#endif") >= 14
+    ref = "/root/reference"
+    if os.path.isdir(os.path.join(ref, "src")) and shutil.which("patch"):
+        gen = subprocess.run([sys.executable, os.path.join(ROOT, "patches", "make_patch.py"), ref], capture_output=True, text=True,
+                             cwd=str(tmp_path), env=dict(os.environ, SWCU_PATCH_OUT=str(tmp_path / "out.diff")))
+        assert gen.returncode == 0, gen.stderr
+        assert open(tmp_path / "out.diff").read() == diff, "patches/swiftest_use_cuda.diff is stale: rerun patches/make_patch.py"
+        work = tmp_path / "tree"
+        shutil.copytree(os.path.join(ref, "src"), work / "src")
+        shutil.copy(os.path.join(ref, "CMakeLists.txt"), work / "CMakeLists.txt")
+        ap = subprocess.run(["patch", "-p1", "--dry-run", "-i", os.path.join(ROOT, "patches", "swiftest_use_cuda.diff")],
+                            capture_output=True, text=True, cwd=str(work))
+        assert ap.returncode == 0, ap.stdout + ap.stderr
