@@ -1,0 +1,345 @@
+"""REFERENCE-GENERATED golden vectors for gravity, sort-and-sweep and drift, produced by EXECUTING THE REFERENCE'S FORTRAN
+SOURCE (read from /root/reference/src when this script runs) with the Fortran-subset interpreter oracle/f90interp.py.
+
+  python tests/golden/gen_golden_fortran.py          # ~ a few minutes; writes tests/golden/fortran_*.npz
+
+Run in the build container only: /root/reference does not exist on the GPU box and nothing reads it at test time; the
+committed .npz files are what the tests load.  No Fortran compiler exists here or on the GPU box
+(profiles/r02_fortran_probe.txt), so the reference cannot be compiled into oracle/_ref; instead its own statements are
+interpreted one IEEE operation at a time (serial loop order, no FMA contraction), which is exactly what the C restatement
+oracle/swiftest_oracle.c claims to reproduce.  tests/test_oracle_fortran_goldens.py holds the restatement to these vectors
+BIT FOR BIT (accelerations, drifted states, iflag, pair lists in the reference's own output order), and the GPU tests
+compare the CUDA path with the same vectors at the tolerance of the north star.
+
+Routines executed (file:line in /root/reference/src):
+  swiftest/swiftest_kick.f90:69-470     flat_rad/flat_norad/tri_rad/tri_norad_pl (all nplm branches), all_tp, one_pl, one_tp
+  swiftest/swiftest_util.f90:1031-1131  flatten_eucl_plpl (the k_plpl table the flat kernels index)
+  swiftest/swiftest_drift.f90:60-580    drift_all (with and without GR), drift_one, dan, kepmd, kepu family, stumpff
+  swiftest/swiftest_orbel.f90:147-172   orbel_scget
+  encounter/encounter_check.f90:14-990  all_plpl/_plplm/_pltp dispatch, sort_and_sweep_*, triangular_*, sweep_one, check_one,
+                                        collapse_ragged_list, remove_duplicates, sort_aabb_1D, sweep_aabb_single/double_list
+  encounter/encounter_util.f90:332-365  setup_aabb
+  base/base_module.f90:1346-2060        util_sort (index quicksorts), util_sort_rearrange
+  swiftest/swiftest_util.f90:1494-1526  index_array
+"""
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+from oracle import f90interp as F  # noqa: E402
+
+SRC = "/root/reference/src"
+FILES = ["globals/globals_module.f90", "base/base_module.f90", "swiftest/swiftest_module.f90",
+         "swiftest/swiftest_kick.f90", "swiftest/swiftest_drift.f90", "swiftest/swiftest_orbel.f90",
+         "swiftest/swiftest_util.f90", "encounter/encounter_module.f90", "encounter/encounter_check.f90",
+         "encounter/encounter_util.f90", "collision/collision_module.f90"]
+
+
+def world():
+    return F.load_world(SRC, FILES)
+
+
+def fa(a):
+    """(n,3) C-order (the repo's convention) -> Fortran r(3,n)."""
+    return np.array(np.asarray(a, dtype=np.float64).T, order="F", copy=True)
+
+
+def back(a):
+    return np.ascontiguousarray(a.T)
+
+
+def disk(n, seed, a0=1.0, a1=1.3, mscale=1e-7, hot=0.02):
+    """A thin planetesimal disk around a unit-GM star: dense enough for many encounters at a few Hill radii."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(a0, a1, n)
+    th = rng.uniform(0, 2 * np.pi, n)
+    z = rng.normal(0, 0.002, n) * a
+    r = np.stack([a * np.cos(th), a * np.sin(th), z], 1)
+    vc = 1.0 / np.sqrt(a)
+    v = np.stack([-vc * np.sin(th), vc * np.cos(th), np.zeros(n)], 1) * (1 + rng.normal(0, hot, (n, 1)))
+    v += rng.normal(0, hot * 0.3, (n, 3))
+    Gm = mscale * rng.lognormal(0, 1.0, n)
+    rhill = a * (Gm / 3.0) ** (1.0 / 3.0)
+    radius = 0.02 * rhill
+    return r, v, Gm, rhill, radius
+
+
+# ---------------------------------------------------------------------------------------------------------- gravity
+def gen_kick(w, out):
+    fx = np.load(os.path.join(HERE, "fixture_108pl_50tp.npz"))
+    cases = {}
+    # (1) the 108 massive bodies of the reference's own example system (heliocentric; the Sun is the central body)
+    cases["fx108"] = dict(r=fx["pl_rh"][:], Gm=fx["pl_Gmass"][:], radius=fx["pl_radius"][:])
+    # (2) a disk with physical overlaps (radius check rejects pairs) and a few coincident-distance cases
+    r, v, Gm, rhill, radius = disk(160, 11)
+    radius = radius * 400.0          # 63 of the 12720 pairs overlap physically
+    cases["disk160"] = dict(r=r, Gm=Gm, radius=radius)
+    # (3) small hand-made system: touching pair exactly at the limit (rji2 == rlim2 is rejected by '>')
+    r3 = np.array([[1.0, 0, 0], [1.5, 0, 0], [0, 2.0, 0], [0, 0, -3.0], [1.0, 1.0, 1.0]])
+    rad3 = np.array([0.25, 0.25, 0.1, 0.1, 0.05])
+    cases["tiny5"] = dict(r=r3, Gm=np.array([1e-3, 2e-3, 3e-4, 0.0, 5e-5]), radius=rad3)
+    pl = w.new_object("swiftest_pl")
+    param = w.new_object("swiftest_parameters")
+    param.c["lflatten_interactions"] = True
+    for name, c in cases.items():
+        r, Gm, radius = fa(c["r"]), np.array(c["Gm"], dtype=np.float64), np.array(c["radius"], dtype=np.float64)
+        npl = len(Gm)
+        rng = np.random.default_rng(5)
+        acc0 = np.asfortranarray(rng.normal(0, 1e-6, (3, npl)))      # accumulates onto a non-zero acc (intent inout)
+        out[name + "_r"], out[name + "_Gm"], out[name + "_radius"], out[name + "_acc0"] = c["r"], Gm, radius, back(acc0)
+        # k_plpl by the reference's flatten
+        pl.c["nbody"] = npl
+        w.call("swiftest_util_flatten_eucl_plpl", pl, param)
+        k_plpl = pl.c["k_plpl"]
+        nplpl = int(pl.c["nplpl"])
+        assert k_plpl.shape == (2, nplpl)
+        out[name + "_k_plpl"] = np.ascontiguousarray(k_plpl.T)
+        nplms = sorted({npl, (2 * npl) // 3, npl // 3, 1})           # full, nplt<=nplm, lmtiny, single massive
+        out[name + "_nplm"] = np.array(nplms)
+        for nplm in nplms:
+            for rad in (True, False):
+                acc = acc0.copy(order="F")
+                if rad:
+                    w.call("swiftest_kick_getacch_int_all_tri_rad_pl", npl, nplm, r, Gm, radius, acc)
+                else:
+                    w.call("swiftest_kick_getacch_int_all_tri_norad_pl", npl, nplm, r, Gm, acc)
+                out["%s_tri_%s_nplm%d" % (name, "rad" if rad else "norad", nplm)] = back(acc)
+                # flat: nplplm = nplm*npl - nplm*(nplm+1)/2 pairs (symba_kick.f90:23-29), the head of the k_plpl table
+                nplplm = nplm * npl - nplm * (nplm + 1) // 2
+                acc = acc0.copy(order="F")
+                if rad:
+                    w.call("swiftest_kick_getacch_int_all_flat_rad_pl", npl, nplplm, k_plpl, r, Gm, radius, acc)
+                else:
+                    w.call("swiftest_kick_getacch_int_all_flat_norad_pl", npl, nplplm, k_plpl, r, Gm, acc)
+                out["%s_flat_%s_nplm%d" % (name, "rad" if rad else "norad", nplm)] = back(acc)
+        # flat kernel over an explicit (encounter) pair list, as symba_kick_getacch_pl uses it (symba_kick.f90:59-70)
+        rng = np.random.default_rng(9)
+        npair = min(40, nplpl)
+        sel = np.sort(rng.choice(nplpl, npair, replace=False))
+        k_enc = np.asfortranarray(k_plpl[:, sel])
+        acc = np.zeros((3, npl), order="F")
+        w.call("swiftest_kick_getacch_int_all_flat_rad_pl", npl, npair, k_enc, r, Gm, radius, acc)
+        out[name + "_enc_pairs"] = np.ascontiguousarray(k_enc.T)
+        out[name + "_enc_acc"] = back(acc)
+    # pl -> tp
+    rpl = fa(fx["pl_rh"][:8]); GMpl = np.array(fx["pl_Gmass"][:8])
+    rtp = fa(fx["tp_rh"])
+    ntp = rtp.shape[1]
+    lmask = np.ones(ntp, dtype=bool); lmask[::7] = False
+    acc0 = np.asfortranarray(np.random.default_rng(3).normal(0, 1e-6, (3, ntp)))
+    acc = acc0.copy(order="F")
+    w.call("swiftest_kick_getacch_int_all_tp", ntp, 8, rtp, rpl, GMpl, lmask, acc)
+    out["tp_rtp"], out["tp_rpl"], out["tp_GMpl"] = back(rtp), back(rpl), GMpl
+    out["tp_lmask"], out["tp_acc0"], out["tp_acc"] = lmask, back(acc0), back(acc)
+
+
+# ---------------------------------------------------------------------------------------------------------- drift
+def drift_sample(seed, n):
+    """States covering every branch: kepmd (small dM, e), universal-variable Newton, Laguerre fallback, hyperbolic with the
+    cubic guess, near-parabolic, a step that fails (iflag /= 0) and masked bodies."""
+    rng = np.random.default_rng(seed)
+    mu = np.full(n, 4 * np.pi ** 2) * rng.uniform(0.5, 1.5, n)
+    x = np.zeros((n, 3)); v = np.zeros((n, 3))
+    for i in range(n):
+        kind = i % 8
+        rmag = 10 ** rng.uniform(-1.0, 1.5)
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        t = np.cross(d, rng.normal(size=3)); t /= np.linalg.norm(t)
+        vc = np.sqrt(mu[i] / rmag)
+        if kind in (0, 1, 2):                 # moderate ellipse
+            f, rad = rng.uniform(0.7, 1.15), rng.uniform(-0.2, 0.2)
+        elif kind == 3:                       # very eccentric ellipse
+            f, rad = rng.uniform(0.05, 0.4), rng.uniform(-0.5, 0.5)
+        elif kind == 4:                       # near parabolic
+            f, rad = np.sqrt(2.0) * (1 + rng.uniform(-1e-6, 1e-6)), rng.uniform(-0.1, 0.1)
+        elif kind == 5:                       # hyperbolic
+            f, rad = rng.uniform(1.5, 4.0), rng.uniform(-1.0, 1.0)
+        elif kind == 6:                       # plunging, nearly radial
+            f, rad = rng.uniform(0.0, 0.05), -rng.uniform(0.5, 1.3)
+        else:                                 # strongly hyperbolic, deep
+            f, rad = rng.uniform(5.0, 30.0), rng.uniform(-3.0, 3.0)
+        x[i] = rmag * d
+        v[i] = vc * (f * t + rad * d)
+    return mu, x, v
+
+
+def gen_drift(w, out):
+    param = w.new_object("swiftest_parameters")
+    for tag, (seed, n, dt, lgr) in {"a": (21, 240, 0.05, False), "b": (22, 160, 2.5, False),
+                                    "gr": (23, 120, 0.3, True), "long": (24, 80, 400.0, False)}.items():
+        mu, x, v = drift_sample(seed, n)
+        lmask = np.ones(n, dtype=bool); lmask[5::11] = False
+        param.c["lgr"] = lgr
+        param.c["inv_c2"] = 1.0 / 63241.077 ** 2 if lgr else 0.0      # (AU/yr)^-2
+        xf, vf = fa(x), fa(v)
+        iflag = np.full(n, -7, dtype=np.int32)      # intent(out), only written where lmask: the rest must stay untouched
+        w.call("swiftest_drift_all", mu, xf, vf, n, param, float(dt), lmask, iflag)
+        out["drift_%s_mu" % tag], out["drift_%s_x0" % tag], out["drift_%s_v0" % tag] = mu, x, v
+        out["drift_%s_dt" % tag], out["drift_%s_lgr" % tag] = float(dt), lgr
+        out["drift_%s_inv_c2" % tag] = param.c["inv_c2"]
+        out["drift_%s_lmask" % tag] = lmask
+        out["drift_%s_x1" % tag], out["drift_%s_v1" % tag], out["drift_%s_iflag" % tag] = back(xf), back(vf), iflag
+        print("  drift", tag, "iflag counts", dict(zip(*np.unique(iflag, return_counts=True))), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------- encounters
+def reset_encounter_state(w):
+    for name in ("encounter_check_all_sort_and_sweep_plpl", "encounter_check_all_sort_and_sweep_pltp",
+                 "encounter_check_all_sort_and_sweep_plplm", "encounter_check_sweep_aabb_single_list",
+                 "encounter_check_sweep_aabb_double_list", "encounter_check_all_triangular_plpl",
+                 "encounter_check_all_triangular_pltp", "encounter_check_all_triangular_plplm"):
+        w.procs[name].static.clear()
+
+
+def lists(res, k):
+    nenc, i1, i2, lv = res[k], res[k + 1], res[k + 2], res[k + 3]
+    nenc = int(nenc)
+    if nenc == 0 or i1 is None:
+        z = np.zeros(0, dtype=np.int32)
+        return z, z.copy(), np.zeros(0, dtype=bool)
+    return np.array(i1[:nenc], dtype=np.int32), np.array(i2[:nenc], dtype=np.int32), np.array(lv[:nenc], dtype=bool)
+
+
+def gen_encounter(w, out):
+    fx = np.load(os.path.join(HERE, "fixture_108pl_50tp.npz"))
+    param_sas = w.new_object("base_parameters")
+    param_sas.c["lencounter_sas_plpl"] = True
+    param_sas.c["lencounter_sas_pltp"] = True
+    param_tri = w.new_object("base_parameters")
+    param_tri.c["lencounter_sas_plpl"] = False
+    param_tri.c["lencounter_sas_pltp"] = False
+
+    # ---- check_one on a spread of relative states (every branch: r2 <= r2crit, receding, v2 tiny, tmin < dt, tmin >= dt)
+    rng = np.random.default_rng(31)
+    n1 = 400
+    rel = rng.normal(0, 1.0, (n1, 3)) * 10 ** rng.uniform(-2, 0.5, (n1, 1))
+    vel = rng.normal(0, 1.0, (n1, 3)) * 10 ** rng.uniform(-3, 1, (n1, 1))
+    vel[::37] = 0.0
+    vel[5::41] *= 1e-160
+    renc = 10 ** rng.uniform(-2, 0.3, n1)
+    dt = 0.3
+    lenc = np.zeros(n1, dtype=bool); lvd = np.zeros(n1, dtype=bool)
+    for k in range(n1):
+        a, b = F.Cell(False), F.Cell(False)
+        w.call("encounter_check_one", *map(float, rel[k]), *map(float, vel[k]), float(renc[k]), dt, a, b)
+        lenc[k], lvd[k] = a.v, b.v
+    out["one_rel"], out["one_vel"], out["one_renc"], out["one_dt"] = rel, vel, renc, dt
+    out["one_lencounter"], out["one_lvdotr"] = lenc, lvd
+    print("  check_one: %d encounters, %d approaching of %d" % (lenc.sum(), lvd.sum(), n1), flush=True)
+
+    # ---- pl-pl: the 108-body fixture, then a dense disk, then a smaller population (the saved bounding box shrinks)
+    plpl_cases = []
+    r, v, rh = fx["pl_rh"][:], fx["pl_vh"][:], fx["pl_rhill"][:]
+    plpl_cases.append(("fx108", r, v, 3.0 * rh, 0.05))
+    r, v, Gm, rhill, radius = disk(300, 41)
+    plpl_cases.append(("disk300", r, v, 4.0 * rhill, 0.02))
+    r, v, Gm, rhill, radius = disk(120, 42, hot=0.05)
+    plpl_cases.append(("disk120", r, v, 6.0 * rhill, 0.05))
+    reset_encounter_state(w)
+    for name, r, v, renc, dt in plpl_cases:       # consecutive calls share the reference's SAVEd bounding box, as in a run
+        t0 = time.time()
+        npl = len(renc)
+        res = w.call("encounter_check_all_plpl", param_sas, npl, fa(r), fa(v), np.array(renc), float(dt), 0, None, None, None)
+        i1, i2, lv = lists(res, 6)
+        res = w.call("encounter_check_all_plpl", param_tri, npl, fa(r), fa(v), np.array(renc), float(dt), 0, None, None, None)
+        t1, t2, tl = lists(res, 6)
+        out["plpl_%s_r" % name], out["plpl_%s_v" % name], out["plpl_%s_renc" % name] = r, v, np.array(renc)
+        out["plpl_%s_dt" % name] = float(dt)
+        out["plpl_%s_sas" % name] = np.stack([i1, i2, lv.astype(np.int32)], 1)
+        out["plpl_%s_tri" % name] = np.stack([t1, t2, tl.astype(np.int32)], 1)
+        print("  plpl %-8s npl=%d  sweep nenc=%d  triangular nenc=%d  (%.1fs)" % (name, npl, len(i1), len(t1), time.time() - t0),
+              flush=True)
+
+    # ---- pl-tp: fixture planets and particles; disk planets against a particle swarm
+    pltp_cases = []
+    pltp_cases.append(("fx", fx["pl_rh"][:8], fx["pl_vh"][:8], fx["tp_rh"], fx["tp_vh"], 8.0 * fx["pl_rhill"][:8], 0.5))
+    r, v, Gm, rhill, radius = disk(40, 51, mscale=3e-6)
+    rt, vt, _, _, _ = disk(500, 52)
+    pltp_cases.append(("disk", r, v, rt, vt, 3.5 * rhill, 0.02))
+    reset_encounter_state(w)
+    for name, rpl, vpl, rtp, vtp, renc, dt in pltp_cases:
+        t0 = time.time()
+        npl, ntp = len(renc), len(rtp)
+        res = w.call("encounter_check_all_pltp", param_sas, npl, ntp, fa(rpl), fa(vpl), fa(rtp), fa(vtp), np.array(renc),
+                     float(dt), 0, None, None, None)
+        i1, i2, lv = lists(res, 9)
+        res = w.call("encounter_check_all_pltp", param_tri, npl, ntp, fa(rpl), fa(vpl), fa(rtp), fa(vtp), np.array(renc),
+                     float(dt), 0, None, None, None)
+        t1, t2, tl = lists(res, 9)
+        for key, val in dict(rpl=rpl, vpl=vpl, rtp=rtp, vtp=vtp, renc=np.array(renc), dt=float(dt)).items():
+            out["pltp_%s_%s" % (name, key)] = val
+        out["pltp_%s_sas" % name] = np.stack([i1, i2, lv.astype(np.int32)], 1)
+        out["pltp_%s_tri" % name] = np.stack([t1, t2, tl.astype(np.int32)], 1)
+        print("  pltp %-8s npl=%d ntp=%d  sweep nenc=%d  triangular nenc=%d  (%.1fs)" %
+              (name, npl, ntp, len(i1), len(t1), time.time() - t0), flush=True)
+
+    # ---- plm-plt and the merged list (SyMBA with GMTINY): bodies ordered massive first
+    r, v, Gm, rhill, radius = disk(260, 61)
+    order = np.argsort(-Gm, kind="stable")
+    r, v, rhill = r[order], v[order], rhill[order]
+    for name, nplm in (("m60", 60), ("m200", 200)):
+        t0 = time.time()
+        nplt = len(rhill) - nplm
+        renc = 4.0 * rhill
+        args = (nplm, nplt, fa(r[:nplm]), fa(v[:nplm]), fa(r[nplm:]), fa(v[nplm:]), np.array(renc[:nplm]),
+                np.array(renc[nplm:]), 0.03)
+        reset_encounter_state(w)
+        res = w.call("encounter_check_all_sort_and_sweep_plplm", *args, 0, None, None, None)
+        i1, i2, lv = lists(res, 9)
+        reset_encounter_state(w)
+        res = w.call("encounter_check_all_plplm", param_sas, *args, 0, None, None, None)
+        m1, m2, ml = lists(res, 10)
+        res = w.call("encounter_check_all_plplm", param_tri, *args, 0, None, None, None)
+        t1, t2, tl = lists(res, 10)
+        out["plplm_%s_r" % name], out["plplm_%s_v" % name], out["plplm_%s_renc" % name] = r, v, renc
+        out["plplm_%s_nplm" % name], out["plplm_%s_dt" % name] = nplm, 0.03
+        out["plplm_%s_sas" % name] = np.stack([i1, i2, lv.astype(np.int32)], 1)
+        out["plplm_%s_merged" % name] = np.stack([m1, m2, ml.astype(np.int32)], 1)
+        out["plplm_%s_merged_tri" % name] = np.stack([t1, t2, tl.astype(np.int32)], 1)
+        print("  plplm %-5s nplm=%d nplt=%d  plm-plt nenc=%d  merged nenc=%d  merged triangular nenc=%d  (%.1fs)" %
+              (name, nplm, nplt, len(i1), len(m1), len(t1), time.time() - t0), flush=True)
+
+
+def main():
+    import collections
+    import json
+    which = sys.argv[1:] or ["kick", "drift", "encounter"]
+    w = world()
+    cov_path = os.path.join(HERE, "fortran_coverage.json")
+    coverage = json.load(open(cov_path)) if os.path.exists(cov_path) else {}
+    for part, fn in (("kick", gen_kick), ("drift", gen_drift), ("encounter", gen_encounter)):
+        if part not in which:
+            continue
+        t0 = time.time()
+        out = {}
+        w.trace = []
+        fn(w, out)
+        # which reference procedures were executed, and how often (tests assert the list)
+        coverage[part] = dict(sorted(collections.Counter(t.strip() for t in w.trace).items()))
+        w.trace = None
+        if part == "encounter":
+            # norm2 is processor dependent: the pair lists must not depend on the variant
+            F.NORM2_MODE = "libgfortran"
+            w2 = world()
+            out2 = {}
+            gen_encounter(w2, out2)
+            F.NORM2_MODE = "plain"
+            same = all(np.array_equal(out[k], out2[k]) for k in out)
+            print("  pair lists identical under libgfortran's scaled norm2:", same)
+            assert same
+            out["norm2_variants_identical"] = np.array(same)
+        path = os.path.join(HERE, "fortran_%s.npz" % part)
+        np.savez_compressed(path, **out)
+        print("%s: %d arrays -> %s (%.0f s)" % (part, len(out), path, time.time() - t0), flush=True)
+    with open(cov_path, "w") as f:
+        json.dump(coverage, f, indent=1, sort_keys=True)
+        f.write("\n")
+
+
+if __name__ == "__main__":
+    main()
