@@ -599,6 +599,9 @@ class World:
                 m = re.match(r"^module\s+procedure\s*(?:::)?\s*(.*)$", s)
                 if m and iface_name:
                     self.generics.setdefault(iface_name, []).extend(x.strip() for x in m.group(1).split(","))
+                m = PROC_HEAD.match(s)
+                if m and iface_name and not s.startswith("end"):      # interface body inside a named (generic) interface
+                    self.generics.setdefault(iface_name, []).append(m.group(2))
                 i += 1
                 continue
             m = PROC_HEAD.match(s)
@@ -714,6 +717,14 @@ class World:
             return convert_scalar((frame or Frame(self, None)).eval(d.init), d)
         return {"real": 0.0, "integer": 0, "logical": False}.get(d.base, None)
 
+    def type_chain(self, tname):
+        chain = []
+        while tname is not None:
+            chain.append(tname)
+            td = self.types.get(tname)
+            tname = td.parent if td is not None else None
+        return chain
+
     def find_binding(self, tname, name):
         """-> list of candidate procedure names for obj%name."""
         td = self.types.get(tname)
@@ -735,6 +746,10 @@ class World:
             s = lines[k][1]
             if DECL_START.match(s) and "::" in s:
                 for d in parse_decl(s):
+                    decls[d.name] = d
+            elif s.startswith("character") and find_assign(s) < 0:
+                m = re.match(r"^character\s*(\(.*?\))?\s*(.*)$", s)          # old-style: no '::'
+                for d in parse_decl("character%s :: %s" % (m.group(1) or "", m.group(2))):
                     decls[d.name] = d
             elif s.startswith(("implicit", "use ", "import", "external", "intrinsic")):
                 pass
@@ -950,6 +965,47 @@ def _parse_stmt(lines, k, s):
             m2 = parse_expr(t[o + 1:match_paren(t, o)]) if o >= 0 else None
             body, k = parse_block(lines, k + 1, (r"^else\s*where\b", r"^end\s*where\b"))
             branches.append((m2, body))
+    m = re.match(r"^select\s+type\s*\(", s)
+    if m:
+        o = s.index("(")
+        inside = s[o + 1:match_paren(s, o)]
+        if "=>" in inside:
+            a, b = inside.split("=>", 1)
+            name, sel = a.strip(), parse_expr(b.strip())
+        else:
+            name, sel = inside.strip(), parse_expr(inside.strip())
+        guards = []
+        k += 1
+        term = (r"^class\s+is\b", r"^type\s+is\b", r"^class\s+default\b", r"^end\s*select\b")
+        while not re.match(r"^end\s*select\b", lines[k][1]):
+            t = lines[k][1]
+            mg = re.match(r"^(class|type)\s+is\s*\(\s*(\w+)\s*\)", t)
+            if mg:
+                guard = (mg.group(1), mg.group(2))
+            elif re.match(r"^class\s+default\b", t):
+                guard = ("default", None)
+            else:
+                raise FortranError("unexpected statement in select type: %r" % t)
+            body, k = parse_block(lines, k + 1, term)
+            guards.append((guard, body))
+        return ("selecttype", name, sel, guards), k + 1
+    m = re.match(r"^select\s+case\s*\(", s)
+    if m:
+        o = s.index("(")
+        sel = parse_expr(s[o + 1:match_paren(s, o)])
+        cases = []
+        k += 1
+        term = (r"^case\b", r"^end\s*select\b")
+        while not re.match(r"^end\s*select\b", lines[k][1]):
+            t = lines[k][1]
+            if re.match(r"^case\s+default\b", t):
+                vals = None
+            else:
+                o = t.index("(")
+                vals = [Parser(tokenize(x)).arg() for x in split_top(t[o + 1:match_paren(t, o)])]
+            body, k = parse_block(lines, k + 1, term)
+            cases.append((vals, body))
+        return ("selectcase", sel, cases), k + 1
     if re.match(r"^associate\s*\(", s):
         o = s.index("(")
         pairs = []
@@ -1431,6 +1487,10 @@ class Frame:
         if name == "real":
             v = self.eval(pos[0])
             return v.astype(np.float64) if isinstance(v, np.ndarray) else float(v)
+        if name == "sum" and (len(pos) == 2 or "mask" in kws) and "dim" not in kws:
+            a = np.asarray(self.eval(pos[0]))
+            m = np.asarray(self.eval(kws.get("mask", pos[1] if len(pos) > 1 else None)), dtype=bool)
+            return f_sum(a[m] if m.ndim else (a if m else a[:0]))
         if name in ("sum", "count", "any", "all", "minval", "maxval") and (len(pos) > 1 or kws):
             raise FortranError("%s with dim/mask is not supported" % name)
         fn = INTRINSICS.get(name)
@@ -1560,6 +1620,53 @@ class Frame:
                         del self.vars[name]
                     else:
                         self.vars[name] = old
+        elif k == "selecttype":
+            _, name, sel, guards = st
+            r = self.ref(sel)
+            obj = r.v
+            chain = self.w.type_chain(obj.tname) if isinstance(obj, FObj) else []
+            chosen = None
+            for (kind, tname), body in guards:             # type is > class is (most derived) > class default
+                if kind == "type" and chain and chain[0] == tname:
+                    chosen = body
+                    break
+            if chosen is None:
+                best = None
+                for (kind, tname), body in guards:
+                    if kind == "class" and tname in chain and (best is None or chain.index(tname) < best[0]):
+                        best = (chain.index(tname), body)
+                chosen = best[1] if best else next((b for (kd, _), b in guards if kd == "default"), None)
+            if chosen is not None:
+                saved = self.vars.get(name)
+                self.vars[name] = r
+                try:
+                    self.run(chosen)
+                finally:
+                    if saved is None:
+                        del self.vars[name]
+                    else:
+                        self.vars[name] = saved
+        elif k == "selectcase":
+            v = self.eval(st[1])
+            default = None
+            for vals, body in st[2]:
+                if vals is None:
+                    default = body
+                    continue
+                hit = False
+                for a in vals:
+                    if a[0] == "slice":
+                        lo = None if a[1] is None else self.eval(a[1])
+                        hi = None if a[2] is None else self.eval(a[2])
+                        hit = hit or ((lo is None or v >= lo) and (hi is None or v <= hi))
+                    else:
+                        hit = hit or v == self.eval(a)
+                if hit:
+                    self.run(body)
+                    break
+            else:
+                if default is not None:
+                    self.run(default)
         elif k == "allocate":
             self.exec_allocate(st[1])
         elif k == "deallocate":

@@ -37,7 +37,10 @@ SRC = "/root/reference/src"
 FILES = ["globals/globals_module.f90", "base/base_module.f90", "swiftest/swiftest_module.f90",
          "swiftest/swiftest_kick.f90", "swiftest/swiftest_drift.f90", "swiftest/swiftest_orbel.f90",
          "swiftest/swiftest_util.f90", "encounter/encounter_module.f90", "encounter/encounter_check.f90",
-         "encounter/encounter_util.f90", "collision/collision_module.f90"]
+         "encounter/encounter_util.f90", "collision/collision_module.f90",
+         "helio/helio_module.f90", "helio/helio_step.f90", "helio/helio_kick.f90", "helio/helio_drift.f90",
+         "helio/helio_util.f90", "whm/whm_module.f90", "whm/whm_step.f90", "whm/whm_kick.f90", "whm/whm_drift.f90",
+         "whm/whm_coord.f90", "whm/whm_util.f90"]
 
 
 def world():
@@ -50,7 +53,7 @@ def fa(a):
 
 
 def back(a):
-    return np.ascontiguousarray(a.T)
+    return np.array(a.T, order="C", copy=True)
 
 
 def disk(n, seed, a0=1.0, a1=1.3, mscale=1e-7, hot=0.02):
@@ -305,14 +308,81 @@ def gen_encounter(w, out):
               (name, nplm, nplt, len(i1), len(m1), len(t1), time.time() - t0), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------- whole steps
+def setc(obj, **kw):
+    for k, v in kw.items():
+        obj.c[k.lower()] = v
+
+
+def make_system(w, kind, fx, npl, lflat, masked):
+    """A helio or whm nbody_system object as the reference's setup leaves it before the first step."""
+    GMcb = float(fx["cb_Gmass"])
+    ntp = len(fx["tp_rh"])
+    z = lambda m: np.zeros((3, m), order="F")
+    pl, tp = w.new_object(kind + "_pl"), w.new_object(kind + "_tp")
+    cb = w.new_object("helio_cb" if kind == "helio" else "swiftest_cb")
+    system, param = w.new_object(kind + "_nbody_system"), w.new_object("swiftest_parameters")
+    lm_pl, lm_tp = np.ones(npl, dtype=bool), np.ones(ntp, dtype=bool)
+    if masked:
+        lm_pl[npl // 2] = False
+        lm_tp[::9] = False
+    setc(pl, nbody=npl, rh=fa(fx["pl_rh"][:npl]), vh=fa(fx["pl_vh"][:npl]), vb=z(npl), ah=z(npl),
+         Gmass=np.array(fx["pl_Gmass"][:npl]), radius=np.array(fx["pl_radius"][:npl]), mu=GMcb + np.array(fx["pl_Gmass"][:npl]),
+         lmask=lm_pl, lfirst=True, status=np.zeros(npl, dtype=np.int32))
+    setc(tp, nbody=ntp, rh=fa(fx["tp_rh"]), vh=fa(fx["tp_vh"]), vb=z(ntp), ah=z(ntp), mu=np.full(ntp, GMcb), lmask=lm_tp,
+         lfirst=True, status=np.zeros(ntp, dtype=np.int32))
+    setc(cb, Gmass=GMcb)
+    setc(system, cb=cb, pl=pl, tp=tp)
+    setc(param, lflatten_interactions=lflat, lclose=True, lgr=False, loblatecb=False, lextra_force=False)
+    if lflat:
+        w.call("swiftest_util_flatten_eucl_plpl", pl, param)
+    if kind == "whm":
+        setc(pl, xj=z(npl), vj=z(npl), eta=np.zeros(npl), muj=np.zeros(npl), ir3j=np.zeros(npl), ir3h=np.zeros(npl))
+        setc(tp, ir3h=np.zeros(ntp))
+        w.call("whm_util_set_mu_eta_pl", pl, cb)
+    return pl, tp, cb, system, param
+
+
+def gen_steps(w, out):
+    """helio_step_pl/_tp (helio/helio_step.f90:37-123) and whm_step_pl/_tp (whm/whm_step.f90:37-100) with everything they
+    call (coordinate changes, linear drift, kicks, accelerations, Jacobi chains, Kepler drift), several consecutive steps."""
+    fx = np.load(os.path.join(HERE, "fixture_108pl_50tp.npz"))
+    nsteps, dt = 5, 0.02
+    for kind in ("helio", "whm"):
+        for tag, npl, lflat, masked in (("p8", 8, False, False), ("p8flat", 8, True, False), ("p8mask", 8, False, True),
+                                        ("p30", 30, False, False)):
+            t0 = time.time()
+            pl, tp, cb, system, param = make_system(w, kind, fx, npl, lflat, masked)
+            key = "%s_%s_" % (kind, tag)
+            out[key + "npl"], out[key + "lflat"], out[key + "dt"], out[key + "nsteps"] = npl, lflat, dt, nsteps
+            out[key + "GMcb"] = float(fx["cb_Gmass"])
+            out[key + "lmask_pl"], out[key + "lmask_tp"] = pl.c["lmask"].copy(), tp.c["lmask"].copy()
+            for nm in ("rh", "vh"):
+                out[key + "pl_%s0" % nm], out[key + "tp_%s0" % nm] = back(pl.c[nm]), back(tp.c[nm])
+            out[key + "pl_Gmass"], out[key + "pl_radius"] = pl.c["gmass"].copy(), pl.c["radius"].copy()
+            hist = {k: [] for k in ("pl_rh", "pl_vh", "tp_rh", "tp_vh", "pl_vb", "tp_vb")}
+            for s in range(nsteps):
+                w.call(kind + "_step_pl", pl, system, param, s * dt, dt)
+                w.call(kind + "_step_tp", tp, system, param, s * dt, dt)
+                for o, nm in ((pl, "pl"), (tp, "tp")):
+                    hist[nm + "_rh"].append(back(o.c["rh"])); hist[nm + "_vh"].append(back(o.c["vh"]))
+                    hist[nm + "_vb"].append(back(o.c["vb"]))
+            for k2, v in hist.items():
+                out[key + k2] = np.array(v)
+            if kind == "whm":
+                out[key + "eta"], out[key + "muj"] = pl.c["eta"].copy(), pl.c["muj"].copy()
+                out[key + "xj"], out[key + "vj"] = back(pl.c["xj"]), back(pl.c["vj"])
+            print("  %s %-7s npl=%d ntp=%d  %d steps (%.1fs)" % (kind, tag, npl, tp.c["nbody"], nsteps, time.time() - t0), flush=True)
+
+
 def main():
     import collections
     import json
-    which = sys.argv[1:] or ["kick", "drift", "encounter"]
+    which = sys.argv[1:] or ["kick", "drift", "encounter", "steps"]
     w = world()
     cov_path = os.path.join(HERE, "fortran_coverage.json")
     coverage = json.load(open(cov_path)) if os.path.exists(cov_path) else {}
-    for part, fn in (("kick", gen_kick), ("drift", gen_drift), ("encounter", gen_encounter)):
+    for part, fn in (("kick", gen_kick), ("drift", gen_drift), ("encounter", gen_encounter), ("steps", gen_steps)):
         if part not in which:
             continue
         t0 = time.time()

@@ -163,3 +163,63 @@ def test_cuda_plplm_and_merged_lists_are_the_fortran_lists(ctx, ge, case):
     a = (r[:nplm], v[:nplm], r[nplm:], v[nplm:], renc[:nplm], renc[nplm:], dt)
     _same(ctx.encounter_check_all_sort_and_sweep_plplm(nplm, nplt, *a), ge["plplm_%s_sas" % case])
     _same(ctx.encounter_check_all_plplm(nplm, nplt, *a), ge["plplm_%s_merged" % case])
+
+
+# ------------------------------------------------------------------------------------------------------- whole steps
+@pytest.fixture(scope="module")
+def gs():
+    return np.load(os.path.join(GOLD, "fortran_steps.npz"))
+
+
+def _sync_system(ctx, gs, kind, tag, gen):
+    from swiftest_b200 import PL, TP
+    key = "%s_%s_" % (kind, tag)
+    g = lambda k: gs[key + k]
+    GMcb = float(g("GMcb"))
+    Gm, radius = g("pl_Gmass"), g("pl_radius")
+    n, ntp = len(Gm), len(g("tp_rh0"))
+    rhill = np.linalg.norm(g("pl_rh0"), axis=1) * (Gm / (3 * GMcb)) ** (1.0 / 3.0)
+    ctx.body_sync(PL, n, nplm=n, r=g("pl_rh0"), v=g("pl_vh0"), Gmass=Gm, radius=radius, rhill=rhill, mu=GMcb + Gm,
+                  lmask=g("lmask_pl").astype(np.int32), generation=gen)
+    ctx.body_sync(TP, ntp, r=g("tp_rh0"), v=g("tp_vh0"), mu=np.full(ntp, GMcb), lmask=g("lmask_tp").astype(np.int32),
+                  generation=gen + 1)
+    return g, GMcb, float(g("dt")), int(g("nsteps")), bool(g("lflat"))
+
+
+def _close(a, b, tol):
+    s = np.linalg.norm(b, axis=-1, keepdims=True)
+    return float(np.max(np.abs(a - b) / np.where(s > 0, s, 1.0))) < tol
+
+
+@pytest.mark.parametrize("tag", ["p8", "p8flat", "p8mask", "p30"])
+def test_cuda_helio_steps_against_the_fortran(ctx, gs, tag):
+    """swcu_helio_step_pl + swcu_helio_step_tp (device resident, nothing crosses PCIe between steps) against the states the
+    reference's helio_step_pl / helio_step_tp produce, step after step."""
+    from swiftest_b200 import PL, TP, LOOP_TRIANGULAR, LOOP_FLAT
+    g, GMcb, dt, nsteps, lflat = _sync_system(ctx, gs, "helio", tag, 7100 + 10 * ["p8", "p8flat", "p8mask", "p30"].index(tag))
+    on_pl, on_tp = g("lmask_pl"), g("lmask_tp")
+    for s in range(nsteps):
+        assert ctx.helio_step_pl(GMcb, dt, loop_variant=LOOP_FLAT if lflat else LOOP_TRIANGULAR, lclose=True, lfirst=(s == 0)) == 0
+        assert ctx.helio_step_tp(GMcb, dt, lfirst=(s == 0)) == 0
+        pl, tp = ctx.body_get(PL), ctx.body_get(TP)
+        assert _close(pl["r"], g("pl_rh")[s], 1e-12) and _close(pl["v"], g("pl_vh")[s], 1e-12), (tag, s)
+        assert _close(tp["r"][on_tp], g("tp_rh")[s][on_tp], 1e-12) and _close(tp["v"][on_tp], g("tp_vh")[s][on_tp], 1e-12), (tag, s)
+        assert np.array_equal(tp["r"][~on_tp], g("tp_rh0")[~on_tp])          # masked particles never move
+        assert _close(ctx.body_get_vb(PL)["vb"][on_pl], g("pl_vb")[s][on_pl], 1e-12)
+
+
+@pytest.mark.parametrize("tag", ["p8", "p8flat", "p8mask", "p30"])
+def test_cuda_whm_steps_against_the_fortran(ctx, gs, tag):
+    """swcu_whm_step_pl + swcu_whm_tp_step(ah0 from the device) against the reference's whm_step_pl / whm_step_tp."""
+    from swiftest_b200 import PL, TP, LOOP_TRIANGULAR, LOOP_FLAT
+    g, GMcb, dt, nsteps, lflat = _sync_system(ctx, gs, "whm", tag, 7200 + 10 * ["p8", "p8flat", "p8mask", "p30"].index(tag))
+    on_tp = g("lmask_tp")
+    ctx.whm_tp_first_accel()
+    for s in range(nsteps):
+        assert ctx.whm_step_pl(GMcb, dt, LOOP_FLAT if lflat else LOOP_TRIANGULAR, True, lfirst=(s == 0)) == 0
+        assert ctx.whm_tp_step(dt, None) == 0
+        pl, tp = ctx.body_get(PL), ctx.body_get(TP)
+        assert _close(pl["r"], g("pl_rh")[s], 1e-12) and _close(pl["v"], g("pl_vh")[s], 1e-12), (tag, s)
+        assert _close(tp["r"][on_tp], g("tp_rh")[s][on_tp], 1e-12) and _close(tp["v"][on_tp], g("tp_vh")[s][on_tp], 1e-12), (tag, s)
+    xj, vj = ctx.whm_get_jacobi()
+    assert _close(xj, g("xj"), 1e-12) and _close(vj, g("vj"), 1e-12)

@@ -582,3 +582,56 @@ def test_committed_goldens_regenerate_from_the_reference_tree(gk, gd):
            gd["drift_long_lmask"][:n].copy(), fl)
     assert_bit_equal(G.back(x), gd["drift_long_x1"][:n], "regenerated drift x")
     assert np.array_equal(fl, gd["drift_long_iflag"][:n])
+
+
+# ------------------------------------------------------------------------------------------------------- whole steps
+@pytest.fixture(scope="module")
+def gs():
+    return np.load(os.path.join(GOLD, "fortran_steps.npz"))
+
+
+STEP_CASES = ["p8", "p8flat", "p8mask", "p30"]
+
+
+def _run_oracle_steps(oracle, gs, kind, tag):
+    key = "%s_%s_" % (kind, tag)
+    g = lambda k: gs[key + k]
+    GMcb, dt, nsteps, lflat = float(g("GMcb")), float(g("dt")), int(g("nsteps")), bool(g("lflat"))
+    Gm, radius = g("pl_Gmass"), g("pl_radius")
+    lm_pl, lm_tp = g("lmask_pl").astype(np.int32), g("lmask_tp").astype(np.int32)
+    pl = dict(rh=g("pl_rh0").copy(), vh=g("pl_vh0").copy())
+    tp = dict(rh=g("tp_rh0").copy(), vh=g("tp_vh0").copy())
+    if kind == "helio":
+        pl["vb"], tp["vb"] = np.zeros_like(pl["rh"]), np.zeros_like(tp["rh"])
+    step_pl = oracle.helio_step_pl if kind == "helio" else oracle.whm_step_pl
+    step_tp = oracle.helio_step_tp if kind == "helio" else oracle.whm_step_tp
+    for s in range(nsteps):
+        assert not step_pl(pl, GMcb, Gm, radius, dt, lflat=lflat, lmask=lm_pl).any()
+        assert not step_tp(tp, pl, GMcb, Gm, dt, lmask=lm_tp)[lm_tp == 1].any()
+        yield s, pl, tp
+
+
+@pytest.mark.parametrize("tag", STEP_CASES)
+def test_helio_steps_are_bit_identical_to_the_fortran(oracle, gs, tag):
+    """helio_step_pl + helio_step_tp (helio/helio_step.f90:37-123 and everything below: vh2vb, lindrift, kick_vb, getacch,
+    drift, vb2vh), 5 consecutive steps of planets and test particles, tri and flat loops, with masked bodies."""
+    for s, pl, tp in _run_oracle_steps(oracle, gs, "helio", tag):
+        for nm, st in (("pl", pl), ("tp", tp)):
+            for q in ("rh", "vh", "vb"):
+                assert_bit_equal(st[q], gs["helio_%s_%s_%s" % (tag, nm, q)][s], "helio %s step %d %s %s" % (tag, s, nm, q))
+
+
+@pytest.mark.parametrize("tag", STEP_CASES)
+def test_whm_steps_are_bit_identical_to_the_fortran(oracle, gs, tag):
+    """whm_step_pl + whm_step_tp (whm/whm_step.f90:37-100 and below: kick_vh, getacch ah0/ah1/ah2, h2j, vh2vj, Jacobi drift,
+    j2h), 5 consecutive steps."""
+    last = None
+    for s, pl, tp in _run_oracle_steps(oracle, gs, "whm", tag):
+        for nm, st in (("pl", pl), ("tp", tp)):
+            for q in ("rh", "vh"):
+                assert_bit_equal(st[q], gs["whm_%s_%s_%s" % (tag, nm, q)][s], "whm %s step %d %s %s" % (tag, s, nm, q))
+        last = pl
+    assert_bit_equal(last["eta"], gs["whm_%s_eta" % tag], "eta")
+    assert_bit_equal(last["muj"], gs["whm_%s_muj" % tag], "muj")
+    assert_bit_equal(last["xj"], gs["whm_%s_xj" % tag], "xj")
+    assert_bit_equal(last["vj"], gs["whm_%s_vj" % tag], "vj")
