@@ -143,6 +143,7 @@ TOKEN_RE = re.compile(r"""
   | (?P<real>(?:\d+\.\d*|\.\d+|\d+)(?:[ed][+-]?\d+)(?:_\w+)?|(?:\d+\.\d*|\.\d+)(?:_\w+)?)
   | (?P<int>\d+(?:_\w+)?)
   | (?P<dotop>\.(?:and|or|not|eqv|neqv|true|false|eq|ne|lt|le|gt|ge)\.(?:_\w+)?)
+  | (?P<defop>\.[a-z]+\.)
   | (?P<name>[a-z_]\w*)
   | (?P<str>'(?:[^']|'')*'|"(?:[^"]|"")*")
   | (?P<op>\*\*|==|/=|<=|>=|=>|::|//|\(/|/\)|[-+*/<>=(),:%\[\]])
@@ -170,6 +171,8 @@ def tokenize(s):
                 toks.append(("log", v == ".true."))
             else:
                 toks.append(("op", v))
+        elif k == "defop":
+            toks.append(("defop", v))
         elif k == "real":
             body = re.sub(r"_\w+$", "", v)
             toks.append(("num", float(body.replace("d", "e"))))
@@ -213,7 +216,11 @@ class Parser:
 
     # precedence climbing, lowest first
     def expr(self):
-        return self.p_eqv()
+        a = self.p_eqv()
+        while self.peek()[0] == "defop":                 # defined binary operators bind loosest
+            op = self.next()[1]
+            a = ("defop", op, [a, self.p_eqv()])
+        return a
 
     def p_eqv(self):
         a = self.p_or()
@@ -315,6 +322,8 @@ class Parser:
         if k == "name":
             node = ("name", v)
             return self.postfix(node)
+        if k == "defop":                                  # defined unary operators bind tightest
+            return ("defop", v, [self.p_primary()])
         raise FortranError("unexpected token %r in %r" % (tok, self.t))
 
     def ac_item(self):
@@ -586,8 +595,8 @@ class World:
             no, s = lines[i]
             if re.match(r"^(abstract\s+)?interface\b", s):
                 iface_depth += 1
-                m = re.match(r"^interface\s+(\w+)$", s)
-                iface_name = m.group(1) if m else None
+                m = re.match(r"^interface\s+(\w+|operator\s*\(\s*\.[a-z]+\.\s*\))$", s)
+                iface_name = re.sub(r"\s", "", m.group(1)) if m else None
                 i += 1
                 continue
             if re.match(r"^end\s*interface\b", s):
@@ -1354,6 +1363,10 @@ class Frame:
             return base.c[e[2]]
         if k == "arr":
             return self.array_constructor(e[1])
+        if k == "defop":
+            cells = [(None, self.ref(a)) for a in e[2]]
+            p = self.w.resolve(self.w.generics["operator(%s)" % e[1]], cells)
+            return self.w.invoke(p, cells)
         if k == "str":
             return e[1]
         raise FortranError("cannot evaluate %r" % (e,))
@@ -1702,6 +1715,8 @@ class Frame:
             dst.v = src.v
             src.v = None
             return
+        if callee[0] == "name" and callee[1].startswith("ieee_") and callee[1] not in self.w.procs:
+            return                                      # floating-point environment calls: nothing to do here
         for a in args:
             if a[0] == "kw":
                 cells.append((a[1], self.ref(a[2])))
@@ -1715,6 +1730,8 @@ class Frame:
             name = callee[1]
             cands = self.w.generics.get(name, [name])
             if cands == [name] and name not in self.w.procs:
+                if name.startswith("ieee_"):
+                    return                              # floating-point environment calls: nothing to do here
                 raise FortranError("call to unknown procedure %s" % name)
         p = self.w.resolve(cands, cells)
         self.w.invoke(p, cells)

@@ -40,7 +40,10 @@ FILES = ["globals/globals_module.f90", "base/base_module.f90", "swiftest/swiftes
          "encounter/encounter_util.f90", "collision/collision_module.f90",
          "helio/helio_module.f90", "helio/helio_step.f90", "helio/helio_kick.f90", "helio/helio_drift.f90",
          "helio/helio_util.f90", "whm/whm_module.f90", "whm/whm_step.f90", "whm/whm_kick.f90", "whm/whm_drift.f90",
-         "whm/whm_coord.f90", "whm/whm_util.f90"]
+         "whm/whm_coord.f90", "whm/whm_util.f90",
+         "operator/operator_module.f90", "operator/operator_cross.f90", "symba/symba_module.f90", "symba/symba_kick.f90",
+         "symba/symba_encounter_check.f90", "symba/symba_util.f90", "collision/collision_check.f90",
+         "swiftest/swiftest_discard.f90"]
 
 
 def world():
@@ -375,14 +378,157 @@ def gen_steps(w, out):
             print("  %s %-7s npl=%d ntp=%d  %d steps (%.1fs)" % (kind, tag, npl, tp.c["nbody"], nsteps, time.time() - t0), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------------------- energy, lists
+def gen_lists(w, out):
+    """swiftest_util_get_energy_and_momentum_system (swiftest_util.f90:1172-1394), symba_kick_list_plpl/_pltp
+    (symba/symba_kick.f90:126-337), symba_encounter_check_list_plpl/_pltp (symba/symba_encounter_check.f90:88-235) with
+    symba_util_set_renc, collision_check_one + swiftest_orbel_xv2aeq (collision/collision_check.f90:16-57,
+    swiftest_orbel.f90:700-764), swiftest_discard_pl_close (swiftest_discard.f90:295-337)."""
+    ACTIVE, INACTIVE = int(w.const("active")), int(w.const("inactive"))
+    n, ntp = 70, 90
+    r, v, Gm, rhill, radius = disk(n, 71, mscale=3e-6)
+    rt, vt, _, _, _ = disk(ntp, 72)
+    rng = np.random.default_rng(73)
+
+    # ---- energy and momentum: barycentric state, one inactive body, flat and triangular potential loops, lclose on/off
+    GMcb, mcb = 39.476926408897626, 1.0
+    status = np.full(n, ACTIVE, dtype=np.int32); status[7] = INACTIVE
+    mass = Gm / GMcb
+    rbcb, vbcb = np.array([1e-5, -2e-5, 3e-7]), np.array([2e-6, 1e-6, -4e-8])
+    out["en_GMcb"], out["en_mass_cb"], out["en_radius_cb"], out["en_rbcb"], out["en_vbcb"] = GMcb, mcb, 0.00465, rbcb, vbcb
+    out["en_Gmass"], out["en_mass"], out["en_radius"], out["en_rb"], out["en_vb"], out["en_status"] = Gm, mass, radius, r, v, status
+    for tag, lflat, lclose in (("tri", False, True), ("flat", True, True), ("tri_noclose", False, False)):
+        pl, cb = w.new_object("symba_pl"), w.new_object("symba_cb")
+        system, param = w.new_object("symba_nbody_system"), w.new_object("swiftest_parameters")
+        setc(pl, nbody=n, rb=fa(r), vb=fa(v), Gmass=Gm.copy(), mass=mass.copy(), radius=radius.copy(), lmask=np.ones(n, dtype=bool),
+             status=status.copy(), ip=np.zeros((3, n), order="F"), rot=np.zeros((3, n), order="F"))
+        setc(cb, Gmass=GMcb, mass=mcb, radius=0.00465, rb=rbcb.copy(), vb=vbcb.copy(), ip=np.zeros(3), rot=np.zeros(3))
+        setc(system, pl=pl, cb=cb)
+        setc(param, lrotation=False, lflatten_interactions=lflat, loblatecb=False, lclose=lclose)
+        if lflat:
+            w.call("swiftest_util_flatten_eucl_plpl", pl, param)
+        w.call("swiftest_util_get_energy_and_momentum_system", system, param)
+        for k in ("ke_orbit", "pe", "be", "te", "gmtot"):
+            out["en_%s_%s" % (tag, k)] = float(system.c[k])
+        out["en_%s_l_orbit" % tag] = np.array(system.c["l_orbit"])
+
+    # ---- SyMBA recursion kicks over an encounter list: close pairs so that all three regimes (inside the inner shell,
+    #      in the shell, outside) occur; mixed levels, some inactive pairs, both signs, several recursion levels
+    rhill_big = np.full(n, 0.012) * rng.uniform(0.7, 1.3, n)
+    d = np.linalg.norm(r[:, None] - r[None], axis=2)
+    iu = np.triu_indices(n, 1)
+    order = np.argsort(d[iu])
+    pick = np.concatenate([order[:110], rng.choice(order[110:], 40, replace=False)])
+    rng.shuffle(pick)
+    i1, i2 = (iu[0][pick] + 1).astype(np.int32), (iu[1][pick] + 1).astype(np.int32)
+    nenc = len(i1)
+    lstatus = np.full(nenc, ACTIVE, dtype=np.int32); lstatus[::13] = INACTIVE
+    levelg = rng.integers(0, 3, n).astype(np.int32)
+    out["kl_rh"], out["kl_rhill"], out["kl_Gmass"], out["kl_levelg"] = r, rhill_big, Gm, levelg
+    out["kl_index1"], out["kl_index2"], out["kl_lactive"] = i1, i2, lstatus == ACTIVE
+    vb0 = v.copy()
+    ah0 = rng.normal(0, 1e-3, (n, 3))
+    out["kl_vb0"], out["kl_ah0"] = vb0, ah0
+    dtk = 0.004
+    out["kl_dt"] = dtk
+    for irec, sgn in ((1, 1), (1, -1), (2, 1), (2, -1), (3, 1)):
+        pl, system, lst = w.new_object("symba_pl"), w.new_object("symba_nbody_system"), w.new_object("symba_list_plpl")
+        setc(pl, nbody=n, rh=fa(r), vb=fa(vb0), ah=fa(ah0), Gmass=Gm.copy(), rhill=rhill_big.copy(), lmask=np.ones(n, dtype=bool),
+             status=np.full(n, ACTIVE, dtype=np.int32), levelg=levelg.copy())
+        setc(system, pl=pl)
+        setc(lst, nenc=nenc, index1=i1.copy(), index2=i2.copy(), status=lstatus.copy())
+        w.call("symba_kick_list_plpl", lst, system, dtk, irec, sgn)
+        out["kl_plpl_irec%d_sgn%d_vb" % (irec, sgn)] = back(pl.c["vb"])
+        out["kl_plpl_irec%d_sgn%d_ah" % (irec, sgn)] = back(pl.c["ah"])
+    # pl-tp list
+    dd = np.linalg.norm(r[:, None] - rt[None], axis=2)
+    flat_order = np.argsort(dd.ravel())
+    pick = np.concatenate([flat_order[:100], rng.choice(flat_order[100:], 30, replace=False)])
+    rng.shuffle(pick)
+    p1, p2 = (pick // ntp + 1).astype(np.int32), (pick % ntp + 1).astype(np.int32)
+    ne2 = len(p1)
+    st2 = np.full(ne2, ACTIVE, dtype=np.int32); st2[5::11] = INACTIVE
+    levelg_tp = rng.integers(0, 3, ntp).astype(np.int32)
+    vbt0, aht0 = vt.copy(), rng.normal(0, 1e-3, (ntp, 3))
+    out["kt_rh_tp"], out["kt_levelg_tp"], out["kt_index1"], out["kt_index2"], out["kt_lactive"] = rt, levelg_tp, p1, p2, st2 == ACTIVE
+    out["kt_vb0"], out["kt_ah0"] = vbt0, aht0
+    for irec, sgn in ((1, 1), (2, -1), (2, 1)):
+        pl, tp = w.new_object("symba_pl"), w.new_object("symba_tp")
+        system, lst = w.new_object("symba_nbody_system"), w.new_object("symba_list_pltp")
+        setc(pl, nbody=n, rh=fa(r), Gmass=Gm.copy(), rhill=rhill_big.copy(), lmask=np.ones(n, dtype=bool),
+             status=np.full(n, ACTIVE, dtype=np.int32), levelg=levelg.copy())
+        setc(tp, nbody=ntp, rh=fa(rt), vb=fa(vbt0), ah=fa(aht0), lmask=np.ones(ntp, dtype=bool),
+             status=np.full(ntp, ACTIVE, dtype=np.int32), levelg=levelg_tp.copy())
+        setc(system, pl=pl, tp=tp)
+        setc(lst, nenc=ne2, index1=p1.copy(), index2=p2.copy(), status=st2.copy())
+        w.call("symba_kick_list_pltp", lst, system, dtk, irec, sgn)
+        out["kt_pltp_irec%d_sgn%d_vb" % (irec, sgn)] = back(tp.c["vb"])
+        out["kt_pltp_irec%d_sgn%d_ah" % (irec, sgn)] = back(tp.c["ah"])
+
+    # ---- the recursion's encounter re-check over the list (with symba_util_set_renc)
+    param = w.new_object("swiftest_parameters")
+    radius_big = rhill_big * 0.35                       # some listed pairs overlap physically and must be dropped
+    out["el_radius"], out["el_vb_pl"], out["el_vb_tp"] = radius_big, v, vt
+    for irec in (1, 2):
+        level = np.where(np.arange(nenc) % 5 == 0, irec, irec - 1).astype(np.int32)      # only level == irec-1 is examined
+        pl, system, lst = w.new_object("symba_pl"), w.new_object("symba_nbody_system"), w.new_object("symba_list_plpl")
+        setc(pl, nbody=n, rh=fa(r), vb=fa(v), rhill=rhill_big.copy(), radius=radius_big.copy(), renc=np.zeros(n),
+             levelg=np.zeros(n, dtype=np.int32), levelm=np.zeros(n, dtype=np.int32))
+        setc(system, pl=pl)
+        setc(lst, nenc=nenc, index1=i1.copy(), index2=i2.copy(), status=lstatus.copy(), level=level.copy(),
+             lvdotr=np.zeros(nenc, dtype=bool))
+        lany = w.call("symba_encounter_check_list_plpl", lst, param, system, 0.05, irec)
+        out["el_plpl_irec%d_level0" % irec] = level
+        out["el_plpl_irec%d_level" % irec], out["el_plpl_irec%d_lvdotr" % irec] = lst.c["level"].copy(), lst.c["lvdotr"].copy()
+        out["el_plpl_irec%d_renc" % irec], out["el_plpl_irec%d_lany" % irec] = pl.c["renc"].copy(), bool(lany)
+        out["el_plpl_irec%d_levelg" % irec] = pl.c["levelg"].copy()
+        level2 = np.where(np.arange(ne2) % 4 == 0, irec, irec - 1).astype(np.int32)
+        pl, tp = w.new_object("symba_pl"), w.new_object("symba_tp")
+        system, lst = w.new_object("symba_nbody_system"), w.new_object("symba_list_pltp")
+        setc(pl, nbody=n, rh=fa(r), vb=fa(v), rhill=rhill_big.copy(), radius=radius_big.copy(), renc=np.zeros(n),
+             levelg=np.zeros(n, dtype=np.int32), levelm=np.zeros(n, dtype=np.int32))
+        setc(tp, nbody=ntp, rh=fa(rt), vb=fa(vt), levelg=np.zeros(ntp, dtype=np.int32), levelm=np.zeros(ntp, dtype=np.int32))
+        setc(system, pl=pl, tp=tp)
+        setc(lst, nenc=ne2, index1=p1.copy(), index2=p2.copy(), status=st2.copy(), level=level2.copy(),
+             lvdotr=np.zeros(ne2, dtype=bool))
+        lany = w.call("symba_encounter_check_list_pltp", lst, param, system, 0.05, irec)
+        out["el_pltp_irec%d_level0" % irec] = level2
+        out["el_pltp_irec%d_level" % irec], out["el_pltp_irec%d_lvdotr" % irec] = lst.c["level"].copy(), lst.c["lvdotr"].copy()
+        out["el_pltp_irec%d_lany" % irec] = bool(lany)
+
+    # ---- collision_check_one (with xv2aeq) and discard_pl_close on a spread of relative states
+    m = 400
+    rel = rng.normal(0, 1.0, (m, 3)) * 10 ** rng.uniform(-3, 0, (m, 1))
+    vel = rng.normal(0, 1.0, (m, 3)) * 10 ** rng.uniform(-1, 1.5, (m, 1))
+    vel[::3] = rel[::3] * rng.uniform(0.5, 50, (len(rel[::3]), 1)) + vel[::3] * 0.05     # mostly receding: the xv2aeq branch
+    Gmtot = 10 ** rng.uniform(-7, -3, m)
+    rlim = 10 ** rng.uniform(-4, -1.5, m)
+    lvd = rng.uniform(size=m) > 0.3
+    dtc = 0.02
+    lcol, lclo = np.zeros(m, dtype=bool), np.zeros(m, dtype=bool)
+    iflag, r2min = np.zeros(m, dtype=np.int32), np.zeros(m)
+    for k in range(m):
+        a, b = F.Cell(False), F.Cell(False)
+        w.call("collision_check_one", *map(float, rel[k]), *map(float, vel[k]), float(Gmtot[k]), float(rlim[k]), dtc, bool(lvd[k]), a, b)
+        lcol[k], lclo[k] = a.v, b.v
+        fl, rm = F.Cell(0), F.Cell(float("nan"))     # r2min stays undefined on the early exits: NaN marks them
+        w.call("swiftest_discard_pl_close", rel[k].copy(), vel[k].copy(), dtc, float(rlim[k]) ** 2, fl, rm)
+        iflag[k], r2min[k] = fl.v, rm.v
+    out["cc_rel"], out["cc_vel"], out["cc_Gmtot"], out["cc_rlim"], out["cc_lvdotr"], out["cc_dt"] = rel, vel, Gmtot, rlim, lvd, dtc
+    out["cc_lcollision"], out["cc_lclosest"], out["dc_iflag"], out["dc_r2min"] = lcol, lclo, iflag, r2min
+    print("  collision_check_one: %d collisions, %d closest; discard_pl_close: %d flagged" % (lcol.sum(), lclo.sum(), iflag.sum()),
+          flush=True)
+
+
 def main():
     import collections
     import json
-    which = sys.argv[1:] or ["kick", "drift", "encounter", "steps"]
+    which = sys.argv[1:] or ["kick", "drift", "encounter", "steps", "lists"]
     w = world()
     cov_path = os.path.join(HERE, "fortran_coverage.json")
     coverage = json.load(open(cov_path)) if os.path.exists(cov_path) else {}
-    for part, fn in (("kick", gen_kick), ("drift", gen_drift), ("encounter", gen_encounter), ("steps", gen_steps)):
+    for part, fn in (("kick", gen_kick), ("drift", gen_drift), ("encounter", gen_encounter), ("steps", gen_steps),
+                     ("lists", gen_lists)):
         if part not in which:
             continue
         t0 = time.time()

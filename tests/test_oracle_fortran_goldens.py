@@ -555,6 +555,17 @@ def test_goldens_executed_every_reference_procedure_on_the_path():
                       "base_util_sort_index_i4b_i8bind", "encounter_check_all_triangular_plpl",
                       "encounter_check_all_triangular_pltp", "encounter_check_all_triangular_plplm"],
     }
+    need["steps"] = ["helio_step_pl", "helio_step_tp", "helio_kick_vb_pl", "helio_kick_vb_tp", "helio_kick_getacch_pl",
+                     "helio_kick_getacch_tp", "helio_drift_linear_pl", "helio_drift_linear_tp", "helio_drift_body",
+                     "swiftest_util_coord_vh2vb_pl", "swiftest_util_coord_vb2vh_pl", "swiftest_util_coord_vh2vb_tp",
+                     "swiftest_util_coord_vb2vh_tp", "swiftest_kick_getacch_int_pl", "swiftest_kick_getacch_int_tp",
+                     "whm_step_pl", "whm_step_tp", "whm_kick_vh_pl", "whm_kick_vh_tp", "whm_kick_getacch_pl", "whm_kick_getacch_tp",
+                     "whm_kick_getacch_ah0", "whm_kick_getacch_ah1", "whm_kick_getacch_ah2", "whm_coord_h2j_pl", "whm_coord_j2h_pl",
+                     "whm_coord_vh2vj_pl", "whm_drift_pl", "whm_util_set_mu_eta_pl", "swiftest_drift_all"]
+    need["lists"] = ["swiftest_util_get_energy_and_momentum_system", "swiftest_util_get_potential_energy_flat",
+                     "swiftest_util_get_potential_energy_triangular", "symba_kick_list_plpl", "symba_kick_list_pltp",
+                     "symba_encounter_check_list_plpl", "symba_encounter_check_list_pltp", "symba_util_set_renc",
+                     "collision_check_one", "swiftest_orbel_xv2aeq", "swiftest_discard_pl_close", "operator_cross_dp"]
     for part, names in need.items():
         for n in names:
             assert cov[part].get(n, 0) > 0, (part, n)
@@ -635,3 +646,107 @@ def test_whm_steps_are_bit_identical_to_the_fortran(oracle, gs, tag):
     assert_bit_equal(last["muj"], gs["whm_%s_muj" % tag], "muj")
     assert_bit_equal(last["xj"], gs["whm_%s_xj" % tag], "xj")
     assert_bit_equal(last["vj"], gs["whm_%s_vj" % tag], "vj")
+
+
+# ------------------------------------------------------------------------------------------------------- energy, lists
+@pytest.fixture(scope="module")
+def gl():
+    return np.load(os.path.join(GOLD, "fortran_lists.npz"))
+
+
+@pytest.mark.parametrize("tag,flat,lclose", [("tri", False, True), ("flat", True, True), ("tri_noclose", False, False)])
+def test_energy_and_momentum_are_bit_identical_to_the_fortran(oracle, gl, tag, flat, lclose):
+    """swiftest_util_get_energy_and_momentum_system with the flat and the triangular potential loop (swiftest_util.f90:1172-1394)."""
+    lmask = (gl["en_status"] != 1).astype(np.int32)                 # INACTIVE = 1 (globals_module.f90)
+    assert lmask.sum() == len(lmask) - 1
+    got = oracle.get_energy_and_momentum(float(gl["en_GMcb"]), float(gl["en_mass_cb"]), gl["en_rbcb"], gl["en_vbcb"], gl["en_Gmass"],
+                                         gl["en_mass"], gl["en_radius"], gl["en_rb"], gl["en_vb"], lmask=lmask, lclose=lclose, flat=flat)
+    for k, ok in (("ke_orbit", "ke_orbit"), ("pe", "pe"), ("be", "be"), ("te", "te"), ("gmtot", "GMtot")):
+        assert_bit_equal(np.array([got[ok]]), np.array([float(gl["en_%s_%s" % (tag, k)])]), "%s %s" % (tag, k))
+    assert_bit_equal(got["L_orbit"], gl["en_%s_l_orbit" % tag], tag + " L")
+
+
+@pytest.mark.parametrize("irec,sgn", [(1, 1), (1, -1), (2, 1), (2, -1), (3, 1)])
+def test_symba_kick_list_plpl_is_bit_identical_to_the_fortran(oracle, gl, irec, sgn):
+    """symba_kick_list_plpl (symba/symba_kick.f90:126-235): level mask, shell regimes, serial accumulation, kick."""
+    vb, lgood, ah = oracle.symba_kick_list_plpl(gl["kl_index1"], gl["kl_index2"], gl["kl_lactive"].astype(np.int32), gl["kl_levelg"],
+                                               gl["kl_rh"], gl["kl_rhill"], gl["kl_Gmass"], float(gl["kl_dt"]), irec, sgn,
+                                               gl["kl_vb0"], ah=gl["kl_ah0"])
+    assert_bit_equal(vb, gl["kl_plpl_irec%d_sgn%d_vb" % (irec, sgn)], "vb")
+    assert_bit_equal(ah, gl["kl_plpl_irec%d_sgn%d_ah" % (irec, sgn)], "ah")
+    assert not np.array_equal(vb, gl["kl_vb0"])
+
+
+def test_symba_kick_list_goldens_cover_all_three_regimes(gl):
+    """inside the inner shell (pair dropped), in the shell (smoothed factor through pow), outside (plain r^-3)."""
+    RHSCALE, RSHELL = 6.5, 0.48075
+    r, rh = gl["kl_rh"], gl["kl_rhill"]
+    i, j = gl["kl_index1"] - 1, gl["kl_index2"] - 1
+    r2 = ((r[j] - r[i]) ** 2).sum(1)
+    ri = (rh[i] + rh[j]) ** 2 * RHSCALE ** 2 * RSHELL ** 2
+    assert (r2 < ri * RSHELL ** 2).sum() > 3 and ((r2 >= ri * RSHELL ** 2) & (r2 < ri)).sum() > 3 and (r2 >= ri).sum() > 3
+
+
+@pytest.mark.parametrize("irec,sgn", [(1, 1), (2, -1), (2, 1)])
+def test_symba_kick_list_pltp_is_bit_identical_to_the_fortran(oracle, gl, irec, sgn):
+    """symba_kick_list_pltp (symba/symba_kick.f90:237-337)."""
+    vb, lgood, ah = oracle.symba_kick_list_pltp(gl["kt_index1"], gl["kt_index2"], gl["kt_lactive"].astype(np.int32), gl["kl_levelg"],
+                                               gl["kt_levelg_tp"], gl["kl_rh"], gl["kl_rhill"], gl["kl_Gmass"], gl["kt_rh_tp"],
+                                               float(gl["kl_dt"]), irec, sgn, gl["kt_vb0"])
+    assert_bit_equal(vb, gl["kt_pltp_irec%d_sgn%d_vb" % (irec, sgn)], "vb")
+    ref_ah = gl["kt_pltp_irec%d_sgn%d_ah" % (irec, sgn)]
+    touched = (ref_ah != gl["kt_ah0"]).any(1)               # the reference zeroes ah of the particles it kicked
+    assert touched.sum() > 5 and np.all(ref_ah[touched] == 0.0)
+    assert np.all(ah[touched] == 0.0) and np.all(ah[~touched] == 123.0)      # the wrapper pre-fills ah with 123
+
+
+@pytest.mark.parametrize("irec", [1, 2])
+def test_symba_encounter_check_list_is_identical_to_the_fortran(oracle, gl, irec):
+    """symba_encounter_check_list_plpl/_pltp with symba_util_set_renc (symba/symba_encounter_check.f90:88-235)."""
+    renc = oracle.set_renc(gl["kl_rhill"], irec)
+    assert_bit_equal(renc, gl["el_plpl_irec%d_renc" % irec], "renc")
+    for kind, i1, i2, lact in (("plpl", gl["kl_index1"], gl["kl_index2"], gl["kl_lactive"]),
+                               ("pltp", gl["kt_index1"], gl["kt_index2"], gl["kt_lactive"])):
+        level0, level1 = gl["el_%s_irec%d_level0" % (kind, irec)], gl["el_%s_irec%d_level" % (kind, irec)]
+        mask = lact & (level0 == irec - 1)
+        want = mask & (level1 == irec)
+        if kind == "plpl":
+            lenc, lvd, n = oracle.symba_encounter_check_list(i1, i2, mask.astype(np.int32), gl["kl_rh"], gl["el_vb_pl"], renc,
+                                                             gl["el_radius"], 0.05)
+        else:
+            lenc, lvd, n = oracle.symba_encounter_check_list(i1, i2, mask.astype(np.int32), gl["kl_rh"], gl["el_vb_pl"], renc,
+                                                             gl["el_radius"], 0.05, r2=gl["kt_rh_tp"], v2=gl["el_vb_tp"])
+        assert np.array_equal(lenc.astype(bool), want), kind
+        assert np.array_equal(lvd.astype(bool)[mask], gl["el_%s_irec%d_lvdotr" % (kind, irec)][mask]), kind
+        assert n == want.sum() and bool(gl["el_%s_irec%d_lany" % (kind, irec)]) == bool(want.any())
+        assert 0 < want.sum() < mask.sum()
+    lg = np.zeros(len(gl["kl_rhill"]), np.int32)
+    want = (gl["kl_lactive"] & (gl["el_plpl_irec%d_level0" % irec] == irec - 1)) & (gl["el_plpl_irec%d_level" % irec] == irec)
+    lg[gl["kl_index1"][want] - 1] = irec
+    lg[gl["kl_index2"][want] - 1] = irec
+    assert np.array_equal(lg, gl["el_plpl_irec%d_levelg" % irec])
+
+
+def test_collision_check_one_and_discard_pl_close_are_identical_to_the_fortran(oracle, gl):
+    """collision_check_one + swiftest_orbel_xv2aeq (collision_check.f90:16-57, swiftest_orbel.f90:700-764) through the
+    list wrapper (one pair per row), and swiftest_discard_pl_close (swiftest_discard.f90:295-337)."""
+    import ctypes as C
+    m = len(gl["cc_rlim"])
+    idx = np.arange(1, m + 1, dtype=np.int32)
+    z = np.zeros((m, 3))
+    lcol, lclo, n = oracle.collision_check_list(idx, idx, None, gl["cc_lvdotr"].astype(np.int32), gl["cc_rel"], gl["cc_vel"],
+                                                gl["cc_Gmtot"], gl["cc_rlim"], float(gl["cc_dt"]), r2=z, v2=z)
+    assert np.array_equal(lcol.astype(bool), gl["cc_lcollision"]) and np.array_equal(lclo.astype(bool), gl["cc_lclosest"])
+    inside = (gl["cc_rel"] ** 2).sum(1) <= gl["cc_rlim"] ** 2
+    assert (gl["cc_lcollision"] & ~inside).sum() > 3          # collisions predicted through the pericentre distance q
+    f = oracle.lib.swo_discard_pl_close
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_void_p, C.c_void_p]
+    f.restype = None
+    for k in range(m):
+        dx, dv = np.ascontiguousarray(gl["cc_rel"][k]), np.ascontiguousarray(gl["cc_vel"][k])
+        fl, rm = C.c_int32(-1), C.c_double(-1.0)
+        f(dx.ctypes.data, dv.ctypes.data, float(gl["cc_dt"]), float(gl["cc_rlim"][k]) ** 2, C.byref(fl), C.byref(rm))
+        assert fl.value == gl["dc_iflag"][k], k
+        if not np.isnan(gl["dc_r2min"][k]):                   # the reference leaves r2min undefined on its early exits
+            assert np.float64(rm.value).view(np.uint64) == gl["dc_r2min"][k].view(np.uint64), k
+    assert 10 < gl["dc_iflag"].sum() < m - 10 and 50 < np.isfinite(gl["dc_r2min"]).sum() < m
