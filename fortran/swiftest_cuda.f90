@@ -322,6 +322,12 @@ module swiftest_cuda
          integer(c_int), value :: kind
          real(c_double), intent(in) :: vb(3,*)
       end function
+      integer(c_int) function swcu_body_set_active(ctx, kind, lactive) bind(C, name="swcu_body_set_active")
+         import :: c_int, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         type(c_ptr), value :: lactive     !! c_loc of merge(1, 0, body%status(1:n) /= INACTIVE), or c_null_ptr: all active
+      end function
       integer(c_int) function swcu_body_get_vb(ctx, kind, vb, rbeg, rend) bind(C, name="swcu_body_get_vb")
          import :: c_int, c_ptr
          type(c_ptr), value :: ctx, vb, rbeg, rend

@@ -195,8 +195,13 @@ int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *nenc);
  * tree above (reproducible run to run; compare with a tolerance). */
 /* swiftest_util_coord_vh2vb_pl (swiftest_util.f90:424-459): vbcb = -sum(Gm*vh)/(GMcb + sum Gm); vb = vh + vbcb */
 int swcu_pl_vh2vb(swcu_context *ctx, double GMcb, double *vbcb);
-/* swiftest_util_coord_vb2vh_pl (:363-395): vbcb = -sum_{i=npl..1, lmask} Gm*vb/GMcb; vh = vb - vbcb */
+/* swiftest_util_coord_vb2vh_pl (:363-395): vbcb = -sum_{i=npl..1, status(i) /= INACTIVE} Gm*vb/GMcb; vh = vb - vbcb.
+ * The filter is the body STATUS, not lmask (swiftest_util.f90:377); see swcu_body_set_active */
 int swcu_pl_vb2vh(swcu_context *ctx, double GMcb, double *vbcb);
+/* merge(1, 0, body%status(1:n) /= INACTIVE) of a resident population, for the one reduction of the path that filters on
+ * the status instead of lmask (vb2vh above, also inside swcu_helio_step_pl).  NULL, or never called since the last
+ * swcu_body_sync that changed the population: every body is active (the state of a WHM/HELIO run between discards) */
+int swcu_body_set_active(swcu_context *ctx, int32_t kind, const int32_t *lactive);
 /* helio_drift_linear_pl (helio_drift.f90:129-165): pt = sum(Gm*vb, lmask)/GMcb; rh += pt*dt; kept as ptbeg / ptend */
 int swcu_pl_lindrift(swcu_context *ctx, double GMcb, double dt, int32_t lbeg, double *pt);
 /* helio_drift_linear_tp (:168-200) with the resident ptbeg / ptend; swcu_cb_set_pt loads them when the planets were

@@ -1,7 +1,8 @@
 """ctypes binding of oracle/libswiftest_oracle.so (the CPU restatement of the reference loops).
 
-TEST INFRASTRUCTURE ONLY.  PARITY: kick / sweep unpinned, drift pinned to the reference's Python two-body
-propagation (see swiftest_oracle.h).  Arrays follow the Fortran layout r(3,n) == numpy shape (n,3) C-order.
+TEST INFRASTRUCTURE ONLY.  PARITY: pinned bit for bit to the reference's own Fortran statements executed by
+oracle/f90interp.py (tests/golden/fortran_*.npz), drift also to the reference's Python two-body propagation
+(see swiftest_oracle.h).  Arrays follow the Fortran layout r(3,n) == numpy shape (n,3) C-order.
 """
 import ctypes as C
 import os

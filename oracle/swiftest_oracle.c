@@ -2,8 +2,10 @@
  * swiftest_oracle.c -- CPU restatement of Swiftest's force-and-drift hot path (see swiftest_oracle.h).
  *
  * TEST INFRASTRUCTURE ONLY; never linked into or called by the CUDA product path.
- * PARITY: kick and sort-and-sweep are UNPINNED (the reference has no function-level golden vectors and
- * cannot be compiled here); drift is pinned to the reference's Python el2xv/xv2el propagation.
+ * PARITY: PINNED bit for bit to the outputs of the reference's own Fortran statements, executed from
+ * /root/reference/src by the interpreter oracle/f90interp.py (tests/golden/fortran_*.npz,
+ * tests/test_oracle_fortran_goldens.py; the reference cannot be compiled here, see swiftest_oracle.h);
+ * drift additionally pinned to the reference's Python el2xv/xv2el propagation.
  *
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math -fopenmp -fPIC -shared (oracle/Makefile).
  * All "file:line" citations are relative to /root/reference/src.

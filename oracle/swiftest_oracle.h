@@ -7,10 +7,20 @@
  *
  * PARITY STATUS: the reference (Swiftest 2023.10.2, Modern Fortran) holds no function-level
  * golden vectors or known-answer tests for kick / sweep / drift, and no
- * Fortran compiler exists in the build container, so the reference cannot be run here.
- *   - kick and sort-and-sweep: PARITY UNPINNED (line-by-line restatement, self-consistency checks only).
- *   - drift: pinned to the reference's own Python two-body propagation (swiftest/tool.py
+ * Fortran compiler exists in the build container or on the GPU box (profiles/r02_fortran_probe.txt), so
+ * the reference cannot be COMPILED here (there is no oracle/_ref).  Round 2 pins the restatement by
+ * EXECUTING THE REFERENCE'S OWN FORTRAN STATEMENTS with a Fortran-subset interpreter
+ * (oracle/f90interp.py; generator tests/golden/gen_golden_fortran.py reads /root/reference/src):
+ *   - kick (flat/tri, rad/norad, every nplm branch, explicit pair lists, tp), sort-and-sweep and triangular
+ *     encounter checks (plpl, pltp, plplm, merged list; util_sort quicksorts, dedupe, F3 quirk), drift (all
+ *     solver branches, GR, failures): PINNED, BIT FOR BIT, tests/test_oracle_fortran_goldens.py.
+ *   - whole helio and WHM steps, energy/momentum, SyMBA list kernels, collision/discard predicates
+ *     (swiftest_oracle_step.c, swiftest_oracle_whm.c): PINNED the same way.
+ *   - drift additionally agrees with the reference's own Python two-body propagation (swiftest/tool.py
  *     xv2el_one/el2xv_one, imported from /root/reference by tests/golden/gen_golden.py) at 1e-11.
+ *   What the interpreter cannot show is compiler-specific code generation (FMA contraction, reassociation
+ *   under the reference's -ffast-math release flags, OpenMP reduction order): the pinned semantics are
+ *   "one IEEE operation per Fortran operation, serial loop order", the same contract as -ffp-contract=off here.
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference/src).
  * Arrays use the Fortran memory layout: r(3,n) column-major == C r[3*i + {0,1,2}].

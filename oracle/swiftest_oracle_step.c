@@ -2,11 +2,14 @@
  * swiftest_oracle_step.c -- CPU restatement of the O(N) glue around the hot path and of the energy sums
  * (SURVEY.md section 8f, ranks 1 and 2).  TEST INFRASTRUCTURE ONLY, see swiftest_oracle.h.
  *
- * PARITY STATUS: UNPINNED (the reference holds no function-level vectors for these routines) except
- * swo_orbel_xv2aeq, which is PINNED to a and e from the reference's own Python xv2el_one (swiftest/tool.py:377-455;
- * tests/golden/xv2aeq_ref.npz, generated by tests/golden/gen_golden.py) at 1e-11.  The other pins are the system-level
- * conservation thresholds of tests/test_swiftest.py:119-121, which tests/test_oracle.py re-checks on the restated
- * democratic-heliocentric step.
+ * PARITY STATUS: PINNED bit for bit (round 2) to the reference's own Fortran executed by oracle/f90interp.py:
+ * helio_step_pl/_tp over consecutive steps, energy and momentum (flat and triangular potential loops),
+ * symba_kick_list_plpl/_pltp, symba_encounter_check_list_*, collision_check_one, discard_pl_close
+ * (tests/golden/fortran_steps.npz, fortran_lists.npz; tests/test_oracle_fortran_goldens.py).  swo_discard_pl_tp's
+ * bookkeeping loop and swo_collision_check_list's wrapper loop are restated by hand around pinned predicates.
+ * swo_orbel_xv2aeq is also pinned to a and e from the reference's Python xv2el_one (swiftest/tool.py:377-455;
+ * tests/golden/xv2aeq_ref.npz) at 1e-11; the system-level pin is the conservation thresholds of
+ * tests/test_swiftest.py:119-121, which tests/test_oracle.py re-checks on the restated democratic-heliocentric step.
  *
  * Every sum below runs in the order the reference's serial loop / `sum` intrinsic runs it (first to last index unless
  * noted), one IEEE operation per Fortran operation (-ffp-contract=off).  `norm2` is restated as sqrt(x*x+y*y+z*z)

@@ -1,8 +1,10 @@
 /*
  * swiftest_oracle_whm.c -- CPU restatement of the Wisdom-Holman (WHM) step around the hot path: Jacobi coordinate
  * changes, the ah0/ah1/ah2 terms, the planet and test-particle kick-drift-kick (BASELINE.json configs[1]).
- * TEST INFRASTRUCTURE ONLY, see swiftest_oracle.h.  PARITY STATUS: UNPINNED (no function-level vectors in the reference);
- * checked through two-body / conservation properties in tests/test_oracle.py.
+ * TEST INFRASTRUCTURE ONLY, see swiftest_oracle.h.  PARITY STATUS: PINNED bit for bit (round 2): whm_step_pl + whm_step_tp
+ * of the reference, executed from its Fortran source by oracle/f90interp.py over consecutive steps (tri and flat loops,
+ * masked bodies; tests/golden/fortran_steps.npz, tests/test_oracle_fortran_goldens.py), plus the two-body / conservation
+ * properties in tests/test_oracle.py.
  *
  * Reference (paths relative to src/): whm/whm_step.f90:37-100, whm/whm_kick.f90:14-314, whm/whm_coord.f90:14-115,
  * whm/whm_drift.f90:14-58, whm/whm_util.f90:117-198, swiftest/swiftest_util.f90:2121-2149.

@@ -82,6 +82,7 @@ def load():
         "swcu_body_kick_vb": [p, i32, d, i32],
         "swcu_body_drift_vb": [p, i32, d, d, p],
         "swcu_body_put_vb": [p, i32, p],
+        "swcu_body_set_active": [p, i32, p],
         "swcu_body_get_vb": [p, i32, p, p, p],
         "swcu_helio_step_pl": [p, d, d, i32, i32, i32, p],
         "swcu_helio_step_tp": [p, d, d, i32, p],

@@ -360,6 +360,14 @@ class Context:
         vb = _vec3(vb, self.body_count(kind)[0])
         self._ck(self._L.swcu_body_put_vb(self._h, kind, _ptr(vb)))
 
+    def body_set_active(self, kind, lactive):
+        """status /= INACTIVE per body (None: all active); only swiftest_util_coord_vb2vh_pl filters on it."""
+        if lactive is None:
+            self._ck(self._L.swcu_body_set_active(self._h, kind, None))
+        else:
+            la = np.ascontiguousarray(lactive, dtype=np.int32)
+            self._ck(self._L.swcu_body_set_active(self._h, kind, _ptr(la)))
+
     def body_get_vb(self, kind, vb=True, rbeg=False, rend=False):
         n = self.body_count(kind)[0]
         res = {k: np.empty((n, 3), _f64) for k, w in (("vb", vb), ("rbeg", rbeg), ("rend", rend)) if w}

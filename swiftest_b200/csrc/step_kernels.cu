@@ -97,11 +97,13 @@ __global__ void kick_vb_save_kernel(int n, const int32_t *__restrict__ lmask, do
     wz[i] = wz[i] + az[i] * dt;
 }
 
-int reduce_gmv(swcu_context *ctx, const Body &b, const double *vx, const double *vy, const double *vz, bool masked,
+// masked: 0 none, 1 lmask, 2 the active flags (status /= INACTIVE; all active unless swcu_body_set_active loaded them)
+int reduce_gmv(swcu_context *ctx, const Body &b, const double *vx, const double *vy, const double *vz, int masked,
                bool use_div, bool reverse, double gmcb, int op, int slot)
 {
     SWCU_TRY(ensure_step_state(ctx));
-    GmvTerm term{b.Gm.as<double>(), vx, vy, vz, masked ? b.lmask.as<int32_t>() : nullptr, gmcb, use_div};
+    const int32_t *mask = masked == 1 ? b.lmask.as<int32_t>() : (masked == 2 && b.has_active ? b.lactive.as<int32_t>() : nullptr);
+    GmvTerm term{b.Gm.as<double>(), vx, vy, vz, mask, gmcb, use_div};
     CbFin fin{ctx->cbs.as<double>(), gmcb, op, slot};
     if (b.n <= SERIAL_SUM_MAX) {
         sum_serial_kernel<4><<<1, 32, 0, ctx->stream>>>(b.n, reverse, term, fin);
@@ -159,7 +161,7 @@ int pl_vh2vb(swcu_context *ctx, double gmcb)
     Body &pl = ctx->pl;
     if (pl.n == 0) return SWCU_OK;  // swiftest_util.f90:438
     SWCU_TRY(ensure_helio(ctx, pl));
-    SWCU_TRY(reduce_gmv(ctx, pl, pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>(), false, false, false, gmcb,
+    SWCU_TRY(reduce_gmv(ctx, pl, pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>(), 0, false, false, gmcb,
                         FIN_VH2VB, 0));
     return add_vec3(ctx, pl.n, nullptr, ctx->cbs.as<double>() + CBS_VBCB, 1.0, pl.vx.as<double>(), pl.vy.as<double>(),
                     pl.vz.as<double>(), pl.wx.as<double>(), pl.wy.as<double>(), pl.wz.as<double>());
@@ -170,7 +172,8 @@ int pl_vb2vh(swcu_context *ctx, double gmcb)
     Body &pl = ctx->pl;
     if (pl.n == 0) return SWCU_OK;  // swiftest_util.f90:377
     SWCU_TRY(ensure_helio(ctx, pl));
-    SWCU_TRY(reduce_gmv(ctx, pl, pl.wx.as<double>(), pl.wy.as<double>(), pl.wz.as<double>(), true, true, true, gmcb,
+    // swiftest_util.f90:377: `if (pl%status(i) /= INACTIVE)` -- the status, not lmask
+    SWCU_TRY(reduce_gmv(ctx, pl, pl.wx.as<double>(), pl.wy.as<double>(), pl.wz.as<double>(), 2, true, true, gmcb,
                         FIN_VB2VH, 0));
     return add_vec3(ctx, pl.n, nullptr, ctx->cbs.as<double>() + CBS_VBCB, -1.0, pl.wx.as<double>(), pl.wy.as<double>(),
                     pl.wz.as<double>(), pl.vx.as<double>(), pl.vy.as<double>(), pl.vz.as<double>());
@@ -182,7 +185,7 @@ int pl_lindrift(swcu_context *ctx, double gmcb, double dt, int lbeg)
     if (pl.n == 0) return SWCU_OK;  // helio_drift.f90:144
     SWCU_TRY(ensure_helio(ctx, pl));
     const int slot = lbeg ? CBS_PTBEG : CBS_PTEND;
-    SWCU_TRY(reduce_gmv(ctx, pl, pl.wx.as<double>(), pl.wy.as<double>(), pl.wz.as<double>(), true, false, false, gmcb,
+    SWCU_TRY(reduce_gmv(ctx, pl, pl.wx.as<double>(), pl.wy.as<double>(), pl.wz.as<double>(), 1, false, false, gmcb,
                         FIN_PT, slot));
     return add_vec3(ctx, pl.n, pl.lmask.as<int32_t>(), ctx->cbs.as<double>() + slot, dt, pl.rx.as<double>(),
                     pl.ry.as<double>(), pl.rz.as<double>(), pl.rx.as<double>(), pl.ry.as<double>(), pl.rz.as<double>());

@@ -517,6 +517,7 @@ extern "C" int swcu_body_sync(swcu_context *ctx, int32_t kind, int32_t n, int32_
     SWCU_TRY(fill_i32(ctx, b.iflag.as<int32_t>(), 0, n));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // host arrays may be reused by the caller right away
     b.generation = generation;
+    b.has_active = false;  // a new population: all active until swcu_body_set_active says otherwise
     b.valid = true;
     return SWCU_OK;
 }
@@ -952,6 +953,21 @@ extern "C" int swcu_body_put_vb(swcu_context *ctx, int32_t kind, const double *v
     SWCU_TRY(ensure_helio(ctx, b));
     SWCU_TRY(upload_vec3(ctx, vb, b.n, 1, b.wx, b.wy, b.wz));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
+extern "C" int swcu_body_set_active(swcu_context *ctx, int32_t kind, const int32_t *lactive)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &b = body_of(ctx, kind);
+    if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "body_set_active: population not resident");
+    if (!lactive) {
+        b.has_active = false;  // every body active again
+        return SWCU_OK;
+    }
+    SWCU_TRY(upload_arr(ctx, lactive, sizeof(int32_t) * (size_t)b.n, b.lactive));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    b.has_active = true;
     return SWCU_OK;
 }
 

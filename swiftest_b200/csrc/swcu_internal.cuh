@@ -52,6 +52,10 @@ struct Body {
     DevBuf rx, ry, rz, vx, vy, vz, ax, ay, az;
     DevBuf Gm, radius, rhill, renc, mu;
     DevBuf lmask, iflag;  // int32
+    // status /= INACTIVE of the reference (swcu_body_set_active); not loaded = every body active.  Distinct from lmask:
+    // swiftest_util_coord_vb2vh_pl filters on status, helio_drift_linear_pl and the kicks on lmask
+    DevBuf lactive;
+    bool has_active = false;
     // democratic-heliocentric integrators keep two velocities: v* above is vh, w* is vb (allocated on first use);
     // b* / e* are the planet positions at the begin / end kick (pl%rbeg, pl%rend: swiftest_util.f90:2057-2080)
     DevBuf wx, wy, wz, bx, by, bz, ex, ey, ez;
@@ -59,8 +63,9 @@ struct Body {
     void release()
     {
         DevBuf *all[] = {&rx, &ry, &rz, &vx, &vy, &vz, &ax, &ay, &az, &Gm, &radius, &rhill, &renc, &mu, &lmask, &iflag,
-                         &wx, &wy, &wz, &bx, &by, &bz, &ex, &ey, &ez};
+                         &wx, &wy, &wz, &bx, &by, &bz, &ex, &ey, &ez, &lactive};
         helio_ready = false;
+        has_active = false;
         for (DevBuf *b : all) b->release();
         valid = false;
         n = 0;

@@ -50,12 +50,22 @@ def test_glue_calls_bit_exact_on_the_108_body_fixture(ctx, oracle):
     got = ctx.body_get_vb(PL, vb=True, rbeg=True)
     assert np.array_equal(got["vb"], oracle.helio_kick_vb(ah, vb_ref, 0.5 * dt, mask))
     assert np.array_equal(got["rbeg"], r_ref)
-    # vb2vh: reversed masked sum with a division per term, unmasked update
+    # vb2vh: reversed sum with a division per term, unmasked update.  The reference filters on status /= INACTIVE
+    # (swiftest_util.f90:377), NOT on lmask: with no active flags loaded every body counts ...
     vb_now = got["vb"]
-    vh_ref, vbcb2_ref = oracle.coord_vb2vh_pl(GMcb, Gm, vb_now, mask)
+    vh_ref, vbcb2_ref = oracle.coord_vb2vh_pl(GMcb, Gm, vb_now, None)
     vbcb2 = ctx.pl_vb2vh(GMcb)
     assert np.array_equal(vbcb2, vbcb2_ref)
     assert np.array_equal(ctx.body_get(PL)["v"], vh_ref)
+    # ... and with swcu_body_set_active the inactive ones drop out of the sum
+    lactive = np.ones(108, np.int32)
+    lactive[[3, 50, 107]] = 0
+    ctx.body_set_active(PL, lactive)
+    vh_ref, vbcb2_ref = oracle.coord_vb2vh_pl(GMcb, Gm, vb_now, lactive)
+    assert np.array_equal(ctx.pl_vb2vh(GMcb), vbcb2_ref)
+    assert np.array_equal(ctx.body_get(PL)["v"], vh_ref)
+    ctx.body_set_active(PL, None)
+    assert np.array_equal(ctx.pl_vb2vh(GMcb), oracle.coord_vb2vh_pl(GMcb, Gm, vb_now, None)[1])
 
 
 @pytest.mark.parametrize("n", [1025, 5000, 70001])

@@ -537,7 +537,7 @@ def test_workload_el2xv_matches_reference_python_golden():
     assert np.max(np.abs(v - z["v"]) / np.linalg.norm(z["v"], axis=1, keepdims=True)) < 1e-12
 
 
-# ---------------------------------------------------------------- symmetry properties (the kick and the sweep are unpinned)
+# ---------------------------------------------------------------- symmetry properties (on top of the Fortran-generated pins)
 def _rot(rng):
     q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
     return q * np.sign(np.linalg.det(q))
