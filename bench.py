@@ -713,7 +713,7 @@ def symba_1e4_leg(ctx, hbm_peak, fp64_peak):
 
 def side_legs(ctx, args, d, hbm_peak, peak_src):
     """Sweep on the same disk and the WHM tp configuration; timed outside the K headline steps."""
-    from swiftest_b200 import PL, TP, workloads as W
+    from swiftest_b200 import PL, TP, LOOP_AUTO, workloads as W
     from swiftest_b200.context import FAM_PLTP, FAM_DRIFT, FAM_SWEEP
     ex = {}
     n = d["n"]
@@ -781,6 +781,31 @@ def side_legs(ctx, args, d, hbm_peak, peak_src):
                                   "roofline": {"bound": "hbm", "achieved": 152.0 * ntp / tf / 1e9, "peak": hbm_peak,
                                                "unit": "GB/s", "frac": 152.0 * ntp / tf / 1e9 / hbm_peak,
                                                "bytes_per_tp": 152}}
+    # BASELINE configs[1] as a run executes it: planets AND test particles resident, swcu_whm_step_pl (one launch for a
+    # small system) + swcu_whm_tp_step(ah0 from the device) per step, nothing crosses PCIe; wall clock over 200 steps
+    ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
+    ctx.body_put(PL, r=p["rh"], v=p["vh"])
+    ctx.whm_tp_first_accel()
+    nw = 200
+    for rep in range(2):
+        ctx.synchronize()
+        n0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for k in range(nw):
+            ctx.whm_step_pl(p["cb_Gmass"], 0.01, LOOP_AUTO, True, lfirst=(rep == 0 and k == 0), want_nfail=False)
+            ctx.whm_tp_step(0.01, None, want_nfail=False)
+        ctx.synchronize()
+        tw = (time.perf_counter() - t0) / nw
+        lps = (ctx.launch_count() - n0) / nw
+    pms, tms = [], []
+    for it in range(8):
+        ctx.whm_step_pl(p["cb_Gmass"], 0.01, LOOP_AUTO, True, lfirst=False, want_nfail=False)
+        pms.append(ctx.last_kernel_ms(FAM_DRIFT))
+        ctx.whm_tp_step(0.01, None, want_nfail=False)
+        tms.append(ctx.last_kernel_ms(FAM_DRIFT))
+    ex["whm_tp"]["whole_step"] = {"ms": tw * 1e3, "tp_steps_per_s": ntp / tw, "launches_per_step": lps,
+                                  "whm_step_pl_8_planets_ms": float(np.mean(pms[3:])), "tp_kernel_ms": float(np.mean(tms[3:])),
+                                  "note": "planet step + fused tp step, device resident, no L2 flush (the tp arrays are 1.2 x L2)"}
     ms = []
     ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
     ctx.pl_set_renc(0)

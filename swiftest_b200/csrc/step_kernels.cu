@@ -248,6 +248,19 @@ int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lc
     if (pl.n == 0) return SWCU_OK;
     const double dth = 0.5 * dt;
     SWCU_TRY(ensure_helio(ctx, pl));
+    // small systems: the whole step is ONE launch (drift_kernels.cu::helio_step_pl_small_kernel), bit-identical to the
+    // reference's statement order for both loop variants; SWCU_HELIO_FUSED=0 keeps the multi-launch form below
+    static const bool fused_ok = !(getenv("SWCU_HELIO_FUSED") && atoi(getenv("SWCU_HELIO_FUSED")) == 0);
+    if (fused_ok && pl.n <= whm_small_max() && pl.nplm == pl.n && pl.slice0 == 0 && pl.slice1 == pl.n && ctx->tune_variant < 0) {
+        const int flat = variant == SWCU_LOOP_FLAT || (variant == SWCU_LOOP_AUTO && pl.n >= 128);
+        SWCU_TRY(ensure_step_state(ctx));
+        SWCU_TRY(helio_step_pl_small(ctx, pl, gmcb, dt, flat, lclose, lfirst));
+        if (nfail) {
+            SWCU_CUDA(ctx, cudaMemcpyAsync(nfail, ctx->scratch64.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return SWCU_OK;
+    }
     if (lfirst) SWCU_TRY(pl_vh2vb(ctx, gmcb));
     SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 1));
     for (int half = 0; half < 2; ++half) {

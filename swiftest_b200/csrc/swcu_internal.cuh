@@ -293,6 +293,10 @@ int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lc
 // ---- Wisdom-Holman planet step : whm_kernels.cu ----
 int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclose, int lfirst, int32_t *nfail);
 int whm_tp_first_accel(swcu_context *ctx);
+// the whole planet step in one launch for small systems (drift_kernels.cu: it shares the drift device functions)
+int whm_small_max();
+int whm_step_pl_small(swcu_context *ctx, Body &pl, double gmcb, double dt, int flat, int lclose, int lfirst);
+int helio_step_pl_small(swcu_context *ctx, Body &pl, double gmcb, double dt, int flat, int lclose, int lfirst);
 int whm_get_jacobi(swcu_context *ctx, double *xj, double *vj);
 int pl_accel_int(swcu_context *ctx, int loop_variant, int lclose);  // swcu_api.cu
 

@@ -249,6 +249,19 @@ int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclo
     const size_t nb = sizeof(double) * (size_t)n;
     const double dth = 0.5 * dt;
     SWCU_TRY(ensure_whm(ctx, pl, gmcb));
+    // small systems: the whole step is ONE launch (drift_kernels.cu::whm_step_pl_small_kernel), bit-identical to the
+    // reference's statement order for both loop variants; SWCU_WHM_FUSED=0 keeps the multi-launch form below
+    static const bool fused_ok = !(getenv("SWCU_WHM_FUSED") && atoi(getenv("SWCU_WHM_FUSED")) == 0);
+    if (fused_ok && n <= whm_small_max() && pl.nplm == n && pl.slice0 == 0 && pl.slice1 == n && ctx->tune_variant < 0) {
+        const int flat = variant == SWCU_LOOP_FLAT || (variant == SWCU_LOOP_AUTO && n >= 128);
+        SWCU_TRY(whm_step_pl_small(ctx, pl, gmcb, dt, flat, lclose, lfirst));
+        W.ah0tp_valid = true;
+        if (nfail) {
+            SWCU_CUDA(ctx, cudaMemcpyAsync(nfail, ctx->scratch64.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        return SWCU_OK;
+    }
     CV3 rh = cv3(pl.rx, pl.ry, pl.rz), vh = cv3(pl.vx, pl.vy, pl.vz);
     V3 xj = v3(W.xjx, W.xjy, W.xjz), vj = v3(W.vjx, W.vjy, W.vjz);
     if (lfirst) {  // whm_kick_vh_pl :236-243

@@ -370,3 +370,74 @@ def test_whm_resident_planets_and_test_particles_never_leave_the_device(ctx, ora
     assert np.max(np.abs(got["r"] - stp["rh"]) / np.linalg.norm(stp["rh"], axis=1, keepdims=True)) < 1e-11
     assert np.max(np.abs(got["v"] - stp["vh"]) / np.linalg.norm(stp["vh"], axis=1, keepdims=True)) < 1e-11
     assert np.max(np.abs(got["a"] - stp["ah"])) <= 1e-11 * np.abs(stp["ah"]).max()
+
+
+@pytest.mark.parametrize("lflat", [False, True])
+def test_whm_small_system_step_is_one_launch_and_bit_identical_to_the_reference_order(ctx, oracle, lflat):
+    """npl <= 128: swcu_whm_step_pl is ONE kernel (drift_kernels.cu::whm_step_pl_small_kernel).  Its pair sums run in the
+    reference's own order with the reference's expression, so 40 steps of Sun + 8 planets reproduce the CPU restatement
+    (itself bit-identical to the interpreted Fortran, tests/test_oracle_fortran_goldens.py) BIT FOR BIT, for the full-row
+    and for the flat loop: r, v, Jacobi coordinates, accelerations, rbeg / rend."""
+    from swiftest_b200 import LOOP_TRIANGULAR, LOOP_FLAT
+    p = W.planets8_year_units()
+    GMcb, dt = p["cb_Gmass"], 0.01
+    st = {"rh": p["rh"].copy(), "vh": p["vh"].copy(), "lfirst": True}
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"],
+                  mu=GMcb + p["Gmass"], generation=8950 + int(lflat))
+    n0 = ctx.launch_count()
+    for k in range(40):
+        assert not oracle.whm_step_pl(st, GMcb, p["Gmass"], p["radius"], dt, lflat=lflat).any()
+        assert ctx.whm_step_pl(GMcb, dt, LOOP_FLAT if lflat else LOOP_TRIANGULAR, True, lfirst=(k == 0)) == 0
+    assert ctx.launch_count() - n0 <= 41          # one launch per step (+ the one-off eta / muj chain)
+    got = ctx.body_get(PL)
+    xj, vj = ctx.whm_get_jacobi()
+    assert np.array_equal(got["r"], st["rh"]) and np.array_equal(got["v"], st["vh"])
+    assert np.array_equal(xj, st["xj"]) and np.array_equal(vj, st["vj"])
+    assert np.array_equal(got["a"], st["ah"])
+    vb = ctx.body_get_vb(PL, vb=False, rbeg=True, rend=True)
+    assert np.array_equal(vb["rbeg"], st["rbeg"]) and np.array_equal(vb["rend"], st["rend"])
+
+
+def test_whm_fused_planet_step_with_masked_bodies_is_bit_identical_on_the_108_body_system(ctx, oracle):
+    """The 108-body fixture through the one-launch step (npl <= 128) against the oracle with masked bodies; the multi-launch
+    form (what larger systems use, SWCU_WHM_FUSED=0 forces it) is covered by test_whm_step_pl_resident_matches_oracle."""
+    from swiftest_b200 import LOOP_TRIANGULAR
+    f = W.fixture("108pl_50tp")
+    order = np.argsort(-f["pl_Gmass"], kind="stable")
+    GMcb, dt = float(f["cb_Gmass"]), float(f["dt"])
+    Gm, rh, vh, rad, rhill = (f["pl_" + k][order] for k in ("Gmass", "rh", "vh", "radius", "rhill"))
+    mask = np.ones(108, np.int32)
+    mask[[5, 77]] = 0
+    st = {"rh": rh.copy(), "vh": vh.copy(), "lfirst": True}
+    ctx.body_sync(PL, 108, nplm=108, r=rh, v=vh, Gmass=Gm, radius=rad, rhill=rhill, mu=GMcb + Gm, lmask=mask, generation=8960)
+    for k in range(10):
+        assert not oracle.whm_step_pl(st, GMcb, Gm, rad, dt, lmask=mask).any()
+        assert ctx.whm_step_pl(GMcb, dt, LOOP_TRIANGULAR, True, lfirst=(k == 0)) == 0
+    got = ctx.body_get(PL)
+    assert np.array_equal(got["r"], st["rh"]) and np.array_equal(got["v"], st["vh"])
+
+
+@pytest.mark.parametrize("lflat", [False, True])
+def test_helio_small_system_step_is_one_launch_and_bit_identical_to_the_reference_order(ctx, oracle, lflat):
+    """npl <= 128: swcu_helio_step_pl is ONE kernel (drift_kernels.cu::helio_step_pl_small_kernel); 40 steps of the 108-body
+    system with masked bodies reproduce the CPU restatement (bit-identical to the interpreted Fortran) BIT FOR BIT."""
+    f, GMcb, dt = _fixture108()
+    Gm, rad = f["pl_Gmass"], f["pl_radius"]
+    mask = np.ones(108, np.int32)
+    mask[[4, 90]] = 0
+    rhill = np.linalg.norm(f["pl_rh"], axis=1) * (Gm / (3 * GMcb)) ** (1.0 / 3.0)
+    ctx.body_sync(PL, 108, nplm=108, r=f["pl_rh"], v=f["pl_vh"], Gmass=Gm, radius=rad, rhill=rhill, mu=GMcb + Gm, lmask=mask,
+                  generation=9300 + int(lflat))
+    st = dict(rh=f["pl_rh"].copy(), vh=f["pl_vh"].copy(), vb=np.zeros((108, 3)), lfirst=True)
+    n0 = ctx.launch_count()
+    for k in range(40):
+        assert not oracle.helio_step_pl(st, GMcb, Gm, rad, dt, lflat=lflat, lmask=mask).any()
+        assert ctx.helio_step_pl(GMcb, dt, loop_variant=LOOP_FLAT if lflat else LOOP_TRIANGULAR, lclose=True, lfirst=(k == 0)) == 0
+    assert ctx.launch_count() - n0 <= 43
+    out = ctx.body_get(PL)
+    hv = ctx.body_get_vb(PL, vb=True, rbeg=True, rend=True)
+    assert np.array_equal(out["r"], st["rh"]) and np.array_equal(out["v"], st["vh"]) and np.array_equal(hv["vb"], st["vb"])
+    assert np.array_equal(out["a"], st["ah"])
+    assert np.array_equal(hv["rbeg"], st["rbeg"]) and np.array_equal(hv["rend"], st["rend"])
+    ptb, pte = ctx.cb_get_pt()
+    assert np.array_equal(ptb, st["ptbeg"]) and np.array_equal(pte, st["ptend"])
