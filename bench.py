@@ -12,7 +12,7 @@ Metric: FP64 pair-interactions/s of the SyMBA planetesimal disk, npl = 1e5 fully
    accelerations out of every rank's memory, kicks and drifts this rank's slice and allgathers it into every rank's
    arrays over NVLink peer memory (--collective nccl: ncclAllReduce instead; --variant tri: row slices + allgather)].
 `value` = N(N-1)/2 pairs per step / step time with everything resident in HBM (strong scaling: the system is fixed).
-Timing: K laps, one CUDA-event pair per step on the library's stream, L2 flushed (160 MiB write) BETWEEN the laps,
+Timing: K laps, one CUDA-event pair per step on the library's stream, L2 flushed (160 MiB written, then another 160 MiB read so that no dirty lines remain) BETWEEN the laps,
 barrier + synchronize on both sides, max over ranks.  `e2e` = the same step with that step's positions and velocities
 copied from pinned host memory and accelerations / positions / velocities read back, every step (N>1: every rank moves
 its own slice of the bodies and the slices are allgathered on the device), host wall clock, max over ranks.
@@ -72,7 +72,7 @@ def common_config(n):
     return {"workload": f"symba_disk_npl{n}_fully_interacting", "npl": n, "nplm": n, "lclose": True,
             "step": "zero_accel + pl-pl accel_int (all N(N-1)/2 pairs, radius-checked) + kick_velocity + Kepler drift",
             "generator": "Chambers-style disk, swiftest_b200/workloads.py::disk", "seed": 3031179,
-            "l2": "GPU arm: L2 flushed between timed steps (160 MiB write = 1.33 x L2, outside the per-step event pairs); "
+            "l2": "GPU arm: L2 flushed between timed steps (160 MiB = 1.33 x L2 written, then 160 MiB read: clean lines only; outside the per-step event pairs); "
                   "CPU arm: not applicable"}
 
 
