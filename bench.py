@@ -806,17 +806,38 @@ def side_legs(ctx, args, d, hbm_peak, peak_src):
     ex["whm_tp"]["whole_step"] = {"ms": tw * 1e3, "tp_steps_per_s": ntp / tw, "launches_per_step": lps,
                                   "whm_step_pl_8_planets_ms": float(np.mean(pms[3:])), "tp_kernel_ms": float(np.mean(tms[3:])),
                                   "note": "planet step + fused tp step, device resident, no L2 flush (the tp arrays are 1.2 x L2)"}
-    ms = []
     ctx.body_put(TP, r=tp["rh"], v=tp["vh"])
     ctx.pl_set_renc(0)
-    for it in range(5):
-        ctx.flush_l2()
-        nenc = ctx.tp_encounter_check(0.01, fetch=False)
-        if it >= 2:
-            ms.append(ctx.last_kernel_ms(FAM_SWEEP))
-    st = ctx.encounter_stats()
-    ex["sweep_pltp"] = {"npl": 8, "ntp": ntp, "nenc": int(nenc), "nbox_total": int(st["nbox_total"]),
-                        "ms": float(np.mean(ms))}
+
+    def sweep_ms():
+        ms = []
+        for it in range(6):
+            ctx.flush_l2()
+            nenc = ctx.tp_encounter_check(0.01, fetch=False)
+            if it >= 2:
+                ms.append(ctx.last_kernel_ms(FAM_SWEEP))
+        return float(np.mean(ms)), int(nenc), ctx.encounter_stats()
+
+    nd0, nf0 = ctx.encounter_direct_count()
+    t_direct, nenc, st = sweep_ms()
+    nd1, nf1 = ctx.encounter_direct_count()
+    os.environ["SWCU_PLTP_DIRECT_MAX"] = "0"   # the sort path of round 1 (2(npl+ntp)-key radix sort, gather, chunked sweep)
+    t_sort, nenc_sort, st_sort = sweep_ms()
+    del os.environ["SWCU_PLTP_DIRECT_MAX"]
+    b_direct = ntp * 48.0 + 8 * 56.0 + 9.0 * nenc          # r, v of every particle once; planets; the pair list out
+    nn = ntp + 8
+    b_survey = nn * 56.0 + 2 * nn * 24.0 + 2 * nn * 56.0 + st_sort["nbox_total"] * 56.0 + 9.0 * nenc
+    ex["sweep_pltp"] = {"npl": 8, "ntp": ntp, "nenc": nenc, "nbox_total": int(st["nbox_total"]), "ms": t_direct * 1.0,
+                        "path": "sort-free pass over the particles (npl <= 128): %d of %d calls, %d fell back to the sort path"
+                                % (nd1 - nd0 - (nf1 - nf0), nd1 - nd0, nf1 - nf0),
+                        "sort_path_ms": t_sort, "sort_path_same_result": bool(nenc_sort == nenc and st_sort["nbox_total"] == st["nbox_total"]),
+                        "algorithmic_bytes": b_direct,
+                        "roofline": {"bound": "hbm", "achieved": b_direct / (t_direct * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": b_direct / (t_direct * 1e-3) / 1e9 / hbm_peak,
+                                     "note": "48 B per particle + 9 B per pair; the launch group includes the count read-back "
+                                             "the two-phase API needs (device -> host -> sort of the hits)"},
+                        "survey_8d_formula": {"bytes": b_survey, "GB/s": b_survey / (t_direct * 1e-3) / 1e9,
+                                              "sort_path_GB/s": b_survey / (t_sort * 1e-3) / 1e9}}
     ctx.enable_kernel_timing(False)
     return ex
 

@@ -596,6 +596,11 @@ module swiftest_cuda
          type(c_ptr), value :: each_ms      !! c_null_ptr, or c_loc of a real(c_double) array of each_cap elements
          integer(c_int), value :: each_cap
       end function
+      integer(c_int) function swcu_encounter_direct_count(ctx, direct, fallbacks) bind(C, name="swcu_encounter_direct_count")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), intent(out) :: direct, fallbacks
+      end function
       integer(c_int) function swcu_flat_redo_count(ctx, chunks) bind(C, name="swcu_flat_redo_count")
          import :: c_int, c_int64_t, c_ptr
          type(c_ptr), value :: ctx

@@ -115,6 +115,10 @@ int swcu_encounter_check_all_plplm(swcu_context *ctx, int32_t nplm, int32_t nplt
 int swcu_encounter_fetch(swcu_context *ctx, int64_t nenc, int32_t *index1, int32_t *index2, int32_t *lvdotr);
 /* statistics of the last sort-and-sweep: broad-phase candidates sum_i nbox_i, and bytes the sweep kernel read */
 int swcu_encounter_stats(swcu_context *ctx, int64_t *nbox_total, int64_t *ncandidates_emitted);
+/* pl-tp sort-and-sweep calls (encounter_check.f90:261-326) since the context was created that were answered by the
+ * sort-free pass over the particles (`direct`: npl <= SWCU_PLTP_DIRECT_MAX, default and maximum 128) and those among them that had
+ * to be repeated on the sort path because a particle's |r| equalled a planet's outer extent bit for bit (`fallbacks`) */
+int swcu_encounter_direct_count(swcu_context *ctx, int64_t *direct, int64_t *fallbacks);
 
 /* ------------------------------------------------------------------------------------------------------
  * Tier 2: device-resident bodies (what the type-bound procedures pl%accel_int, tp%accel_int, body%drift,

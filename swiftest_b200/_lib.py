@@ -120,6 +120,7 @@ def load():
         "swcu_enable_kernel_timing": [p, i32],
         "swcu_kernel_ms_accumulated": [p, i32, p, p],
         "swcu_flat_redo_count": [p, p],
+        "swcu_encounter_direct_count": [p, p, p],
     }
     for name, args in sig.items():
         fn = getattr(L, name)

@@ -604,6 +604,12 @@ class Context:
         self._ck(self._L.swcu_last_kernel_ms(self._h, family, C.byref(ms)))
         return ms.value
 
+    def encounter_direct_count(self):
+        """(pl-tp sweeps answered without the sort, how many of those had to be repeated on the sort path)."""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self._L.swcu_encounter_direct_count(self._h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def flat_redo_count(self):
         """Chunks the third-law gravity kernel rolled back and redid with the IEEE expression since create."""
         n = C.c_uint64()

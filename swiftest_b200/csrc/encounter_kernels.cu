@@ -27,7 +27,9 @@
 
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cub/cub.cuh>
+#include <vector>
 
 namespace swcu {
 namespace {
@@ -246,6 +248,271 @@ __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single
                     if (pos < cap) cand[pos] = key[1];
                 }
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// pl-tp sweep without the sort (few massive bodies, many test particles: BASELINE configs[1], 8 planets + 1e6 tp).
+//
+// A test particle has renc = 0, so its two endpoints carry the same key K = |r_tp| (:305-319) and it never sweeps from
+// its own side; what the 2(npl+ntp)-key sort decides is only WHICH tp endpoints lie strictly between the two endpoints
+// of planet i in the stably sorted sequence.  With ties resolved by position in the [rmin(1:ntot), rmax(1:ntot)] array
+// (planet begin i < tp begin npl+q < planet end ntot+i < tp end ntot+npl+q) that set is known without sorting:
+//     tp begin inside  <=>  rmin_i <= K <= rmax_i          tp end inside  <=>  rmin_i <= K <  rmax_i
+// so nbox_i = (#tp with rmin_i <= K <= rmax_i) + (#tp with rmin_i <= K < rmax_i) + (planet endpoints inside, counted
+// with the same tie rule), planet i is swept iff nbox_i >= 2 (F3, :828), and its candidates are those tp -- twice each in
+// the reference's ragged list, once after remove_duplicates.  One pass over the particles replaces the radix sort of
+// 2e6 (key, id) pairs, the gather into sorted order and the chunked sweep: 48 B per particle instead of ~400.
+// The one situation in which the sorted sequence holds more than this -- a particle whose |r| EQUALS a planet's rmax
+// bit for bit (then the particle's own degenerate interval contains that planet's end point and the reference may sweep
+// from the particle's side, and the planet sees one of the particle's endpoints only) -- raises a flag and the call
+// falls back to the sort path, as do NaN extents.  nbox_total counts the planets' boxes; three or more particles with
+// bit-identical |r| would add their (pairless) boxes in the reference's count, not here.
+struct PlRec {
+    double rmin, rmax, x, y, z, vx, vy, vz, renc;
+};
+
+constexpr int PLTP_T = 256;               // threads per CTA
+constexpr int PLTP_MAXPL = 128;
+
+// encounter_check_one (:591-618) with ONE divergent branch: the three early exits of check_one are evaluated as
+// predicates (a handful of multiplies), only pairs that survive them -- approaching, outside renc, and not excluded by the
+// conservative bound -- take the path with the two IEEE divisions.  Same decisions as check_one for every input.
+__device__ __forceinline__ bool check_one_flat(double xr, double yr, double zr, double vxr, double vyr, double vzr,
+                                               double renc, double dt, double vsmall)
+{
+    const double r2 = xr * xr + yr * yr + zr * zr;
+    const double r2crit = renc * renc;
+    const double vdotr = vxr * xr + vyr * yr + vzr * zr;
+    const bool inside = !(r2 > r2crit);                                            // (:612-615): encounter
+    bool hit = inside;
+    if (!inside && !(vdotr > 0.0) && !(r2 + 2.0 * vdotr * dt > r2crit * 1.000000001)) {
+        double r2min;
+        const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
+        if (v2 <= vsmall) {
+            r2min = r2;
+        } else {
+            const double tmin = -vdotr / v2;
+            if (tmin < dt)
+                r2min = r2 - vdotr * vdotr / v2;
+            else
+                r2min = r2 + 2 * vdotr * dt + v2 * (dt * dt);
+        }
+        hit = (vdotr < 0.0) && (r2min <= r2crit);
+    }
+    return hit;
+}
+
+// shared memory of pltp_direct_kernel<PER> per planet: record, 3 counters, hits per (slot, warp), hit bits per thread
+template <int PER>
+constexpr size_t pltp_shmem_per_planet()
+{
+    return sizeof(PlRec) + 3 * sizeof(unsigned int) + sizeof(unsigned short) * PER * (PLTP_T / 32) + PLTP_T;
+}
+
+// Pass A.  CTA b owns the PER*T particles [b*CHUNK, (b+1)*CHUNK); thread t holds particles b*CHUNK + u*T + t, u < PER
+// (coalesced loads).  The CTA builds the planet records (extents by the expressions of extent_kernel; CTA 0 also counts
+// the planets' endpoints inside each other's interval), tests its particles against every planet, and leaves its hits
+// ORDERED by (planet, particle) in a region of the arena claimed with one atomic; cnt[i*nb + b] = hits of planet i in
+// this chunk, box[i*nb + b] = endpoints of this chunk inside planet i's interval, abase[b] = where the region starts.
+template <int PER>
+__global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(ListDev pl, ListDev tp, int nb, double dt, double vsmall,
+                                                                unsigned long long *__restrict__ arena,
+                                                                unsigned long long cap,
+                                                                unsigned long long *__restrict__ count,
+                                                                unsigned int *__restrict__ box, int *__restrict__ flag,
+                                                                int *__restrict__ cnt, unsigned long long *__restrict__ abase)
+{
+    constexpr int NW = PLTP_T / 32, CHUNK = PLTP_T * PER;
+    extern __shared__ unsigned char sh_raw[];
+    const int n1 = pl.n, n2 = tp.n;
+    PlRec *spl = reinterpret_cast<PlRec *>(sh_raw);                      // n1 records
+    unsigned int *sbox = reinterpret_cast<unsigned int *>(spl + n1);     // n1: endpoints of this chunk inside planet i
+    unsigned int *shit = sbox + n1;                                      // n1: hits of planet i in this chunk
+    unsigned int *soff = shit + n1;                                      // n1: start of planet i's run in the region
+    unsigned short *swtot = reinterpret_cast<unsigned short *>(soff + n1);  // n1 x PER x NW: hits per (slot, warp),
+                                                                            // later their exclusive prefix per planet
+    unsigned char *shb = reinterpret_cast<unsigned char *>(swtot + n1 * PER * NW);  // n1 x T: hit bits per thread
+    __shared__ unsigned long long s_base;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    for (int i = t; i < n1; i += PLTP_T) {
+        const double x = pl.x[i], y = pl.y[i], z = pl.z[i];
+        const double renc = pl.renc ? pl.renc[i] : 0.0;
+        const double rmag = sqrt(x * x + y * y + z * z);
+        const double w = RSWEEP_FACTOR * renc;
+        PlRec r;
+        r.rmin = rmag - w;
+        r.rmax = rmag + w;
+        r.x = x, r.y = y, r.z = z, r.vx = pl.vx[i], r.vy = pl.vy[i], r.vz = pl.vz[i], r.renc = renc;
+        spl[i] = r;
+        sbox[i] = 0u;
+        shit[i] = 0u;
+        if (blockIdx.x == 0 && (r.rmin != r.rmin || r.rmax != r.rmax)) atomicOr(flag, 1);
+    }
+    // persistent CTA: chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the NEXT chunk's particles are loaded into a second
+    // register set before the current chunk is evaluated, so the loads fly under ~5 us of predicate arithmetic
+    double nx[PER], ny[PER], nz[PER], nvx[PER], nvy[PER], nvz[PER];
+    auto fetch = [&](int chunk) {
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            const long long q = (long long)chunk * CHUNK + u * PLTP_T + t;
+            nx[u] = ny[u] = nz[u] = nvx[u] = nvy[u] = nvz[u] = 0.0;
+            if (chunk < nb && q < n2) {
+                nx[u] = tp.x[q], ny[u] = tp.y[q], nz[u] = tp.z[q];
+                nvx[u] = tp.vx[q], nvy[u] = tp.vy[q], nvz[u] = tp.vz[q];
+            }
+        }
+    };
+    fetch(blockIdx.x);
+    const unsigned below = (1u << lane) - 1u;
+    for (int chunk = blockIdx.x; chunk < nb; chunk += gridDim.x) {
+        const long long q0 = (long long)chunk * CHUNK + t;
+        double x[PER], y[PER], z[PER], vx[PER], vy[PER], vz[PER], K[PER];
+        bool valid[PER];
+#pragma unroll
+        for (int u = 0; u < PER; ++u) {
+            x[u] = nx[u], y[u] = ny[u], z[u] = nz[u], vx[u] = nvx[u], vy[u] = nvy[u], vz[u] = nvz[u];
+            valid[u] = q0 + u * PLTP_T < n2;
+        }
+        fetch(chunk + gridDim.x);
+        __syncthreads();  // planet records / zeroed counters visible; the previous chunk's pass is over
+        if (chunk == 0) {  // the planets' own endpoints inside each other's interval, same tie rule as the stable sort
+            for (int i = t; i < n1; i += PLTP_T) {
+                const double lo = spl[i].rmin, hi = spl[i].rmax;
+                unsigned int c = 0;
+                for (int j = 0; j < n1; ++j) {
+                    if (j == i) continue;
+                    const double bj = spl[j].rmin, ej = spl[j].rmax;
+                    // begin of j sits at array position j, end of j at ntot + j; i's own endpoints at i and ntot + i
+                    if ((bj > lo || (bj == lo && j > i)) && bj <= hi) ++c;
+                    if (ej >= lo && (ej < hi || (ej == hi && j < i))) ++c;
+                }
+                if (c) atomicAdd(&sbox[i], c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PER; ++u) K[u] = sqrt(x[u] * x[u] + y[u] * y[u] + z[u] * z[u]);  // rmin = rmax = |r| -/+ 1.1*0
+
+        for (int i = 0; i < n1; ++i) {
+            const double rmin = spl[i].rmin, rmax = spl[i].rmax;
+            unsigned hb = 0u;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                if (valid[u] && K[u] >= rmin && K[u] <= rmax) {  // begin endpoint inside planet i's interval
+                    const bool in_e = K[u] < rmax;               // end endpoint inside
+                    atomicAdd(&sbox[i], in_e ? 2u : 1u);
+                    if (!in_e) atomicOr(flag, 2);                // |r_tp| == rmax_i: the sort path decides
+                    const PlRec &p = spl[i];
+                    if (check_one_flat(x[u] - p.x, y[u] - p.y, z[u] - p.z, vx[u] - p.vx, vy[u] - p.vy, vz[u] - p.vz,
+                                       p.renc + 0.0, dt, vsmall))
+                        hb |= 1u << u;
+                }
+            }
+            shb[i * PLTP_T + t] = (unsigned char)hb;
+        }
+        __syncthreads();
+        // hits per (planet, slot, warp) from the hit bits, their exclusive prefix in particle order, the planet's total
+        for (int i = warp; i < n1; i += NW) {
+            unsigned run = 0u;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned c = __popc(__ballot_sync(0xffffffffu, (shb[i * PLTP_T + w * 32 + lane] >> u) & 1u));
+                    if (lane == 0) swtot[(i * PER + u) * NW + w] = (unsigned short)run;
+                    run += c;
+                }
+            }
+            if (lane == 0) shit[i] = run;
+        }
+        __syncthreads();
+        if (warp == 0) {  // runs of the planets inside this chunk's region; one claim of the arena; counts for pass B
+            unsigned int carry = 0u;
+            for (int i0 = 0; i0 < n1; i0 += 32) {
+                const int i = i0 + lane;
+                const unsigned int c = i < n1 ? shit[i] : 0u;
+                unsigned int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                if (i < n1) {
+                    soff[i] = carry + incl - c;
+                    cnt[(size_t)i * nb + chunk] = (int)c;
+                    box[(size_t)i * nb + chunk] = sbox[i];  // summed by pass B (15 000 atomics on one line cost 40 us)
+                }
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) {
+                unsigned long long base = 0ull;
+                if (carry) base = atomicAdd(count, (unsigned long long)carry);
+                abase[chunk] = base;
+                s_base = base;
+            }
+        }
+        __syncthreads();
+        const unsigned long long base = s_base;
+        for (int i = 0; i < n1; ++i) {
+            if (shit[i] == 0u) continue;
+            const unsigned hb = shb[i * PLTP_T + t];
+            if (!__any_sync(0xffffffffu, hb != 0u)) continue;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, (hb >> u) & 1u);
+                if ((hb >> u) & 1u) {
+                    const unsigned long long pos = base + soff[i] + swtot[(i * PER + u) * NW + warp] + __popc(m & below);
+                    if (pos < cap)
+                        arena[pos] = ((unsigned long long)(i + 1) << 32) | (unsigned long long)(q0 + u * PLTP_T + 1);
+                }
+            }
+        }
+        __syncthreads();  // everybody is done with this chunk's counters
+        for (int i = t; i < n1; i += PLTP_T) sbox[i] = 0u, shit[i] = 0u;
+    }
+}
+
+// Pass B: one warp per chunk moves the chunk's runs to their place in the canonical list: planet-major, chunks in order
+// (offs = exclusive scan of cnt), already ascending in the particle index inside a chunk.  CTAs beyond the chunks add up
+// the box counts of one planet each.
+__global__ void __launch_bounds__(256) pltp_place_kernel(int n1, int nb, int nplace, const int *__restrict__ cnt,
+                                                         const int *__restrict__ offs,
+                                                         const unsigned long long *__restrict__ abase,
+                                                         const unsigned long long *__restrict__ arena,
+                                                         unsigned long long cap, unsigned long long *__restrict__ out,
+                                                         const unsigned int *__restrict__ box,
+                                                         unsigned long long *__restrict__ nbc)
+{
+    const int lane = threadIdx.x & 31;
+    if ((int)blockIdx.x >= nplace) {
+        __shared__ unsigned long long part[8];
+        const int i = blockIdx.x - nplace;
+        unsigned long long sum = 0ull;
+        for (int b = threadIdx.x; b < nb; b += blockDim.x) sum += box[(size_t)i * nb + b];
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) part[threadIdx.x >> 5] = sum;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) sum += part[w];
+            nbc[i] = sum;
+        }
+        return;
+    }
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= nb) return;
+    unsigned long long src = abase[b];
+    for (int i0 = 0; i0 < n1; i0 += 32) {
+        const int i = i0 + lane;
+        const int c = i < n1 ? cnt[(size_t)i * nb + b] : 0;
+        const int d = i < n1 ? offs[(size_t)i * nb + b] : 0;
+        if (!__any_sync(0xffffffffu, c != 0)) continue;
+        for (int j = 0; j < 32 && i0 + j < n1; ++j) {
+            const int cj = __shfl_sync(0xffffffffu, c, j);
+            const int dj = __shfl_sync(0xffffffffu, d, j);
+            for (int k = lane; k < cj; k += 32)
+                if (src + k < cap && (unsigned long long)dj + k < cap) out[(size_t)dj + k] = arena[src + k];  // overflow: rerun
+            src += (unsigned long long)cj;
         }
     }
 }
@@ -506,6 +773,103 @@ int canonical_order(swcu_context *ctx, long long ncand, int64_t *nenc_out)
     return SWCU_OK;
 }
 
+// pl-tp sweep of a few massive bodies over many particles without the sort (see pltp_direct_kernel).  *fell_back is set
+// when the call has to be decided by the sorted sequence after all; the caller then runs the sort path.
+static int pltp_per()  // particles per thread of pltp_direct_kernel: 1, 2 (default, by measurement) or 4
+{
+    const char *pe = getenv("SWCU_PLTP_PER");
+    const int per = pe ? atoi(pe) : 2;
+    return per == 4 ? 4 : per == 1 ? 1 : 2;
+}
+
+int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepList &l2, double dt, int64_t *nenc_out,
+                          bool *fell_back)
+{
+    auto &E = ctx->enc;
+    *fell_back = false;
+    const int n1 = l1.n, n2 = l2.n;
+    const int nb = cdiv(n2, PLTP_T * pltp_per());
+    const size_t ncnt = (size_t)n1 * nb;
+    if (ncnt + 1 > (size_t)0x7fffffff) {
+        *fell_back = true;
+        return SWCU_OK;
+    }
+    FamTimer ft(ctx, FAM_SWEEP);
+    // counters: [0] hits claimed in the arena, [4] flag word, [8 .. 8+n1) box counts of the planets
+    SWCU_CUDA(ctx, E.counters.ensure(sizeof(unsigned long long) * (8 + PLTP_MAXPL)));
+    SWCU_CUDA(ctx, E.nchunk.ensure(sizeof(int) * (ncnt + 1)));   // cnt
+    SWCU_CUDA(ctx, E.choff.ensure(sizeof(int) * (ncnt + 1)));    // offs
+    SWCU_CUDA(ctx, E.abase.ensure(sizeof(unsigned long long) * (size_t)nb));
+    SWCU_CUDA(ctx, E.boxcnt.ensure(sizeof(unsigned int) * ncnt));
+    unsigned long long *d_count = E.counters.as<unsigned long long>();
+    int *d_flag = reinterpret_cast<int *>(d_count + 4);
+    unsigned long long *d_nbc = d_count + 8;
+    int *d_cnt = E.nchunk.as<int>(), *d_offs = E.choff.as<int>();
+    size_t tmp_scan = 0;
+    SWCU_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, d_cnt, d_offs, (int)ncnt + 1, ctx->stream));
+    SWCU_CUDA(ctx, E.cub_tmp.ensure(tmp_scan));
+    const ListDev a = to_dev(l1), b = to_dev(l2);
+    if (E.cand_cap < (size_t)n2 / 4 + 65536) E.cand_cap = (size_t)n2 / 4 + 65536;
+    const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
+    const int per = pltp_per();
+    const size_t shmem = (size_t)n1 * (per == 4 ? pltp_shmem_per_planet<4>() : per == 2 ? pltp_shmem_per_planet<2>()
+                                                                                        : pltp_shmem_per_planet<1>());
+    static bool attr_set = false;
+    if (!attr_set) {
+        SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<1>())));
+        SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<2>())));
+        SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<4>())));
+        attr_set = true;
+    }
+    const int grid = std::min(nb, ctx->prop.multiProcessorCount * (per == 1 ? 4 : 2));  // persistent CTAs (launch bounds)
+    std::vector<unsigned long long> h(8 + (size_t)n1, 0ull);
+    int h_total = 0;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
+        SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * E.cand_cap));
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long) * (8 + (size_t)n1), ctx->stream));
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_cnt + ncnt, 0, sizeof(int), ctx->stream));
+        auto *kern = per == 4 ? pltp_direct_kernel<4> : per == 2 ? pltp_direct_kernel<2> : pltp_direct_kernel<1>;
+        kern<<<grid, PLTP_T, shmem, ctx->stream>>>(a, b, nb, dt, vsmall, E.cand.as<unsigned long long>(),
+                                                   (unsigned long long)E.cand_cap, d_count, E.boxcnt.as<unsigned int>(),
+                                                   d_flag, d_cnt, E.abase.as<unsigned long long>());
+        SWCU_KERNEL_CHECK(ctx);
+        SWCU_CUDA(ctx, cub::DeviceScan::ExclusiveSum(E.cub_tmp.p, tmp_scan, d_cnt, d_offs, (int)ncnt + 1, ctx->stream));
+        ctx->launches += 1;
+        pltp_place_kernel<<<cdiv(nb, 8) + n1, 256, 0, ctx->stream>>>(
+            n1, nb, cdiv(nb, 8), d_cnt, d_offs, E.abase.as<unsigned long long>(), E.cand.as<unsigned long long>(),
+            (unsigned long long)E.cand_cap, E.uniq.as<unsigned long long>(), E.boxcnt.as<unsigned int>(), d_nbc);
+        SWCU_KERNEL_CHECK(ctx);
+        SWCU_CUDA(ctx, cudaMemcpyAsync(h.data(), d_count, sizeof(unsigned long long) * (8 + (size_t)n1),
+                                       cudaMemcpyDeviceToHost, ctx->stream));
+        SWCU_CUDA(ctx, cudaMemcpyAsync(&h_total, d_offs + ncnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((int)(h[4] & 0xffffffffull) != 0) {
+            *fell_back = true;
+            return SWCU_OK;
+        }
+        if (h[0] <= E.cand_cap) break;
+        E.cand_cap = (size_t)(h[0] + h[0] / 4 + 1024);  // the arena was too small: grow it and run again
+        if (attempt == 2) return fail(ctx, SWCU_ERR_STATE, "pl-tp encounter check: candidate buffer overflow persists");
+    }
+    int64_t nbox = 0;
+    for (int i = 0; i < n1; ++i)
+        if (h[8 + i] >= 2ull) nbox += (int64_t)h[8 + i];  // loverlap (:828): ibeg + 1 < iend - 1
+    const long long nhit = (long long)h[0];
+    if ((long long)h_total != nhit) return fail(ctx, SWCU_ERR_STATE, "pl-tp encounter check: %lld hits claimed, %d placed",
+                                                nhit, h_total);
+    E.nbox_total = nbox;
+    E.nemitted = 2 * nhit;  // the reference's ragged list holds every hit once per endpoint
+    if (nhit == 0) return SWCU_OK;
+    E.nenc = nhit;
+    E.result = E.uniq.as<unsigned long long>();
+    *nenc_out = nhit;
+    return SWCU_OK;
+}
+
 int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out)
 {
     auto &E = ctx->enc;
@@ -517,6 +881,18 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     const int n1 = l1.n, n2 = l2 ? l2->n : 0;
     const bool single = (l2 == nullptr);
     if (n1 == 0 || (!single && n2 == 0)) return SWCU_OK;  // :168, :225, :291
+    if (!single && l2->renc == nullptr) {  // pl-tp with few massive bodies: no sort needed
+        const char *dm = getenv("SWCU_PLTP_DIRECT_MAX");  // read per call: tests switch the path at run time
+        const int direct_max = std::min(dm ? atoi(dm) : PLTP_MAXPL, PLTP_MAXPL);
+        if (n1 <= direct_max) {
+            bool fell_back = false;
+            ++E.direct_calls;
+            SWCU_TRY(encounter_pltp_direct(ctx, l1, *l2, dt, nenc_out, &fell_back));
+            if (!fell_back) return SWCU_OK;
+            E.nenc = 0, E.result = nullptr, E.nbox_total = 0, E.nemitted = 0, *nenc_out = 0;
+            ++E.direct_fallbacks;
+        }
+    }
     const int ntot = n1 + n2;
     const int next = 2 * ntot;
     FamTimer ft(ctx, FAM_SWEEP);
@@ -766,6 +1142,14 @@ extern "C" int swcu_encounter_fetch(swcu_context *ctx, int64_t nenc, int32_t *in
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (lvdotr)
         for (int64_t k = 0; k < nenc; ++k) lvdotr[k] = 1;  // lencounter = lvdotr .and. ... (:617-618): always true
+    return SWCU_OK;
+}
+
+extern "C" int swcu_encounter_direct_count(swcu_context *ctx, int64_t *direct, int64_t *fallbacks)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    if (direct) *direct = ctx->enc.direct_calls;
+    if (fallbacks) *fallbacks = ctx->enc.direct_fallbacks;
     return SWCU_OK;
 }
 

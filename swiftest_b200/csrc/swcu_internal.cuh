@@ -111,6 +111,9 @@ struct swcu_context {
         int64_t nbox_total = 0, nemitted = 0;
         // second result buffer for the plplm merge
         swcu::DevBuf merged;
+        // pl-tp without the sort: planet records, per-planet box counts, how often the sort path had to decide
+        swcu::DevBuf abase, boxcnt;
+        int64_t direct_calls = 0, direct_fallbacks = 0;
         const unsigned long long *result = nullptr;  // device pointer to the final sorted unique keys
     } enc;
 

@@ -409,6 +409,81 @@ def test_sweep_pltp_bit_exact(ctx, oracle, ntp):
         assert got[0] > 0
 
 
+def _pltp_both_paths(ctx, oracle, args, expect_fallback=False):
+    """pl-tp sweep through the sort-free pass and through the sort path: both must return the oracle's list."""
+    import os
+    from tests import pltp_rule as R
+    rpl, vpl, rtp, vtp, renc, dt = args
+    ref = oracle.encounter_pltp(rpl, vpl, rtp, vtp, renc, dt)
+    nbox = oracle.nbox_total()
+    d0, f0 = ctx.encounter_direct_count()
+    got = ctx.encounter_check_all_sort_and_sweep_pltp(len(renc), len(rtp), rpl, vpl, rtp, vtp, renc, dt)
+    st = ctx.encounter_stats()
+    d1, f1 = ctx.encounter_direct_count()
+    _same_pairs(got, ref)
+    assert d1 == d0 + 1 and f1 - f0 == (1 if expect_fallback else 0)
+    if expect_fallback:
+        assert st["nbox_total"] == nbox
+    else:
+        assert st["nbox_total"] + R.pairless_particle_boxes(rtp) == nbox
+        assert st["emitted"] == 2 * got[0]
+    os.environ["SWCU_PLTP_DIRECT_MAX"] = "0"
+    try:
+        got2 = ctx.encounter_check_all_sort_and_sweep_pltp(len(renc), len(rtp), rpl, vpl, rtp, vtp, renc, dt)
+        assert ctx.encounter_stats()["nbox_total"] == nbox
+    finally:
+        del os.environ["SWCU_PLTP_DIRECT_MAX"]
+    _same_pairs(got2, ref)
+    assert ctx.encounter_direct_count() == (d1, f1)
+    return got[0]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ntp", [1, 31, 5000, 200000])
+def test_sweep_pltp_sort_free_pass_equals_sort_path_and_oracle(ctx, oracle, ntp):
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(ntp, seed=7 + ntp)
+    n = _pltp_both_paths(ctx, oracle, (p["rh"], p["vh"], tp["rh"], tp["vh"], p["rhill"] * 6.5, 0.05))
+    if ntp >= 5000:
+        assert n > 0
+
+
+@pytest.mark.gpu
+def test_sweep_pltp_sort_free_pass_on_the_reference_fixture(ctx, oracle):
+    f, pl, _ = _fixture108()
+    for boost in (1.0, 3.0, 10.0):
+        _pltp_both_paths(ctx, oracle, (pl["rh"], pl["vh"], f["tp_rh"], f["tp_vh"], pl["rhill"] * 6.5 * boost, 0.05))
+
+
+@pytest.mark.gpu
+def test_sweep_pltp_extent_ties(ctx, oracle):
+    """Particles exactly on a planet's inner extent and particles sharing |r| stay on the sort-free pass; a particle
+    exactly on an OUTER extent is the one case the sorted sequence decides: the call repeats itself on the sort path."""
+    from tests import pltp_rule as R
+    assert _pltp_both_paths(ctx, oracle, R.tie_case("rmin")) > 0
+    assert _pltp_both_paths(ctx, oracle, R.tie_case("dup")) > 0
+    assert _pltp_both_paths(ctx, oracle, R.tie_case("rmax"), expect_fallback=True) > 0
+    # planets with identical extents, renc = 0 and renc < 0
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(3000, seed=8)
+    rpl, renc = p["rh"].copy(), p["rhill"] * 6.5
+    rpl[3] = rpl[2]
+    renc[3], renc[6], renc[7] = renc[2], 0.0, -renc[7]
+    _pltp_both_paths(ctx, oracle, (rpl, p["vh"], tp["rh"], tp["vh"], renc, 0.05))
+
+
+@pytest.mark.gpu
+def test_sweep_pltp_sort_free_pass_with_more_hits_than_the_first_candidate_buffer(ctx, oracle):
+    """Every particle inside Jupiter's sphere: far more hits than the initial candidate capacity."""
+    p = W.planets8_year_units()
+    rng = np.random.default_rng(4)
+    ntp = 300000
+    rtp = p["rh"][4] + rng.normal(size=(ntp, 3)) * 0.02
+    vtp = p["vh"][4] + rng.normal(size=(ntp, 3)) * 0.1
+    n = _pltp_both_paths(ctx, oracle, (p["rh"], p["vh"], rtp, vtp, p["rhill"] * 6.5, 0.05))
+    assert n > ntp // 4 + 65536
+
+
 def test_sweep_plplm_and_merged_list_bit_exact(ctx, oracle):
     n, nplm = 3000, 700
     d = W.disk(n, seed=12)
