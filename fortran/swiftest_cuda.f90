@@ -459,6 +459,50 @@ module swiftest_cuda
          integer(c_int), intent(out) :: lcollision(*), lclosest(*)
          integer(c_int64_t), intent(out) :: ncollision
       end function
+      ! tier 2 of the list loops: resident populations (pl%rh, pl%vb, ... stay on the device)
+      integer(c_int) function swcu_pl_symba_kick_list(ctx, nenc, index1, index2, lactive, levelg, dt, irec, sgn, lgood) &
+            bind(C, name="swcu_pl_symba_kick_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lactive(*), levelg(*)
+         real(c_double), value :: dt
+         integer(c_int), value :: irec, sgn
+         type(c_ptr), value :: lgood     !! c_loc of an integer(c_int) array of nenc elements, or c_null_ptr (no synchronisation)
+      end function
+      integer(c_int) function swcu_tp_symba_kick_list(ctx, nenc, index1, index2, lactive, levelg_pl, levelg_tp, dt, irec, &
+            sgn, lgood) bind(C, name="swcu_tp_symba_kick_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lactive(*), levelg_pl(*), levelg_tp(*)
+         real(c_double), value :: dt
+         integer(c_int), value :: irec, sgn
+         type(c_ptr), value :: lgood
+      end function
+      integer(c_int) function swcu_body_symba_encounter_check_list(ctx, kind, nenc, index1, index2, lencmask, dt, &
+            lencounter, lvdotr, nfound) bind(C, name="swcu_body_symba_encounter_check_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind     !! SWCU_PL: pl-pl list, SWCU_TP: pl-tp list
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lencmask(*)
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: lencounter(*)
+         integer(c_int), intent(inout) :: lvdotr(*)
+         integer(c_int64_t), intent(out) :: nfound
+      end function
+      integer(c_int) function swcu_body_collision_check_list(ctx, kind, nenc, index1, index2, lmask, lvdotr, dt, &
+            lcollision, lclosest, ncollision) bind(C, name="swcu_body_collision_check_list")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         integer(c_int), value :: kind
+         integer(c_int64_t), value :: nenc
+         integer(c_int), intent(in) :: index1(*), index2(*), lmask(*), lvdotr(*)
+         real(c_double), value :: dt
+         integer(c_int), intent(out) :: lcollision(*), lclosest(*)
+         integer(c_int64_t), intent(out) :: ncollision
+      end function
 
       ! ---- the rest of the ABI: context services, multi-GPU plumbing, statistics and measurement helpers ----
       integer(c_int) function swcu_version() bind(C, name="swcu_version")

@@ -278,6 +278,29 @@ int swcu_collision_check_list(swcu_context *ctx, int64_t nenc, const int32_t *in
                               const double *Gmass1, const double *radius1, int32_t n2, const double *r2, const double *v2,
                               double dt, int32_t *lcollision, int32_t *lclosest, int64_t *ncollision);
 
+/* ---- tier 2 of the SyMBA recursion's list loops: the same kernels on the RESIDENT populations (swcu_body_sync /
+ * swcu_body_put_vb): pl%rh, pl%vb, pl%rhill, pl%Gmass, pl%radius, pl%renc and tp%rh, tp%vb stay in HBM, a recursion level
+ * moves the pair list (8 B per pair), the level arrays (4 B per body) and the flags -- not 48 B per body each way as the
+ * host-pointer forms above do.  Same arithmetic, same results bit for bit.
+ *   swcu_pl_symba_kick_list / swcu_tp_symba_kick_list   symba_kick_list_plpl / _pltp (symba/symba_kick.f90:126-337):
+ *       vb of the resident pl (tp) is kicked in place; lgood may be NULL, then the call does not synchronise
+ *   swcu_body_symba_encounter_check_list   kind SWCU_PL: symba_encounter_check_list_plpl (symba_encounter_check.f90:88-140),
+ *       SWCU_TP: _pltp (:163-214); renc as left by swcu_pl_set_renc(irec)
+ *   swcu_body_collision_check_list   kind SWCU_PL: pair loop of collision_check_plpl (collision_check.f90:96-110),
+ *       SWCU_TP: of collision_check_pltp (:213-223) */
+int swcu_pl_symba_kick_list(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                            const int32_t *lactive, const int32_t *levelg, double dt, int32_t irec, int32_t sgn,
+                            int32_t *lgood);
+int swcu_tp_symba_kick_list(swcu_context *ctx, int64_t nenc, const int32_t *index1, const int32_t *index2,
+                            const int32_t *lactive, const int32_t *levelg_pl, const int32_t *levelg_tp, double dt,
+                            int32_t irec, int32_t sgn, int32_t *lgood);
+int swcu_body_symba_encounter_check_list(swcu_context *ctx, int32_t kind, int64_t nenc, const int32_t *index1,
+                                         const int32_t *index2, const int32_t *lencmask, double dt, int32_t *lencounter,
+                                         int32_t *lvdotr, int64_t *nfound);
+int swcu_body_collision_check_list(swcu_context *ctx, int32_t kind, int64_t nenc, const int32_t *index1,
+                                   const int32_t *index2, const int32_t *lmask, const int32_t *lvdotr, double dt,
+                                   int32_t *lcollision, int32_t *lclosest, int64_t *ncollision);
+
 /* ---- tier 1: energy and angular momentum of the massive bodies -------------------------------
  * swiftest_util_get_potential_energy_flat / _triangular (swiftest_util.f90:1291-1394): both add the same terms, one
  * kernel serves both.  rb(3,npl) barycentric positions, mass = Gmass/GU; lmask may be NULL (all bodies). */

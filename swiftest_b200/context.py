@@ -501,6 +501,51 @@ class Context:
                                                    float(dt), _ptr(lcol), _ptr(lclo), C.byref(nc)))
         return lcol, lclo, nc.value
 
+    # ---- the same list loops on the resident populations (tier 2) ----
+    def pl_symba_kick_list(self, index1, index2, lactive, levelg, dt, irec, sgn, want_lgood=True):
+        """symba_kick_list_plpl on the resident pl: vb is kicked on the device.  Returns lgood (or None)."""
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lactive = None if lactive is None else _vec(lactive, nenc, _i32)
+        levelg = _vec(levelg, dt=_i32)
+        lgood = np.zeros(nenc, _i32) if want_lgood else None
+        self._ck(self._L.swcu_pl_symba_kick_list(self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lactive), _ptr(levelg),
+                                                 float(dt), int(irec), int(sgn), _ptr(lgood)))
+        return lgood
+
+    def tp_symba_kick_list(self, index1, index2, lactive, levelg_pl, levelg_tp, dt, irec, sgn, want_lgood=True):
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lactive = None if lactive is None else _vec(lactive, nenc, _i32)
+        levelg_pl, levelg_tp = _vec(levelg_pl, dt=_i32), _vec(levelg_tp, dt=_i32)
+        lgood = np.zeros(nenc, _i32) if want_lgood else None
+        self._ck(self._L.swcu_tp_symba_kick_list(self._h, nenc, _ptr(index1), _ptr(index2), _ptr(lactive), _ptr(levelg_pl),
+                                                 _ptr(levelg_tp), float(dt), int(irec), int(sgn), _ptr(lgood)))
+        return lgood
+
+    def body_symba_encounter_check_list(self, kind, index1, index2, lencmask, dt, lvdotr=None):
+        """Pair loop of symba_encounter_check_list_plpl (kind PL) / _pltp (kind TP) on the resident populations."""
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lencmask = None if lencmask is None else _vec(lencmask, nenc, _i32)
+        lenc = np.zeros(nenc, _i32)
+        lvd = np.zeros(nenc, _i32) if lvdotr is None else _vec(lvdotr, nenc, _i32).copy()
+        nf = C.c_int64()
+        self._ck(self._L.swcu_body_symba_encounter_check_list(self._h, int(kind), nenc, _ptr(index1), _ptr(index2),
+                                                              _ptr(lencmask), float(dt), _ptr(lenc), _ptr(lvd), C.byref(nf)))
+        return lenc, lvd, nf.value
+
+    def body_collision_check_list(self, kind, index1, index2, lmask, lvdotr, dt):
+        index1, index2 = _vec(index1, dt=_i32), _vec(index2, dt=_i32)
+        nenc = len(index1)
+        lmask = None if lmask is None else _vec(lmask, nenc, _i32)
+        lvdotr = _vec(lvdotr, nenc, _i32)
+        lcol, lclo = np.zeros(nenc, _i32), np.zeros(nenc, _i32)
+        nc = C.c_int64()
+        self._ck(self._L.swcu_body_collision_check_list(self._h, int(kind), nenc, _ptr(index1), _ptr(index2), _ptr(lmask),
+                                                        _ptr(lvdotr), float(dt), _ptr(lcol), _ptr(lclo), C.byref(nc)))
+        return lcol, lclo, nc.value
+
     # ---- energy and momentum (swiftest_util.f90:1172-1394) ----
     def util_get_potential_energy(self, npl, lmask, GMcb, Gmass, mass, rb):
         lmask = None if lmask is None else _vec(lmask, npl, _i32)

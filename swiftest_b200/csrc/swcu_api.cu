@@ -1211,6 +1211,56 @@ extern "C" int swcu_symba_encounter_check_list(swcu_context *ctx, int64_t nenc, 
     return SWCU_OK;
 }
 
+// tier 2 of the above: the pair loop on the resident populations -- pl%rh, pl%vb, pl%renc (swcu_pl_set_renc), pl%radius and
+// tp%rh, tp%vb stay on the device; a recursion level moves the pair list, the mask and the flags only.
+// kind = SWCU_PL: symba_encounter_check_list_plpl (:88-140), SWCU_TP: _pltp (:163-214).
+extern "C" int swcu_body_symba_encounter_check_list(swcu_context *ctx, int32_t kind, int64_t nenc, const int32_t *index1,
+                                                    const int32_t *index2, const int32_t *lencmask, double dt,
+                                                    int32_t *lencounter, int32_t *lvdotr, int64_t *nfound)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (nfound) *nfound = 0;
+    if (kind != SWCU_PL && kind != SWCU_TP) return fail(ctx, SWCU_ERR_ARG, "body_symba_encounter_check_list: kind");
+    const bool two = (kind == SWCU_TP);
+    Body &pl = ctx->pl, &tp = ctx->tp;
+    if (!pl.valid || (two && !tp.valid))
+        return fail(ctx, SWCU_ERR_STATE, "body_symba_encounter_check_list: population not resident");
+    if (nenc < 0) return fail(ctx, SWCU_ERR_ARG, "body_symba_encounter_check_list: bad argument");
+    if (nenc == 0) return SWCU_OK;  // symba_encounter_check.f90:105
+    if (!index1 || !index2 || !lencounter || !lvdotr || pl.n == 0)
+        return fail(ctx, SWCU_ERR_ARG, "body_symba_encounter_check_list: null array");
+    const int32_t nmax2 = two ? tp.n : pl.n;
+    for (int64_t k = 0; k < nenc; ++k) {
+        if (lencmask && !lencmask[k]) continue;
+        if (index1[k] < 1 || index1[k] > pl.n || index2[k] < 1 || index2[k] > nmax2)
+            return fail(ctx, SWCU_ERR_ARG, "body_symba_encounter_check_list: pair %lld = (%d,%d) out of range", (long long)k,
+                        index1[k], index2[k]);
+    }
+    SWCU_TRY(ensure_helio(ctx, pl));
+    if (two) SWCU_TRY(ensure_helio(ctx, tp));
+    auto vb_list = [](Body &b, bool with_renc) {
+        SweepList l = sweep_list(b, 0, b.n, with_renc);
+        l.vx = b.wx.as<double>(), l.vy = b.wy.as<double>(), l.vz = b.wz.as<double>();
+        return l;
+    };
+    const SweepList l1 = vb_list(pl, true), l2 = two ? vb_list(tp, false) : l1;
+    const size_t ib = sizeof(int32_t) * (size_t)nenc;
+    SWCU_CUDA(ctx, ctx->istage[0].ensure(2 * ib));
+    SWCU_CUDA(ctx, ctx->istage[1].ensure(3 * ib));
+    int32_t *d_i1 = ctx->istage[0].as<int32_t>(), *d_i2 = d_i1 + nenc;
+    int32_t *d_mask = ctx->istage[1].as<int32_t>(), *d_lenc = d_mask + nenc, *d_lvd = d_lenc + nenc;
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_i1, index1, ib, cudaMemcpyHostToDevice, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_i2, index2, ib, cudaMemcpyHostToDevice, ctx->stream));
+    if (lencmask) SWCU_CUDA(ctx, cudaMemcpyAsync(d_mask, lencmask, ib, cudaMemcpyHostToDevice, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(d_lvd, lvdotr, ib, cudaMemcpyHostToDevice, ctx->stream));  // kept outside the mask
+    SWCU_TRY(symba_check_list(ctx, nenc, d_i1, d_i2, lencmask ? d_mask : nullptr, l1, pl.radius.as<double>(), l2,
+                              two ? nullptr : pl.radius.as<double>(), dt, d_lenc, d_lvd, nfound));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(lencounter, d_lenc, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaMemcpyAsync(lvdotr, d_lvd, ib, cudaMemcpyDeviceToHost, ctx->stream));
+    SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SWCU_OK;
+}
+
 // ======================================================================================================
 // measurement helpers
 // ======================================================================================================

@@ -210,3 +210,138 @@ def test_collision_check_list_matches_oracle(ctx, oracle):
                                    v2=tp["vh"])
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
     assert ctx.collision_check_list([], [], None, [], p["rh"], p["vh"], p["Gmass"], p["radius"], 1.0)[2] == 0
+
+
+# ------------------------------------------------------------------------------------------------- tier 2 (resident)
+import itertools
+
+_generation = itertools.count(1000)  # swcu_body_sync re-uploads only when the generation (or the count) changes
+
+def _resident_disk(ctx, oracle, n, seed, boost, rhill_scale=1.0, radius_scale=1.0):
+    """A disk resident on the device (rh, vb = vh, Gmass, radius, rhill) and its all-pairs encounter list."""
+    from swiftest_b200 import PL
+    d, i1, i2 = _disk_list(ctx, oracle, n, seed, boost)
+    d = dict(d)
+    d["rhill"] = d["rhill"] * rhill_scale
+    d["radius"] = d["radius"] * radius_scale
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"], generation=next(_generation))
+    ctx.body_put_vb(PL, d["vh"])
+    return d, i1, i2
+
+
+@pytest.mark.parametrize("irec,sgn", [(0, 1), (1, 1), (1, -1), (2, -1)])
+def test_resident_symba_kick_list_plpl_equals_host_pointer_form_and_oracle(ctx, oracle, irec, sgn):
+    """The resident form kicks pl%vb on the device: same bits as the host-pointer form (same kernels, SoA instead of AoS),
+    same bar against the serial oracle; only the pair list and the level array cross PCIe."""
+    from swiftest_b200 import PL
+    n = 3000
+    d, i1, i2 = _resident_disk(ctx, oracle, n, 21, 6.0, rhill_scale=3.0 if irec == 0 else 6.0)
+    rng = np.random.default_rng(irec * 7 + sgn)
+    levelg = rng.integers(max(irec - 1, 0), irec + 2, n).astype(np.int32)
+    active = (rng.uniform(size=len(i1)) > 0.1).astype(np.int32)
+    vb0 = d["vh"].copy()
+    ref_vb, ref_good, _ = oracle.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], d["rhill"], d["Gmass"], d["dt"], irec,
+                                                      sgn, vb0)
+    t1_vb, t1_good = ctx.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], d["rhill"], d["Gmass"], d["dt"], irec, sgn, vb0)
+    good = ctx.pl_symba_kick_list(i1, i2, active, levelg, d["dt"], irec, sgn)
+    vb = ctx.body_get_vb(PL)["vb"]
+    assert np.array_equal(good, ref_good) and np.array_equal(good, t1_good) and 0 < good.sum() < len(i1)
+    assert np.array_equal(vb, t1_vb)
+    touched = np.abs(ref_vb - vb0).sum(1) > 0
+    scale = np.abs(ref_vb - vb0).max(1, keepdims=True)[touched]
+    assert np.max(np.abs(vb[touched] - ref_vb[touched]) / scale) < 1e-14
+    assert np.array_equal(vb[~touched], vb0[~touched])
+    # a second level on top of the first, without reading lgood back (asynchronous call): vb keeps accumulating on the device
+    assert ctx.pl_symba_kick_list(i1, i2, active, levelg, d["dt"] / 3, irec, -sgn, want_lgood=False) is None
+    t1_vb2, _ = ctx.symba_kick_list_plpl(i1, i2, active, levelg, d["rh"], d["rhill"], d["Gmass"], d["dt"] / 3, irec, -sgn, t1_vb)
+    assert np.array_equal(ctx.body_get_vb(PL)["vb"], t1_vb2)
+
+
+def test_resident_symba_kick_list_pltp_equals_host_pointer_form_and_oracle(ctx, oracle):
+    from swiftest_b200 import PL, TP
+    p = W.planets8_year_units()
+    ntp = 4000
+    tp = W.tp_cloud(ntp, seed=8)
+    rc = p["rhill"] * 6.5 * 6
+    _, i1, i2, _ = ctx.encounter_check_all_triangular_pltp(8, ntp, p["rh"], p["vh"], tp["rh"], tp["vh"], rc, 0.05)
+    rng = np.random.default_rng(4)
+    lev_pl, lev_tp = np.ones(8, np.int32), rng.integers(0, 2, ntp).astype(np.int32)
+    vb0 = tp["vh"].copy()
+    for rh_scale in (6.0, 1e-6):
+        ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"] * rh_scale, generation=next(_generation))
+        ctx.body_sync(TP, ntp, r=tp["rh"], v=tp["vh"], generation=next(_generation))
+        ctx.body_put_vb(TP, vb0)
+        ref_vb, ref_good, _ = oracle.symba_kick_list_pltp(i1, i2, None, lev_pl, lev_tp, p["rh"], p["rhill"] * rh_scale,
+                                                          p["Gmass"], tp["rh"], 0.01, 1, 1, vb0)
+        t1_vb, t1_good = ctx.symba_kick_list_pltp(i1, i2, None, lev_pl, lev_tp, p["rh"], p["rhill"] * rh_scale, p["Gmass"],
+                                                  tp["rh"], 0.01, 1, 1, vb0)
+        good = ctx.tp_symba_kick_list(i1, i2, None, lev_pl, lev_tp, 0.01, 1, 1)
+        vb = ctx.body_get_vb(TP)["vb"]
+        assert np.array_equal(good, ref_good) and ref_good.sum() > 0
+        assert np.array_equal(vb, t1_vb)
+        if rh_scale < 1:
+            assert np.array_equal(vb, ref_vb)
+        else:
+            assert np.max(np.abs(vb - ref_vb)) < 1e-14 * np.abs(ref_vb - vb0).max()
+
+
+def test_resident_symba_encounter_check_list_matches_oracle(ctx, oracle):
+    from swiftest_b200 import PL, TP
+    import swiftest_b200 as S
+    n = 4000
+    d, i1, i2 = _resident_disk(ctx, oracle, n, 77, 3.0, rhill_scale=3.0, radius_scale=200.0)
+    rng = np.random.default_rng(1)
+    mask = (rng.uniform(size=len(i1)) > 0.3).astype(np.int32)
+    lv0 = np.full(len(i1), 5, np.int32)
+    ctx.pl_set_renc(1)
+    renc1 = oracle.set_renc(d["rhill"], 1)
+    ref = oracle.symba_encounter_check_list(i1, i2, mask, d["rh"], d["vh"], renc1, d["radius"], d["dt"] / 3, lvdotr=lv0)
+    got = ctx.body_symba_encounter_check_list(PL, i1, i2, mask, d["dt"] / 3, lvdotr=lv0)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert 0 < ref[2] < mask.sum() and (got[1][mask == 0] == 5).all()
+    # the check reads pl%vb, not pl%vh: change vb on the device and the answer follows
+    vb2 = d["vh"] * (1.0 + 0.3 * rng.normal(size=(n, 1)))
+    ctx.body_put_vb(PL, vb2)
+    ref2 = oracle.symba_encounter_check_list(i1, i2, mask, d["rh"], vb2, renc1, d["radius"], d["dt"] / 3, lvdotr=lv0)
+    got2 = ctx.body_symba_encounter_check_list(PL, i1, i2, mask, d["dt"] / 3, lvdotr=lv0)
+    assert np.array_equal(got2[0], ref2[0]) and np.array_equal(got2[1], ref2[1]) and got2[2] == ref2[2]
+    assert not np.array_equal(ref2[0], ref[0])
+    # pl-tp list
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(3000, seed=2)
+    rhill4 = p["rhill"] * 4
+    _, j1, j2, _ = ctx.encounter_check_all_triangular_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], rhill4 * 6.5, 0.05)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=rhill4, generation=next(_generation))
+    ctx.body_sync(TP, 3000, r=tp["rh"], v=tp["vh"], generation=next(_generation))
+    ctx.pl_set_renc(1)
+    ref = oracle.symba_encounter_check_list(j1, j2, None, p["rh"], p["vh"], oracle.set_renc(rhill4, 1), p["radius"], 0.02,
+                                            r2=tp["rh"], v2=tp["vh"])
+    got = ctx.body_symba_encounter_check_list(TP, j1, j2, None, 0.02)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2] and len(j1) > 5
+    with pytest.raises(S.SwcuError):
+        ctx.body_symba_encounter_check_list(PL, [1], [9999], None, 0.02)
+    assert ctx.body_symba_encounter_check_list(PL, [], [], None, 0.02)[2] == 0
+
+
+def test_resident_collision_check_list_matches_oracle(ctx, oracle):
+    from swiftest_b200 import PL, TP
+    n = 3000
+    d, i1, i2 = _resident_disk(ctx, oracle, n, 33, 6.0, radius_scale=300.0)
+    rng = np.random.default_rng(6)
+    mask = (rng.uniform(size=len(i1)) > 0.2).astype(np.int32)
+    lvdotr = (rng.uniform(size=len(i1)) > 0.3).astype(np.int32)
+    for dt in (d["dt"], 50 * d["dt"]):
+        ref = oracle.collision_check_list(i1, i2, mask, lvdotr, d["rh"], d["vh"], d["Gmass"], d["radius"], dt)
+        got = ctx.body_collision_check_list(PL, i1, i2, mask, lvdotr, dt)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+    assert ref[0].sum() > 0 and ref[1].sum() > 0
+    p = W.planets8_year_units()
+    tp = W.tp_cloud(3000, seed=12)
+    _, j1, j2, _ = ctx.encounter_check_all_triangular_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], p["rhill"] * 39, 0.05)
+    lv = np.ones(len(j1), np.int32)
+    ctx.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["rhill"] * 2, rhill=p["rhill"], generation=next(_generation))
+    ctx.body_sync(TP, 3000, r=tp["rh"], v=tp["vh"], generation=next(_generation))
+    ref = oracle.collision_check_list(j1, j2, None, lv, p["rh"], p["vh"], p["Gmass"], p["rhill"] * 2, 5.0, r2=tp["rh"],
+                                      v2=tp["vh"])
+    got = ctx.body_collision_check_list(TP, j1, j2, None, lv, 5.0)
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
