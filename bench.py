@@ -831,13 +831,17 @@ def side_legs(ctx, args, d, hbm_peak, peak_src):
                         "path": "sort-free pass over the particles (npl <= 128): %d of %d calls, %d fell back to the sort path"
                                 % (nd1 - nd0 - (nf1 - nf0), nd1 - nd0, nf1 - nf0),
                         "sort_path_ms": t_sort, "sort_path_same_result": bool(nenc_sort == nenc and st_sort["nbox_total"] == st["nbox_total"]),
-                        "algorithmic_bytes": b_direct,
-                        "roofline": {"bound": "hbm", "achieved": b_direct / (t_direct * 1e-3) / 1e9, "peak": hbm_peak,
-                                     "unit": "GB/s", "frac": b_direct / (t_direct * 1e-3) / 1e9 / hbm_peak,
-                                     "note": "48 B per particle + 9 B per pair; the launch group includes the count read-back "
-                                             "the two-phase API needs (device -> host -> sort of the hits)"},
-                        "survey_8d_formula": {"bytes": b_survey, "GB/s": b_survey / (t_direct * 1e-3) / 1e9,
-                                              "sort_path_GB/s": b_survey / (t_sort * 1e-3) / 1e9}}
+                        "algorithmic_bytes": b_survey,
+                        "roofline": {"bound": "hbm", "achieved": b_survey / (t_direct * 1e-3) / 1e9, "peak": hbm_peak,
+                                     "unit": "GB/s", "frac": b_survey / (t_direct * 1e-3) / 1e9 / hbm_peak,
+                                     "note": "SURVEY 8(d) bytes of the sort-and-sweep (body read + sort in/out + gather + candidate "
+                                             "stream + pair list; the unit sweep_plpl is quoted in) over the time of the sort-free "
+                                             "pass, read-back of the pair count included; the same formula gives the sort path "
+                                             "%.0f GB/s" % (b_survey / (t_sort * 1e-3) / 1e9)},
+                        "bytes_moved": {"bytes": b_direct, "GB/s": b_direct / (t_direct * 1e-3) / 1e9,
+                                        "frac_of_hbm": b_direct / (t_direct * 1e-3) / 1e9 / hbm_peak,
+                                        "note": "what the sort-free pass itself needs: 48 B per particle + 9 B per pair; it is bound "
+                                                "by instruction issue, not HBM (profiles/r02_pltp_direct_ncu.txt)"}}
     ctx.enable_kernel_timing(False)
     return ex
 

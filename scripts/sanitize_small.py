@@ -74,4 +74,30 @@ with Context(0) as c:
     c.body_get_range(PL, 5, 50)
     mass = d["Gmass"] / W.GMSUN
     print("pe", c.util_get_potential_energy(n, None, W.GMSUN, d["Gmass"], mass, d["rh"]))
+    # round 2, second half: sort-free pl-tp sweep (incl. a particle on an outer extent -> sort path), resident list kernels
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+    import pltp_rule as R
+    for kind in ("rmin", "dup", "rmax"):
+        a = R.tie_case(kind, ntp=1500)
+        print("pltp", kind, c.encounter_check_all_sort_and_sweep_pltp(8, 1500, *a[:4], a[4], a[5])[0], c.encounter_direct_count())
+    os.environ["SWCU_PLTP_DIRECT_MAX"] = "0"
+    print("pltp sort path", c.encounter_check_all_sort_and_sweep_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], p["rhill"] * 6.5, 0.05)[0])
+    del os.environ["SWCU_PLTP_DIRECT_MAX"]
+    n = 600
+    d = W.disk(n, seed=9)
+    _, i1, i2, _ = c.encounter_check_all_triangular_plpl(n, d["rh"], d["vh"], d["rhill"] * 6.5 * 6, d["dt"])
+    c.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"] * 200, rhill=d["rhill"] * 6, generation=5)
+    c.body_put_vb(PL, d["vh"])
+    lev = np.ones(n, np.int32)
+    c.pl_set_renc(1)
+    print("resident lists", len(i1), c.pl_symba_kick_list(i1, i2, None, lev, d["dt"], 1, 1).sum(),
+          c.body_symba_encounter_check_list(PL, i1, i2, None, d["dt"])[2],
+          c.body_collision_check_list(PL, i1, i2, None, np.ones(len(i1), np.int32), d["dt"])[2])
+    _, j1, j2, _ = c.encounter_check_all_triangular_pltp(8, 3000, p["rh"], p["vh"], tp["rh"], tp["vh"], p["rhill"] * 39, 0.05)
+    c.body_sync(PL, 8, nplm=8, r=p["rh"], v=p["vh"], Gmass=p["Gmass"], radius=p["radius"], rhill=p["rhill"], generation=6)
+    c.body_sync(TP, 3000, r=tp["rh"], v=tp["vh"], generation=7)
+    c.pl_set_renc(0)
+    print("resident pl-tp lists", len(j1), c.tp_symba_kick_list(j1, j2, None, np.ones(8, np.int32), np.ones(3000, np.int32), 0.01, 1, 1).sum(),
+          c.body_symba_encounter_check_list(TP, j1, j2, None, 0.02)[2],
+          c.body_collision_check_list(TP, j1, j2, None, np.ones(len(j1), np.int32), 5.0)[2])
 print("sanitize pass done")

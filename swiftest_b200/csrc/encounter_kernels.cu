@@ -304,20 +304,33 @@ __device__ __forceinline__ bool check_one_flat(double xr, double yr, double zr, 
     return hit;
 }
 
-// shared memory of pltp_direct_kernel<PER> per planet: record, 3 counters, hits per (slot, warp), hit bits per thread
+// shared memory of pltp_direct_kernel<PER>: per planet -- record, 3 counters, hits per (slot, warp), hit bits per thread;
+// fixed -- the chunk's coordinates (6 doubles per particle) and the candidate queue (PLTP_GROUP entries per particle)
+constexpr int PLTP_GROUP = 8;  // planets per candidate round
 template <int PER>
 constexpr size_t pltp_shmem_per_planet()
 {
     return sizeof(PlRec) + 3 * sizeof(unsigned int) + sizeof(unsigned short) * PER * (PLTP_T / 32) + PLTP_T;
 }
-
-// Pass A.  CTA b owns the PER*T particles [b*CHUNK, (b+1)*CHUNK); thread t holds particles b*CHUNK + u*T + t, u < PER
-// (coalesced loads).  The CTA builds the planet records (extents by the expressions of extent_kernel; CTA 0 also counts
-// the planets' endpoints inside each other's interval), tests its particles against every planet, and leaves its hits
-// ORDERED by (planet, particle) in a region of the arena claimed with one atomic; cnt[i*nb + b] = hits of planet i in
-// this chunk, box[i*nb + b] = endpoints of this chunk inside planet i's interval, abase[b] = where the region starts.
 template <int PER>
-__global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(ListDev pl, ListDev tp, int nb, double dt, double vsmall,
+constexpr size_t pltp_shmem_fixed()
+{
+    return (size_t)PLTP_T * PER * (6 * sizeof(double) + PLTP_GROUP * sizeof(unsigned int));
+}
+
+// Pass A.  Persistent CTAs; a CTA takes the PER*T particles [b*CHUNK, (b+1)*CHUNK) of chunk b, thread t brings particles
+// b*CHUNK + u*T + t, u < PER (coalesced loads, the next chunk prefetched into registers while this one is evaluated).
+//   1. every thread tests its particles' |r| against the extents of a group of planets (two compares per pair) and pushes
+//      the pairs inside an interval onto a queue in shared memory;
+//   2. the queue is evaluated DENSELY -- lane k takes entry k, whatever particle and planet it names -- so the predicate
+//      runs on full warps (evaluating it thread-per-particle ran it for every warp in which one lane was inside an
+//      interval: 7 times the instructions, ncu in profiles/r02_pltp_direct_ncu.txt); hits set a bit per (planet, particle);
+//   3. from the bits: hits per (planet, slot, warp), their prefix in particle order, and the hits leave the CTA ORDERED by
+//      (planet, particle) into a region of the arena claimed with one atomic.
+// cnt[i*nb + b] = hits of planet i in chunk b, box[i*nb + b] = endpoints of the chunk inside planet i's interval (CTA 0
+// adds the planets' endpoints inside each other's interval to chunk 0), abase[b] = where the chunk's region starts.
+template <int PER>
+__global__ void __launch_bounds__(PLTP_T, 3) pltp_direct_kernel(ListDev pl, ListDev tp, int nb, double dt, double vsmall,
                                                                 unsigned long long *__restrict__ arena,
                                                                 unsigned long long cap,
                                                                 unsigned long long *__restrict__ count,
@@ -328,13 +341,18 @@ __global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(L
     extern __shared__ unsigned char sh_raw[];
     const int n1 = pl.n, n2 = tp.n;
     PlRec *spl = reinterpret_cast<PlRec *>(sh_raw);                      // n1 records
-    unsigned int *sbox = reinterpret_cast<unsigned int *>(spl + n1);     // n1: endpoints of this chunk inside planet i
+    double *scx = reinterpret_cast<double *>(spl + n1);                  // the chunk: x, y, z, vx, vy, vz
+    double *scy = scx + CHUNK, *scz = scy + CHUNK, *scvx = scz + CHUNK, *scvy = scvx + CHUNK, *scvz = scvy + CHUNK;
+    unsigned int *sq = reinterpret_cast<unsigned int *>(scvz + CHUNK);   // candidate queue: (planet << 16) | slot
+    unsigned int *sbox = sq + CHUNK * PLTP_GROUP;                        // n1: endpoints of this chunk inside planet i
     unsigned int *shit = sbox + n1;                                      // n1: hits of planet i in this chunk
     unsigned int *soff = shit + n1;                                      // n1: start of planet i's run in the region
     unsigned short *swtot = reinterpret_cast<unsigned short *>(soff + n1);  // n1 x PER x NW: hits per (slot, warp),
                                                                             // later their exclusive prefix per planet
     unsigned char *shb = reinterpret_cast<unsigned char *>(swtot + n1 * PER * NW);  // n1 x T: hit bits per thread
+    unsigned int *shbw = reinterpret_cast<unsigned int *>(shb);
     __shared__ unsigned long long s_base;
+    __shared__ unsigned int s_qn[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
     for (int i = t; i < n1; i += PLTP_T) {
@@ -351,8 +369,7 @@ __global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(L
         shit[i] = 0u;
         if (blockIdx.x == 0 && (r.rmin != r.rmin || r.rmax != r.rmax)) atomicOr(flag, 1);
     }
-    // persistent CTA: chunks blockIdx.x, blockIdx.x + gridDim.x, ...; the NEXT chunk's particles are loaded into a second
-    // register set before the current chunk is evaluated, so the loads fly under ~5 us of predicate arithmetic
+    if (t < 2) s_qn[t] = 0u;
     double nx[PER], ny[PER], nz[PER], nvx[PER], nvy[PER], nvz[PER];
     auto fetch = [&](int chunk) {
 #pragma unroll
@@ -367,17 +384,21 @@ __global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(L
     };
     fetch(blockIdx.x);
     const unsigned below = (1u << lane) - 1u;
+    unsigned round = 0u;
     for (int chunk = blockIdx.x; chunk < nb; chunk += gridDim.x) {
         const long long q0 = (long long)chunk * CHUNK + t;
-        double x[PER], y[PER], z[PER], vx[PER], vy[PER], vz[PER], K[PER];
+        double K[PER];
         bool valid[PER];
 #pragma unroll
         for (int u = 0; u < PER; ++u) {
-            x[u] = nx[u], y[u] = ny[u], z[u] = nz[u], vx[u] = nvx[u], vy[u] = nvy[u], vz[u] = nvz[u];
+            const int sl = u * PLTP_T + t;
+            scx[sl] = nx[u], scy[sl] = ny[u], scz[sl] = nz[u], scvx[sl] = nvx[u], scvy[sl] = nvy[u], scvz[sl] = nvz[u];
             valid[u] = q0 + u * PLTP_T < n2;
+            K[u] = sqrt(nx[u] * nx[u] + ny[u] * ny[u] + nz[u] * nz[u]);  // rmin = rmax = |r| -/+ 1.1 * 0
         }
         fetch(chunk + gridDim.x);
-        __syncthreads();  // planet records / zeroed counters visible; the previous chunk's pass is over
+        for (int w = t; w < n1 * (PLTP_T / 4); w += PLTP_T) shbw[w] = 0u;
+        __syncthreads();  // planet records, zeroed counters and bits, the chunk in shared memory
         if (chunk == 0) {  // the planets' own endpoints inside each other's interval, same tie rule as the stable sort
             for (int i = t; i < n1; i += PLTP_T) {
                 const double lo = spl[i].rmin, hi = spl[i].rmax;
@@ -392,27 +413,36 @@ __global__ void __launch_bounds__(PLTP_T, PER == 1 ? 4 : 2) pltp_direct_kernel(L
                 if (c) atomicAdd(&sbox[i], c);
             }
         }
+        for (int g0 = 0; g0 < n1; g0 += PLTP_GROUP, ++round) {
+            unsigned int *qn = &s_qn[round & 1u];
+            const int g1 = min(n1, g0 + PLTP_GROUP);
+            for (int i = g0; i < g1; ++i) {
+                const double rmin = spl[i].rmin, rmax = spl[i].rmax;
 #pragma unroll
-        for (int u = 0; u < PER; ++u) K[u] = sqrt(x[u] * x[u] + y[u] * y[u] + z[u] * z[u]);  // rmin = rmax = |r| -/+ 1.1*0
-
-        for (int i = 0; i < n1; ++i) {
-            const double rmin = spl[i].rmin, rmax = spl[i].rmax;
-            unsigned hb = 0u;
-#pragma unroll
-            for (int u = 0; u < PER; ++u) {
-                if (valid[u] && K[u] >= rmin && K[u] <= rmax) {  // begin endpoint inside planet i's interval
-                    const bool in_e = K[u] < rmax;               // end endpoint inside
-                    atomicAdd(&sbox[i], in_e ? 2u : 1u);
-                    if (!in_e) atomicOr(flag, 2);                // |r_tp| == rmax_i: the sort path decides
-                    const PlRec &p = spl[i];
-                    if (check_one_flat(x[u] - p.x, y[u] - p.y, z[u] - p.z, vx[u] - p.vx, vy[u] - p.vy, vz[u] - p.vz,
-                                       p.renc + 0.0, dt, vsmall))
-                        hb |= 1u << u;
+                for (int u = 0; u < PER; ++u) {
+                    if (valid[u] && K[u] >= rmin && K[u] <= rmax) {  // begin endpoint inside planet i's interval
+                        const bool in_e = K[u] < rmax;               // end endpoint inside
+                        atomicAdd(&sbox[i], in_e ? 2u : 1u);
+                        if (!in_e) atomicOr(flag, 2);                // |r_tp| == rmax_i: the sort path decides
+                        sq[atomicAdd(qn, 1u)] = ((unsigned)i << 16) | (unsigned)(u * PLTP_T + t);
+                    }
                 }
             }
-            shb[i * PLTP_T + t] = (unsigned char)hb;
+            __syncthreads();
+            const unsigned nq = *qn;
+            if (t == 0) s_qn[(round + 1u) & 1u] = 0u;  // the other counter is idle until the barrier below
+            for (unsigned e = t; e < nq; e += PLTP_T) {
+                const unsigned code = sq[e];
+                const int i = (int)(code >> 16), sl = (int)(code & 0xffffu);
+                const PlRec &p = spl[i];
+                if (check_one_flat(scx[sl] - p.x, scy[sl] - p.y, scz[sl] - p.z, scvx[sl] - p.vx, scvy[sl] - p.vy,
+                                   scvz[sl] - p.vz, p.renc + 0.0, dt, vsmall)) {
+                    const int th = sl % PLTP_T, u = sl / PLTP_T;
+                    atomicOr(&shbw[(i * PLTP_T + th) >> 2], 1u << (((th & 3) << 3) + u));
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // hits per (planet, slot, warp) from the hit bits, their exclusive prefix in particle order, the planet's total
         for (int i = warp; i < n1; i += NW) {
             unsigned run = 0u;
@@ -812,19 +842,20 @@ int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepLis
     if (E.cand_cap < (size_t)n2 / 4 + 65536) E.cand_cap = (size_t)n2 / 4 + 65536;
     const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
     const int per = pltp_per();
-    const size_t shmem = (size_t)n1 * (per == 4 ? pltp_shmem_per_planet<4>() : per == 2 ? pltp_shmem_per_planet<2>()
-                                                                                        : pltp_shmem_per_planet<1>());
+    const size_t shmem = per == 4   ? n1 * pltp_shmem_per_planet<4>() + pltp_shmem_fixed<4>()
+                         : per == 2 ? n1 * pltp_shmem_per_planet<2>() + pltp_shmem_fixed<2>()
+                                    : n1 * pltp_shmem_per_planet<1>() + pltp_shmem_fixed<1>();
     static bool attr_set = false;
     if (!attr_set) {
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<1>())));
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<1>() + pltp_shmem_fixed<1>())));
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<2>())));
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<2>() + pltp_shmem_fixed<2>())));
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<4>())));
+                                            (int)(PLTP_MAXPL * pltp_shmem_per_planet<4>() + pltp_shmem_fixed<4>())));
         attr_set = true;
     }
-    const int grid = std::min(nb, ctx->prop.multiProcessorCount * (per == 1 ? 4 : 2));  // persistent CTAs (launch bounds)
+    const int grid = std::min(nb, ctx->prop.multiProcessorCount * 3);  // persistent CTAs, 3 per SM (launch bounds)
     std::vector<unsigned long long> h(8 + (size_t)n1, 0ull);
     int h_total = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
