@@ -119,6 +119,10 @@ int swcu_encounter_stats(swcu_context *ctx, int64_t *nbox_total, int64_t *ncandi
  * sort-free pass over the particles (`direct`: npl <= SWCU_PLTP_DIRECT_MAX, default and maximum 128) and those among them that had
  * to be repeated on the sort path because a particle's |r| equalled a planet's outer extent bit for bit (`fallbacks`) */
 int swcu_encounter_direct_count(swcu_context *ctx, int64_t *direct, int64_t *fallbacks);
+/* sort-and-sweep calls since the context was created whose extents could not be bucket sorted (more than 2048 endpoints in
+ * one of up to 65 536 equal slices of [min, max], or a non-finite extent) and were repeated with the radix sort;
+ * SWCU_SWEEP_BUCKET=0 switches the bucket sort off */
+int swcu_encounter_bucket_fallbacks(swcu_context *ctx, int64_t *count);
 
 /* ------------------------------------------------------------------------------------------------------
  * Tier 2: device-resident bodies (what the type-bound procedures pl%accel_int, tp%accel_int, body%drift,

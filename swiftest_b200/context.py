@@ -655,6 +655,12 @@ class Context:
         self._ck(self._L.swcu_encounter_direct_count(self._h, C.byref(a), C.byref(b)))
         return int(a.value), int(b.value)
 
+    def encounter_bucket_fallbacks(self):
+        """Sort-and-sweep calls that were repeated with the radix sort (clump of equal radii / non-finite extent)."""
+        a = C.c_int64()
+        self._ck(self._L.swcu_encounter_bucket_fallbacks(self._h, C.byref(a)))
+        return int(a.value)
+
     def flat_redo_count(self):
         """Chunks the third-law gravity kernel rolled back and redid with the IEEE expression since create."""
         n = C.c_uint64()

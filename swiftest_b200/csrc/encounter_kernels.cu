@@ -43,14 +43,50 @@ struct ListDev {
     int n;
 };
 
+// order-preserving map double -> uint64 (the radix sort's own key transform) and back
+__device__ __forceinline__ unsigned long long sortable(double x)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double unsortable(unsigned long long u)
+{
+    const unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    return __longlong_as_double((long long)b);
+}
+
+// mm[0] = min, mm[1] = max of all extents (sortable form), mm[2] != 0: a non-finite extent was seen (bucket sort refuses)
+__device__ __forceinline__ void extent_minmax(unsigned long long *mm, double lo, double hi, bool valid)
+{
+    unsigned long long a = valid ? sortable(lo) : ~0ull, b = valid ? sortable(hi) : 0ull;
+    if (valid && hi < lo) {  // negative renc
+        const unsigned long long t = a;
+        a = b, b = t;
+    }
+    const bool bad = valid && !(isfinite(lo) && isfinite(hi));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&mm[0], a);
+        atomicMax(&mm[1], b);
+    }
+    if (bad) atomicOr(reinterpret_cast<unsigned int *>(&mm[2]), 1u);
+}
+
 // K7: extents (encounter_check.f90:180-185, 237-251, 305-319) and the concatenated copy of both lists
 __global__ void extent_kernel(ListDev l1, ListDev l2, int ntot, double *__restrict__ cx, double *__restrict__ cy,
                               double *__restrict__ cz, double *__restrict__ cvx, double *__restrict__ cvy,
                               double *__restrict__ cvz, double *__restrict__ crenc, double *__restrict__ keys,
-                              int *__restrict__ vals)
+                              int *__restrict__ vals, unsigned long long *__restrict__ mm)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ntot) return;
+    if (i >= ntot) {
+        if (mm) extent_minmax(mm, 0.0, 0.0, false);  // the whole warp takes part in the reduction
+        return;
+    }
     const bool in1 = i < l1.n;
     const ListDev &l = in1 ? l1 : l2;
     const int q = in1 ? i : i - l1.n;
@@ -69,6 +105,150 @@ __global__ void extent_kernel(ListDev l1, ListDev l2, int ntot, double *__restri
     keys[ntot + i] = rmag + w;  // rmax -> end endpoint id ntot+i
     vals[i] = i;
     vals[ntot + i] = ntot + i;
+    if (mm) extent_minmax(mm, rmag - w, rmag + w, true);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K8': bucket sort of the 2N (extent, endpoint id) pairs -- the same result as the stable radix sort (a stable sort by key IS
+// the sort by (key, position), and the endpoint id is the position), in 4 launches instead of the 10 of an 8-pass radix
+// sort whose passes are latency bound at these sizes (10 us per pass at 2e4 keys: 88 of the 146 us of kernel time of the
+// npl = 1e4 sweep).  Buckets are equal slices of [min, max] of the extents (the map key -> bucket is a chain of rounded,
+// hence monotone, operations); a CTA sorts one bucket in shared memory with a bitonic network on (key, id) and does K9's
+// work for its endpoints right away.  A bucket beyond the shared-memory capacity (a clump of equal radii) or a non-finite
+// extent raises a flag: the buffers stay in-bounds, the call repeats itself with the radix sort.
+constexpr int BUCKET_CAP = 2048;      // endpoints a CTA can sort
+constexpr int BUCKET_TARGET = 128;    // average endpoints per bucket
+constexpr int BUCKET_MAXNB = 1 << 16;
+constexpr int BUCKET_MAXKEYS = 1 << 19;  // beyond ~5e5 keys the 8-pass radix sort is faster (2e6 keys: 0.61 vs 0.69 ms per sweep)
+
+struct BucketMap {
+    double kmin, scale;
+    int nb;
+    __device__ __forceinline__ int of(double key) const
+    {
+        int b = (int)((key - kmin) * scale);  // NaN -> 0; monotone in key
+        return min(max(b, 0), nb - 1);
+    }
+};
+__device__ __forceinline__ BucketMap bucket_map(const unsigned long long *mm, int nb)
+{
+    BucketMap m;
+    const double kmin = unsortable(mm[0]), kmax = unsortable(mm[1]);
+    m.kmin = kmin;
+    m.scale = (kmax > kmin) ? (double)nb / (kmax - kmin) : 0.0;
+    m.nb = nb;
+    return m;
+}
+
+__global__ void bucket_hist_kernel(const double *__restrict__ keys, int next, const unsigned long long *__restrict__ mm,
+                                   int nb, int *__restrict__ hist)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= next) return;
+    atomicAdd(&hist[bucket_map(mm, nb).of(keys[k])], 1);
+}
+
+// one CTA: offs = exclusive scan of hist (offs[nb] = total), cursor = offs; flags a bucket beyond the capacity
+__global__ void __launch_bounds__(1024) bucket_scan_kernel(const int *__restrict__ hist, int nb, int *__restrict__ offs,
+                                                           int *__restrict__ cursor, unsigned long long *__restrict__ mm)
+{
+    __shared__ int part[1024];
+    const int t = threadIdx.x, per = (nb + 1023) / 1024;
+    const int b0 = min(t * per, nb), b1 = min(b0 + per, nb);
+    int sum = 0, big = 0;
+    for (int b = b0; b < b1; ++b) {
+        sum += hist[b];
+        big |= hist[b] > BUCKET_CAP;
+    }
+    part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - sum;
+    for (int b = b0; b < b1; ++b) {
+        offs[b] = run;
+        cursor[b] = run;
+        run += hist[b];
+    }
+    if (t == 1023) offs[nb] = part[1023];
+    if (big) atomicOr(reinterpret_cast<unsigned int *>(&mm[2]), 2u);
+}
+
+__global__ void bucket_scatter_kernel(const double *__restrict__ keys, int next, const unsigned long long *__restrict__ mm,
+                                      int nb, int *__restrict__ cursor, double *__restrict__ bkeys, int *__restrict__ bids)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= next) return;
+    const double key = keys[k];
+    const int pos = atomicAdd(&cursor[bucket_map(mm, nb).of(key)], 1);
+    bkeys[pos] = key;
+    bids[pos] = k;  // vals_in[k] == k
+}
+
+// one CTA per bucket: bitonic sort on (key, id), then K9 for the bucket's endpoints (encounter_check.f90:778-789, :937-949)
+__global__ void __launch_bounds__(128) bucket_sort_kernel(const int *__restrict__ offs, const double *__restrict__ bkeys,
+                                                          const int *__restrict__ bids, int ntot,
+                                                          const double *__restrict__ cx, const double *__restrict__ cy,
+                                                          const double *__restrict__ cz, const double *__restrict__ cvx,
+                                                          const double *__restrict__ cvy, const double *__restrict__ cvz,
+                                                          const double *__restrict__ crenc, int *__restrict__ ibeg,
+                                                          int *__restrict__ iend, double *__restrict__ sx,
+                                                          double *__restrict__ sy, double *__restrict__ sz,
+                                                          double *__restrict__ svx, double *__restrict__ svy,
+                                                          double *__restrict__ svz, double *__restrict__ srenc,
+                                                          int *__restrict__ sbody)
+{
+    __shared__ double sk[BUCKET_CAP];
+    __shared__ int si[BUCKET_CAP];
+    const int o0 = offs[blockIdx.x], cnt = offs[blockIdx.x + 1] - o0;
+    if (cnt == 0) return;
+    const bool sortit = cnt <= BUCKET_CAP;  // otherwise pass the bucket through unsorted (flag already raised)
+    int m = 1;
+    if (sortit) {
+        while (m < cnt) m <<= 1;
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            sk[k] = k < cnt ? bkeys[o0 + k] : INFINITY;
+            si[k] = k < cnt ? bids[o0 + k] : 0x7fffffff;
+        }
+        __syncthreads();
+        for (int size = 2; size <= m; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int k = threadIdx.x; k < (m >> 1); k += blockDim.x) {
+                    const int lo = ((k & ~(stride - 1)) << 1) | (k & (stride - 1)), hi = lo + stride;  // stride is a power of 2
+                    const bool up = ((lo & size) == 0);
+                    const double ka = sk[lo], kb = sk[hi];
+                    const int ia = si[lo], ib = si[hi];
+                    const bool a_after_b = (ka > kb) || (ka == kb && ia > ib);
+                    if (a_after_b == up) {
+                        sk[lo] = kb, sk[hi] = ka;
+                        si[lo] = ib, si[hi] = ia;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+    for (int r = threadIdx.x; r < cnt; r += blockDim.x) {
+        const int id = sortit ? si[r] : bids[o0 + r];
+        const int k = o0 + r;
+        const int body = id < ntot ? id : id - ntot;
+        if (id < ntot)
+            ibeg[body] = k;
+        else
+            iend[body] = k;
+        sx[k] = cx[body];
+        sy[k] = cy[body];
+        sz[k] = cz[body];
+        svx[k] = cvx[body];
+        svy[k] = cvy[body];
+        svz[k] = cvz[body];
+        srenc[k] = crenc[body];
+        sbody[k] = body;
+    }
 }
 
 // K9: encounter_check.f90:778-789 (ibeg/iend) and :937-949 (gather into sorted order)
@@ -118,9 +298,10 @@ __global__ void chunk_count_kernel(int ntot, const int *__restrict__ ibeg, const
 // chunk -> body map for the sweep (bodies own consecutive chunk ids from the prefix sum); chunks beyond the capacity of
 // the map fall back to a binary search in the sweep kernel
 __global__ void chunk_owner_kernel(int ntot, const int *__restrict__ nchunk, const int *__restrict__ choff,
-                                   int *__restrict__ owner, int cap)
+                                   int *__restrict__ owner, int cap, unsigned long long *__restrict__ total_chunks)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *total_chunks = (unsigned long long)choff[ntot];  // read back with the other counters in one copy
     if (i >= ntot) return;
     const int c0 = choff[i], nc = nchunk[i];
     for (int q = 0; q < nc && c0 + q < cap; ++q) owner[c0 + q] = i;
@@ -168,8 +349,10 @@ __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single
                                                     const double *__restrict__ svz, const double *__restrict__ srenc,
                                                     const int *__restrict__ sbody, double dt, double vsmall,
                                                     unsigned long long *__restrict__ cand, unsigned long long cap,
-                                                    unsigned long long *__restrict__ count)
+                                                    unsigned long long *__restrict__ count, int b2)
 {
+    // keys are packed (index1 << b2) | index2 with b2 = bits of the largest index2: the key sort then runs over
+    // bits(index1) + b2 bits (34 at npl = 1e5) instead of 64
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -226,7 +409,7 @@ __global__ void __launch_bounds__(128) sweep_kernel(int ntot, int n1, int single
                                 a = (unsigned)j + 1u;
                                 b = (unsigned)(i - n1) + 1u;
                             }
-                            key[u] = ((unsigned long long)a << 32) | b;
+                            key[u] = ((unsigned long long)a << b2) | b;
                         }
                     }
                 }
@@ -547,6 +730,61 @@ __global__ void __launch_bounds__(256) pltp_place_kernel(int n1, int nb, int npl
     }
 }
 
+// K11 for short candidate lists, on the device and without a host round trip in the middle: one CTA sorts up to
+// CAND_SMALL keys in shared memory (bitonic), drops equal neighbours and leaves the list and its length where
+// canonical_order would; longer lists set flag = 1 and the host runs the radix sort + unique after all.
+constexpr int CAND_SMALL = 4096;
+__global__ void __launch_bounds__(1024) finalize_small_kernel(const unsigned long long *__restrict__ cand,
+                                                              unsigned long long cap,
+                                                              const unsigned long long *__restrict__ count,
+                                                              unsigned long long *__restrict__ uniq, int *__restrict__ nuniq,
+                                                              unsigned long long *__restrict__ flag, int b2)
+{
+    __shared__ unsigned long long sk[CAND_SMALL];
+    __shared__ int part[1024];
+    const unsigned long long n64 = *count;
+    const int t = threadIdx.x;
+    if (n64 > (unsigned long long)CAND_SMALL || n64 > cap) {
+        if (t == 0) *flag = 1ull, *nuniq = 0;
+        return;
+    }
+    const int n = (int)n64;
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int k = t; k < m; k += 1024) sk[k] = k < n ? cand[k] : ~0ull;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = t; k < (m >> 1); k += 1024) {
+                const int lo = ((k & ~(stride - 1)) << 1) | (k & (stride - 1)), hi = lo + stride;  // stride is a power of 2
+                const unsigned long long a = sk[lo], b = sk[hi];
+                if ((a > b) == ((lo & size) == 0)) sk[lo] = b, sk[hi] = a;
+            }
+            __syncthreads();
+        }
+    // heads of runs of equal keys, in the CAND_SMALL / 1024 = 4 consecutive slots of this thread
+    constexpr int PER = CAND_SMALL / 1024;
+    int heads = 0;
+    for (int q = 0; q < PER; ++q) {
+        const int k = t * PER + q;
+        heads += (k < n && (k == 0 || sk[k] != sk[k - 1])) ? 1 : 0;
+    }
+    part[t] = heads;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int pos = part[t] - heads;
+    for (int q = 0; q < PER; ++q) {
+        const int k = t * PER + q;
+        if (k < n && (k == 0 || sk[k] != sk[k - 1])) uniq[pos++] = ((sk[k] >> b2) << 32) | (sk[k] & ((1ull << b2) - 1ull));
+    }
+    if (t == 1023) *nuniq = part[1023], *flag = 0ull;
+}
+
 __global__ void unpack_keys_kernel(const unsigned long long *__restrict__ keys, long long n, int32_t *__restrict__ i1,
                                    int32_t *__restrict__ i2)
 {
@@ -777,23 +1015,45 @@ int set_renc(swcu_context *ctx, Body &pl, int irec)
 
 // Sort-and-sweep of one list (l2 == nullptr) or two lists.  Leaves the sorted unique keys in ctx->enc.uniq.
 // K11 canonical order + duplicate removal (:976-985, :703-757) of the ncand keys in E.cand
-int canonical_order(swcu_context *ctx, long long ncand, int64_t *nenc_out)
+static int bits_for(unsigned long long v)
+{
+    int b = 1;
+    while ((v >> b) != 0ull) ++b;
+    return b;
+}
+
+// packed (index1 << b2 | index2) keys -> the canonical (index1 << 32 | index2) keys the fetch expects, in place
+__global__ void expand_keys_kernel(unsigned long long *__restrict__ keys, const int *__restrict__ n, int b2)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *n) return;
+    const unsigned long long c = keys[k];
+    keys[k] = ((c >> b2) << 32) | (c & ((1ull << b2) - 1ull));
+}
+
+// keys packed with b2 < 32 are sorted over b1 + b2 bits and expanded afterwards; b2 == 32: canonical keys, all 64 bits
+int canonical_order(swcu_context *ctx, long long ncand, int64_t *nenc_out, int b1 = 32, int b2 = 32)
 {
     auto &E = ctx->enc;
+    const int end_bit = (b2 >= 32) ? 64 : b1 + b2;
     int *d_nuniq = reinterpret_cast<int *>(E.counters.as<unsigned long long>() + 2);
     SWCU_CUDA(ctx, E.cand_sorted.ensure(sizeof(unsigned long long) * ncand));
     SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * ncand));
     size_t tmp_k = 0, tmp_u = 0;
     SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(nullptr, tmp_k, E.cand.as<unsigned long long>(),
-                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, end_bit, ctx->stream));
     SWCU_CUDA(ctx, cub::DeviceSelect::Unique(nullptr, tmp_u, E.cand_sorted.as<unsigned long long>(),
                                              E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
     SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_k, tmp_u)));
     SWCU_CUDA(ctx, cub::DeviceRadixSort::SortKeys(E.cub_tmp.p, tmp_k, E.cand.as<unsigned long long>(),
-                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, 64, ctx->stream));
+                                                  E.cand_sorted.as<unsigned long long>(), ncand, 0, end_bit, ctx->stream));
     SWCU_CUDA(ctx, cub::DeviceSelect::Unique(E.cub_tmp.p, tmp_u, E.cand_sorted.as<unsigned long long>(),
                                              E.uniq.as<unsigned long long>(), d_nuniq, ncand, ctx->stream));
     ctx->launches += 6;
+    if (b2 < 32) {
+        expand_keys_kernel<<<cdiv(ncand, 256), 256, 0, ctx->stream>>>(E.uniq.as<unsigned long long>(), d_nuniq, b2);
+        SWCU_KERNEL_CHECK(ctx);
+    }
     int h_nuniq = 0;
     SWCU_CUDA(ctx, cudaMemcpyAsync(&h_nuniq, d_nuniq, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -901,7 +1161,16 @@ int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepLis
     return SWCU_OK;
 }
 
+static int encounter_sweep_impl(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out,
+                                bool allow_direct, bool allow_bucket);
+
 int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out)
+{
+    return encounter_sweep_impl(ctx, l1, l2, dt, nenc_out, true, true);
+}
+
+static int encounter_sweep_impl(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc_out,
+                                bool allow_direct, bool allow_bucket)
 {
     auto &E = ctx->enc;
     E.nenc = 0;
@@ -912,7 +1181,7 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     const int n1 = l1.n, n2 = l2 ? l2->n : 0;
     const bool single = (l2 == nullptr);
     if (n1 == 0 || (!single && n2 == 0)) return SWCU_OK;  // :168, :225, :291
-    if (!single && l2->renc == nullptr) {  // pl-tp with few massive bodies: no sort needed
+    if (allow_direct && !single && l2->renc == nullptr) {  // pl-tp with few massive bodies: no sort needed
         const char *dm = getenv("SWCU_PLTP_DIRECT_MAX");  // read per call: tests switch the path at run time
         const int direct_max = std::min(dm ? atoi(dm) : PLTP_MAXPL, PLTP_MAXPL);
         if (n1 <= direct_max) {
@@ -942,18 +1211,34 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     SWCU_CUDA(ctx, E.iend.ensure(ib * ntot));
     SWCU_CUDA(ctx, E.nchunk.ensure(ib * (ntot + 1)));
     SWCU_CUDA(ctx, E.choff.ensure(ib * (ntot + 1)));
-    SWCU_CUDA(ctx, E.counters.ensure(64));
+    SWCU_CUDA(ctx, E.counters.ensure(sizeof(unsigned long long) * (8 + PLTP_MAXPL)));
+    if (!E.h_counters) SWCU_CUDA(ctx, cudaHostAlloc((void **)&E.h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
     unsigned long long *d_count = E.counters.as<unsigned long long>();       // [0] candidates emitted
     unsigned long long *d_nbox = d_count + 1;                                 // [1] sum nbox
+    unsigned long long *d_small = d_count + 8;                                // [8] 0: finalize_small_kernel made the list
     // [2] unique count (canonical_order), [3] hits of the list check
     SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, 32, ctx->stream));
 
     ListDev a = to_dev(l1), b;
     if (l2) b = to_dev(*l2); else { b = a; b.n = 0; }
+    // bucket sort (4 launches, K9 fused) unless switched off or the population is large enough for the radix sort to win
+    const char *bs = getenv("SWCU_SWEEP_BUCKET");
+    const bool bucket = allow_bucket && (bs ? atoi(bs) != 0 : true) && next <= BUCKET_MAXKEYS;
+    int nbk = 1;
+    while (nbk < BUCKET_MAXNB && (long long)nbk * BUCKET_TARGET < next) nbk <<= 1;
+    unsigned long long *d_mm = d_count + 5;  // [5] min, [6] max, [7] flags of the bucket sort
+    if (bucket) {
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_mm, 0xff, sizeof(unsigned long long), ctx->stream));          // min = ~0
+        SWCU_CUDA(ctx, cudaMemsetAsync(d_mm + 1, 0, 2 * sizeof(unsigned long long), ctx->stream));    // max = 0, flags = 0
+        SWCU_CUDA(ctx, E.bk_hist.ensure(ib * (size_t)(2 * nbk + 1)));
+        SWCU_CUDA(ctx, E.bk_offs.ensure(ib * (size_t)(nbk + 1)));
+        SWCU_CUDA(ctx, cudaMemsetAsync(E.bk_hist.p, 0, ib * (size_t)nbk, ctx->stream));
+    }
     extent_kernel<<<cdiv(ntot, 256), 256, 0, ctx->stream>>>(a, b, ntot, E.cx.as<double>(), E.cy.as<double>(),
                                                            E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(),
                                                            E.cvz.as<double>(), E.crenc.as<double>(),
-                                                           E.keys_in.as<double>(), E.vals_in.as<int>());
+                                                           E.keys_in.as<double>(), E.vals_in.as<int>(),
+                                                           bucket ? d_mm : nullptr);
     SWCU_KERNEL_CHECK(ctx);
 
     size_t tmp_sort = 0, tmp_scan = 0;
@@ -962,16 +1247,34 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     SWCU_CUDA(ctx, cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, E.nchunk.as<int>(), E.choff.as<int>(), ntot + 1,
                                                  ctx->stream));
     SWCU_CUDA(ctx, E.cub_tmp.ensure(std::max(tmp_sort, tmp_scan)));
-    SWCU_CUDA(ctx, cub::DeviceRadixSort::SortPairs(E.cub_tmp.p, tmp_sort, E.keys_in.as<double>(), E.keys_out.as<double>(),
-                                                   E.vals_in.as<int>(), E.vals_out.as<int>(), next, 0, 64, ctx->stream));
-    ctx->launches += 4;  // CUB's onesweep: histogram + 3..4 passes (counted as library launches of ours)
+    if (bucket) {
+        int *hist = E.bk_hist.as<int>(), *cursor = hist + nbk, *offs = E.bk_offs.as<int>();
+        bucket_hist_kernel<<<cdiv(next, 256), 256, 0, ctx->stream>>>(E.keys_in.as<double>(), next, d_mm, nbk, hist);
+        SWCU_KERNEL_CHECK(ctx);
+        bucket_scan_kernel<<<1, 1024, 0, ctx->stream>>>(hist, nbk, offs, cursor, d_mm);
+        SWCU_KERNEL_CHECK(ctx);
+        bucket_scatter_kernel<<<cdiv(next, 256), 256, 0, ctx->stream>>>(E.keys_in.as<double>(), next, d_mm, nbk, cursor,
+                                                                       E.keys_out.as<double>(), E.vals_out.as<int>());
+        SWCU_KERNEL_CHECK(ctx);
+        bucket_sort_kernel<<<nbk, 128, 0, ctx->stream>>>(
+            offs, E.keys_out.as<double>(), E.vals_out.as<int>(), ntot, E.cx.as<double>(), E.cy.as<double>(),
+            E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(), E.cvz.as<double>(), E.crenc.as<double>(),
+            E.ibeg.as<int>(), E.iend.as<int>(), E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(),
+            E.svy.as<double>(), E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>());
+        SWCU_KERNEL_CHECK(ctx);
+    } else {
+        SWCU_CUDA(ctx, cub::DeviceRadixSort::SortPairs(E.cub_tmp.p, tmp_sort, E.keys_in.as<double>(),
+                                                       E.keys_out.as<double>(), E.vals_in.as<int>(), E.vals_out.as<int>(),
+                                                       next, 0, 64, ctx->stream));
+        ctx->launches += 4;  // CUB's onesweep: histogram + 3..4 passes (counted as library launches of ours)
 
-    endpoint_kernel<<<cdiv(next, 256), 256, 0, ctx->stream>>>(
-        ntot, E.vals_out.as<int>(), E.cx.as<double>(), E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(),
-        E.cvy.as<double>(), E.cvz.as<double>(), E.crenc.as<double>(), E.ibeg.as<int>(), E.iend.as<int>(),
-        E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(), E.svy.as<double>(),
-        E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>());
-    SWCU_KERNEL_CHECK(ctx);
+        endpoint_kernel<<<cdiv(next, 256), 256, 0, ctx->stream>>>(
+            ntot, E.vals_out.as<int>(), E.cx.as<double>(), E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(),
+            E.cvy.as<double>(), E.cvz.as<double>(), E.crenc.as<double>(), E.ibeg.as<int>(), E.iend.as<int>(),
+            E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(), E.svy.as<double>(),
+            E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>());
+        SWCU_KERNEL_CHECK(ctx);
+    }
 
     chunk_count_kernel<<<cdiv(ntot + 1, 256), 256, 0, ctx->stream>>>(ntot, E.ibeg.as<int>(), E.iend.as<int>(),
                                                                     E.nchunk.as<int>(), d_nbox);
@@ -985,14 +1288,15 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     SWCU_CUDA(ctx, E.owner.ensure(ib * E.owner_cap));
     const int owner_cap = (int)std::min<size_t>(E.owner_cap, 0x7fffffff);
     chunk_owner_kernel<<<cdiv(ntot, 256), 256, 0, ctx->stream>>>(ntot, E.nchunk.as<int>(), E.choff.as<int>(),
-                                                                E.owner.as<int>(), owner_cap);
+                                                                E.owner.as<int>(), owner_cap, d_count + 9);
     SWCU_KERNEL_CHECK(ctx);
 
     if (E.cand_cap < (size_t)4 * ntot + 65536) E.cand_cap = (size_t)4 * ntot + 65536;
     const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
+    const int b1 = bits_for((unsigned long long)n1), b2 = bits_for((unsigned long long)(single ? n1 : n2));
     const int sweep_blocks = ctx->prop.multiProcessorCount * 8;
-    unsigned long long h_counts[2] = {0, 0};
-    int h_total_chunks = 0;
+    unsigned long long h_counts[2] = {0, 0}, h_small[1] = {1};
+    int h_total_chunks = 0, h_nuniq = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
         SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
         SWCU_CUDA(ctx, cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), ctx->stream));
@@ -1001,13 +1305,26 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
             E.cy.as<double>(), E.cz.as<double>(), E.cvx.as<double>(), E.cvy.as<double>(), E.cvz.as<double>(),
             E.crenc.as<double>(), E.sx.as<double>(), E.sy.as<double>(), E.sz.as<double>(), E.svx.as<double>(),
             E.svy.as<double>(), E.svz.as<double>(), E.srenc.as<double>(), E.sbody.as<int>(), dt, vsmall,
-            E.cand.as<unsigned long long>(), (unsigned long long)E.cand_cap, d_count);
+            E.cand.as<unsigned long long>(), (unsigned long long)E.cand_cap, d_count, b2);
         SWCU_KERNEL_CHECK(ctx);
-        SWCU_CUDA(ctx, cudaMemcpyAsync(h_counts, d_count, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
-                                       ctx->stream));
-        SWCU_CUDA(ctx, cudaMemcpyAsync(&h_total_chunks, E.choff.as<int>() + ntot, sizeof(int), cudaMemcpyDeviceToHost,
+        SWCU_CUDA(ctx, E.uniq.ensure(sizeof(unsigned long long) * CAND_SMALL));
+        finalize_small_kernel<<<1, 1024, 0, ctx->stream>>>(E.cand.as<unsigned long long>(), (unsigned long long)E.cand_cap,
+                                                           d_count, E.uniq.as<unsigned long long>(),
+                                                           reinterpret_cast<int *>(d_count + 2), d_small, b2);
+        SWCU_KERNEL_CHECK(ctx);
+        // one read-back: [0] candidates, [1] sum nbox, [2] unique count, [7] bucket-sort flags, [8] short-list flag, [9] chunks
+        SWCU_CUDA(ctx, cudaMemcpyAsync(E.h_counters, d_count, 10 * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                                        ctx->stream));
         SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h_counts[0] = E.h_counters[0], h_counts[1] = E.h_counters[1];
+        h_nuniq = (int)(E.h_counters[2] & 0xffffffffull);
+        h_small[0] = E.h_counters[8];
+        h_total_chunks = (int)E.h_counters[9];
+        const unsigned long long h_bflag = bucket ? E.h_counters[7] : 0ull;
+        if (h_bflag != 0ull) {  // a clump of equal radii or a non-finite extent: the radix sort decides
+            ++E.bucket_fallbacks;
+            return encounter_sweep_impl(ctx, l1, l2, dt, nenc_out, false, false);
+        }
         if (h_counts[0] <= E.cand_cap) break;
         E.cand_cap = (size_t)(h_counts[0] + h_counts[0] / 4 + 1024);  // overflow: grow and sweep again
         if (attempt == 2) return fail(ctx, SWCU_ERR_STATE, "encounter sweep: candidate buffer overflow persists");
@@ -1017,8 +1334,13 @@ int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2,
     E.nemitted = (int64_t)h_counts[0];
     const long long ncand = (long long)h_counts[0];
     if (ncand == 0) return SWCU_OK;
-
-    return canonical_order(ctx, ncand, nenc_out);
+    if (h_small[0] == 0ull) {  // short list: sorted and deduplicated on the device already
+        E.nenc = h_nuniq;
+        E.result = E.uniq.as<unsigned long long>();
+        *nenc_out = h_nuniq;
+        return SWCU_OK;
+    }
+    return canonical_order(ctx, ncand, nenc_out, b1, b2);
 }
 
 // encounter_check_all_plplm (:42-109): plpl on the fully interacting block, then plm x plt with index2 shifted
@@ -1181,6 +1503,13 @@ extern "C" int swcu_encounter_direct_count(swcu_context *ctx, int64_t *direct, i
     if (!ctx) return SWCU_ERR_ARG;
     if (direct) *direct = ctx->enc.direct_calls;
     if (fallbacks) *fallbacks = ctx->enc.direct_fallbacks;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_encounter_bucket_fallbacks(swcu_context *ctx, int64_t *count)
+{
+    if (!ctx) return SWCU_ERR_ARG;
+    if (count) *count = ctx->enc.bucket_fallbacks;
     return SWCU_OK;
 }
 

@@ -206,8 +206,10 @@ extern "C" int swcu_destroy(swcu_context *ctx)
     auto &E = ctx->enc;
     DevBuf *eb[] = {&E.keys_in, &E.keys_out, &E.vals_in, &E.vals_out, &E.cub_tmp, &E.cx, &E.cy, &E.cz, &E.cvx, &E.cvy,
                     &E.cvz, &E.crenc, &E.sx, &E.sy, &E.sz, &E.svx, &E.svy, &E.svz, &E.srenc, &E.sbody, &E.ibeg, &E.iend,
-                    &E.nchunk, &E.choff, &E.owner, &E.cand, &E.cand_sorted, &E.uniq, &E.counters, &E.out1, &E.out2, &E.merged};
+                    &E.nchunk, &E.choff, &E.owner, &E.cand, &E.cand_sorted, &E.uniq, &E.counters, &E.out1, &E.out2, &E.merged, &E.abase, &E.boxcnt, &E.bk_hist, &E.bk_offs};
     for (DevBuf *b : eb) b->release();
+    if (E.h_counters) cudaFreeHost(E.h_counters);
+    E.h_counters = nullptr;
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int f = 0; f < FAM_COUNT; ++f) {

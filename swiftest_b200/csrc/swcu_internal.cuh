@@ -113,6 +113,10 @@ struct swcu_context {
         swcu::DevBuf merged;
         // pl-tp without the sort: planet records, per-planet box counts, how often the sort path had to decide
         swcu::DevBuf abase, boxcnt;
+        // bucket sort of the extents: histogram + cursors, offsets; how often the radix sort had to take over
+        swcu::DevBuf bk_hist, bk_offs;
+        int64_t bucket_fallbacks = 0;
+        unsigned long long *h_counters = nullptr;  // pinned: the sweep's counters come back in one copy
         int64_t direct_calls = 0, direct_fallbacks = 0;
         const unsigned long long *result = nullptr;  // device pointer to the final sorted unique keys
     } enc;

@@ -381,6 +381,48 @@ def test_sweep_plpl_bit_exact(ctx, oracle, n, boost):
         assert got[0] > 0
 
 
+def test_sweep_bucket_sort_equals_radix_sort_and_falls_back_on_clumps(ctx, oracle):
+    """The extents are bucket sorted (equal slices of [min, max], bitonic sort on (key, id) per bucket = the stable sort);
+    SWCU_SWEEP_BUCKET=0 takes the radix sort: same list, same nbox.  3000 bodies at bit-identical |r| overflow a bucket:
+    the call must notice and repeat itself with the radix sort; so must a call with a non-finite extent."""
+    d = W.disk(6000, seed=77)
+    r, v, renc = d["rh"].copy(), d["vh"], d["rhill"] * 6.5 * 3
+    ref = oracle.encounter_plpl(r, v, renc, d["dt"])
+    nbox = oracle.nbox_total()
+    f0 = ctx.encounter_bucket_fallbacks()
+    got = ctx.encounter_check_all_sort_and_sweep_plpl(6000, r, v, renc, d["dt"])
+    _same_pairs(got, ref)
+    assert ctx.encounter_stats()["nbox_total"] == nbox and ctx.encounter_bucket_fallbacks() == f0 and got[0] > 0
+    os.environ["SWCU_SWEEP_BUCKET"] = "0"
+    try:
+        _same_pairs(ctx.encounter_check_all_sort_and_sweep_plpl(6000, r, v, renc, d["dt"]), ref)
+        assert ctx.encounter_stats()["nbox_total"] == nbox
+    finally:
+        del os.environ["SWCU_SWEEP_BUCKET"]
+    # a clump: 3000 bodies on one sphere, |r| = 1 exactly (unit vectors along the axes scaled by exact powers of two)
+    rng = np.random.default_rng(5)
+    axis = rng.integers(0, 3, 3000)
+    r[:3000] = 0.0
+    r[np.arange(3000), axis] = np.where(rng.uniform(size=3000) < 0.5, 1.0, -1.0)
+    renc2 = renc.copy()
+    renc2[:3000] = 0.0  # all 3000 begin AND end extents equal 1.0: 6000 equal keys, in position order after the sort
+    ref = oracle.encounter_plpl(r, v, renc2, d["dt"])
+    nbox = oracle.nbox_total()
+    got = ctx.encounter_check_all_sort_and_sweep_plpl(6000, r, v, renc2, d["dt"])
+    _same_pairs(got, ref)
+    assert ctx.encounter_stats()["nbox_total"] == nbox and ctx.encounter_bucket_fallbacks() == f0 + 1
+    # the same clump below the capacity stays on the bucket sort: ties are ordered by position, as the stable sort does
+    r[900:3000] = d["rh"][900:3000]
+    renc2[900:3000] = renc[900:3000]
+    ref = oracle.encounter_plpl(r, v, renc2, d["dt"])
+    nbox = oracle.nbox_total()
+    _same_pairs(ctx.encounter_check_all_sort_and_sweep_plpl(6000, r, v, renc2, d["dt"]), ref)
+    assert ctx.encounter_stats()["nbox_total"] == nbox and ctx.encounter_bucket_fallbacks() == f0 + 1
+    r[5] = np.inf
+    ctx.encounter_check_all_sort_and_sweep_plpl(6000, r, v, renc2, d["dt"])  # garbage in; must not crash, must fall back
+    assert ctx.encounter_bucket_fallbacks() == f0 + 2
+
+
 def test_sweep_F3_quirk_is_reproduced(ctx, oracle):
     r = np.array([[1.0, 0, 0], [1.05, 0, 0]])
     v = np.array([[0.0, 6.0, 0], [0.0, -6.0, 0]])
