@@ -1294,7 +1294,8 @@ static int encounter_sweep_impl(swcu_context *ctx, const SweepList &l1, const Sw
     if (E.cand_cap < (size_t)4 * ntot + 65536) E.cand_cap = (size_t)4 * ntot + 65536;
     const double vsmall = std::sqrt(DBL_MIN);  // globals_module.f90:135
     const int b1 = bits_for((unsigned long long)n1), b2 = bits_for((unsigned long long)(single ? n1 : n2));
-    const int sweep_blocks = ctx->prop.multiProcessorCount * 8;
+    const char *sbe = getenv("SWCU_SWEEP_CTAS");
+    const int sweep_blocks = ctx->prop.multiProcessorCount * (sbe ? atoi(sbe) : 8);  // 12 and 16 CTAs per SM measured no faster: the kernel is bound by the L2 -> SM path (40 B per clock and SM)
     unsigned long long h_counts[2] = {0, 0}, h_small[1] = {1};
     int h_total_chunks = 0, h_nuniq = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
