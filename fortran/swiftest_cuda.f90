@@ -650,6 +650,11 @@ module swiftest_cuda
          type(c_ptr), value :: ctx
          integer(c_int64_t), intent(out) :: count
       end function
+      integer(c_int) function swcu_step_graph_replays(ctx, count) bind(C, name="swcu_step_graph_replays")
+         import :: c_int, c_int64_t, c_ptr
+         type(c_ptr), value :: ctx
+         integer(c_int64_t), intent(out) :: count
+      end function
       integer(c_int) function swcu_flat_redo_count(ctx, chunks) bind(C, name="swcu_flat_redo_count")
          import :: c_int, c_int64_t, c_ptr
          type(c_ptr), value :: ctx

@@ -376,6 +376,9 @@ int swcu_kernel_ms_accumulated(swcu_context *ctx, int32_t family, double *total_
 /* third-law gravity kernel: 32-column chunks that were rolled back and recomputed with the reference's IEEE expression
  * (overlapping bodies, coincident bodies, coordinates outside the seeded range) since the context was created */
 int swcu_flat_redo_count(swcu_context *ctx, uint64_t *chunks);
+/* multi-launch swcu_helio_step_pl calls (npl > 128) since the context was created that were replayed as one CUDA graph
+ * launch (the second step with unchanged arguments is captured, later ones replay it; SWCU_STEP_GRAPH=0 switches it off) */
+int swcu_step_graph_replays(swcu_context *ctx, int64_t *count);
 
 #ifdef __cplusplus
 }

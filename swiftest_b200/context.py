@@ -661,6 +661,12 @@ class Context:
         self._ck(self._L.swcu_encounter_bucket_fallbacks(self._h, C.byref(a)))
         return int(a.value)
 
+    def step_graph_replays(self):
+        """helio_step_pl calls that were replayed as one CUDA graph launch since create."""
+        a = C.c_int64()
+        self._ck(self._L.swcu_step_graph_replays(self._h, C.byref(a)))
+        return int(a.value)
+
     def flat_redo_count(self):
         """Chunks the third-law gravity kernel rolled back and redid with the IEEE expression since create."""
         n = C.c_uint64()

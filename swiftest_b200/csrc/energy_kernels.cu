@@ -149,7 +149,7 @@ int run_sum(swcu_context *ctx, int n, Term term, double *d_out)
 {
     StoreFin fin{d_out, K};
     if (n <= SERIAL_SUM_MAX) {
-        sum_serial_kernel<K><<<1, 32, 0, ctx->stream>>>(n, false, term, fin);
+        sum_serial_kernel<K><<<1, SERIAL_THREADS, 0, ctx->stream>>>(n, false, term, fin);
     } else {
         double *partials = ctx->sumbuf.as<double>();
         unsigned *ticket = reinterpret_cast<unsigned *>(partials + (size_t)SUM_MAX_CTAS * 8);

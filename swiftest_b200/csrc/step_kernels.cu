@@ -106,7 +106,7 @@ int reduce_gmv(swcu_context *ctx, const Body &b, const double *vx, const double 
     GmvTerm term{b.Gm.as<double>(), vx, vy, vz, mask, gmcb, use_div};
     CbFin fin{ctx->cbs.as<double>(), gmcb, op, slot};
     if (b.n <= SERIAL_SUM_MAX) {
-        sum_serial_kernel<4><<<1, 32, 0, ctx->stream>>>(b.n, reverse, term, fin);
+        sum_serial_kernel<4><<<1, SERIAL_THREADS, 0, ctx->stream>>>(b.n, reverse, term, fin);
     } else {
         const int g = sum_grid(b.n);
         double *partials = ctx->sumbuf.as<double>();
@@ -261,19 +261,78 @@ int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lc
         }
         return SWCU_OK;
     }
+    auto body = [&]() -> int {  // the ~21 launches of a step (after the first)
+        SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 1));
+        for (int half = 0; half < 2; ++half) {
+            // helio_kick_vb_pl: ah = 0, interaction accelerations, set_beg_end, vb += ah*dth
+            SWCU_TRY(fill_f64(ctx, pl.ax.as<double>(), 0.0, pl.n));
+            SWCU_TRY(fill_f64(ctx, pl.ay.as<double>(), 0.0, pl.n));
+            SWCU_TRY(fill_f64(ctx, pl.az.as<double>(), 0.0, pl.n));
+            SWCU_TRY(pl_accel_int(ctx, variant, lclose));
+            SWCU_TRY(kick_vb_save(ctx, pl, dth, half == 0 ? 1 : 2));
+            if (half == 0) SWCU_TRY(drift_bodies(ctx, pl, 0, pl.n, dt, 0, 0.0, nullptr, 1, gmcb));
+        }
+        SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 0));
+        return pl_vb2vh(ctx, gmcb);
+    };
+    // Steps after the first are the same ~21 launches with the same arguments (the two force evaluations flip the guard
+    // parity of flat_prologue_kernel back to where it was): the second such step is captured into a CUDA graph and every
+    // later one is a single cudaGraphLaunch -- at npl = 1e3 ... 1e4 the stream-ordered launches cost as much as the kernels.
+    // Not with kernel timing on (events per launch group), not on a multi-GPU slice, SWCU_STEP_GRAPH=0 switches it off.
+    const char *ge = getenv("SWCU_STEP_GRAPH");  // read per call: tests switch it at run time
+    const bool graph_env = !(ge && atoi(ge) == 0);
+    auto &G = ctx->helio_graph;
+    const bool graph_ok = graph_env && !lfirst && !G.disabled && ctx->kernel_timing == 0 && !ctx->p2p.ready &&
+                          pl.slice0 == 0 && pl.slice1 == pl.n && !getenv("SWCU_FLAT_TRACE");
     if (lfirst) SWCU_TRY(pl_vh2vb(ctx, gmcb));
-    SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 1));
-    for (int half = 0; half < 2; ++half) {
-        // helio_kick_vb_pl: ah = 0, interaction accelerations, set_beg_end, vb += ah*dth
-        SWCU_TRY(fill_f64(ctx, pl.ax.as<double>(), 0.0, pl.n));
-        SWCU_TRY(fill_f64(ctx, pl.ay.as<double>(), 0.0, pl.n));
-        SWCU_TRY(fill_f64(ctx, pl.az.as<double>(), 0.0, pl.n));
-        SWCU_TRY(pl_accel_int(ctx, variant, lclose));
-        SWCU_TRY(kick_vb_save(ctx, pl, dth, half == 0 ? 1 : 2));
-        if (half == 0) SWCU_TRY(drift_bodies(ctx, pl, 0, pl.n, dt, 0, 0.0, nullptr, 1, gmcb));
+    if (!graph_ok) {
+        SWCU_TRY(body());
+    } else {
+        const bool same = G.n == pl.n && G.nplm == pl.nplm && G.variant == variant && G.lclose == lclose &&
+                          G.tune_variant == ctx->tune_variant && G.tune_nsplit == ctx->tune_nsplit && G.gmcb == gmcb &&
+                          G.dt == dt && G.generation == pl.generation && G.p0 == pl.rx.p && G.stream == ctx->stream &&
+                          G.has_active == pl.has_active && G.tune_ib == ctx->tune_ib;
+        if (same && G.exec) {
+            SWCU_CUDA(ctx, cudaGraphLaunch(G.exec, ctx->stream));
+            ctx->launches += G.launches;
+            ++G.replays;
+        } else if (same && G.warm >= 1) {  // every lazy allocation has happened: capture this step
+            const long long l0 = ctx->launches;
+            cudaGraph_t g = nullptr;
+            int rc = SWCU_OK;
+            if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                rc = body();
+                const cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+                if (rc == SWCU_OK && e == cudaSuccess && g && cudaGraphInstantiate(&G.exec, g, 0) == cudaSuccess) {
+                    G.launches = ctx->launches - l0;
+                    cudaGraphDestroy(g);
+                    SWCU_CUDA(ctx, cudaGraphLaunch(G.exec, ctx->stream));
+                } else {  // something in the sequence cannot be captured: never try again, run the step the plain way
+                    if (g) cudaGraphDestroy(g);
+                    G.exec = nullptr;
+                    G.disabled = true;
+                    (void)cudaGetLastError();
+                    ctx->launches = l0;
+                    SWCU_TRY(body());
+                }
+            } else {
+                G.disabled = true;
+                (void)cudaGetLastError();
+                SWCU_TRY(body());
+            }
+        } else {
+            if (!same) {
+                if (G.exec) cudaGraphExecDestroy(G.exec);
+                G.exec = nullptr;
+                G.n = pl.n, G.nplm = pl.nplm, G.variant = variant, G.lclose = lclose, G.tune_variant = ctx->tune_variant;
+                G.tune_nsplit = ctx->tune_nsplit, G.gmcb = gmcb, G.dt = dt, G.generation = pl.generation, G.p0 = pl.rx.p;
+                G.stream = ctx->stream, G.has_active = pl.has_active, G.tune_ib = ctx->tune_ib;
+                G.warm = 0;
+            }
+            SWCU_TRY(body());
+            ++G.warm;
+        }
     }
-    SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 0));
-    SWCU_TRY(pl_vb2vh(ctx, gmcb));
     if (nfail) {  // the drift kernel counted its failures in scratch64[0]
         SWCU_CUDA(ctx, cudaMemcpyAsync(nfail, ctx->scratch64.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

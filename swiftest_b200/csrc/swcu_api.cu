@@ -220,6 +220,8 @@ extern "C" int swcu_destroy(swcu_context *ctx)
         cudaEventDestroy(ctx->fam_ev0[f]);
         cudaEventDestroy(ctx->fam_ev1[f]);
     }
+    if (ctx->helio_graph.exec) cudaGraphExecDestroy(ctx->helio_graph.exec);
+    ctx->helio_graph.exec = nullptr;
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return SWCU_OK;
@@ -1388,6 +1390,13 @@ extern "C" int swcu_probe_fp64_peak(swcu_context *ctx, double *tflops)
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     *tflops = best;
+    return SWCU_OK;
+}
+
+extern "C" int swcu_step_graph_replays(swcu_context *ctx, int64_t *count)
+{
+    SWCU_TRY(check_ctx(ctx));
+    if (count) *count = ctx->helio_graph.replays;
     return SWCU_OK;
 }
 

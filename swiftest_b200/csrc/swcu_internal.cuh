@@ -160,6 +160,20 @@ struct swcu_context {
     swcu::DevBuf flat_blockrad; // max radius per block of 128 bodies (third-law kernel)
     swcu::DevBuf flat_guard; // 2 x u64: max |coordinate| bit pattern of the current / next launch (flat_prologue_kernel)
     int flat_parity = 0;
+    // whole multi-launch steps replayed as a CUDA graph (step_kernels.cu): captured on the second step with the same key
+    struct StepGraph {
+        cudaGraphExec_t exec = nullptr;
+        int n = -1, nplm = -1, variant = 0, lclose = 0, tune_variant = 0, tune_nsplit = 0, tune_ib = 0;
+        bool has_active = false;
+        double gmcb = 0.0, dt = 0.0;
+        uint64_t generation = 0;
+        const void *p0 = nullptr;
+        cudaStream_t stream = nullptr;
+        long long launches = 0;
+        int warm = 0;
+        bool disabled = false;
+        int64_t replays = 0;
+    } helio_graph;
     swcu::DevBuf flat_redo;  // u64 count of chunks the third-law kernel redid exactly (zeroed when allocated)
     swcu::DevBuf flat_trace; // per-warp timeline of the third-law kernel (development aid, SWCU_FLAT_TRACE)
 

@@ -130,6 +130,41 @@ def test_helio_step_pl_tracks_oracle_on_fixture(ctx, oracle, variant):
     assert np.max(np.abs(pte - st["ptend"])) < 1e-11 * np.abs(st["ptend"]).max()
 
 
+@pytest.mark.parametrize("variant", [LOOP_TRIANGULAR, LOOP_FLAT])
+def test_helio_step_pl_graph_replay_equals_stream_ordered_launches(ctx, variant):
+    """npl > 128: the step is ~21 launches; from the third step on it is replayed as one CUDA graph.  Same kernels, same
+    arguments: the full-row variant must give identical bits with SWCU_STEP_GRAPH=0, the third-law variant (FP64 atomics)
+    agrees to rounding; the launch count per step is the same; the drift-failure count still comes back."""
+    import os
+    n, nsteps = 700, 9
+    d = W.disk(n, seed=41)
+    GMcb = W.GMSUN
+
+    def run(graph, gen):
+        if not graph:
+            os.environ["SWCU_STEP_GRAPH"] = "0"
+        try:
+            ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                          mu=np.full(n, GMcb), generation=gen)
+            r0, l0 = ctx.step_graph_replays(), ctx.launch_count()
+            for k in range(nsteps):
+                assert ctx.helio_step_pl(GMcb, d["dt"], loop_variant=variant, lclose=True, lfirst=(k == 0),
+                                         want_nfail=(k % 2 == 0)) == 0
+            out = ctx.body_get(PL)
+            return out["r"], out["v"], ctx.body_get_vb(PL)["vb"], ctx.step_graph_replays() - r0, ctx.launch_count() - l0
+        finally:
+            os.environ.pop("SWCU_STEP_GRAPH", None)
+
+    rg, vg, bg, nrep, nl = run(True, 9400 + variant)
+    rs, vs, bs, nrep0, nl0 = run(False, 9410 + variant)
+    assert nrep == nsteps - 3 and nrep0 == 0      # step 0 is the first step, 1 warms up, 2 is captured (and run), 3.. replay
+    assert nl == nl0
+    if variant == LOOP_TRIANGULAR:
+        assert np.array_equal(rg, rs) and np.array_equal(vg, vs) and np.array_equal(bg, bs)
+    else:
+        assert np.max(np.abs(rg - rs)) < 1e-13 * np.abs(rs).max() and np.max(np.abs(vg - vs)) < 1e-13 * np.abs(vs).max()
+
+
 def test_helio_step_pl_first_step_matches_unfused_device_calls(ctx):
     """The one-call step and the same step issued call by call through the ABI give identical bits."""
     f, GMcb, dt = _fixture108()
