@@ -708,6 +708,33 @@ def symba_1e4_leg(ctx, hbm_peak, fp64_peak):
                          "roofline": {"bound": "hbm", "achieved": bytes_alg / t / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                       "frac": bytes_alg / t / 1e9 / hbm_peak}}
     ctx.enable_kernel_timing(False)
+    # the whole device-resident step of this configuration: helio_step_pl (two force evaluations, glue, drift; replayed as one
+    # CUDA graph from the third step) + the pl-pl encounter sweep, host wall clock over 200 steps, nothing crossing PCIe but
+    # the pair count
+    from swiftest_b200 import LOOP_AUTO
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                  mu=np.full(n, W.GMSUN), generation=42)
+    r0 = ctx.step_graph_replays()
+    for rep in range(2):
+        ctx.synchronize()
+        n0 = ctx.launch_count()
+        t0 = time.perf_counter()
+        for k in range(200):
+            ctx.helio_step_pl(W.GMSUN, d["dt"], LOOP_AUTO, True, lfirst=(rep == 0 and k == 0), want_nfail=False)
+        ctx.synchronize()
+        t_step = (time.perf_counter() - t0) / 200
+        lps = (ctx.launch_count() - n0) / 200
+    t0 = time.perf_counter()
+    for k in range(100):
+        ctx.helio_step_pl(W.GMSUN, d["dt"], LOOP_AUTO, True, lfirst=False, want_nfail=False)
+        ctx.pl_encounter_check(d["dt"], fetch=False)
+    ctx.synchronize()
+    t_both = (time.perf_counter() - t0) / 100
+    res["whole_step"] = {"helio_step_pl_ms": t_step * 1e3, "kernels_per_step": lps,
+                         "graph_replays": ctx.step_graph_replays() - r0,
+                         "helio_step_pl_plus_sweep_ms": t_both * 1e3,
+                         "pairs_per_s_whole_step": 2.0 * pairs / t_step,
+                         "note": "r1 / first half of r2: 0.255 ms per step stream-ordered + 0.222 ms sweep"}
     return res
 
 

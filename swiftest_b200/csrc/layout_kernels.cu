@@ -58,6 +58,11 @@ __global__ void fill_f64_kernel(double *d, double v, int n)
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) d[i] = v;
 }
+__global__ void fill3_f64_kernel(double *a, double *b, double *c, double v, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = v, b[i] = v, c[i] = v;
+}
 __global__ void fill_i32_kernel(int32_t *d, int32_t v, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,6 +120,15 @@ int fill_f64(swcu_context *ctx, double *d, double value, int n)
 {
     if (n <= 0) return SWCU_OK;
     fill_f64_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(d, value, n);
+    SWCU_KERNEL_CHECK(ctx);
+    return SWCU_OK;
+}
+
+// three arrays of one vector quantity (ah = 0 before every force evaluation) in one launch
+int fill3_f64(swcu_context *ctx, double *a, double *b, double *c, double value, int n)
+{
+    if (n <= 0) return SWCU_OK;
+    fill3_f64_kernel<<<cdiv(n, 256), 256, 0, ctx->stream>>>(a, b, c, value, n);
     SWCU_KERNEL_CHECK(ctx);
     return SWCU_OK;
 }

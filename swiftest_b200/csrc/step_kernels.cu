@@ -265,9 +265,7 @@ int helio_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lc
         SWCU_TRY(pl_lindrift(ctx, gmcb, dth, 1));
         for (int half = 0; half < 2; ++half) {
             // helio_kick_vb_pl: ah = 0, interaction accelerations, set_beg_end, vb += ah*dth
-            SWCU_TRY(fill_f64(ctx, pl.ax.as<double>(), 0.0, pl.n));
-            SWCU_TRY(fill_f64(ctx, pl.ay.as<double>(), 0.0, pl.n));
-            SWCU_TRY(fill_f64(ctx, pl.az.as<double>(), 0.0, pl.n));
+            SWCU_TRY(fill3_f64(ctx, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), 0.0, pl.n));
             SWCU_TRY(pl_accel_int(ctx, variant, lclose));
             SWCU_TRY(kick_vb_save(ctx, pl, dth, half == 0 ? 1 : 2));
             if (half == 0) SWCU_TRY(drift_bodies(ctx, pl, 0, pl.n, dt, 0, 0.0, nullptr, 1, gmcb));

@@ -729,9 +729,7 @@ extern "C" int swcu_body_zero_accel(swcu_context *ctx, int32_t kind)
     SWCU_TRY(check_ctx(ctx));
     Body &b = body_of(ctx, kind);
     if (!b.valid) return fail(ctx, SWCU_ERR_STATE, "zero_accel: population not resident");
-    SWCU_TRY(fill_f64(ctx, b.ax.as<double>(), 0.0, b.n));
-    SWCU_TRY(fill_f64(ctx, b.ay.as<double>(), 0.0, b.n));
-    return fill_f64(ctx, b.az.as<double>(), 0.0, b.n);
+    return fill3_f64(ctx, b.ax.as<double>(), b.ay.as<double>(), b.az.as<double>(), 0.0, b.n);
 }
 
 namespace swcu {

@@ -263,6 +263,7 @@ int download_vec3(swcu_context *ctx, double *h_aos, int n, int stage_slot, const
                   const DevBuf &z);
 int upload_arr(swcu_context *ctx, const void *h, size_t bytes, DevBuf &d);
 int fill_f64(swcu_context *ctx, double *d, double value, int n);
+int fill3_f64(swcu_context *ctx, double *a, double *b, double *c, double value, int n);
 int fill_i32(swcu_context *ctx, int32_t *d, int32_t value, int n);
 int ensure_body(swcu_context *ctx, Body &b, int n);
 

@@ -218,9 +218,7 @@ int whm_getacch_pl(swcu_context *ctx, Body &pl, double gmcb, int variant, int lc
 {
     auto &W = ctx->whm;
     const int n = pl.n;
-    SWCU_TRY(fill_f64(ctx, pl.ax.as<double>(), 0.0, n));
-    SWCU_TRY(fill_f64(ctx, pl.ay.as<double>(), 0.0, n));
-    SWCU_TRY(fill_f64(ctx, pl.az.as<double>(), 0.0, n));
+    SWCU_TRY(fill3_f64(ctx, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), 0.0, n));
     double *ah0 = ctx->cbs.as<double>() + CBS_AH0PL;
     whm_ah0_kernel<<<1, 32, 0, ctx->stream>>>(1, n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);  // bodies 2..npl (:33)
     SWCU_KERNEL_CHECK(ctx);
@@ -309,9 +307,7 @@ int whm_tp_first_accel(swcu_context *ctx)
     double *ah0 = ctx->cbs.as<double>() + CBS_AH0TP;
     whm_ah0_kernel<<<1, 32, 0, ctx->stream>>>(0, pl.n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);
     SWCU_KERNEL_CHECK(ctx);
-    SWCU_TRY(fill_f64(ctx, tp.ax.as<double>(), 0.0, tp.n));
-    SWCU_TRY(fill_f64(ctx, tp.ay.as<double>(), 0.0, tp.n));
-    SWCU_TRY(fill_f64(ctx, tp.az.as<double>(), 0.0, tp.n));
+    SWCU_TRY(fill3_f64(ctx, tp.ax.as<double>(), tp.ay.as<double>(), tp.az.as<double>(), 0.0, tp.n));
     whm_add_const_kernel<<<cdiv(tp.n, 256), 256, 0, ctx->stream>>>(tp.n, tp.lmask.as<int32_t>(), ah0, v3(tp.ax, tp.ay, tp.az));
     SWCU_KERNEL_CHECK(ctx);
     KickProblem k;
