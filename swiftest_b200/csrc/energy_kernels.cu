@@ -11,10 +11,10 @@
 //
 // Pair kernel: blocks of PE_T = 256 bodies, cyclic block pairing (row block bi against column blocks bi, bi+1, ...,
 // bi + nb/2 mod nb: every unordered block pair exactly once, equal work per row block).  A thread keeps one row body in
-// registers and walks the column block staged in shared memory as (x, y, z, m); 1/r comes from the FP32 MUFU.RSQ seed
-// and one third-order Newton step of kick_math.cuh (12 FP64 + ~10 other instructions per pair against 20 + 9 for the
-// force: the FP64 issue model of profiles/r01_fp64_pipe.md applies unchanged).  Pairs the seed cannot take (coincident
-// bodies, coordinates outside the FP32 exponent range) make the thread redo its tile row with IEEE sqrt and divide.
+// registers and walks the column block staged in shared memory as (x, y, z, m); 1/r comes from the FP64 MUFU.RSQ64H seed
+// and one third-order Newton step of kick_math.cuh (12 FP64 + ~5 other instructions per pair; round 1 used the FP32 seed:
+// 12 + ~10).  No per-pair test: the loop keeps the running minimum of the high words of r2; coincident bodies (r2 below
+// 2^-600) or a coordinate beyond 2^500 in the tile make the thread redo its tile row with IEEE sqrt and divide.
 // Per-CTA partial sums are folded by a fixed tree: same bits run to run, independent of the SM count.
 #include "kick_math.cuh"
 #include "reduce.cuh"
@@ -41,14 +41,18 @@ __global__ void __launch_bounds__(PE_T) pe_pairs_kernel(int n, int nb, const dou
     if (!dead) {
         const int j = bj * PE_T + threadIdx.x;
         const bool jon = j < n && lmask[j] != 0;
-        col[threadIdx.x] = jon ? make_double4(x[j], y[j], z[j], mass[j]) : make_double4(0.0, 0.0, 0.0, 0.0);
+        const double4 cj = jon ? make_double4(x[j], y[j], z[j], mass[j]) : make_double4(0.0, 0.0, 0.0, 0.0);
+        col[threadIdx.x] = cj;
         const int i = bi * PE_T + threadIdx.x;
         const bool ion = i < n && lmask[i] != 0;
         const double xi = ion ? x[i] : 0.0, yi = ion ? y[i] : 0.0, zi = ion ? z[i] : 0.0;
         const double gi = ion ? gm[i] : 0.0;
-        __syncthreads();
-        unsigned thr, span, hymin = 0xffffffffu;
-        seed_threshold(0.0, thr, span);
+        // the FP64 seed (MUFU.RSQ64H) needs r2 in [2^-600, inf): every |coordinate| of the tile below 2^500 (NaN fails the
+        // test), and the running minimum of the high words of r2 below catches coincident bodies
+        const bool wild = !(fabs(cj.x) < COORD_SAFE_MAX_F64 && fabs(cj.y) < COORD_SAFE_MAX_F64 && fabs(cj.z) < COORD_SAFE_MAX_F64 &&
+                            fabs(xi) < COORD_SAFE_MAX_F64 && fabs(yi) < COORD_SAFE_MAX_F64 && fabs(zi) < COORD_SAFE_MAX_F64);
+        const int unsafe = __syncthreads_or(wild ? 1 : 0);
+        unsigned hmin = 0xffffffffu;
         // diagonal block: only j > i; the columns up to and including the thread's own are skipped
         const int jbeg = (c == 0) ? threadIdx.x + 1 : 0;
         double s0 = 0.0, s1 = 0.0;
@@ -57,26 +61,28 @@ __global__ void __launch_bounds__(PE_T) pe_pairs_kernel(int n, int nb, const dou
             const double4 p = col[jj], q = col[jj + 1];
             const double dx0 = p.x - xi, dy0 = p.y - yi, dz0 = p.z - zi;
             const double dx1 = q.x - xi, dy1 = q.y - yi, dz1 = q.z - zi;
-            const double r0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
-            const double r1 = fma(dz1, dz1, fma(dy1, dy1, dx1 * dx1));
+            const double u0 = fma(dy0, dy0, dx0 * dx0), u1 = fma(dy1, dy1, dx1 * dx1);
+            const double r0 = fma(dz0, dz0, u0);
+            const double r1 = fma(dz1, dz1, u1);
             unsigned h0, h1;
-            const double y0 = rsqrt_seeded(r0, thr, span, h0);
-            const double y1 = rsqrt_seeded(r1, thr, span, h1);
-            hymin = min(hymin, min(h0, h1));
+            const double y0 = rsqrt_rsq64h(r0, u0, h0);
+            const double y1 = rsqrt_rsq64h(r1, u1, h1);
+            hmin = min(hmin, min(h0, h1));
             s0 = fma(p.w, y0, s0);
             s1 = fma(q.w, y1, s1);
         }
         if (jj < PE_T) {
             const double4 p = col[jj];
             const double dx0 = p.x - xi, dy0 = p.y - yi, dz0 = p.z - zi;
-            const double r0 = fma(dz0, dz0, fma(dy0, dy0, dx0 * dx0));
+            const double u0 = fma(dy0, dy0, dx0 * dx0);
+            const double r0 = fma(dz0, dz0, u0);
             unsigned h0;
-            const double y0 = rsqrt_seeded(r0, thr, span, h0);
-            hymin = min(hymin, h0);
+            const double y0 = rsqrt_rsq64h(r0, u0, h0);
+            hmin = min(hmin, h0);
             s0 = fma(p.w, y0, s0);
         }
         s = s0 + s1;
-        if (hymin == 0u) {  // some pair was rejected by the seed: redo this thread's tile row with IEEE arithmetic
+        if (unsafe || hmin < RSQ64H_HI_MIN) {  // a pair the seed cannot take: redo this thread's tile row with IEEE arithmetic
             s = 0.0;
             for (int k = jbeg; k < PE_T; ++k) {
                 const double4 p = col[k];

@@ -138,6 +138,17 @@ __device__ __forceinline__ double rcube_rsq64h(double r2, double lo_donor, bool 
     return fma(se, q, s3);
 }
 
+// r2^(-1/2) from the same seed (potential energy): y = s (1 + e/2 + 3/8 e^2), e = 1 - r2 s^2; 5/16 e^3 < 2^-56
+__device__ __forceinline__ double rsqrt_rsq64h(double r2, double lo_donor, unsigned &hi)
+{
+    const double s = rsq64h_seed<false>(r2, lo_donor, true, hi);
+    const double t = r2 * s;
+    const double e = fma(-t, s, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double se = s * e;
+    return fma(se, p, s);
+}
+
 // Same test as rsqrt_seeded without the arithmetic (used by the redo paths to find the skipped pairs).
 __device__ __forceinline__ bool seed_ok(double r2, unsigned thr, unsigned span)
 {

@@ -287,6 +287,11 @@ def test_potential_energy_edge_cases(ctx, oracle):
     ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, big)
     got = ctx.util_get_potential_energy(300, None, GMcb, d["Gmass"], mass, big)
     assert abs(got - ref) <= 1e-13 * abs(ref)
+    # beyond 2^500 the FP64 seed is not used either (r2 may overflow): the whole tile takes the IEEE path
+    huge = d["rh"] * 1e160
+    ref = oracle.get_potential_energy(GMcb, d["Gmass"], mass, huge)
+    got = ctx.util_get_potential_energy(300, None, GMcb, d["Gmass"], mass, huge)
+    assert abs(got - ref) <= 1e-13 * abs(ref)
     assert ctx.util_get_potential_energy(0, None, GMcb, np.zeros(0), np.zeros(0), np.zeros((0, 3))) == 0.0
 
 
