@@ -1105,15 +1105,14 @@ int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepLis
     const size_t shmem = per == 4   ? n1 * pltp_shmem_per_planet<4>() + pltp_shmem_fixed<4>()
                          : per == 2 ? n1 * pltp_shmem_per_planet<2>() + pltp_shmem_fixed<2>()
                                     : n1 * pltp_shmem_per_planet<1>() + pltp_shmem_fixed<1>();
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!E.direct_attr_set) {  // per context: the attribute belongs to the device
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(PLTP_MAXPL * pltp_shmem_per_planet<1>() + pltp_shmem_fixed<1>())));
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(PLTP_MAXPL * pltp_shmem_per_planet<2>() + pltp_shmem_fixed<2>())));
         SWCU_CUDA(ctx, cudaFuncSetAttribute(pltp_direct_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)(PLTP_MAXPL * pltp_shmem_per_planet<4>() + pltp_shmem_fixed<4>())));
-        attr_set = true;
+        E.direct_attr_set = true;
     }
     const int grid = std::min(nb, ctx->prop.multiProcessorCount * 3);  // persistent CTAs, 3 per SM (launch bounds)
     std::vector<unsigned long long> h(8 + (size_t)n1, 0ull);

@@ -118,6 +118,7 @@ struct swcu_context {
         int64_t bucket_fallbacks = 0;
         unsigned long long *h_counters = nullptr;  // pinned: the sweep's counters come back in one copy
         int64_t direct_calls = 0, direct_fallbacks = 0;
+        bool direct_attr_set = false;
         const unsigned long long *result = nullptr;  // device pointer to the final sorted unique keys
     } enc;
 
