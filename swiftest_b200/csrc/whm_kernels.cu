@@ -13,9 +13,9 @@
 //   whm_step_pl                whm/whm_step.f90:37-69
 //
 // The chains (eta, h2j, j2h, vh2vj, ah0, ah2) are SERIAL in the reference: body i needs the running sum over the bodies
-// before it.  They are restated as single-thread loops (one kernel each, loads software-pipelined by the compiler):
-// identical summation order, so with --fmad=false (this file) every chain is bit-identical to the CPU restatement.  A WHM
-// run has a handful to a few hundred massive bodies, so these loops cost microseconds; the O(N^2) part of the step is
+// before it.  Here only the additions stay serial (one lane per component, in index order, out of shared memory); the
+// per-body terms and uses are evaluated in parallel around them: identical operations in identical order, so with
+// --fmad=false (this file) every chain is bit-identical to the CPU restatement.  The O(N^2) part of the step is
 // pl%accel_int (kick_kernels.cu / kick_flat_kernels.cu) and the per-body part the Kepler drift (drift_kernels.cu).
 #include "swcu_internal.cuh"
 
@@ -29,99 +29,158 @@ struct CV3 {
     const double *x, *y, *z;
 };
 
-__global__ void whm_set_mu_eta_kernel(int n, double gmcb, const double *__restrict__ gm, double *__restrict__ eta,
-                                      double *__restrict__ muj)
+// ---- the chains: one CTA, tiles of CH_T bodies ------------------------------------------------------------------
+// Every chain is "running sum of per-body terms, then a per-body use of the sum".  The terms (products, quotients) and
+// the uses do not depend on the chain and are evaluated by CH_T threads in parallel through shared memory; only the
+// additions run serially -- one lane per vector component, in index order, from shared memory -- so the operations and
+// their order are exactly those of the reference's loops (bit-identical with --fmad=false) while the chain costs one
+// dependent DADD per body instead of the dependent global loads of a single thread walking the arrays (the first form of
+// these kernels: 2 us per body, 19 ms per step at npl = 1e4).
+constexpr int CH_T = 256;
+
+// inclusive running sums of K components over the m bodies of a tile, in place, lane k < K owns component k
+template <int K> __device__ __forceinline__ void chain_tile(double (*term)[CH_T], int m, double &carry)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double e = gmcb + gm[0];
-    eta[0] = e;
-    muj[0] = e;
-    for (int i = 1; i < n; ++i) {
-        const double en = e + gm[i];
-        eta[i] = en;
-        muj[i] = gmcb * en / e;
-        e = en;
+    if (threadIdx.x < K) {
+        double s = carry;
+        double *row = term[threadIdx.x];
+        for (int q = 0; q < m; ++q) {
+            s = s + row[q];
+            row[q] = s;
+        }
+        carry = s;
+    }
+}
+
+__global__ void __launch_bounds__(CH_T) whm_set_mu_eta_kernel(int n, double gmcb, const double *__restrict__ gm,
+                                                              double *__restrict__ eta, double *__restrict__ muj)
+{
+    __shared__ double term[1][CH_T];
+    __shared__ double prev_last;
+    const int t = threadIdx.x;
+    double carry = gmcb;  // eta(1) = GMcb + Gm(1), eta(i) = eta(i-1) + Gm(i)
+    for (int base = 0; base < n; base += CH_T) {
+        const int m = min(CH_T, n - base), i = base + t;
+        if (t < m) term[0][t] = gm[i];
+        __syncthreads();
+        chain_tile<1>(term, m, carry);
+        __syncthreads();
+        if (t < m) {
+            const double en = term[0][t];
+            eta[i] = en;
+            muj[i] = (i == 0) ? en : gmcb * en / (t == 0 ? prev_last : term[0][t - 1]);
+        }
+        __syncthreads();
+        if (t == 0) prev_last = term[0][m - 1];
+        __syncthreads();
     }
 }
 
 // mode 0: h2j (positions and velocities), 1: vh2vj (velocities only)
-__global__ void whm_h2j_kernel(int n, int mode, const double *__restrict__ gm, const double *__restrict__ eta, CV3 rh, CV3 vh,
-                               V3 xj, V3 vj)
+__global__ void __launch_bounds__(CH_T) whm_h2j_kernel(int n, int mode, const double *__restrict__ gm,
+                                                       const double *__restrict__ eta, CV3 rh, CV3 vh, V3 xj, V3 vj)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double sx0 = 0.0, sx1 = 0.0, sx2 = 0.0, sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-    if (mode == 0) {
-        xj.x[0] = rh.x[0];
-        xj.y[0] = rh.y[0];
-        xj.z[0] = rh.z[0];
-    }
-    vj.x[0] = vh.x[0];
-    vj.y[0] = vh.y[0];
-    vj.z[0] = vh.z[0];
-    for (int i = 1; i < n; ++i) {
-        const double g = gm[i - 1], e = eta[i - 1];
-        if (mode == 0) {
-            sx0 = sx0 + g * rh.x[i - 1];
-            sx1 = sx1 + g * rh.y[i - 1];
-            sx2 = sx2 + g * rh.z[i - 1];
-            xj.x[i] = rh.x[i] - sx0 / e;
-            xj.y[i] = rh.y[i] - sx1 / e;
-            xj.z[i] = rh.z[i] - sx2 / e;
+    __shared__ double term[6][CH_T];
+    const int t = threadIdx.x;
+    double carry = 0.0;
+    for (int base = 0; base < n; base += CH_T) {
+        const int m = min(CH_T, n - base), i = base + t;
+        if (t < m) {  // body i adds Gm(i-1) * q(i-1) to the running sums (whm_coord.f90:35-41, :104-108); body 1 adds nothing
+            const bool on = i >= 1;
+            const double g = on ? gm[i - 1] : 0.0;
+            if (mode == 0) {
+                term[0][t] = on ? g * rh.x[i - 1] : 0.0;
+                term[1][t] = on ? g * rh.y[i - 1] : 0.0;
+                term[2][t] = on ? g * rh.z[i - 1] : 0.0;
+            }
+            term[3][t] = on ? g * vh.x[i - 1] : 0.0;
+            term[4][t] = on ? g * vh.y[i - 1] : 0.0;
+            term[5][t] = on ? g * vh.z[i - 1] : 0.0;
         }
-        sv0 = sv0 + g * vh.x[i - 1];
-        sv1 = sv1 + g * vh.y[i - 1];
-        sv2 = sv2 + g * vh.z[i - 1];
-        vj.x[i] = vh.x[i] - sv0 / e;
-        vj.y[i] = vh.y[i] - sv1 / e;
-        vj.z[i] = vh.z[i] - sv2 / e;
+        __syncthreads();
+        if (mode == 0 || t >= 3) chain_tile<6>(term, m, carry);
+        __syncthreads();
+        if (t < m) {
+            if (i == 0) {
+                if (mode == 0) xj.x[0] = rh.x[0], xj.y[0] = rh.y[0], xj.z[0] = rh.z[0];
+                vj.x[0] = vh.x[0], vj.y[0] = vh.y[0], vj.z[0] = vh.z[0];
+            } else {
+                const double e = eta[i - 1];
+                if (mode == 0) {
+                    xj.x[i] = rh.x[i] - term[0][t] / e;
+                    xj.y[i] = rh.y[i] - term[1][t] / e;
+                    xj.z[i] = rh.z[i] - term[2][t] / e;
+                }
+                vj.x[i] = vh.x[i] - term[3][t] / e;
+                vj.y[i] = vh.y[i] - term[4][t] / e;
+                vj.z[i] = vh.z[i] - term[5][t] / e;
+            }
+        }
+        __syncthreads();
     }
 }
 
-__global__ void whm_j2h_kernel(int n, const double *__restrict__ gm, const double *__restrict__ eta, CV3 xj, CV3 vj, V3 rh,
-                               V3 vh)
+__global__ void __launch_bounds__(CH_T) whm_j2h_kernel(int n, const double *__restrict__ gm, const double *__restrict__ eta,
+                                                       CV3 xj, CV3 vj, V3 rh, V3 vh)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double sx0 = 0.0, sx1 = 0.0, sx2 = 0.0, sv0 = 0.0, sv1 = 0.0, sv2 = 0.0;
-    rh.x[0] = xj.x[0];
-    rh.y[0] = xj.y[0];
-    rh.z[0] = xj.z[0];
-    vh.x[0] = vj.x[0];
-    vh.y[0] = vj.y[0];
-    vh.z[0] = vj.z[0];
-    for (int i = 1; i < n; ++i) {
-        const double g = gm[i - 1], e = eta[i - 1];
-        sx0 = sx0 + g * xj.x[i - 1] / e;
-        sx1 = sx1 + g * xj.y[i - 1] / e;
-        sx2 = sx2 + g * xj.z[i - 1] / e;
-        sv0 = sv0 + g * vj.x[i - 1] / e;
-        sv1 = sv1 + g * vj.y[i - 1] / e;
-        sv2 = sv2 + g * vj.z[i - 1] / e;
-        rh.x[i] = xj.x[i] + sx0;
-        rh.y[i] = xj.y[i] + sx1;
-        rh.z[i] = xj.z[i] + sx2;
-        vh.x[i] = vj.x[i] + sv0;
-        vh.y[i] = vj.y[i] + sv1;
-        vh.z[i] = vj.z[i] + sv2;
+    __shared__ double term[6][CH_T];
+    const int t = threadIdx.x;
+    double carry = 0.0;
+    for (int base = 0; base < n; base += CH_T) {
+        const int m = min(CH_T, n - base), i = base + t;
+        if (t < m) {  // body i adds Gm(i-1) * q(i-1) / eta(i-1) (whm_coord.f90:69-75)
+            const bool on = i >= 1;
+            const double g = on ? gm[i - 1] : 0.0, e = on ? eta[i - 1] : 1.0;
+            term[0][t] = on ? g * xj.x[i - 1] / e : 0.0;
+            term[1][t] = on ? g * xj.y[i - 1] / e : 0.0;
+            term[2][t] = on ? g * xj.z[i - 1] / e : 0.0;
+            term[3][t] = on ? g * vj.x[i - 1] / e : 0.0;
+            term[4][t] = on ? g * vj.y[i - 1] / e : 0.0;
+            term[5][t] = on ? g * vj.z[i - 1] / e : 0.0;
+        }
+        __syncthreads();
+        chain_tile<6>(term, m, carry);
+        __syncthreads();
+        if (t < m) {
+            if (i == 0) {
+                rh.x[0] = xj.x[0], rh.y[0] = xj.y[0], rh.z[0] = xj.z[0];
+                vh.x[0] = vj.x[0], vh.y[0] = vj.y[0], vh.z[0] = vj.z[0];
+            } else {
+                rh.x[i] = xj.x[i] + term[0][t];
+                rh.y[i] = xj.y[i] + term[1][t];
+                rh.z[i] = xj.z[i] + term[2][t];
+                vh.x[i] = vj.x[i] + term[3][t];
+                vh.y[i] = vj.y[i] + term[4][t];
+                vh.z[i] = vj.z[i] + term[5][t];
+            }
+        }
+        __syncthreads();
     }
 }
 
 // whm_kick_getacch_ah0 (whm_kick.f90:124-149) over bodies [first, n): out = -sum Gm_i r_i / |r_i|^3 (serial order)
-__global__ void whm_ah0_kernel(int first, int n, const double *__restrict__ gm, CV3 r, double *__restrict__ out)
+__global__ void __launch_bounds__(CH_T) whm_ah0_kernel(int first, int n, const double *__restrict__ gm, CV3 r,
+                                                       double *__restrict__ out)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
-    for (int i = first; i < n; ++i) {
-        const double x = r.x[i], y = r.y[i], z = r.z[i];
-        const double r2 = x * x + y * y + z * z;
-        const double ir3h = 1.0 / (r2 * sqrt(r2));
-        const double fac = gm[i] * ir3h;
-        a0 = a0 - fac * x;
-        a1 = a1 - fac * y;
-        a2 = a2 - fac * z;
+    __shared__ double term[3][CH_T];
+    const int t = threadIdx.x;
+    double carry = 0.0;
+    for (int base = first; base < n; base += CH_T) {
+        const int m = min(CH_T, n - base), i = base + t;
+        if (t < m) {
+            const double x = r.x[i], y = r.y[i], z = r.z[i];
+            const double r2 = x * x + y * y + z * z;
+            const double ir3h = 1.0 / (r2 * sqrt(r2));
+            const double fac = gm[i] * ir3h;
+            term[0][t] = -(fac * x);  // a - fac*x == a + (-(fac*x)) bit for bit
+            term[1][t] = -(fac * y);
+            term[2][t] = -(fac * z);
+        }
+        __syncthreads();
+        chain_tile<3>(term, m, carry);
+        __syncthreads();
     }
-    out[0] = a0;
-    out[1] = a1;
-    out[2] = a2;
+    if (t < 3) out[t] = carry;
 }
 
 // ah(i) = ((ah(i) + ah0) + GMcb*(xj*ir3j - rh*ir3h)) for i >= 1 under the mask (ah0 for every body), whm_kick.f90:33-35,150-172
@@ -154,21 +213,36 @@ __global__ void whm_ah01_kernel(int n, double gmcb, const int32_t *__restrict__ 
 
 // whm_kick_getacch_ah2 (whm_kick.f90:175-205): ah2(i) = ah2(i-1) + Gm(i)*GMcb*ir3j(i)/etaj * xj(i), etaj running over
 // the masked bodies
-__global__ void whm_ah2_kernel(int n, double gmcb, const int32_t *__restrict__ lmask, const double *__restrict__ gm,
-                               const double *__restrict__ ir3j, CV3 xj, V3 ah)
+__global__ void __launch_bounds__(CH_T) whm_ah2_kernel(int n, double gmcb, const int32_t *__restrict__ lmask,
+                                                       const double *__restrict__ gm, const double *__restrict__ ir3j, CV3 xj,
+                                                       V3 ah)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double o0 = 0.0, o1 = 0.0, o2 = 0.0, etaj = gmcb;
-    for (int i = 1; i < n; ++i) {
-        if (lmask[i] == 0) continue;
-        etaj = etaj + gm[i - 1];
-        const double fac = gm[i] * gmcb * ir3j[i] / etaj;
-        o0 = o0 + fac * xj.x[i];
-        o1 = o1 + fac * xj.y[i];
-        o2 = o2 + fac * xj.z[i];
-        ah.x[i] = ah.x[i] + o0;
-        ah.y[i] = ah.y[i] + o1;
-        ah.z[i] = ah.z[i] + o2;
+    __shared__ double eterm[1][CH_T];
+    __shared__ double term[3][CH_T];
+    const int t = threadIdx.x;
+    double ecarry = gmcb, carry = 0.0;  // lane 0 carries etaj, lanes 0..2 carry the three components of ah2
+    for (int base = 0; base < n; base += CH_T) {
+        const int m = min(CH_T, n - base), i = base + t;
+        const bool on = t < m && i >= 1 && lmask[i] != 0;  // masked-out bodies (and body 1) add nothing to either chain
+        if (t < m) eterm[0][t] = on ? gm[i - 1] : 0.0;      // etaj = etaj + Gm(i-1): adding +0.0 leaves etaj unchanged
+        __syncthreads();
+        chain_tile<1>(eterm, m, ecarry);
+        __syncthreads();
+        if (t < m) {
+            const double fac = on ? gm[i] * gmcb * ir3j[i] / eterm[0][t] : 0.0;
+            term[0][t] = on ? fac * xj.x[i] : 0.0;
+            term[1][t] = on ? fac * xj.y[i] : 0.0;
+            term[2][t] = on ? fac * xj.z[i] : 0.0;
+        }
+        __syncthreads();
+        chain_tile<3>(term, m, carry);
+        __syncthreads();
+        if (on) {
+            ah.x[i] = ah.x[i] + term[0][t];
+            ah.y[i] = ah.y[i] + term[1][t];
+            ah.z[i] = ah.z[i] + term[2][t];
+        }
+        __syncthreads();
     }
 }
 
@@ -204,7 +278,7 @@ int ensure_whm(swcu_context *ctx, Body &pl, double gmcb)
     SWCU_TRY(ensure_step_state(ctx));
     SWCU_TRY(ensure_helio(ctx, pl));  // rbeg / rend copies live in the helio buffers (b*, e*)
     if (W.generation != pl.generation || W.n != pl.n || W.gmcb != gmcb) {
-        whm_set_mu_eta_kernel<<<1, 32, 0, ctx->stream>>>(pl.n, gmcb, pl.Gm.as<double>(), W.eta.as<double>(), W.muj.as<double>());
+        whm_set_mu_eta_kernel<<<1, CH_T, 0, ctx->stream>>>(pl.n, gmcb, pl.Gm.as<double>(), W.eta.as<double>(), W.muj.as<double>());
         SWCU_KERNEL_CHECK(ctx);
         W.generation = pl.generation;
         W.n = pl.n;
@@ -220,13 +294,13 @@ int whm_getacch_pl(swcu_context *ctx, Body &pl, double gmcb, int variant, int lc
     const int n = pl.n;
     SWCU_TRY(fill3_f64(ctx, pl.ax.as<double>(), pl.ay.as<double>(), pl.az.as<double>(), 0.0, n));
     double *ah0 = ctx->cbs.as<double>() + CBS_AH0PL;
-    whm_ah0_kernel<<<1, 32, 0, ctx->stream>>>(1, n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);  // bodies 2..npl (:33)
+    whm_ah0_kernel<<<1, CH_T, 0, ctx->stream>>>(1, n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);  // bodies 2..npl (:33)
     SWCU_KERNEL_CHECK(ctx);
     whm_ah01_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, gmcb, pl.lmask.as<int32_t>(), cv3(pl.rx, pl.ry, pl.rz),
                                                           cv3(W.xjx, W.xjy, W.xjz), ah0, W.ir3j.as<double>(),
                                                           v3(pl.ax, pl.ay, pl.az));
     SWCU_KERNEL_CHECK(ctx);
-    whm_ah2_kernel<<<1, 32, 0, ctx->stream>>>(n, gmcb, pl.lmask.as<int32_t>(), pl.Gm.as<double>(), W.ir3j.as<double>(),
+    whm_ah2_kernel<<<1, CH_T, 0, ctx->stream>>>(n, gmcb, pl.lmask.as<int32_t>(), pl.Gm.as<double>(), W.ir3j.as<double>(),
                                               cv3(W.xjx, W.xjy, W.xjz), v3(pl.ax, pl.ay, pl.az));
     SWCU_KERNEL_CHECK(ctx);
     return pl_accel_int(ctx, variant, lclose);
@@ -263,7 +337,7 @@ int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclo
     CV3 rh = cv3(pl.rx, pl.ry, pl.rz), vh = cv3(pl.vx, pl.vy, pl.vz);
     V3 xj = v3(W.xjx, W.xjy, W.xjz), vj = v3(W.vjx, W.vjy, W.vjz);
     if (lfirst) {  // whm_kick_vh_pl :236-243
-        whm_h2j_kernel<<<1, 32, 0, ctx->stream>>>(n, 0, pl.Gm.as<double>(), W.eta.as<double>(), rh, vh, xj, vj);
+        whm_h2j_kernel<<<1, CH_T, 0, ctx->stream>>>(n, 0, pl.Gm.as<double>(), W.eta.as<double>(), rh, vh, xj, vj);
         SWCU_KERNEL_CHECK(ctx);
         SWCU_TRY(whm_getacch_pl(ctx, pl, gmcb, variant, lclose));
     }
@@ -272,12 +346,12 @@ int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclo
     whm_kick_vh_kernel<<<cdiv(n, 128), 128, 0, ctx->stream>>>(n, pl.lmask.as<int32_t>(), dth, cv3(pl.ax, pl.ay, pl.az),
                                                             v3(pl.vx, pl.vy, pl.vz));  // vh += ah*dth
     SWCU_KERNEL_CHECK(ctx);
-    whm_h2j_kernel<<<1, 32, 0, ctx->stream>>>(n, 1, pl.Gm.as<double>(), W.eta.as<double>(), rh, vh, xj, vj);  // vh2vj
+    whm_h2j_kernel<<<1, CH_T, 0, ctx->stream>>>(n, 1, pl.Gm.as<double>(), W.eta.as<double>(), rh, vh, xj, vj);  // vh2vj
     SWCU_KERNEL_CHECK(ctx);
     SWCU_TRY(drift_arrays(ctx, n, W.muj.as<double>(), W.xjx.as<double>(), W.xjy.as<double>(), W.xjz.as<double>(),
                           W.vjx.as<double>(), W.vjy.as<double>(), W.vjz.as<double>(), pl.lmask.as<int32_t>(),
                           pl.iflag.as<int32_t>(), dt));
-    whm_j2h_kernel<<<1, 32, 0, ctx->stream>>>(n, pl.Gm.as<double>(), W.eta.as<double>(), cv3(W.xjx, W.xjy, W.xjz),
+    whm_j2h_kernel<<<1, CH_T, 0, ctx->stream>>>(n, pl.Gm.as<double>(), W.eta.as<double>(), cv3(W.xjx, W.xjy, W.xjz),
                                               cv3(W.vjx, W.vjy, W.vjz), v3(pl.rx, pl.ry, pl.rz), v3(pl.vx, pl.vy, pl.vz));
     SWCU_KERNEL_CHECK(ctx);
     SWCU_TRY(whm_getacch_pl(ctx, pl, gmcb, variant, lclose));  // kick(end)
@@ -286,7 +360,7 @@ int whm_step_pl(swcu_context *ctx, double gmcb, double dt, int variant, int lclo
                                                             v3(pl.vx, pl.vy, pl.vz));
     SWCU_KERNEL_CHECK(ctx);
     // ah0 of the test-particle kick at the end-of-step planets: all npl planets
-    whm_ah0_kernel<<<1, 32, 0, ctx->stream>>>(0, n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz),
+    whm_ah0_kernel<<<1, CH_T, 0, ctx->stream>>>(0, n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz),
                                               ctx->cbs.as<double>() + CBS_AH0TP);
     SWCU_KERNEL_CHECK(ctx);
     W.ah0tp_valid = true;
@@ -305,7 +379,7 @@ int whm_tp_first_accel(swcu_context *ctx)
     if (tp.n == 0 || pl.n == 0) return SWCU_OK;
     SWCU_TRY(ensure_step_state(ctx));
     double *ah0 = ctx->cbs.as<double>() + CBS_AH0TP;
-    whm_ah0_kernel<<<1, 32, 0, ctx->stream>>>(0, pl.n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);
+    whm_ah0_kernel<<<1, CH_T, 0, ctx->stream>>>(0, pl.n, pl.Gm.as<double>(), cv3(pl.rx, pl.ry, pl.rz), ah0);
     SWCU_KERNEL_CHECK(ctx);
     SWCU_TRY(fill3_f64(ctx, tp.ax.as<double>(), tp.ay.as<double>(), tp.az.as<double>(), 0.0, tp.n));
     whm_add_const_kernel<<<cdiv(tp.n, 256), 256, 0, ctx->stream>>>(tp.n, tp.lmask.as<int32_t>(), ah0, v3(tp.ax, tp.ay, tp.az));

@@ -370,6 +370,35 @@ def test_whm_step_pl_resident_matches_oracle(ctx, oracle):
             assert np.max(np.abs(vb["rend"] - st["rend"])) <= 1e-11 * np.abs(st["rend"]).max()
 
 
+@pytest.mark.parametrize("n", [130, 300, 1500])
+def test_whm_multi_launch_step_on_larger_systems_matches_oracle(ctx, oracle, n):
+    """npl > 128: the multi-launch form.  Its Jacobi chains run tile by tile (256 bodies: terms in parallel, additions in the
+    reference's order from shared memory): after every step the heliocentric positions must be EXACTLY j2h of the device's
+    own Jacobi coordinates (the chain, bit for bit, across tile boundaries), and the step tracks the C restatement of
+    whm_step_pl to the rounding of the O(N^2) term; masked bodies included."""
+    from swiftest_b200 import LOOP_TRIANGULAR
+    d = W.disk(n, seed=900 + n)
+    GMcb, Gm, dt = W.GMSUN, d["Gmass"] * 300.0, d["dt"]   # heavier bodies: the Jacobi corrections are far above rounding
+    mask = np.ones(n, np.int32)
+    mask[[7, n // 2, n - 2]] = 0
+    st = {"rh": d["rh"].copy(), "vh": d["vh"].copy(), "lfirst": True}
+    ctx.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=Gm, radius=d["radius"], rhill=d["rhill"], mu=GMcb + Gm,
+                  lmask=mask, generation=8700 + n)
+    _, eta, _ = oracle.whm_set_mu_eta(GMcb, Gm)
+    for k in range(4):
+        assert not oracle.whm_step_pl(st, GMcb, Gm, d["radius"], dt, lflat=False, lmask=mask).any()
+        assert ctx.whm_step_pl(GMcb, dt, LOOP_TRIANGULAR, True, lfirst=(k == 0)) == 0
+        got = ctx.body_get(PL)
+        xj, vj = ctx.whm_get_jacobi()
+        rh_from_xj, _ = oracle.whm_coord_j2h(Gm, eta, xj, vj)
+        assert np.array_equal(got["r"], rh_from_xj)
+    sr, sv = np.linalg.norm(st["rh"], axis=1, keepdims=True), np.linalg.norm(st["vh"], axis=1, keepdims=True)
+    assert np.max(np.abs(got["r"] - st["rh"]) / sr) < 1e-11 and np.max(np.abs(got["v"] - st["vh"]) / sv) < 1e-11
+    assert np.max(np.abs(xj - st["xj"]) / sr) < 1e-11 and np.max(np.abs(vj - st["vj"]) / sv) < 1e-11
+    on = mask.astype(bool)
+    assert np.max(np.abs(got["a"][on] - st["ah"][on])) <= 1e-11 * np.abs(st["ah"]).max()
+
+
 def test_whm_first_step_is_bit_identical_where_the_chains_decide(ctx, oracle):
     """One first step of the Sun + 8 planets system: eta/muj, h2j and the ah0/ah1/ah2 chains run in the reference's serial
     order with no FMA contraction; only pl%accel_int (28 pairs) and libm-free drift arithmetic follow, so positions agree
