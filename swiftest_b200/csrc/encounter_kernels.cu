@@ -709,6 +709,7 @@ __global__ void __launch_bounds__(256) pltp_place_kernel(int n1, int nb, int npl
         if (threadIdx.x == 0) {
             for (int w = 1; w < 8; ++w) sum += part[w];
             nbc[i] = sum;
+            if (i == 0) nbc[-3] = (unsigned long long)offs[(size_t)n1 * nb];  // counters[5]: hits placed (read back with the rest)
         }
         return;
     }
@@ -1115,7 +1116,9 @@ int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepLis
         E.direct_attr_set = true;
     }
     const int grid = std::min(nb, ctx->prop.multiProcessorCount * 3);  // persistent CTAs, 3 per SM (launch bounds)
-    std::vector<unsigned long long> h(8 + (size_t)n1, 0ull);
+    if (!E.h_counters)
+        SWCU_CUDA(ctx, cudaHostAlloc((void **)&E.h_counters, (8 + PLTP_MAXPL) * sizeof(unsigned long long), cudaHostAllocDefault));
+    const unsigned long long *h = E.h_counters;  // pinned: one read-back of [0] hits, [4] flags, [5] hits placed, [8..) boxes
     int h_total = 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
         SWCU_CUDA(ctx, E.cand.ensure(sizeof(unsigned long long) * E.cand_cap));
@@ -1133,10 +1136,10 @@ int encounter_pltp_direct(swcu_context *ctx, const SweepList &l1, const SweepLis
             n1, nb, cdiv(nb, 8), d_cnt, d_offs, E.abase.as<unsigned long long>(), E.cand.as<unsigned long long>(),
             (unsigned long long)E.cand_cap, E.uniq.as<unsigned long long>(), E.boxcnt.as<unsigned int>(), d_nbc);
         SWCU_KERNEL_CHECK(ctx);
-        SWCU_CUDA(ctx, cudaMemcpyAsync(h.data(), d_count, sizeof(unsigned long long) * (8 + (size_t)n1),
+        SWCU_CUDA(ctx, cudaMemcpyAsync(E.h_counters, d_count, sizeof(unsigned long long) * (8 + (size_t)n1),
                                        cudaMemcpyDeviceToHost, ctx->stream));
-        SWCU_CUDA(ctx, cudaMemcpyAsync(&h_total, d_offs + ncnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        h_total = (int)h[5];
         if ((int)(h[4] & 0xffffffffull) != 0) {
             *fell_back = true;
             return SWCU_OK;
@@ -1211,7 +1214,7 @@ static int encounter_sweep_impl(swcu_context *ctx, const SweepList &l1, const Sw
     SWCU_CUDA(ctx, E.nchunk.ensure(ib * (ntot + 1)));
     SWCU_CUDA(ctx, E.choff.ensure(ib * (ntot + 1)));
     SWCU_CUDA(ctx, E.counters.ensure(sizeof(unsigned long long) * (8 + PLTP_MAXPL)));
-    if (!E.h_counters) SWCU_CUDA(ctx, cudaHostAlloc((void **)&E.h_counters, 16 * sizeof(unsigned long long), cudaHostAllocDefault));
+    if (!E.h_counters) SWCU_CUDA(ctx, cudaHostAlloc((void **)&E.h_counters, (8 + PLTP_MAXPL) * sizeof(unsigned long long), cudaHostAllocDefault));
     unsigned long long *d_count = E.counters.as<unsigned long long>();       // [0] candidates emitted
     unsigned long long *d_nbox = d_count + 1;                                 // [1] sum nbox
     unsigned long long *d_small = d_count + 8;                                // [8] 0: finalize_small_kernel made the list
