@@ -100,4 +100,30 @@ with Context(0) as c:
     print("resident pl-tp lists", len(j1), c.tp_symba_kick_list(j1, j2, None, np.ones(8, np.int32), np.ones(3000, np.int32), 0.01, 1, 1).sum(),
           c.body_symba_encounter_check_list(TP, j1, j2, None, 0.02)[2],
           c.body_collision_check_list(TP, j1, j2, None, np.ones(len(j1), np.int32), 5.0)[2])
+    # second half of round 2, later additions: multi-launch WHM step (tiled chains), helio step replayed as a CUDA graph,
+    # bucket sort with a clump (radix fallback) and device-side finalisation, serial-order sums, RSQ64H potential energy
+    n = 300
+    d = W.disk(n, seed=11)
+    c.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"] * 100, radius=d["radius"], rhill=d["rhill"],
+                mu=W.GMSUN + d["Gmass"] * 100, generation=8)
+    for k in range(3):
+        c.whm_step_pl(W.GMSUN, d["dt"], LOOP_TRIANGULAR, True, lfirst=(k == 0))
+    n = 700
+    d = W.disk(n, seed=12)
+    c.body_sync(PL, n, nplm=n, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"],
+                mu=np.full(n, W.GMSUN), generation=9)
+    for k in range(6):
+        c.helio_step_pl(W.GMSUN, d["dt"], LOOP_AUTO, True, lfirst=(k == 0), want_nfail=(k == 5))
+    print("graph replays", c.step_graph_replays())
+    r = d["rh"].copy()
+    r[:3000 if n > 3000 else 0] = 0.0
+    big = W.disk(6000, seed=13)
+    rb = big["rh"].copy()
+    rb[:3000] = 0.0
+    rb[np.arange(3000), np.arange(3000) % 3] = 1.0
+    rencb = big["rhill"] * 6.5 * 3
+    rencb[:3000] = 0.0
+    print("clump sweep", c.encounter_check_all_sort_and_sweep_plpl(6000, rb, big["vh"], rencb, big["dt"])[0],
+          "bucket fallbacks", c.encounter_bucket_fallbacks())
+    print("pe", c.util_get_potential_energy(n, None, W.GMSUN, d["Gmass"], d["Gmass"] / W.GMSUN, d["rh"]))
 print("sanitize pass done")
