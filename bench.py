@@ -59,6 +59,9 @@ def parse_args():
                          "ncclAllReduce of the partial accelerations (nccl)")
     ap.add_argument("--no-extra", action="store_true", help="skip the sweep / tp side legs and the CPU baseline")
     ap.add_argument("--cpu-evals", type=int, default=3, help="full CPU force evaluations timed for cpu_baseline")
+    ap.add_argument("--conservation-long", type=int, default=1000000,
+                    help="steps of the reference's own conservation test (Sun + 8 planets, dt = 0.01 y, 1e4 y = 1e6 steps, 1000 "
+                         "outputs; extra.conservation_reference_test; 0 = skip; stops early after ~100 s)")
     ap.add_argument("--conservation", type=int, default=10000,
                     help="steps of the Sun + 8 planets energy/L tracking run (extra.conservation; 0 = skip)")
     ap.add_argument("--disk-steps", type=int, default=1000,
@@ -482,6 +485,11 @@ def run_ours(args):
                 extra["conservation_disk"] = conservation_disk_run(ctx, args.disk_steps)
             except Exception as e:
                 extra["conservation_disk"] = {"error": str(e)}
+        if args.conservation_long:
+            try:
+                extra["conservation_reference_test"] = conservation_reference_test(ctx, args.conservation_long)
+            except Exception as e:
+                extra["conservation_reference_test"] = {"error": str(e)}
 
     if not args.no_extra:
         legs = {}
@@ -969,6 +977,110 @@ def conservation_run(ctx, nsteps):
             "dE_slope_per_year_cpu": _slope_per_year(ts, np.abs(dEa)), "dL_slope_per_year_cpu": _slope_per_year(ts, dLa),
             "reference_limits": "tests/test_swiftest.py:119-121: |dE/E0| slope < 1e-8 /y, |dL/L0| slope < 1e-10 /y",
             "max_position_difference": float(np.max(np.abs(a.rh - b.rh)))}
+
+
+def conservation_reference_test(ctx, nsteps, nout=1000, budget_s=50.0):
+    """The reference's own quantitative test, at its own length (tests/test_swiftest.py:112-169: Sun + 8 planets, dt = 0.01 y,
+    tstop = 1e4 y = 1e6 steps, 1000 outputs, linear fits of E_error and L_error against time: |slope| < 1e-8 /y and
+    1e-10 /y, |dGM/GM| < 1e-14).  The reference runs it with SyMBA; without close encounters among the planets a SyMBA step IS
+    helio_step_pl, and the run checks that no encounter occurs.  GPU: the planets stay resident, one launch per step
+    (helio_step_pl_small_kernel); CPU: the oracle's C stepper (bit-identical to the interpreted Fortran).  Both states go
+    through the same energy / momentum evaluation, so their difference is the difference of the trajectories.  Each arm stops
+    after budget_s seconds of stepping (steps_done says where)."""
+    import ctypes as C
+    from oracle import load
+    from swiftest_b200 import PL, LOOP_TRIANGULAR, workloads as W
+    o = load()
+    p = W.planets8_year_units()
+    n, GMcb, Gm, rad, dt = 8, p["cb_Gmass"], np.ascontiguousarray(p["Gmass"]), np.ascontiguousarray(p["radius"]), 0.01
+    mass = Gm / GMcb  # any constant G: only ratios enter dE/E0 and dL/L0
+    every = max(1, nsteps // nout)
+
+    def el(rh, vh):
+        rb, vb, rbcb, vbcb = o.coord_h2b_pl(GMcb, Gm, rh, vh)
+        e = o.get_energy_and_momentum(GMcb, 1.0, rbcb, vbcb, Gm, mass, rad, rb, vb, None, True)
+        return e["te"], e["L_orbit"], e["GMtot"]
+
+    def e_true(rh, vh):
+        """The physical energy (central-body term with |rb_i - rb_cb|).  The reference's own sum uses |rb_i|
+        (swiftest_util.f90:1377), so its E_error carries the Sun's barycentric wobble, ~3e-4, whatever the integrator does."""
+        gt = GMcb + Gm.sum()
+        vcb = -(Gm[:, None] * vh).sum(0) / gt
+        vb = vh + vcb
+        d = rh[:, None, :] - rh[None, :, :]
+        iu = np.triu_indices(n, 1)
+        return (0.5 * (Gm * (vb ** 2).sum(1)).sum() + 0.5 * GMcb * (vcb ** 2).sum() -
+                (GMcb * Gm / np.linalg.norm(rh, axis=1)).sum() - (Gm[iu[0]] * Gm[iu[1]] / np.linalg.norm(d, axis=2)[iu]).sum())
+
+    E0, L0, GM0 = el(p["rh"], p["vh"])
+    Et0 = e_true(p["rh"], p["vh"])
+    Etg = []
+    # ---- GPU arm
+    ctx.body_sync(PL, n, nplm=n, r=p["rh"], v=p["vh"], Gmass=Gm, radius=rad, rhill=p["rhill"], mu=np.full(n, GMcb),
+                  generation=777001)
+    ctx.pl_set_renc(0)
+    step = ctx._L.swcu_helio_step_pl
+    h, cGM, cdt = ctx._h, C.c_double(GMcb), C.c_double(dt)
+    tg, Eg, Lg, nenc_seen, done_g = [], [], [], 0, 0
+    t0 = time.perf_counter()
+    l0 = ctx.launch_count()
+    for k in range(1, nsteps + 1):
+        rc = step(h, cGM, cdt, LOOP_TRIANGULAR, 1, 1 if k == 1 else 0, None)
+        if rc != 0:
+            ctx._ck(rc)  # raises with the library's message
+        if k % every == 0 or k == nsteps:
+            out = ctx.body_get(PL, a=False)
+            E, L, GM = el(out["r"], out["v"])
+            tg.append(k * dt), Eg.append((E - E0) / E0), Lg.append(float(np.linalg.norm(L - L0) / np.linalg.norm(L0)))
+            Etg.append((e_true(out["r"], out["v"]) - Et0) / abs(Et0))
+            if len(tg) % 50 == 0:
+                nenc_seen += int(ctx.pl_encounter_check(dt, fetch=False))
+            done_g = k
+            if time.perf_counter() - t0 > budget_s:
+                break
+    t_gpu = time.perf_counter() - t0
+    launches = ctx.launch_count() - l0
+    # ---- CPU arm (the oracle's stepper, called without the Python wrapper's per-call allocations)
+    st = {k2: np.ascontiguousarray(p[k2]).copy() for k2 in ("rh", "vh")}
+    st.update(vb=np.zeros((n, 3)), ah=np.zeros((n, 3)), rbeg=np.zeros((n, 3)), rend=np.zeros((n, 3)), ptbeg=np.zeros(3),
+              ptend=np.zeros(3), vbcb=np.zeros(3))
+    lf, iflag = C.c_int32(1), np.zeros(n, np.int32)
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    args_c = (n, GMcb, ptr(Gm), ptr(rad), 0, None, C.byref(lf), dt, ptr(st["rh"]), ptr(st["vh"]), ptr(st["vb"]), ptr(st["ah"]),
+              ptr(st["rbeg"]), ptr(st["rend"]), ptr(st["ptbeg"]), ptr(st["ptend"]), ptr(st["vbcb"]), ptr(iflag))
+    fn = o.lib.swo_helio_step_pl
+    tc, Ec, Lc, done_c = [], [], [], 0
+    t0 = time.perf_counter()
+    for k in range(1, done_g + 1):
+        fn(*args_c)
+        if k % every == 0 or k == nsteps:
+            E, L, GMc = el(st["rh"], st["vh"])
+            tc.append(k * dt), Ec.append((E - E0) / E0), Lc.append(float(np.linalg.norm(L - L0) / np.linalg.norm(L0)))
+            done_c = k
+            if time.perf_counter() - t0 > budget_s:
+                break
+    t_cpu = time.perf_counter() - t0
+    m = min(len(tg), len(tc))
+    Eg_a, Ec_a, Lg_a, Lc_a = np.array(Eg), np.array(Ec), np.array(Lg), np.array(Lc)
+    res = {"test": "tests/test_swiftest.py:112-169 (test_conservation), Sun + 8 planets of the reference fixture 8pl_0tp, dt 0.01 y",
+           "steps_requested": nsteps, "steps_done_gpu": done_g, "steps_done_cpu": done_c, "years_gpu": done_g * dt,
+           "outputs": len(tg), "seconds_gpu": t_gpu, "seconds_cpu": t_cpu, "us_per_step_gpu": 1e6 * t_gpu / max(done_g, 1),
+           "kernel_launches_per_step_gpu": launches / max(done_g, 1), "encounters_seen": nenc_seen,
+           "E_slope_per_year_gpu": _slope_per_year(tg, Eg_a), "L_slope_per_year_gpu": _slope_per_year(tg, Lg_a),
+           "E_slope_per_year_cpu": _slope_per_year(tc, Ec_a), "L_slope_per_year_cpu": _slope_per_year(tc, Lc_a),
+           "limits": {"E_slope": 1e-8, "L_slope": 1e-10, "GM": 1e-14},
+           "GM_error_final": float((GM - GM0) / GM0),
+           "max_abs_E_error_gpu": float(np.max(np.abs(Eg_a))), "max_L_error_gpu": float(np.max(Lg_a)),
+           "max_abs_true_energy_error_gpu": float(np.max(np.abs(Etg))),
+           "true_energy_slope_per_year_gpu": _slope_per_year(tg, np.array(Etg)),
+           "note": "E_error as the reference defines it (its potential energy takes |rb_i| for the central-body term, "
+                   "swiftest_util.f90:1377: the Sun's wobble shows as a ~3e-4 oscillation); true_energy = the same states in "
+                   "the physical energy",
+           "gpu_minus_cpu_E_error_max": float(np.max(np.abs(Eg_a[:m] - Ec_a[:m]))) if m else None,
+           "gpu_minus_cpu_L_error_max": float(np.max(np.abs(Lg_a[:m] - Lc_a[:m]))) if m else None}
+    res["passes_reference_limits"] = bool(abs(res["E_slope_per_year_gpu"]) < 1e-8 and abs(res["L_slope_per_year_gpu"]) < 1e-10 and
+                                          abs(res["GM_error_final"]) < 1e-14 and nenc_seen == 0)
+    return res
 
 
 def _slope_per_year(t, y):
