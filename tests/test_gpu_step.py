@@ -510,3 +510,16 @@ def test_helio_small_system_step_is_one_launch_and_bit_identical_to_the_referenc
     assert np.array_equal(hv["rbeg"], st["rbeg"]) and np.array_equal(hv["rend"], st["rend"])
     ptb, pte = ctx.cb_get_pt()
     assert np.array_equal(ptb, st["ptbeg"]) and np.array_equal(pte, st["ptend"])
+
+
+def test_reference_conservation_test_on_the_device(ctx):
+    """The reference's only quantitative test (tests/test_swiftest.py:112-169: Sun + 8 planets, dt = 0.01 y, slopes of the
+    energy and angular-momentum errors) over 1e5 of its 1e6 steps, planets resident, one launch per step, against the
+    oracle's C stepper on the same steps; bench.py runs the full 1e6 (extra.conservation_reference_test)."""
+    import bench
+    r = bench.conservation_reference_test(ctx, 100000, nout=100, budget_s=120.0)
+    assert r["steps_done_gpu"] == 100000 and r["steps_done_cpu"] == 100000 and r["encounters_seen"] == 0
+    assert abs(r["E_slope_per_year_gpu"]) < 1e-8 and abs(r["L_slope_per_year_gpu"]) < 1e-10 and abs(r["GM_error_final"]) < 1e-14
+    assert r["gpu_minus_cpu_E_error_max"] < 1e-12 and r["gpu_minus_cpu_L_error_max"] < 1e-12
+    assert r["max_abs_true_energy_error_gpu"] < 1e-7
+    assert r["kernel_launches_per_step_gpu"] < 1.01
