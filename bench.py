@@ -364,6 +364,8 @@ def run_ours(args):
     kick_ms_avg = max_over_ranks(fam_ms["gravity"][0] / max(1, fam_ms["gravity"][1]))
     breakdown = {k: (max_over_ranks(v[0] / args.steps) if v[1] else 0.0) for k, v in fam_ms.items()}
     breakdown["step_min"], breakdown["step_max"] = float(min(laps)), float(max(laps))
+    breakdown["step_median"] = float(np.median(laps))  # `value` is the MEAN lap (the contract's K steps / time); one lap
+    # disturbed by the box (seen once: 9.8 ms among nine of 6.89) moves the mean by 4 % and shows here as max >> median
     fp64_peak = ctx.probe_fp64_peak()
 
     # ---------------- end-to-end: host buffers in, results out, every step ----------------
