@@ -407,6 +407,13 @@ module swiftest_cuda
          real(c_double), value :: dt
          integer(c_int), intent(out) :: iplanet(*), ndiscard
       end function
+      integer(c_int) function swcu_tp_discard_pl(ctx, dt, iplanet, ndiscard) bind(C, name="swcu_tp_discard_pl")
+         import :: c_int, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         type(c_ptr), value :: iplanet   !! c_loc of an integer(c_int) array of ntp elements, or c_null_ptr
+         integer(c_int), intent(out) :: ndiscard
+      end function
       integer(c_int) function swcu_symba_encounter_check_list(ctx, nenc, index1, index2, lencmask, n1, r1, v1, renc1, &
             radius1, n2, r2, v2, renc2, radius2, dt, lencounter, lvdotr, nfound) &
             bind(C, name="swcu_symba_encounter_check_list")

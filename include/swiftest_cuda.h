@@ -250,6 +250,10 @@ int swcu_encounter_check_all_triangular_plplm(swcu_context *ctx, int32_t nplm, i
 int swcu_discard_pl_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double *rtp, const double *vtp,
                        const int32_t *lactive, const double *rpl, const double *vpl, const double *radius, double dt,
                        int32_t *iplanet, int32_t *ndiscard);
+/* tier 2 of swcu_discard_pl_tp: the resident test particles against the resident planets (tp%rh, tp%vh, pl%rh, pl%vh,
+ * pl%radius stay in HBM; particles are tested where their active flag -- swcu_body_set_active, else lmask -- is set).
+ * ndiscard comes back always; iplanet (ntp entries, may be NULL) is copied only when ndiscard > 0, else zero-filled. */
+int swcu_tp_discard_pl(swcu_context *ctx, double dt, int32_t *iplanet, int32_t *ndiscard);
 /* the pair loop of symba_encounter_check_list_plpl / _pltp (symba_encounter_check.f90:122-137, 197-211) over an
  * existing encounter list: lencounter(k), lvdotr(k) for the pairs of lencmask (lvdotr is left alone elsewhere).
  * n2 == 0: both indices address list 1 (pl-pl); else index2 addresses list 2 (renc2 / radius2 may be NULL: 0).

@@ -427,6 +427,14 @@ class Context:
                                             _ptr(radius), float(dt), _ptr(ipl), C.byref(nd)))
         return ipl, nd.value
 
+    def tp_discard_pl(self, dt, want_iplanet=True):
+        """swiftest_discard_pl_tp on the resident populations: (iplanet or None, number discarded)."""
+        ntp = self.body_count(TP)[0]
+        ipl = np.zeros(ntp, _i32) if want_iplanet else None
+        nd = C.c_int32()
+        self._ck(self._L.swcu_tp_discard_pl(self._h, float(dt), _ptr(ipl), C.byref(nd)))
+        return ipl, nd.value
+
     def symba_encounter_check_list(self, index1, index2, lencmask, r1, v1, renc1, radius1, dt, r2=None, v2=None,
                                    renc2=None, radius2=None, lvdotr=None):
         """Pair loop of symba_encounter_check_list_plpl (r2 None) / _pltp.  Returns (lencounter, lvdotr, nfound)."""

@@ -201,6 +201,7 @@ extern "C" int swcu_destroy(swcu_context *ctx)
         for (DevBuf *b : wb) b->release();
     }
     ctx->flat_redo.release();
+    ctx->tp_discard.release();
     ctx->sendbuf.release();
     ctx->recvbuf.release();
     auto &E = ctx->enc;
@@ -1158,6 +1159,30 @@ extern "C" int swcu_discard_pl_tp(swcu_context *ctx, int32_t ntp, int32_t npl, c
     SWCU_CUDA(ctx, cudaMemcpyAsync(iplanet, ctx->s_tp.iflag.p, sizeof(int32_t) * (size_t)ntp, cudaMemcpyDeviceToHost, ctx->stream));
     SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (ndiscard) *ndiscard = nd;
+    return SWCU_OK;
+}
+
+// tier 2 of the above: resident test particles against resident planets (tp%rh, tp%vh, pl%rh, pl%vh, pl%radius in HBM);
+// only the count, and the planet indices when there is something to discard, cross PCIe
+extern "C" int swcu_tp_discard_pl(swcu_context *ctx, double dt, int32_t *iplanet, int32_t *ndiscard)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl, &tp = ctx->tp;
+    if (ndiscard) *ndiscard = 0;
+    if (!pl.valid || !tp.valid) return fail(ctx, SWCU_ERR_STATE, "tp_discard_pl: populations not resident");
+    if (tp.n == 0) return SWCU_OK;
+    SWCU_CUDA(ctx, ctx->tp_discard.ensure(sizeof(int32_t) * (size_t)tp.n));
+    int32_t nd = 0;
+    const int32_t *d_active = tp.has_active ? tp.lactive.as<int32_t>() : tp.lmask.as<int32_t>();
+    SWCU_TRY(discard_pl_tp(ctx, tp, pl, d_active, dt, ctx->tp_discard.as<int32_t>(), &nd));
+    if (ndiscard) *ndiscard = nd;
+    if (iplanet && (nd > 0 || pl.n == 0)) {
+        SWCU_CUDA(ctx, cudaMemcpyAsync(iplanet, ctx->tp_discard.p, sizeof(int32_t) * (size_t)tp.n, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+        SWCU_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    } else if (iplanet) {
+        memset(iplanet, 0, sizeof(int32_t) * (size_t)tp.n);  // nobody is discarded: nothing to read back
+    }
     return SWCU_OK;
 }
 

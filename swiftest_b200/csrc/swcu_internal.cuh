@@ -159,6 +159,7 @@ struct swcu_context {
     } whm;
     swcu::DevBuf lists[16];  // staging of the encounter-list kernels (list_kernels.cu)
     swcu::DevBuf flat_blockrad; // max radius per block of 128 bodies (third-law kernel)
+    swcu::DevBuf tp_discard;  // iplanet of the last swcu_tp_discard_pl
     swcu::DevBuf flat_guard; // 2 x u64: max |coordinate| bit pattern of the current / next launch (flat_prologue_kernel)
     int flat_parity = 0;
     // whole multi-launch steps replayed as a CUDA graph (step_kernels.cu): captured on the second step with the same key

@@ -345,3 +345,37 @@ def test_resident_collision_check_list_matches_oracle(ctx, oracle):
                                       v2=tp["vh"])
     got = ctx.body_collision_check_list(TP, j1, j2, None, lv, 5.0)
     assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and got[2] == ref[2]
+
+
+@pytest.mark.parametrize("npl,ntp", [(8, 20000), (300, 5000)])
+def test_resident_discard_pl_tp_matches_oracle(ctx, oracle, npl, ntp):
+    """swcu_tp_discard_pl: the same double loop on the resident populations -- active flags from swcu_body_set_active, else
+    lmask, else everybody; the indices come back only when somebody is discarded."""
+    from swiftest_b200 import PL, TP
+    rng = np.random.default_rng(npl + ntp)
+    if npl == 8:
+        p = W.planets8_year_units()
+        rpl, vpl = p["rh"], p["vh"]
+    else:
+        d = W.disk(npl, seed=npl)
+        rpl, vpl = d["rh"], d["vh"]
+    host = rng.integers(0, npl, ntp)
+    rtp = rpl[host] + rng.normal(scale=0.02, size=(ntp, 3))
+    vtp = vpl[host] + rng.normal(scale=1.0, size=(ntp, 3))
+    radius = np.full(npl, 0.01)
+    act = (rng.uniform(size=ntp) > 0.1).astype(np.int32)
+    ctx.body_sync(PL, npl, nplm=npl, r=rpl, v=vpl, Gmass=np.ones(npl), radius=radius, rhill=radius, generation=next(_generation))
+    ctx.body_sync(TP, ntp, r=rtp, v=vtp, generation=next(_generation))
+    ref_all, n_all = oracle.discard_pl_tp(rtp, vtp, None, rpl, vpl, radius, 0.01)
+    got, n = ctx.tp_discard_pl(0.01)
+    assert np.array_equal(got, ref_all) and n == n_all and 0 < n < ntp
+    ctx.body_set_active(TP, act)
+    ref, nref = oracle.discard_pl_tp(rtp, vtp, act, rpl, vpl, radius, 0.01)
+    got, n = ctx.tp_discard_pl(0.01)
+    assert np.array_equal(got, ref) and n == nref and not got[act == 0].any()
+    assert ctx.tp_discard_pl(0.01, want_iplanet=False) == (None, nref)
+    # nobody close: count 0, indices zero-filled without a copy
+    ctx.body_put(TP, r=rtp + 50.0)
+    got, n = ctx.tp_discard_pl(0.01)
+    assert n == 0 and not got.any()
+    ctx.body_set_active(TP, None)
