@@ -940,8 +940,21 @@ def next_row_legs(ctx, args, d, hbm_peak, fp64_peak):
             fms.append(ctx.last_kernel_ms(FAM_DRIFT))
     ctx.enable_kernel_timing(False)
     tf = float(np.mean(fms)) * 1e-3
+    # the whole resident HELIO step (planets in one launch + particles in one launch), host wall clock, no L2 flush
+    for rep in range(2):
+        ctx.synchronize()
+        t0 = time.perf_counter()
+        for k in range(300):
+            ctx.helio_step_pl(p["cb_Gmass"], 0.01, LOOP_AUTO, True, lfirst=False, want_nfail=False)
+            ctx.helio_step_tp(p["cb_Gmass"], 0.01, lfirst=False, want_nfail=False)
+        ctx.synchronize()
+        t_whole = (time.perf_counter() - t0) / 300
     ex["helio_step_tp"] = {"npl": 8, "ntp": ntp, "ms": tf * 1e3, "tp_steps_per_s": ntp / tf,
                            "helio_step_pl_8_planets_ms": float(np.mean(pms[3:])),
+                           "whole_step_ms": t_whole * 1e3,
+                           "note": "ms / helio_step_pl_8_planets_ms are per-launch times after an L2 flush (cold planets: the one-CTA "
+                                   "planet kernel then pays DRAM latency on every dependent load); whole_step_ms is planets + "
+                                   "particles back to back, device resident, no flush",
                            "roofline": {"bound": "hbm", "achieved": HELIO_TP_BYTES * ntp / tf / 1e9, "peak": hbm_peak,
                                         "unit": "GB/s", "frac": HELIO_TP_BYTES * ntp / tf / 1e9 / hbm_peak,
                                         "bytes_per_tp": HELIO_TP_BYTES}}
