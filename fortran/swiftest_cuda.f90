@@ -407,6 +407,18 @@ module swiftest_cuda
          real(c_double), value :: dt
          integer(c_int), intent(out) :: iplanet(*), ndiscard
       end function
+      integer(c_int) function swcu_pl_encounter_check_triangular(ctx, dt, nenc) bind(C, name="swcu_pl_encounter_check_triangular")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
+      integer(c_int) function swcu_tp_encounter_check_triangular(ctx, dt, nenc) bind(C, name="swcu_tp_encounter_check_triangular")
+         import :: c_int, c_int64_t, c_ptr, c_double
+         type(c_ptr), value :: ctx
+         real(c_double), value :: dt
+         integer(c_int64_t), intent(out) :: nenc
+      end function
       integer(c_int) function swcu_tp_discard_pl(ctx, dt, iplanet, ndiscard) bind(C, name="swcu_tp_discard_pl")
          import :: c_int, c_ptr, c_double
          type(c_ptr), value :: ctx

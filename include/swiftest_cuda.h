@@ -254,6 +254,10 @@ int swcu_discard_pl_tp(swcu_context *ctx, int32_t ntp, int32_t npl, const double
  * pl%radius stay in HBM; particles are tested where their active flag -- swcu_body_set_active, else lmask -- is set).
  * ndiscard comes back always; iplanet (ntp entries, may be NULL) is copied only when ndiscard > 0, else zero-filled. */
 int swcu_tp_discard_pl(swcu_context *ctx, double dt, int32_t *iplanet, int32_t *ndiscard);
+/* tier 2 of the triangular checks (ENCOUNTER_CHECK TRIANGULAR): like swcu_pl_encounter_check / swcu_tp_encounter_check with the
+ * all-pairs predicate instead of the sweep; the list is fetched with swcu_encounter_fetch */
+int swcu_pl_encounter_check_triangular(swcu_context *ctx, double dt, int64_t *nenc);
+int swcu_tp_encounter_check_triangular(swcu_context *ctx, double dt, int64_t *nenc);
 /* the pair loop of symba_encounter_check_list_plpl / _pltp (symba_encounter_check.f90:122-137, 197-211) over an
  * existing encounter list: lencounter(k), lvdotr(k) for the pairs of lencmask (lvdotr is left alone elsewhere).
  * n2 == 0: both indices address list 1 (pl-pl); else index2 addresses list 2 (renc2 / radius2 may be NULL: 0).

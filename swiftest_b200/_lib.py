@@ -124,6 +124,8 @@ def load():
         "swcu_encounter_bucket_fallbacks": [p, p],
         "swcu_step_graph_replays": [p, p],
         "swcu_tp_discard_pl": [p, d, p, p],
+        "swcu_pl_encounter_check_triangular": [p, d, p],
+        "swcu_tp_encounter_check_triangular": [p, d, p],
         "swcu_pl_symba_kick_list": [p, i64, p, p, p, p, d, i32, i32, p],
         "swcu_tp_symba_kick_list": [p, i64, p, p, p, p, p, d, i32, i32, p],
         "swcu_body_symba_encounter_check_list": [p, i32, i64, p, p, p, d, p, p, p],

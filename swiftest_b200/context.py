@@ -306,6 +306,16 @@ class Context:
         self._ck(self._L.swcu_pl_encounter_check(self._h, float(dt), C.byref(n)))
         return self._fetch(n.value) if fetch else n.value
 
+    def pl_encounter_check_triangular(self, dt, fetch=True):
+        n = C.c_int64()
+        self._ck(self._L.swcu_pl_encounter_check_triangular(self._h, float(dt), C.byref(n)))
+        return self._fetch(n.value) if fetch else n.value
+
+    def tp_encounter_check_triangular(self, dt, fetch=True):
+        n = C.c_int64()
+        self._ck(self._L.swcu_tp_encounter_check_triangular(self._h, float(dt), C.byref(n)))
+        return self._fetch(n.value) if fetch else n.value
+
     def tp_encounter_check(self, dt, fetch=True):
         n = C.c_int64()
         self._ck(self._L.swcu_tp_encounter_check(self._h, float(dt), C.byref(n)))

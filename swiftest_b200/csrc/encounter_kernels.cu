@@ -1348,17 +1348,19 @@ static int encounter_sweep_impl(swcu_context *ctx, const SweepList &l1, const Sw
 
 // encounter_check_all_plplm (:42-109): plpl on the fully interacting block, then plm x plt with index2 shifted
 // by nplm; the two lists are disjoint, the canonical order is the lexicographic sort of their union.
-int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc_out)
+int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc_out,
+                          bool triangular)
 {
     auto &E = ctx->enc;
     int64_t n_a = 0, n_b = 0;
-    SWCU_TRY(encounter_sweep(ctx, plm, nullptr, dt, &n_a));
+    auto check = triangular ? encounter_triangular : encounter_sweep;  // ENCOUNTER_CHECK TRIANGULAR / SORTSWEEP
+    SWCU_TRY(check(ctx, plm, nullptr, dt, &n_a));
     const int64_t nbox_a = E.nbox_total, nem_a = E.nemitted;
     SWCU_CUDA(ctx, E.out1.ensure(sizeof(unsigned long long) * (size_t)(n_a > 0 ? n_a : 1)));
     if (n_a > 0)
         SWCU_CUDA(ctx, cudaMemcpyAsync(E.out1.p, E.result, sizeof(unsigned long long) * n_a, cudaMemcpyDeviceToDevice,
                                        ctx->stream));
-    SWCU_TRY(encounter_sweep(ctx, plm, &plt, dt, &n_b));
+    SWCU_TRY(check(ctx, plm, &plt, dt, &n_b));
     E.nbox_total += nbox_a;
     E.nemitted += nem_a;
     const int64_t n = n_a + n_b;

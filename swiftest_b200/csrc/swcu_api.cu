@@ -858,6 +858,37 @@ extern "C" int swcu_tp_encounter_check(swcu_context *ctx, double dt, int64_t *ne
     return encounter_sweep(ctx, sweep_list(pl, 0, pl.n, true), &l2, dt, nenc);
 }
 
+// the same two checks with the all-pairs predicate instead of the sweep (ENCOUNTER_CHECK TRIANGULAR, encounter_check.f90:436-570)
+extern "C" int swcu_pl_encounter_check_triangular(swcu_context *ctx, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl;
+    if (!nenc) return fail(ctx, SWCU_ERR_ARG, "pl_encounter_check_triangular: null nenc");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (!pl.valid) return fail(ctx, SWCU_ERR_STATE, "pl_encounter_check_triangular: pl population not resident");
+    if (pl.n == 0) return SWCU_OK;
+    const int nplm = pl.nplm, nplt = pl.n - pl.nplm;
+    if (nplt == 0) return encounter_triangular(ctx, sweep_list(pl, 0, pl.n, true), nullptr, dt, nenc);
+    if (nplm == 0) return SWCU_OK;
+    return encounter_merge_plplm(ctx, sweep_list(pl, 0, nplm, true), sweep_list(pl, nplm, nplt, true), dt, nenc, true);
+}
+
+extern "C" int swcu_tp_encounter_check_triangular(swcu_context *ctx, double dt, int64_t *nenc)
+{
+    SWCU_TRY(check_ctx(ctx));
+    Body &pl = ctx->pl, &tp = ctx->tp;
+    if (!nenc) return fail(ctx, SWCU_ERR_ARG, "tp_encounter_check_triangular: null nenc");
+    *nenc = 0;
+    ctx->enc.nenc = 0;
+    ctx->enc.result = nullptr;
+    if (!pl.valid || !tp.valid) return fail(ctx, SWCU_ERR_STATE, "tp_encounter_check_triangular: populations not resident");
+    if (pl.n == 0 || tp.n == 0) return SWCU_OK;
+    SweepList l2 = sweep_list(tp, 0, tp.n, false);
+    return encounter_triangular(ctx, sweep_list(pl, 0, pl.n, true), &l2, dt, nenc);
+}
+
 // ======================================================================================================
 // tier 2: the O(N) glue of the democratic-heliocentric step
 // ======================================================================================================

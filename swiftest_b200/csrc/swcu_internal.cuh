@@ -336,7 +336,8 @@ struct SweepList {
     int n;
 };
 int encounter_sweep(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc);
-int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc);
+int encounter_merge_plplm(swcu_context *ctx, const SweepList &plm, const SweepList &plt, double dt, int64_t *nenc,
+                          bool triangular = false);
 int set_renc(swcu_context *ctx, Body &pl, int irec);
 int encounter_triangular(swcu_context *ctx, const SweepList &l1, const SweepList *l2, double dt, int64_t *nenc);
 int discard_pl_tp(swcu_context *ctx, const Body &tp, const Body &pl, const int32_t *d_lactive, double dt,

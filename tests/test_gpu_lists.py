@@ -379,3 +379,33 @@ def test_resident_discard_pl_tp_matches_oracle(ctx, oracle, npl, ntp):
     got, n = ctx.tp_discard_pl(0.01)
     assert n == 0 and not got.any()
     ctx.body_set_active(TP, None)
+
+
+def test_resident_triangular_encounter_checks_match_oracle(ctx, oracle):
+    """swcu_pl/tp_encounter_check_triangular: ENCOUNTER_CHECK TRIANGULAR on the resident populations, incl. the GMTINY split
+    (plm x plm + plm x plt merged like encounter_check_all_plplm)."""
+    from swiftest_b200 import PL, TP
+    f = W.fixture("108pl_50tp")
+    order = np.argsort(-f["pl_Gmass"], kind="stable")
+    nplm = int((f["pl_Gmass"] >= float(f["GMTINY"])).sum())
+    r, v, rhill = f["pl_rh"][order], f["pl_vh"][order], f["pl_rhill"][order] * 20
+    ctx.body_sync(PL, 108, nplm=nplm, r=r, v=v, Gmass=f["pl_Gmass"][order], radius=f["pl_radius"][order], rhill=rhill,
+                  generation=next(_generation))
+    ctx.body_sync(TP, 50, r=f["tp_rh"], v=f["tp_vh"], generation=next(_generation))
+    ctx.pl_set_renc(0)
+    rc = oracle.set_renc(rhill, 0)
+    a = oracle.encounter_plpl(r[:nplm], v[:nplm], rc[:nplm], 0.05, triangular=True)
+    b = oracle.encounter_plplm(r[:nplm], v[:nplm], r[nplm:], v[nplm:], rc[:nplm], rc[nplm:], 0.05, triangular=True)
+    ref = sorted(zip(a[0].tolist(), a[1].tolist())) + sorted((i, j + nplm) for i, j in zip(b[0].tolist(), b[1].tolist()))
+    ref = sorted(ref)
+    n, g1, g2, _ = ctx.pl_encounter_check_triangular(0.05)
+    assert n == len(ref) and n > 0 and list(zip(g1.tolist(), g2.tolist())) == ref
+    rt = oracle.encounter_pltp(r, v, f["tp_rh"], f["tp_vh"], rc, 0.05, triangular=True)
+    _same(ctx.tp_encounter_check_triangular(0.05), rt)
+    # fully interacting population: no split
+    d = W.disk(900, seed=3)
+    ctx.body_sync(PL, 900, nplm=900, r=d["rh"], v=d["vh"], Gmass=d["Gmass"], radius=d["radius"], rhill=d["rhill"] * 4,
+                  generation=next(_generation))
+    ctx.pl_set_renc(0)
+    _same(ctx.pl_encounter_check_triangular(d["dt"]),
+          oracle.encounter_plpl(d["rh"], d["vh"], oracle.set_renc(d["rhill"] * 4, 0), d["dt"], triangular=True))
