@@ -877,6 +877,10 @@ __device__ __forceinline__ int discard_pl_close(double dx, double dy, double dz,
     if (r2 <= r2crit) return 1;
     const double vdotr = dx * dvx + dy * dvy + dz * dvz;
     if (vdotr > 0.0) return 0;
+    // Exact conservative pre-rejection (as in check_one): for vdotr <= 0 both branches below satisfy
+    // min(r2min, r2) >= r2 + 2*vdotr*dt, so a pair whose bound clears r2crit by 1e-9 of r2 -- a million times the rounding
+    // of either side, whatever the ratio r2 / r2crit -- is kept without the two IEEE divisions.
+    if (r2 + 2.0 * vdotr * dt > r2crit + 1e-9 * r2) return 0;
     const double v2 = dvx * dvx + dvy * dvy + dvz * dvz;
     const double tmin = -vdotr / v2;
     double r2min;
