@@ -310,8 +310,9 @@ __global__ void chunk_owner_kernel(int ntot, const int *__restrict__ nchunk, con
 // encounter_check_one, encounter_check.f90:591-618.
 // The exact expressions (two IEEE divisions) are only evaluated for pairs that can possibly be an encounter: for
 // vdotr <= 0 both branches of r2min satisfy r2min >= r2 + 2*vdotr*dt (tmin < dt implies vdotr^2/v2 < -vdotr*dt), so
-// r2 + 2*vdotr*dt > r2crit*(1 + 1e-9) proves "no encounter" with a margin 1e7 times the rounding error of either side.
-// The decision is therefore identical to the reference expression for every input.
+// r2 + 2*vdotr*dt > r2crit + 1e-9*r2 proves "no encounter": every quantity involved is computed to a few ulp of r2
+// (the largest term), and the margin is a million times that whatever the ratio r2 / r2crit (the all-pairs checks see
+// pairs a thousand encounter radii apart).  The decision is therefore identical to the reference expression.
 __device__ __forceinline__ bool check_one(double xr, double yr, double zr, double vxr, double vyr, double vzr,
                                           double renc, double dt, double vsmall)
 {
@@ -320,7 +321,7 @@ __device__ __forceinline__ bool check_one(double xr, double yr, double zr, doubl
     if (!(r2 > r2crit)) return true;  // vdotr = -1, r2min = r2 <= r2crit  (:612-615)
     const double vdotr = vxr * xr + vyr * yr + vzr * zr;
     if (vdotr > 0.0) return false;    // lvdotr false (:596-597, :617)
-    if (r2 + 2.0 * vdotr * dt > r2crit * 1.000000001) return false;  // conservative: cannot come close enough
+    if (r2 + 2.0 * vdotr * dt > r2crit + 1e-9 * r2) return false;  // conservative: cannot come close enough
     double r2min;
     const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
     if (v2 <= vsmall) {
@@ -470,7 +471,7 @@ __device__ __forceinline__ bool check_one_flat(double xr, double yr, double zr, 
     const double vdotr = vxr * xr + vyr * yr + vzr * zr;
     const bool inside = !(r2 > r2crit);                                            // (:612-615): encounter
     bool hit = inside;
-    if (!inside && !(vdotr > 0.0) && !(r2 + 2.0 * vdotr * dt > r2crit * 1.000000001)) {
+    if (!inside && !(vdotr > 0.0) && !(r2 + 2.0 * vdotr * dt > r2crit + 1e-9 * r2)) {
         double r2min;
         const double v2 = vxr * vxr + vyr * vyr + vzr * vzr;
         if (v2 <= vsmall) {
